@@ -1,0 +1,222 @@
+#!/usr/bin/env python
+"""bench.py — BSRNN audio-seconds enhanced per second at 48 kHz (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W            # our arm (libbsrnn_b200 through the C ABI)
+  python bench.py --impl reference ...                     # the reference's CPU path (oracle port) on host cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU, utterances sharded, no collective
+
+A step = one BSRNN_SE forward (STFT -> BandSplit -> 6x[time BLSTM, band BLSTM] -> MaskDecoder -> mask+iSTFT) over
+one batch of synthetic noisy utterances with random-init BSRNN_baseline.yaml weights (N=196, 6 layers).
+`value` times the forward with inputs resident in HBM; `e2e` times the public model call with pinned HOST buffers,
+H2D of the waveforms and D2H of the enhanced waveforms inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+FS = 48000
+NUM_CHANNEL, NUM_LAYER = 196, 6                      # conf/models/BSRNN_baseline.yaml:36-38
+
+
+def algorithmic_flops(B, T, K, N=NUM_CHANNEL, layers=NUM_LAYER):
+    """2 x MACs of the weight GEMMs: per token-layer 4 directions x 4H(N+H) + 2 x 4N*N."""
+    H = 2 * N
+    tokens = B * T * K
+    lstm_rec = tokens * layers * 4 * (4 * H * H) * 2
+    lstm_in = tokens * layers * 4 * (4 * H * N) * 2
+    fc = tokens * layers * 2 * (4 * N * N) * 2
+    return dict(lstm_rec=lstm_rec, lstm_in=lstm_in, fc=fc)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line) via NVML."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_throughput(seconds, threads, steps=1, warmup=0):
+    """The reference's CPU path for this workload: oracle/restated.py (port of the reference's PyTorch code on the
+    espnet2 shim) on the box's host cores.  Returns (audio_s_per_s, cores, sample description)."""
+    from oracle import restated as R
+    from urgent2026_challenge_track1_b200.bsrnn import BSRNN_SE
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = BSRNN_SE(NUM_CHANNEL, NUM_LAYER).state_dict()
+    n = int(seconds * FS)
+    x = R.synth_noisy(1, n, FS)
+    lens = torch.tensor([n])
+    with torch.no_grad():
+        for _ in range(warmup):
+            R.bsrnn_se_forward(sd, x, lens, FS, NUM_LAYER)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            R.bsrnn_se_forward(sd, x, lens, FS, NUM_LAYER)
+        dt = (time.perf_counter() - t0) / steps
+    return seconds / dt, threads, f"1x{seconds:g}s@48kHz utterance, f32, {steps} run(s) after {warmup} warm-up"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BSRNN_B200_PRECISION", "fp32"))
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU (BASELINE config 2: 64)")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--cpu-seconds", type=float, default=4.0, help="length of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"BSRNN_baseline (N=196, L=6) inference, {args.batch}x{args.seconds:g}s@48kHz synthetic utterances per GPU"
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, c, sample = cpu_reference_throughput(args.cpu_seconds, cores, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "BSRNN audio-sec/sec enhanced at 48 kHz", "value": v, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_seconds / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": c, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+    from oracle import restated as R                                  # synthetic input generator + cpu_baseline only
+    from urgent2026_challenge_track1_b200 import BSRNN_SE, _lib, runtime
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+
+    torch.manual_seed(0)
+    model = BSRNN_SE(NUM_CHANNEL, NUM_LAYER, precision=args.precision).to(dev)
+    B, n = args.batch, int(args.seconds * FS)
+    base = R.synth_noisy(min(B, 4), n, FS, seed=1 + rank)
+    host = base.repeat((B + base.size(0) - 1) // base.size(0), 1)[:B].contiguous()
+    host = (host * (1.0 + 0.01 * torch.arange(B)[:, None])).pin_memory()      # distinct utterances
+    lens = torch.full((B,), n, dtype=torch.int32)
+    x_dev = host.to(dev)
+    out_host = torch.empty(B, n, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        model(x_dev, lens, FS)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib = _lib.lib()
+    lib.bsrnn_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with runtime.Profile() as prof:
+        e0.record()
+        for _ in range(args.steps):
+            model(x_dev, lens, FS)
+        e1.record()
+        barrier()
+        regions = prof.totals_ms()
+    launches = lib.bsrnn_launch_count(0)
+    ms = e0.elapsed_time(e1)
+    # ---- end to end through the public call with host buffers
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        wav, _ = model(host, lens, FS)                       # H2D inside (pinned, non_blocking)
+        out_host.copy_(wav, non_blocking=True)               # D2H of the enhanced waveforms
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    audio_s = world * B * args.seconds * args.steps
+    value, e2e = audio_s / (ms / 1e3), audio_s / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pp):
+            peaks = json.load(open(pp))
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        T, K = 1 + n // 480, 34
+        fl = algorithmic_flops(B, T, K)
+        rec_ms, rec_calls = regions.get("lstm_time", (0.0, 0))
+        rec_ms_b, rec_calls_b = regions.get("lstm_freq", (0.0, 0))
+        # dominant kernel family: the BLSTM recurrence (60 % of algorithmic FLOPs); one "launch" = one BLSTM layer call
+        calls = max(1, rec_calls + rec_calls_b)
+        flops_per_call = fl["lstm_rec"] / (2 * NUM_LAYER)
+        achieved = flops_per_call / ((rec_ms + rec_ms_b) / calls / 1e3) / 1e12 if rec_ms + rec_ms_b > 0 else 0.0
+        line = {
+            "metric": "BSRNN audio-sec/sec enhanced at 48 kHz", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": workload, "precision": args.precision, "weights": "random-init seed 0",
+                       "l2": "inputs and activations larger than L2 (no flush needed)", "sharding": "utterances, no collective"},
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * n * 4 + B * 4, "d2h_bytes_per_step": B * n * 4},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "kernel": "blstm_recurrence", "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                         "regions_ms_per_step": {k: v[0] / args.steps for k, v in regions.items()}},
+        }
+        if not args.no_cpu_baseline:
+            v, c, sample = cpu_reference_throughput(args.cpu_seconds, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": c, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Builds libbsrnn_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+SRC=urgent2026_challenge_track1_b200/csrc
+OUT=urgent2026_challenge_track1_b200/_C
+mkdir -p $OUT
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --use_fast_math"
+# fast-math is NOT applied to the f32-mode kernels' transcendental calls: they use expf/tanhf explicitly... see per-file flags
+for f in api fft norm gemm_f32 lstm_f32 flow $EXTRA; do
+  FF="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
+  $NVCC $FF -c $SRC/$f.cu -o $OUT/$f.o 2> $OUT/$f.ptxas.log || { cat $OUT/$f.ptxas.log; exit 1; }
+done
+$NVCC -shared -o $OUT/libbsrnn_b200.so $OUT/*.o -lcudart
+echo built $OUT/libbsrnn_b200.so

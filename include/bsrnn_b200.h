@@ -1,0 +1,139 @@
+/* bsrnn_b200.h — C ABI of the B200-native BSRNN / FlowSE hot path (libbsrnn_b200.so, sm_100a only).
+ *
+ * The reference (urgent-challenge/urgent2026_challenge_track1) defines NO FFI for this path: every device op is
+ * a PyTorch library call.  The entry points below are therefore build-defined; each one cites the
+ * reference call it replaces (file:line relative to the reference root; `espnet2/...` = the un-vendored
+ * espnet==202412 dependency, behaviour in SURVEY.md Appendix A).
+ *
+ * Conventions
+ *   - Stateless and stream-ordered: every pointer is a DEVICE pointer owned by the caller (torch allocates), every
+ *     call enqueues on `stream` (a cudaStream_t passed as void*) and returns without synchronising.
+ *   - No allocation inside; scratch comes from the caller, sized by the matching *_workspace_bytes() query.
+ *   - Return value: 0 = ok, non-zero = error; bsrnn_last_error() returns a thread-local message.
+ *   - "spec" tensors are complex64 stored as interleaved float pairs, layout (B, T, F, 2).
+ *   - "token-major" activations are (B, T, K, N) f32: token index ((b*T + t)*K + k).
+ *   - precision modes: the *_f32 entry points compute in f32 on CUDA cores (parity bar 1e-3); the *_bf16 ones
+ *     use tcgen05 tensor cores with bf16 operands and f32 accumulation in TMEM (parity bar 1e-2).
+ */
+#ifndef BSRNN_B200_H_
+#define BSRNN_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------- misc */
+const char* bsrnn_last_error(void);
+int bsrnn_abi_version(void);                 /* bumped whenever a signature changes */
+int bsrnn_device_check(void);                /* 0 iff the current device is compute capability 10.x */
+long bsrnn_launch_count(int reset);          /* kernels launched by this library since the last reset */
+
+/* ---------------------------------------------------------------------------------------------- STFT / iSTFT
+ * bsrnn_stft_fwd  replaces STFTEncoder.forward -> Stft.forward -> torch.stft (+ frame masking, + optional
+ *   "exponent" compression)           [baseline_code/models/bsrnn.py:37, baseline_code/flow_model.py:136]
+ *   wav (B, L) f32, lens (B) int32 (may be NULL = all L) -> spec (B, T, F, 2), T = 1 + L/hop, F = n_fft/2+1.
+ *   Periodic Hann window of n_fft points, center=True reflect padding over the whole (padded) row of L samples,
+ *   frames >= olens[b] = (lens[b] + 2*(n_fft/2) - n_fft)/hop + 1 written as zeros.
+ *   transform: 0 none; 1 "exponent": |X|^exponent * e^{j arg X} * factor.
+ *   twiddle: (n_fft, 2) f32 table exp(-2*pi*i*n/n_fft) from bsrnn_fft_twiddle().
+ */
+int bsrnn_fft_twiddle(float* twiddle, int n_fft, void* stream);
+int bsrnn_stft_fwd(const float* wav, const int32_t* lens, float* spec, const float* twiddle, int B, int L,
+                   int n_fft, int hop, int transform, float exponent, float factor, void* stream);
+
+/* bsrnn_istft_fwd replaces the complex mask  s = m*x + r  (espnet2 BSRNN.forward tail; flow analogue
+ *   baseline_code/models/bsrnn_flowse.py:311-316) fused with STFTDecoder.forward -> torch.istft
+ *   [baseline_code/models/bsrnn.py:40, baseline_code/flow_model.py:145].
+ *   spec (B,T,F,2); mask/resid (B,T,F,2) or NULL (then s = spec).  If spec_out != NULL the masked spectrum s is
+ *   also written there (the `enhanced_feature` BSRNN_SE.forward returns).  transform 1 = inverse "exponent"
+ *   (s/factor, |.|^(1/exponent)) applied after masking.  wav_out (B, L_out): inverse real DFT, Hann window,
+ *   overlap-add, division by the window-square envelope, trim n_fft/2 (center=True), length = L_out.
+ */
+int bsrnn_istft_fwd(const float* spec, const float* mask, const float* resid, float* spec_out, float* wav_out,
+                    const float* twiddle, int B, int T, int L_out, int n_fft, int hop, int transform,
+                    float exponent, float factor, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- GroupNorm(1, C)
+ * Statistics are per sample over everything else, zeros of padded frames/bins included.
+ * bsrnn_gn_stats:   x viewed as (B, rows_per_sample, C) with row stride `row_stride` floats, sample stride
+ *                   rows_per_sample*row_stride; accumulates {sum, sumsq} as double into stats (B,2).
+ *                   Replaces the reduction half of nn.GroupNorm at bsrnn_flowse.py:291,302 (norm_time/norm_freq).
+ * bsrnn_band_stats: per (b, band) statistics over rows (b,t) of row_len floats; band k = floats
+ *                   [band_off[k], band_off[k]+band_width[k]) of every row (device int32 arrays).  BandSplit:
+ *                   x = spec (B,T,F,2), row_len 2F, off 2*bin0, width 2*min(s, F-bin0) (missing bins are zeros and
+ *                   only enter through the count)  [bsrnn_flowse.py:65-73]; mask / grad decoders: x = skip (B,T,K,N),
+ *                   row_len K*N, off k*N, width N  [espnet2 MaskDecoder; bsrnn_flowse.py:146-152].
+ *                   stats (B, n_bands, 2) double, zeroed by the call.
+ * bsrnn_gn_finalize: scale[b,c] = rstd_b*gamma_c, shift[b,c] = beta_c - mean_b*rstd_b*gamma_c (+ extra[b,c] if
+ *                   non-NULL: the FlowSE time embedding added after the norm, bsrnn_flowse.py:293-294).
+ *                   stats (G,2) double; gamma/beta (G_inner, C) and counts (G_inner) double (device), selected by
+ *                   g % G_inner (G_inner = 1 for a plain layer norm, = n_bands for per-band norms with C the
+ *                   padded channel width); scale/shift (G, C).  gn_stats zeroes `stats` itself.
+ */
+int bsrnn_gn_stats(const float* x, double* stats, int B, long rows_per_sample, int C, long row_stride, void* stream);
+int bsrnn_band_stats(const float* x, double* stats, int B, int T, long row_len, const int32_t* band_off,
+                     const int32_t* band_width, int n_bands, void* stream);
+int bsrnn_gn_finalize(const double* stats, const float* gamma, const float* beta, const float* extra,
+                      float* scale, float* shift, int G, int C, const double* counts, float eps, int G_inner,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------- grouped GEMM (f32)
+ * One descriptor per group g (band / MLP / plain layer):
+ *     C[row, n] = epi( sum_k A'[row, k] * W[n, k] + bias[n] ),   A'[row,k] = A[row,k]*scale[s,k] + shift[s,k]
+ * with s = row / rows_per_sample (scale==NULL: identity).  Row r of A lives at
+ *     A + (r / a_inner) * a_outer_stride + (r % a_inner) * a_inner_stride          (floats), same for C.
+ * k >= k_valid reads as 0 before the affine (truncated last band, bsrnn_flowse.py:68-71).
+ * epilogue: 0 store, 1 tanh, 2 C += result (residual, bsrnn_flowse.py:300,307), 3 GLU over the N axis
+ *           (out[n] = v[n] * sigmoid(v[n + N/2]), n < N/2; nn.GLU(dim=1) in espnet2 MaskDecoder).
+ * Only output columns n < n_store are written (bins beyond F of a truncated band are dropped, espnet2
+ * BSRNN.forward `m[..., :F]`).
+ */
+typedef struct {
+  const float* A; const float* W; const float* bias; float* C;
+  const float* scale; const float* shift;
+  long a_inner, a_outer_stride, a_inner_stride;
+  long c_inner, c_outer_stride, c_inner_stride;
+  long rows_per_sample, ss_stride;      /* scale/shift row of sample s starts at s*ss_stride */
+  int M, N, K, k_valid, ldw, epilogue, n_store, pad_;
+} bsrnn_gemm_desc;
+/* descs: DEVICE array of n_groups descriptors; max_m/max_n: maxima over groups (grid sizing). */
+int bsrnn_gemm_f32(const bsrnn_gemm_desc* descs, int n_groups, int max_m, int max_n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- BLSTM (f32)
+ * Replaces nn.LSTM(N, H, batch_first=True, bidirectional=True) forward with zero initial state
+ * [bsrnn_flowse.py:226-238 construct, :296-297 (time axis) and :303-304 (band axis) call]; gate order i,f,g,o.
+ * Sequences are addressed inside token-major tensors: sequence r = (r / seq_inner, r % seq_inner), step s:
+ *     token(r, s) = (r / seq_inner) * seq_outer + (r % seq_inner) * seq_inner_stride + s * step_stride
+ * time axis of (B,T,K): seq_inner=K, seq_outer=T*K, seq_inner_stride=1, step_stride=K, steps=T, R=B*K
+ * band axis           : seq_inner=1, seq_outer=K,   seq_inner_stride=0, step_stride=1, steps=K, R=B*T
+ *   gates_x (tokens, 2, 4H) f32 : x W_ih^T + b_ih + b_hh for both directions (from bsrnn_gemm_f32)
+ *   w_hh    (2, 4H, H) f32      : weight_hh_l0, weight_hh_l0_reverse
+ *   y       (tokens, 2H) f32    : output, [fwd | bwd] per token (also the h carrier between steps)
+ *   c_state (2, R, H) f32       : scratch
+ */
+int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y, float* c_state,
+                               int R, int steps, int H, long seq_inner, long seq_outer, long seq_inner_stride,
+                               long step_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- FlowSE pieces
+ * bsrnn_time_embed: GaussianFourierProjection [bsrnn_flowse.py:90-99]: out (B, 2*E) = [sin(2*pi*t*W), cos(...)].
+ * bsrnn_conv5x5_glu: GradDecoder.conv_after_* = Conv2d(16->4, 5x5, pad 2) + GLU(dim=1) [bsrnn_flowse.py:114-117,
+ *   163-164] on g (B, T, Fp, 16) channel-last -> out (B, T, F, 2) (bins >= Fp zero, bsrnn_flowse.py:166-167).
+ *   weight (4,16,5,5) as in the state_dict, kernel dims ordered (freq, time) like the reference's (F', T) image.
+ * bsrnn_euler_step: x <- x + step*(m*x + r)  [sampling/odesolvers.py:76-81 with VF = -dnn, flow_model.py:203-209];
+ *   all (B,T,F,2); in place on x.
+ * bsrnn_fm_prior: x = y + sigma*z  [models/odes.py:84-91].
+ */
+int bsrnn_time_embed(const float* t, const float* W, float* out, int B, int E, void* stream);
+int bsrnn_conv5x5_glu(const float* g, const float* weight, const float* bias, float* out, int B, int T, int Fp,
+                      int F, void* stream);
+int bsrnn_euler_step(float* x, const float* mask, const float* resid, float step, long n_complex, void* stream);
+int bsrnn_axpy_complex(float* out, const float* y, const float* z, float sigma, long n_complex, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* BSRNN_B200_H_ */

@@ -1,0 +1,83 @@
+"""BSRNN_SE — drop-in for ``baseline_code/models/bsrnn.py::BSRNN_SE`` (reference bsrnn.py:9-41).
+
+Same constructor (``num_channel=192, num_layer=6``), same forward signature and return value, same state_dict
+keys (``bsrnn.bsrnn.*``); the STFT encoder / BSRNN separator / iSTFT decoder all run in the sm_100a
+kernels of libbsrnn_b200 (include/bsrnn_b200.h).  Non-causal (bidirectional) only, num_spk=1, as the reference
+instantiates it (bsrnn.py:27-34).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import runtime as R
+from .layers import BandSplitParams, MaskDecoderParams, add_dual_path
+
+
+class _BSRNNCore(nn.Module):
+    """Parameter tree of espnet2.enh.layers.bsrnn.BSRNN (attribute names per SURVEY.md Appendix A)."""
+
+    def __init__(self, input_dim=481, num_channel=16, num_layer=6, target_fs=48000, num_spk=1):
+        super().__init__()
+        self.num_layer, self.num_channel, self.input_dim = num_layer, num_channel, input_dim
+        self.band_split = BandSplitParams(input_dim, target_fs=target_fs, channels=num_channel)
+        add_dual_path(self, num_channel, num_layer)
+        self.mask_decoder = MaskDecoderParams(input_dim, self.band_split.subbands, channels=num_channel, num_spk=num_spk)
+
+
+class _Separator(nn.Module):
+    """espnet2 BSRNNSeparator holds its network under ``.bsrnn`` — hence the ``bsrnn.bsrnn.`` key prefix."""
+
+    def __init__(self, input_dim, num_channels, num_layers, target_fs):
+        super().__init__()
+        self.bsrnn = _BSRNNCore(input_dim, num_channels, num_layers, target_fs)
+
+
+class BSRNN_SE(nn.Module):
+    N_FFT, HOP, DEFAULT_FS = 960, 480, 48000          # reference bsrnn.py:14-25
+
+    def __init__(self, num_channel=192, num_layer=6, precision=None):
+        super().__init__()
+        self.bsrnn = _Separator(self.N_FFT // 2 + 1, num_channel, num_layer, self.DEFAULT_FS)
+        self.num_channel, self.num_layer = num_channel, num_layer
+        self.precision = precision or os.environ.get("BSRNN_B200_PRECISION", "fp32")
+        core = self.bsrnn.bsrnn
+        self._dual = R.PackedCache(core, R.pack_dual_path)
+        self._bs = R.PackedCache(core.band_split, R.pack_band_split)
+        self._md = R.PackedCache(core.mask_decoder, R.pack_mask_decoder)
+
+    # ------------------------------------------------------------------------------------------------
+    def _device(self):
+        return self.bsrnn.bsrnn.fc_time[0].weight.device
+
+    @torch.no_grad()
+    def forward(self, speech_mix, speech_lengths, fs):
+        """speech_mix (B,L) float, speech_lengths (B,) int, fs int or 0-dim tensor ->
+        (enhanced_wav (B, max(lengths)) f32, enhanced_feature (B,T,F) complex64)   [reference bsrnn.py:36-41]"""
+        L.require_device()
+        dev = self._device()
+        if dev.type != "cuda":
+            raise L.NativeLibraryError("BSRNN_SE parameters must live on a CUDA device (no CPU fallback)")
+        fs = int(fs)
+        wav = speech_mix.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if wav.dim() != 2:
+            raise ValueError(f"speech_mix must be (B, L), got {tuple(wav.shape)}")
+        lens_host = speech_lengths.detach().to("cpu") if torch.is_tensor(speech_lengths) else torch.as_tensor(speech_lengths)
+        L_out = int(lens_host.max())
+        lens = lens_host.to(device=dev, dtype=torch.int32, non_blocking=True)
+        n_fft, hop = R.stft_dims(fs, self.N_FFT, self.HOP, self.DEFAULT_FS)
+        core = self.bsrnn.bsrnn
+        plan = R.BandPlan.make(core.band_split.subbands, n_fft // 2 + 1)
+
+        spec = R.stft(wav, lens, n_fft, hop)
+        if self.precision == "fp32":
+            skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel)
+            R.dual_path_f32(skip, self._dual.get())
+            mask, resid = R.mask_decoder_f32(skip, plan, self._md.get())
+        else:
+            raise NotImplementedError(f"precision {self.precision!r}")
+        wav_out, est = R.istft(spec, mask, resid, L_out, n_fft, hop, want_spec=True)
+        return wav_out, torch.view_as_complex(est)

@@ -1,0 +1,379 @@
+// fft.cu — batched multi-sample-rate STFT / iSTFT for sm_100a.
+//
+// One CTA owns a run of consecutive frames of one utterance.  Frames are windowed while they are staged into
+// shared memory, transformed there by a Stockham mixed-radix FFT (radices 4/2/3/5/7, generic odd primes for the
+// FlowSE 22.05/44.1 kHz sizes 705 = 3*5*47 and 1411 = 17*83), and written back with coalesced float2 stores in the
+// (B,T,F,2) layout BandSplit reads.  The inverse kernel fuses the complex mask (s = m*x + r), the optional inverse
+// spectral compression, the synthesis window, the overlap-add and the window-envelope division, so the mask and
+// the residual are never re-read and the masked spectrum is written exactly once.
+//
+// Replaces: espnet2 Stft.forward / Stft.inverse (torch.stft / torch.istft), called from
+// baseline_code/models/bsrnn.py:37,40 and baseline_code/flow_model.py:136,145.
+#include "common.cuh"
+
+namespace bsrnn {
+
+constexpr int kMaxStages = 16;
+constexpr int kMaxGenericRadix = 96;
+
+struct FftPlan {
+  int n;
+  int nstages;
+  int radix[kMaxStages];
+};
+
+static bool make_plan(int n, FftPlan* p) {
+  p->n = n;
+  p->nstages = 0;
+  int m = n;
+  const int pref[] = {4, 2, 3, 5, 7};
+  for (int r : pref) {
+    while (m % r == 0) {
+      if (p->nstages >= kMaxStages) return false;
+      p->radix[p->nstages++] = r;
+      m /= r;
+    }
+  }
+  for (int r = 11; m > 1; r += 2) {
+    while (m % r == 0) {
+      if (p->nstages >= kMaxStages || r > kMaxGenericRadix) return false;
+      p->radix[p->nstages++] = r;
+      m /= r;
+    }
+    if (r > kMaxGenericRadix && m > 1) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// tw[i] = exp(-2*pi*i/N); inverse transform uses the conjugate.
+template <bool INV>
+__device__ __forceinline__ float2 twd(const float2* tw, int i) {
+  float2 w = tw[i];
+  if (INV) w.y = -w.y;
+  return w;
+}
+
+// One Stockham butterfly of radix R: element index j in [0, N/R).
+template <int R, bool INV>
+__device__ __forceinline__ void butterfly(const float2* __restrict__ in, float2* __restrict__ out,
+                                          const float2* __restrict__ tw, int N, int Ns, int j) {
+  const int k = j % Ns;
+  const int nr = N / R;
+  const int tstep = N / (Ns * R);
+  float2 v[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) {
+    v[q] = in[j + q * nr];
+    if (q > 0 && k > 0) v[q] = cmul(v[q], twd<INV>(tw, q * k * tstep));
+  }
+  float2 o[R];
+  if (R == 2) {
+    o[0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
+    o[1] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+  } else if (R == 4) {
+    float2 a = make_float2(v[0].x + v[2].x, v[0].y + v[2].y);
+    float2 b = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+    float2 c = make_float2(v[1].x + v[3].x, v[1].y + v[3].y);
+    float2 d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+    // forward: multiply d by -i ; inverse: by +i
+    float2 dj = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+    o[0] = make_float2(a.x + c.x, a.y + c.y);
+    o[1] = make_float2(b.x + dj.x, b.y + dj.y);
+    o[2] = make_float2(a.x - c.x, a.y - c.y);
+    o[3] = make_float2(b.x - dj.x, b.y - dj.y);
+  } else {
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+      float2 acc = v[0];
+#pragma unroll
+      for (int q = 1; q < R; ++q) {
+        float2 w = twd<INV>(tw, ((p * q) % R) * nr);
+        acc.x += v[q].x * w.x - v[q].y * w.y;
+        acc.y += v[q].x * w.y + v[q].y * w.x;
+      }
+      o[p] = acc;
+    }
+  }
+  const int j0 = (j / Ns) * Ns * R + k;
+#pragma unroll
+  for (int q = 0; q < R; ++q) out[j0 + q * Ns] = o[q];
+}
+
+// Generic (runtime) radix for large odd primes; rare path (FlowSE at 22.05 / 44.1 kHz).
+template <bool INV>
+__device__ void butterfly_generic(const float2* __restrict__ in, float2* __restrict__ out,
+                                  const float2* __restrict__ tw, int N, int Ns, int R, int j) {
+  const int k = j % Ns;
+  const int nr = N / R;
+  const int tstep = N / (Ns * R);
+  float2 v[kMaxGenericRadix];
+  for (int q = 0; q < R; ++q) {
+    v[q] = in[j + q * nr];
+    if (q > 0 && k > 0) v[q] = cmul(v[q], twd<INV>(tw, q * k * tstep));
+  }
+  const int j0 = (j / Ns) * Ns * R + k;
+  for (int p = 0; p < R; ++p) {
+    float2 acc = v[0];
+    int pq = 0;
+    for (int q = 1; q < R; ++q) {
+      pq += p;
+      if (pq >= R) pq -= R;
+      float2 w = twd<INV>(tw, pq * nr);
+      acc.x += v[q].x * w.x - v[q].y * w.y;
+      acc.y += v[q].x * w.y + v[q].y * w.x;
+    }
+    out[j0 + p * Ns] = acc;
+  }
+}
+
+// Transforms `nframes` frames held contiguously (N float2 each) in buf0 using buf1 as the ping-pong partner.
+// Returns the buffer holding the result.  All threads of the CTA must call it.
+template <bool INV>
+__device__ float2* fft_frames(float2* buf0, float2* buf1, const float2* tw, const FftPlan& plan, int nframes) {
+  const int N = plan.n;
+  int Ns = 1;
+  float2* src = buf0;
+  float2* dst = buf1;
+  for (int s = 0; s < plan.nstages; ++s) {
+    const int R = plan.radix[s];
+    const int per = N / R;
+    const int total = nframes * per;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+      const int f = idx / per;
+      const int j = idx - f * per;
+      const float2* in = src + (size_t)f * N;
+      float2* out = dst + (size_t)f * N;
+      switch (R) {
+        case 2: butterfly<2, INV>(in, out, tw, N, Ns, j); break;
+        case 3: butterfly<3, INV>(in, out, tw, N, Ns, j); break;
+        case 4: butterfly<4, INV>(in, out, tw, N, Ns, j); break;
+        case 5: butterfly<5, INV>(in, out, tw, N, Ns, j); break;
+        case 7: butterfly<7, INV>(in, out, tw, N, Ns, j); break;
+        default: butterfly_generic<INV>(in, out, tw, N, Ns, R, j); break;
+      }
+    }
+    __syncthreads();
+    Ns *= R;
+    float2* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+__global__ void twiddle_kernel(float2* tw, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)n, &s, &c);
+    tw[i] = make_float2((float)c, (float)s);
+  }
+}
+
+constexpr int kStftThreads = 256;
+
+// grid (ceil(T/FPB), B)
+__global__ void __launch_bounds__(kStftThreads)
+stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, float2* __restrict__ spec,
+            const float2* __restrict__ twiddle, FftPlan plan, int L, int T, int hop, int fpb, int transform,
+            float exponent, float factor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = plan.n;
+  const int F = N / 2 + 1;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* buf0 = tw + N;
+  float2* buf1 = buf0 + (size_t)fpb * N;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * fpb;
+  const int nfr = min(fpb, T - t0);
+  const int len_b = lens ? lens[b] : L;
+  const int olen = (len_b + 2 * (N / 2) - N) / hop + 1;
+  // live frames of this CTA form a prefix [t0, t0+nlive)
+  const int nlive = max(0, min(nfr, olen - t0));
+
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = twiddle[i];
+  __syncthreads();
+  const float* row = wav + (size_t)b * L;
+  for (int idx = threadIdx.x; idx < nlive * N; idx += blockDim.x) {
+    const int f = idx / N;
+    const int n = idx - f * N;
+    int i = (t0 + f) * hop - N / 2 + n;
+    if (i < 0) i = -i;
+    if (i >= L) i = 2 * (L - 1) - i;
+    const float w = 0.5f - 0.5f * tw[n].x;          // periodic Hann: cos(2*pi*n/N) = Re tw[n]
+    buf0[idx] = make_float2(row[i] * w, 0.0f);
+  }
+  __syncthreads();
+  float2* res = buf0;
+  if (nlive > 0) res = fft_frames<false>(buf0, buf1, tw, plan, nlive);
+  for (int idx = threadIdx.x; idx < nfr * F; idx += blockDim.x) {
+    const int f = idx / F;
+    const int k = idx - f * F;
+    float2 v = make_float2(0.f, 0.f);
+    if (f < nlive) {
+      v = res[(size_t)f * N + k];
+      if (transform == 1) {
+        const float mag = sqrtf(v.x * v.x + v.y * v.y);
+        const float sc = mag > 0.f ? __powf(mag, exponent - 1.0f) * factor : 0.f;
+        v.x *= sc; v.y *= sc;
+      }
+    }
+    spec[((size_t)b * T + t0 + f) * F + k] = v;
+  }
+}
+
+// grid (nblocks, B); block c covers padded output samples [c*G*hop, (c+1)*G*hop) and owns frames [c*G, (c+1)*G).
+__global__ void __launch_bounds__(kStftThreads)
+istft_kernel(const float2* __restrict__ spec, const float2* __restrict__ mask, const float2* __restrict__ resid,
+             float2* __restrict__ spec_out, float* __restrict__ wav_out, const float2* __restrict__ twiddle,
+             FftPlan plan, int T, int L_out, int hop, int fpb, int G, int transform, float inv_exponent,
+             float inv_factor) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = plan.n;
+  const int F = N / 2 + 1;
+  float2* tw = reinterpret_cast<float2*>(smem_raw);
+  float2* buf0 = tw + N;
+  float2* buf1 = buf0 + (size_t)fpb * N;
+  float* acc = reinterpret_cast<float*>(buf1 + (size_t)fpb * N);
+  const int b = blockIdx.y;
+  const int span = G * hop;
+  const long p0 = (long)blockIdx.x * span;
+  const long p1 = p0 + span;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = twiddle[i];
+  for (int i = threadIdx.x; i < span; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  // frames touching [p0, p1): t*hop + N > p0  and  t*hop < p1
+  long tlo = (p0 - N + 1 + hop - 1);
+  tlo = tlo <= 0 ? 0 : tlo / hop;
+  long thi = (p1 - 1) / hop;
+  const int own_lo = blockIdx.x * G, own_hi = own_lo + G;     // frames whose masked spectrum this CTA writes
+  if (thi < own_hi - 1) thi = own_hi - 1;
+  if (thi > T - 1) thi = T - 1;
+  const float inv_n = 1.0f / (float)N;
+  const bool nyq = (N % 2 == 0);
+
+  for (long tb = tlo; tb <= thi; tb += fpb) {
+    const int nfr = (int)min((long)fpb, thi - tb + 1);
+    // ---- stage the masked, Hermitian-extended spectra
+    for (int idx = threadIdx.x; idx < nfr * F; idx += blockDim.x) {
+      const int f = idx / F;
+      const int k = idx - f * F;
+      const int t = (int)tb + f;
+      const size_t g = ((size_t)b * T + t) * F + k;
+      float2 v = spec[g];
+      if (mask) {
+        const float2 m = mask[g], r = resid[g];
+        v = make_float2(m.x * v.x - m.y * v.y + r.x, m.x * v.y + m.y * v.x + r.y);
+      }
+      if (spec_out && t >= own_lo && t < own_hi) spec_out[g] = v;
+      if (transform == 1) {
+        v.x *= inv_factor; v.y *= inv_factor;
+        const float mag = sqrtf(v.x * v.x + v.y * v.y);
+        const float sc = mag > 0.f ? __powf(mag, inv_exponent - 1.0f) : 0.f;
+        v.x *= sc; v.y *= sc;
+      }
+      float2* fr = buf0 + (size_t)f * N;
+      if (k == 0 || (nyq && k == N / 2)) {
+        fr[k] = make_float2(v.x, 0.f);                 // irfft ignores Im of DC / Nyquist
+      } else {
+        fr[k] = v;
+        fr[N - k] = make_float2(v.x, -v.y);
+      }
+    }
+    __syncthreads();
+    float2* res = fft_frames<true>(buf0, buf1, tw, plan, nfr);
+    // ---- synthesis window + overlap-add; frames of a batch overlap, so they are added one after another
+    for (int f = 0; f < nfr; ++f) {
+      const long base = (tb + f) * hop;
+      for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const long i = base + n;
+        if (i >= p0 && i < p1) {
+          const float w = 0.5f - 0.5f * tw[n].x;
+          acc[i - p0] += res[(size_t)f * N + n].x * inv_n * w;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- envelope division, trim, store
+  const long half = N / 2;
+  for (int o = threadIdx.x; o < span; o += blockDim.x) {
+    const long i = p0 + o;
+    const long i_out = i - half;
+    if (i_out < 0 || i_out >= L_out) continue;
+    long a = i - N + 1;
+    a = a <= 0 ? 0 : (a + hop - 1) / hop;
+    long z = i / hop;
+    if (z > T - 1) z = T - 1;
+    float env = 0.f;
+    for (long t = a; t <= z; ++t) {
+      const float w = 0.5f - 0.5f * tw[i - t * hop].x;
+      env += w * w;
+    }
+    wav_out[(size_t)b * L_out + i_out] = env > 1e-11f ? acc[o] / env : 0.f;
+  }
+}
+
+}  // namespace bsrnn
+
+using namespace bsrnn;
+
+extern "C" int bsrnn_fft_twiddle(float* twiddle, int n_fft, void* stream) {
+  BSRNN_CHECK_ARG(twiddle && n_fft >= 2, "fft_twiddle: bad arguments");
+  twiddle_kernel<<<cdiv(n_fft, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(twiddle), n_fft);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+
+static int pick_fpb(int n_fft, size_t extra, int want) {
+  // keep the CTA under ~100 KB so two fit on an SM
+  int fpb = want;
+  while (fpb > 1 && (size_t)n_fft * 8 * (1 + 2 * fpb) + extra > 100 * 1024) fpb >>= 1;
+  return fpb;
+}
+
+extern "C" int bsrnn_stft_fwd(const float* wav, const int32_t* lens, float* spec, const float* twiddle, int B,
+                              int L, int n_fft, int hop, int transform, float exponent, float factor,
+                              void* stream) {
+  BSRNN_CHECK_ARG(wav && spec && twiddle, "stft_fwd: null pointer");
+  BSRNN_CHECK_ARG(B > 0 && n_fft >= 4 && hop > 0 && L > n_fft / 2, "stft_fwd: bad dims B=%d L=%d n_fft=%d hop=%d", B, L,
+                  n_fft, hop);
+  FftPlan plan;
+  BSRNN_CHECK_ARG(make_plan(n_fft, &plan), "stft_fwd: cannot factorise n_fft=%d", n_fft);
+  const int T = 1 + L / hop;
+  const int fpb = pick_fpb(n_fft, 0, 8);
+  const size_t smem = (size_t)n_fft * 8 * (1 + 2 * fpb);
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(T, fpb), B);
+  stft_kernel<<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(
+      wav, lens, reinterpret_cast<float2*>(spec), reinterpret_cast<const float2*>(twiddle), plan, L, T, hop, fpb,
+      transform, exponent, factor);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int bsrnn_istft_fwd(const float* spec, const float* mask, const float* resid, float* spec_out,
+                               float* wav_out, const float* twiddle, int B, int T, int L_out, int n_fft, int hop,
+                               int transform, float exponent, float factor, void* stream) {
+  BSRNN_CHECK_ARG(spec && wav_out && twiddle, "istft_fwd: null pointer");
+  BSRNN_CHECK_ARG((mask == nullptr) == (resid == nullptr), "istft_fwd: mask and resid must come together");
+  BSRNN_CHECK_ARG(B > 0 && T > 0 && L_out > 0 && n_fft >= 4 && hop > 0, "istft_fwd: bad dims");
+  FftPlan plan;
+  BSRNN_CHECK_ARG(make_plan(n_fft, &plan), "istft_fwd: cannot factorise n_fft=%d", n_fft);
+  const int G = 8;
+  const int fpb = pick_fpb(n_fft, (size_t)G * hop * 4, 4);
+  const size_t smem = (size_t)n_fft * 8 * (1 + 2 * fpb) + (size_t)G * hop * 4;
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long span = (long)G * hop;
+  int nblocks = cdiv(n_fft / 2 + (long)L_out, span);
+  if (nblocks < cdiv(T, G)) nblocks = cdiv(T, G);
+  dim3 grid(nblocks, B);
+  istft_kernel<<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(spec), reinterpret_cast<const float2*>(mask),
+      reinterpret_cast<const float2*>(resid), reinterpret_cast<float2*>(spec_out), wav_out,
+      reinterpret_cast<const float2*>(twiddle), plan, T, L_out, hop, fpb, G, transform,
+      transform == 1 ? 1.0f / exponent : 1.0f, transform == 1 ? 1.0f / factor : 1.0f);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}

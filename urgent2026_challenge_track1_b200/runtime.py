@@ -1,0 +1,422 @@
+"""Host-side runtime of the B200 BSRNN / FlowSE path: packs weights, owns workspaces, and sequences the C-ABI
+kernels (include/bsrnn_b200.h).  PyTorch is used for device memory and streams only — no torch op computes on the
+hot path.
+
+Layouts: spectra (B,T,F,2) f32; residual stream ``skip`` token-major (B,T,K',N) f32.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+SUBBANDS = {
+    481: (5,) + (4,) * 19 + (10,) * 6 + (40,) * 7 + (60,),          # reference bsrnn_flowse.py:29
+    769: (5,) + (4,) * 26 + (10,) * 10 + (50,) * 10 + (60,),        # reference bsrnn_flowse.py:36
+}
+
+
+def subbands_for(input_dim: int, target_fs: int = 48000):
+    if target_fs == 48000 and input_dim in SUBBANDS:
+        return SUBBANDS[input_dim]
+    raise NotImplementedError(                                     # same error as bsrnn_flowse.py:37-41
+        f"Please define your own subbands for input_dim={input_dim} and target_fs={target_fs}")
+
+
+@dataclass
+class BandPlan:
+    """Which bands a spectrum with F bins touches (BandSplit.forward loop, bsrnn_flowse.py:64-85, fs=None)."""
+    subbands: tuple
+    F: int
+    K: int                 # K' = bands used
+    bin0: list             # first bin of each used band
+    width: list            # real bins of each used band (last one may be truncated)
+
+    @staticmethod
+    def make(subbands, F):
+        bin0, width, lo = [], [], 0
+        for s in subbands:
+            bin0.append(lo)
+            width.append(min(s, F - lo))
+            lo += s
+            if lo >= F:
+                break
+        return BandPlan(tuple(subbands), F, len(bin0), bin0, width)
+
+
+def stft_dims(fs, n_fft, hop, default_fs=48000):
+    fs = int(fs)
+    return n_fft * fs // default_fs, hop * fs // default_fs
+
+
+class Profile:
+    """Optional CUDA-event timing of named regions on the current stream (bench.py's roofline leg)."""
+    active = None
+
+    def __init__(self):
+        self.events = {}
+
+    def __enter__(self):
+        Profile.active = self
+        return self
+
+    def __exit__(self, *a):
+        Profile.active = None
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+
+class region:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        p = Profile.active
+        if p is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        p = Profile.active
+        if p is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            p.events.setdefault(self.name, []).append((self.a, b))
+
+
+class DescList:
+    """Collects bsrnn_gemm_desc records for one forward and uploads them with a single H2D copy."""
+
+    def __init__(self):
+        self.recs = []
+        self.dev = None
+
+    def add(self, **kw):
+        self.recs.append(kw)
+        return len(self.recs) - 1
+
+    def upload(self, device):
+        arr = np.zeros(len(self.recs), dtype=L.GEMM_DESC)
+        for i, r in enumerate(self.recs):
+            for k, v in r.items():
+                arr[i][k] = v if v is not None else 0
+        self.dev = torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(device, non_blocking=False)
+        return self.dev
+
+    def ptr(self, idx):
+        return self.dev.data_ptr() + idx * L.GEMM_DESC.itemsize
+
+
+def _rows_desc(A, W, bias, C, M, N, K, *, a_stride, c_stride, k_valid=None, ldw=None, epilogue=0, n_store=None,
+               scale=None, shift=None, rows_per_sample=1, ss_stride=0):
+    """Descriptor for the common case: row r of A at A + r*a_stride, row r of C at C + r*c_stride (floats)."""
+    big = 1 << 60
+    return dict(A=A, W=W, bias=bias, C=C, scale=scale, shift=shift,
+                a_inner=big, a_outer_stride=0, a_inner_stride=a_stride,
+                c_inner=big, c_outer_stride=0, c_inner_stride=c_stride,
+                rows_per_sample=rows_per_sample, ss_stride=ss_stride,
+                M=M, N=N, K=K, k_valid=K if k_valid is None else k_valid, ldw=K if ldw is None else ldw,
+                epilogue=epilogue, n_store=(N if n_store is None else n_store), pad_=0)
+
+
+_TWIDDLE = {}
+
+
+def twiddle(n_fft, device):
+    key = (n_fft, str(device))
+    tw = _TWIDDLE.get(key)
+    if tw is None:
+        tw = torch.empty(n_fft, 2, dtype=torch.float32, device=device)
+        L.call("bsrnn_fft_twiddle", tw.data_ptr(), n_fft, L.stream_ptr())
+        _TWIDDLE[key] = tw
+    return tw
+
+
+def stft(wav, lens, n_fft, hop, transform=0, exponent=1.0, factor=1.0):
+    """wav (B,L) f32 cuda, lens (B,) int32 cuda or None -> spec (B,T,F,2) f32."""
+    B, Ls = wav.shape
+    T, F = 1 + Ls // hop, n_fft // 2 + 1
+    spec = torch.empty(B, T, F, 2, dtype=torch.float32, device=wav.device)
+    L.call("bsrnn_stft_fwd", wav.data_ptr(), L.ptr(lens), spec.data_ptr(), twiddle(n_fft, wav.device).data_ptr(),
+           B, Ls, n_fft, hop, transform, exponent, factor, L.stream_ptr())
+    return spec
+
+
+def istft(spec, mask, resid, L_out, n_fft, hop, want_spec=True, transform=0, exponent=1.0, factor=1.0):
+    """spec/mask/resid (B,T,F,2) -> (wav (B,L_out), masked spec or None)."""
+    B, T, F, _ = spec.shape
+    wav = torch.empty(B, L_out, dtype=torch.float32, device=spec.device)
+    out = torch.empty_like(spec) if (want_spec and mask is not None) else None
+    L.call("bsrnn_istft_fwd", spec.data_ptr(), L.ptr(mask), L.ptr(resid), L.ptr(out), wav.data_ptr(),
+           twiddle(n_fft, spec.device).data_ptr(), B, T, L_out, n_fft, hop, transform, exponent, factor,
+           L.stream_ptr())
+    return wav, (out if out is not None else (spec if want_spec else None))
+
+
+# ------------------------------------------------------------------------------------------------ weight packing
+def _param_key(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class PackedCache:
+    """Packed copies of module parameters, rebuilt when any source tensor changes in place or is replaced
+    (the optimizer and FlowSEModel.eval()'s EMA swap both mutate parameters in place, flow_model.py:98-109)."""
+
+    def __init__(self, module, builder):
+        self.module, self.builder = module, builder
+        self.key, self.value = None, None
+
+    def get(self):
+        params = list(self.module.parameters())
+        key = _param_key(params)
+        if key != self.key:
+            with torch.no_grad():
+                self.value = self.builder(self.module)
+            self.key = key
+        return self.value
+
+
+def pack_dual_path(mod):
+    """f32 packing of the 2*num_layer (GN, BLSTM, Linear) blocks.  `mod` owns norm_time/rnn_time/fc_time/
+    norm_freq/rnn_freq/fc_freq ModuleLists with the reference's names."""
+    layers = []
+    for i in range(mod.num_layer):
+        entry = {}
+        for axis in ("time", "freq"):
+            norm, rnn, fc = getattr(mod, f"norm_{axis}")[i], getattr(mod, f"rnn_{axis}")[i], getattr(mod, f"fc_{axis}")[i]
+            wih = torch.cat([rnn.weight_ih_l0, rnn.weight_ih_l0_reverse], 0).float().contiguous()       # (8H, N)
+            bih = torch.cat([rnn.bias_ih_l0 + rnn.bias_hh_l0,
+                             rnn.bias_ih_l0_reverse + rnn.bias_hh_l0_reverse], 0).float().contiguous()
+            whh = torch.stack([rnn.weight_hh_l0, rnn.weight_hh_l0_reverse], 0).float().contiguous()     # (2,4H,H)
+            entry[axis] = dict(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(),
+                               wih=wih, bih=bih, whh=whh, fcw=fc.weight.float().contiguous(),
+                               fcb=fc.bias.float().contiguous())
+        layers.append(entry)
+    return layers
+
+
+def pack_band_split(bs):
+    """BandSplit (norm.{k}: GroupNorm(1,2s); fc.{k}: Conv1d(2s->N,1)) -> padded (K, Cmax) affine tables + weights."""
+    K = len(bs.subbands)
+    cmax = 2 * max(bs.subbands)
+    dev = bs.fc[0].weight.device
+    gamma = torch.zeros(K, cmax, device=dev)
+    beta = torch.zeros(K, cmax, device=dev)
+    for k, s in enumerate(bs.subbands):
+        gamma[k, : 2 * s] = bs.norm[k].weight
+        beta[k, : 2 * s] = bs.norm[k].bias
+    w = [bs.fc[k].weight[:, :, 0].float().contiguous() for k in range(K)]
+    b = [bs.fc[k].bias.float().contiguous() for k in range(K)]
+    return dict(gamma=gamma, beta=beta, w=w, b=b, cmax=cmax)
+
+
+def pack_mask_decoder(md):
+    """espnet2-style MaskDecoder: mlp_{mask,residual}.{k} = [GN, Conv1d(N,4N), Tanh, Conv1d(4N,4s), GLU]."""
+    out = {}
+    for name in ("mlp_mask", "mlp_residual"):
+        mlps = getattr(md, name)
+        out[name] = dict(
+            gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
+            beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
+            w1=[m[1].weight[:, :, 0].float().contiguous() for m in mlps], b1=[m[1].bias.float().contiguous() for m in mlps],
+            w2=[m[3].weight[:, :, 0].float().contiguous() for m in mlps], b2=[m[3].bias.float().contiguous() for m in mlps])
+    return out
+
+
+def pack_grad_decoder(gd):
+    """GradDecoder (bsrnn_flowse.py:103-168).  Conv1d(N->16 s) rows are permuted from c = sc*s + f to
+    c' = f*16 + sc so the GEMM writes the channel-last (B,T,F',16) image the 5x5 conv kernel reads."""
+    out = {}
+    for name, conv in (("mlp_mask", "conv_after_mask"), ("mlp_residual", "conv_after_residual")):
+        mlps = getattr(gd, name)
+        w1, b1 = [], []
+        for k, m in enumerate(mlps):
+            s = gd.subbands[k]
+            w = m[1].weight[:, :, 0].float()                                      # (16 s, N)
+            w1.append(w.reshape(gd.sub_channel, s, -1).permute(1, 0, 2).reshape(gd.sub_channel * s, -1).contiguous())
+            b1.append(m[1].bias.float().reshape(gd.sub_channel, s).t().reshape(-1).contiguous())
+        c = getattr(gd, conv)[0]
+        out[name] = dict(gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
+                         beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
+                         w1=w1, b1=b1, cw=c.weight.float().contiguous(), cb=c.bias.float().contiguous())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ f32 building blocks
+def _i32(vals, device):
+    return torch.tensor(vals, dtype=torch.int32, device=device)
+
+
+def _f64(vals, device):
+    return torch.tensor(vals, dtype=torch.float64, device=device)
+
+
+def band_split_f32(spec, plan: BandPlan, bs_pack, N, out=None, out_col=0, out_width=None):
+    """spec (B,T,F,2) -> z (B,T,K',N) (or into columns [out_col, out_col+N) of a wider `out`)."""
+    B, T, F, _ = spec.shape
+    dev = spec.device
+    K = plan.K
+    cmax = bs_pack["cmax"]
+    st = L.stream_ptr()
+    stats = torch.empty(B, K, 2, dtype=torch.float64, device=dev)
+    off = _i32([2 * b0 for b0 in plan.bin0], dev)
+    wid = _i32([2 * w for w in plan.width], dev)
+    L.call("bsrnn_band_stats", spec.data_ptr(), stats.data_ptr(), B, T, 2 * F, off.data_ptr(), wid.data_ptr(), K, st)
+    counts = _f64([2.0 * plan.subbands[k] * T for k in range(K)], dev)      # padded bins count (bsrnn_flowse.py:68-73)
+    scale = torch.empty(B * K, cmax, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    L.call("bsrnn_gn_finalize", stats.data_ptr(), bs_pack["gamma"].data_ptr(), bs_pack["beta"].data_ptr(), None,
+           scale.data_ptr(), shift.data_ptr(), B * K, cmax, counts.data_ptr(), 1e-5, K, st)
+    width = out_width or N
+    if out is None:
+        out = torch.empty(B, T, K, width, dtype=torch.float32, device=dev)
+    dl = DescList()
+    for k in range(K):
+        s = plan.subbands[k]
+        dl.add(**_rows_desc(spec.data_ptr() + 8 * plan.bin0[k], bs_pack["w"][k].data_ptr(), bs_pack["b"][k].data_ptr(),
+                            out.data_ptr() + 4 * (k * width + out_col), B * T, N, 2 * s,
+                            a_stride=2 * F, c_stride=K * width, k_valid=2 * plan.width[k],
+                            scale=scale.data_ptr() + 4 * k * cmax, shift=shift.data_ptr() + 4 * k * cmax,
+                            rows_per_sample=T, ss_stride=K * cmax))
+    dl.upload(dev)
+    L.call("bsrnn_gemm_f32", dl.ptr(0), K, B * T, N, st)
+    return out
+
+
+def _layer_norm_tables(skip, gamma, beta, extra=None):
+    """GroupNorm(1,N) over (N,T,K) per sample -> (scale, shift) (B,N)."""
+    B, T, K, N = skip.shape
+    dev = skip.device
+    st = L.stream_ptr()
+    stats = torch.empty(B, 2, dtype=torch.float64, device=dev)
+    L.call("bsrnn_gn_stats", skip.data_ptr(), stats.data_ptr(), B, T * K, N, N, st)
+    scale = torch.empty(B, N, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    counts = _f64([float(T) * K * N], dev)
+    L.call("bsrnn_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), L.ptr(extra), scale.data_ptr(),
+           shift.data_ptr(), B, N, counts.data_ptr(), 1e-5, 1, st)
+    return scale, shift
+
+
+def dual_path_f32(skip, layers, t_emb=None):
+    """In-place 2*num_layer residual blocks on skip (B,T,K,N).  t_emb: list of (B,N) per layer (FlowSE) or None."""
+    B, T, K, N = skip.shape
+    dev = skip.device
+    st = L.stream_ptr()
+    M = B * T * K
+    H = layers[0]["time"]["whh"].shape[2]
+    gates = torch.empty(M, 8 * H, dtype=torch.float32, device=dev)
+    y = torch.empty(M, 2 * H, dtype=torch.float32, device=dev)
+    cst = torch.empty(2 * max(B * K, B * T) * H, dtype=torch.float32, device=dev)
+    for i, lay in enumerate(layers):
+        for axis in ("time", "freq"):
+            w = lay[axis]
+            extra = t_emb[i] if (t_emb is not None and axis == "time") else None      # bsrnn_flowse.py:293-294
+            scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra)
+            dl = DescList()
+            dl.add(**_rows_desc(skip.data_ptr(), w["wih"].data_ptr(), w["bih"].data_ptr(), gates.data_ptr(),
+                                M, 8 * H, N, a_stride=N, c_stride=8 * H, scale=scale.data_ptr(), shift=shift.data_ptr(),
+                                rows_per_sample=T * K, ss_stride=N))
+            dl.add(**_rows_desc(y.data_ptr(), w["fcw"].data_ptr(), w["fcb"].data_ptr(), skip.data_ptr(),
+                                M, N, 2 * H, a_stride=2 * H, c_stride=N, epilogue=L.EPI_RESIDUAL))
+            dl.upload(dev)
+            with region("inproj"):
+                L.call("bsrnn_gemm_f32", dl.ptr(0), 1, M, 8 * H, st)
+            with region(f"lstm_{axis}"):
+                if axis == "time":
+                    L.call("bsrnn_blstm_recurrence_f32", gates.data_ptr(), w["whh"].data_ptr(), y.data_ptr(),
+                           cst.data_ptr(), B * K, T, H, K, T * K, 1, K, st)
+                else:
+                    L.call("bsrnn_blstm_recurrence_f32", gates.data_ptr(), w["whh"].data_ptr(), y.data_ptr(),
+                           cst.data_ptr(), B * T, K, H, 1, K, 0, 1, st)
+            with region("fc"):
+                L.call("bsrnn_gemm_f32", dl.ptr(1), 1, M, N, st)
+    return skip
+
+
+def _decoder_norm_tables(skip, packs):
+    """Per-(sample, band) GroupNorm(1,N) over (N,T) for each MLP family -> {name: (scale, shift)} (B*K, N)."""
+    B, T, K, N = skip.shape
+    dev = skip.device
+    st = L.stream_ptr()
+    stats = torch.empty(B, K, 2, dtype=torch.float64, device=dev)
+    off = _i32([k * N for k in range(K)], dev)
+    wid = _i32([N] * K, dev)
+    L.call("bsrnn_band_stats", skip.data_ptr(), stats.data_ptr(), B, T, K * N, off.data_ptr(), wid.data_ptr(), K, st)
+    counts = _f64([float(N) * T] * K, dev)
+    out = {}
+    for name, p in packs.items():
+        scale = torch.empty(B * K, N, dtype=torch.float32, device=dev)
+        shift = torch.empty_like(scale)
+        gamma, beta = p["gamma"][:K].contiguous(), p["beta"][:K].contiguous()
+        L.call("bsrnn_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), None, scale.data_ptr(),
+               shift.data_ptr(), B * K, N, counts.data_ptr(), 1e-5, K, st)
+        out[name] = (scale, shift, gamma, beta)
+    return out
+
+
+def mask_decoder_f32(skip, plan: BandPlan, md_pack):
+    """skip (B,T,K',N) -> mask, resid (B,T,F,2) (espnet2 MaskDecoder + the [:F] slice of BSRNN.forward)."""
+    B, T, K, N = skip.shape
+    F = plan.F
+    dev = skip.device
+    st = L.stream_ptr()
+    tabs = _decoder_norm_tables(skip, md_pack)
+    hidden = torch.empty(2 * K, B * T, 4 * N, dtype=torch.float32, device=dev)
+    outs = {n: torch.empty(B, T, F, 2, dtype=torch.float32, device=dev) for n in ("mlp_mask", "mlp_residual")}
+    d1, d2 = DescList(), DescList()
+    for gi, name in enumerate(("mlp_mask", "mlp_residual")):
+        p = md_pack[name]
+        scale, shift = tabs[name][0], tabs[name][1]
+        for k in range(K):
+            s = plan.subbands[k]
+            hptr = hidden.data_ptr() + 4 * (gi * K + k) * B * T * 4 * N
+            d1.add(**_rows_desc(skip.data_ptr() + 4 * k * N, p["w1"][k].data_ptr(), p["b1"][k].data_ptr(), hptr,
+                                B * T, 4 * N, N, a_stride=K * N, c_stride=4 * N, epilogue=L.EPI_TANH,
+                                scale=scale.data_ptr() + 4 * k * N, shift=shift.data_ptr() + 4 * k * N,
+                                rows_per_sample=T, ss_stride=K * N))
+            d2.add(**_rows_desc(hptr, p["w2"][k].data_ptr(), p["b2"][k].data_ptr(),
+                                outs[name].data_ptr() + 8 * plan.bin0[k], B * T, 4 * s, 4 * N,
+                                a_stride=4 * N, c_stride=2 * F, epilogue=L.EPI_GLU, n_store=2 * plan.width[k]))
+    d1.upload(dev)
+    d2.upload(dev)
+    L.call("bsrnn_gemm_f32", d1.ptr(0), 2 * K, B * T, 4 * N, st)
+    L.call("bsrnn_gemm_f32", d2.ptr(0), 2 * K, B * T, 2 * max(plan.subbands[:K]), st)
+    return outs["mlp_mask"], outs["mlp_residual"]
+
+
+def grad_decoder_f32(skip, plan: BandPlan, gd_pack, sub_channel=16):
+    """skip (B,T,K',N) -> mask, resid (B,T,F,2)  (GradDecoder.forward bsrnn_flowse.py:136-168 + [:F] slice :313-314)."""
+    B, T, K, N = skip.shape
+    F = plan.F
+    Fp = sum(plan.subbands[:K])
+    dev = skip.device
+    st = L.stream_ptr()
+    tabs = _decoder_norm_tables(skip, gd_pack)
+    img = torch.empty(2, B, T, Fp, sub_channel, dtype=torch.float32, device=dev)
+    outs = []
+    d1 = DescList()
+    for gi, name in enumerate(("mlp_mask", "mlp_residual")):
+        p = gd_pack[name]
+        scale, shift = tabs[name][0], tabs[name][1]
+        for k in range(K):
+            s = plan.subbands[k]
+            cptr = img.data_ptr() + 4 * (gi * B * T * Fp * sub_channel + plan.bin0[k] * sub_channel)
+            d1.add(**_rows_desc(skip.data_ptr() + 4 * k * N, p["w1"][k].data_ptr(), p["b1"][k].data_ptr(), cptr,
+                                B * T, sub_channel * s, N, a_stride=K * N, c_stride=Fp * sub_channel,
+                                epilogue=L.EPI_TANH, scale=scale.data_ptr() + 4 * k * N,
+                                shift=shift.data_ptr() + 4 * k * N, rows_per_sample=T, ss_stride=K * N))
+    d1.upload(dev)
+    L.call("bsrnn_gemm_f32", d1.ptr(0), 2 * K, B * T, sub_channel * max(plan.subbands[:K]), st)
+    for gi, name in enumerate(("mlp_mask", "mlp_residual")):
+        p = gd_pack[name]
+        o = torch.empty(B, T, F, 2, dtype=torch.float32, device=dev)
+        L.call("bsrnn_conv5x5_glu", img[gi].data_ptr(), p["cw"].data_ptr(), p["cb"].data_ptr(), o.data_ptr(),
+               B, T, Fp, F, st)
+        outs.append(o)
+    return outs[0], outs[1]
