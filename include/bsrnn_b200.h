@@ -118,6 +118,38 @@ int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y
                                int R, int steps, int H, long seq_inner, long seq_outer, long seq_inner_stride,
                                long step_stride, void* stream);
 
+/* ---------------------------------------------------------------------------------------------- tensor-core mode
+ * fp16 operands, f32 accumulation in TMEM (tcgen05).  Operands use the UMMA-native "KB8" tiling
+ *     X_kb8[tile][K/8][rows_per_tile][8]      (rows_per_tile = 128 for activations, BN for weights)
+ * so every pipeline stage is one contiguous bulk copy.  Row tiles map to tokens through
+ *     m_tile = step*tiles_per_step + j ;  seq = j*128 + r (valid iff seq < R) ;
+ *     token  = (seq / seq_inner)*seq_outer + (seq % seq_inner)*seq_inner_stride + step*step_stride .
+ *
+ * bsrnn_norm_cast_kb8: out_kb8 = fp16( x[token, col0:col0+C] * scale[g] + shift[g] ), zero padded to kcores*8 columns;
+ *     g = (token / tokens_per_sample)*g_inner + (g_inner > 1 ? token % g_inner : 0).  The apply half of
+ *     nn.GroupNorm(1,N) [bsrnn_flowse.py:291,302,146-152] fused with the operand re-tiling.
+ * bsrnn_gemm_tc: C = A_kb8 * W_kb8^T + bias with epilogue
+ *     0: fp16 rows      out[token*ldo + col]                              (LSTM input projection, :296,:303)
+ *     1: f32 residual   out[token*ldo + col] += .., col < n_valid; optional per-sample {sum,sumsq} of the new
+ *                       values added into stats (samples,2) double        (Linear + skip :298-300,:305-307 and the
+ *                       statistics of the next GroupNorm)
+ *     2: tanh -> fp16 KB8 operand with out_kcores k-cores                 (MaskDecoder Conv1d(N->4N)+Tanh)
+ *     3: GLU on (value,gate)-interleaved columns -> f32 out[token*ldo + col/2], col/2 < n_valid
+ * bsrnn_blstm_recurrence_tc: persistent cluster kernel, H = 392 only (see csrc/lstm_tc.cu for the layouts of
+ *     gates_x, w_pack and y).  max_clusters <= 0: use every co-resident cluster.
+ */
+int bsrnn_norm_cast_kb8(const float* x, const float* scale, const float* shift, void* out, long ldx, int col0, int C,
+                        int kcores, int m_tiles, int tiles_per_step, int R, long seq_inner, long seq_outer,
+                        long seq_inner_stride, long step_stride, long tokens_per_sample, int g_inner, void* stream);
+int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, double* stats, int m_tiles, int n_tiles,
+                  int kcores, int BN, int epilogue, long ldo, int n_valid, int out_kcores, long tokens_per_sample,
+                  int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
+                  void* stream);
+int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, void* y, int R, int steps, int seq_tiles,
+                              long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
+                              int max_clusters, void* stream);
+int bsrnn_blstm_tc_max_clusters(void);
+
 /* ---------------------------------------------------------------------------------------------- FlowSE pieces
  * bsrnn_time_embed: GaussianFourierProjection [bsrnn_flowse.py:90-99]: out (B, 2*E) = [sin(2*pi*t*W), cos(...)].
  * bsrnn_conv5x5_glu: GradDecoder.conv_after_* = Conv2d(16->4, 5x5, pad 2) + GLU(dim=1) [bsrnn_flowse.py:114-117,

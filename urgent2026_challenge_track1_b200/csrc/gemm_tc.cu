@@ -1,0 +1,308 @@
+// gemm_tc.cu — persistent, warp-specialised fp16-operand GEMM on tcgen05 tensor cores (sm_100a), f32 accumulation
+// in TMEM.  (fp16 rather than bf16 operands: same tensor-pipe rate, 3 more mantissa bits; every operand on this path
+// is GroupNorm-normalised, a tanh/sigmoid product, or a weight, so the fp16 range is never an issue.)
+//
+//   C[128*m_tiles, BN*n_tiles] = A_kb8 * W_kb8^T   (+ fused epilogue)
+//
+// Operands live in HBM in the UMMA-native "KB8" layout (umma.cuh), so each pipeline stage is filled by two plain
+// cp.async.bulk copies.  Roles: warp 0 = bulk-copy producer, warp 1 = single-thread tcgen05.mma issuer, warps 2-5 =
+// epilogue (tcgen05.ld -> registers -> fused op -> global).  Two 256-column TMEM accumulators let the epilogue of
+// tile i overlap the MMAs of tile i+1.  One CTA per SM, static round-robin tile schedule with the N tile innermost so
+// concurrently running CTAs share the same A tile through L2.
+//
+// Used for (fp16 tensor-core mode): LSTM input projections, Linear(4N->N)+skip (+GroupNorm statistics of the result),
+// MaskDecoder Conv1d(N->4N)+tanh and Conv1d(4N->4s)+GLU   [reference bsrnn_flowse.py:296-307 pattern, espnet2
+// MaskDecoder].
+#include "common.cuh"
+#include "umma.cuh"
+#include <cuda_fp16.h>
+
+namespace bsrnn {
+using namespace umma;
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_KS = 8;            // k-cores (8 halves each) per pipeline stage -> K = 64 per stage
+constexpr int TC_THREADS = 192;
+constexpr int TC_ACC_COLS = 256;
+
+struct RowMap {                     // global row (m_tile, r) -> token
+  int tiles_per_step;               // m_tile = step * tiles_per_step + j ; seq = j*128 + r
+  int R;                            // valid sequences
+  long seq_inner, seq_outer, seq_inner_stride, step_stride;
+  __device__ __forceinline__ bool map(int m_tile, int r, long* token) const {
+    const int step = m_tile / tiles_per_step;
+    const int j = m_tile - step * tiles_per_step;
+    const long seq = (long)j * 128 + r;
+    if (seq >= R) return false;
+    *token = (seq / seq_inner) * seq_outer + (seq % seq_inner) * seq_inner_stride + (long)step * step_stride;
+    return true;
+  }
+};
+
+struct GemmTcArgs {
+  const __half* A;           // [m_tiles][kcores][128][8]
+  const __half* W;           // [n_tiles][kcores][BN][8]
+  const float* bias;                // [n_tiles*BN] or null
+  void* out;
+  double* stats;                    // EPI_RESID: (samples, 2) sum / sumsq accumulators or null
+  long ldo;                         // output row stride (elements)
+  long tokens_per_sample;
+  int m_tiles, n_tiles, kcores, BN;
+  int n_valid;                      // logical output columns kept
+  int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
+  RowMap rows;
+};
+
+enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3 };
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(fast_tanh(0.5f * x), 0.5f, 0.5f); }
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Epilogue for NC (16 or 32) accumulator columns [c0, c0+NC) of row r of tile (m, n).
+template <int EPI, int NC>
+__device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n, int r, int c0, const uint32_t* acc,
+                                               bool row_ok, long token, float& s_sum, float& s_sq) {
+  const int gc0 = n * a.BN + c0;                      // global output column of acc[0]
+  float v[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) + (a.bias ? __ldg(a.bias + gc0 + i) : 0.f);
+
+  if (EPI == EPI_F16_ROWS) {
+    if (!row_ok) return;
+    __half* o = reinterpret_cast<__half*>(a.out) + token * a.ldo + gc0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 8) {
+      uint4 pk = make_uint4(pack_h2(v[i], v[i + 1]), pack_h2(v[i + 2], v[i + 3]), pack_h2(v[i + 4], v[i + 5]),
+                            pack_h2(v[i + 6], v[i + 7]));
+      *reinterpret_cast<uint4*>(o + i) = pk;
+    }
+  } else if (EPI == EPI_RESID_F32) {
+    if (!row_ok) return;
+    float* o = reinterpret_cast<float*>(a.out) + token * a.ldo + gc0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 4) {
+      if (gc0 + i + 3 < a.n_valid) {
+        float4 old = *reinterpret_cast<float4*>(o + i);
+        old.x += v[i]; old.y += v[i + 1]; old.z += v[i + 2]; old.w += v[i + 3];
+        *reinterpret_cast<float4*>(o + i) = old;
+        s_sum += old.x + old.y + old.z + old.w;
+        s_sq += old.x * old.x + old.y * old.y + old.z * old.z + old.w * old.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gc0 + i + j < a.n_valid) {
+            const float nv = o[i + j] + v[i + j];
+            o[i + j] = nv;
+            s_sum += nv; s_sq += nv * nv;
+          }
+      }
+    }
+  } else if (EPI == EPI_TANH_KB8) {
+    __half* o = reinterpret_cast<__half*>(a.out);
+#pragma unroll
+    for (int i = 0; i < NC; i += 8) {
+      const int kc = (gc0 + i) >> 3;
+      if (kc >= a.out_kcores) break;
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = (gc0 + i + j < a.n_valid) ? fast_tanh(v[i + j]) : 0.f;
+      uint4 pk = make_uint4(pack_h2(t[0], t[1]), pack_h2(t[2], t[3]), pack_h2(t[4], t[5]), pack_h2(t[6], t[7]));
+      *reinterpret_cast<uint4*>(o + (((long)m * a.out_kcores + kc) * 128 + r) * 8) = pk;
+    }
+  } else if (EPI == EPI_GLU_F32) {
+    if (!row_ok) return;
+    // packed weight rows alternate (value, gate): output column = global column / 2
+    float* o = reinterpret_cast<float*>(a.out) + token * a.ldo + (gc0 >> 1);
+#pragma unroll
+    for (int i = 0; i < NC; i += 2)
+      if (((gc0 + i) >> 1) < a.n_valid) o[i >> 1] = v[i] * fast_sigmoid(v[i + 1]);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int BN = a.BN;
+  const uint32_t a_stage_bytes = TC_KS * 128 * 16;
+  const uint32_t b_stage_bytes = TC_KS * BN * 16;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + TC_STAGES * a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * b_stage_bytes);
+  uint64_t* full = bars;                     // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
+  uint64_t* acc_full = bars + 2 * TC_STAGES;     // [2]
+  uint64_t* acc_empty = bars + 2 * TC_STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * TC_ACC_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total = a.m_tiles * a.n_tiles;
+  const int nstage_k = (a.kcores + TC_KS - 1) / TC_KS;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m = t / a.n_tiles, n = t - m * a.n_tiles;
+        const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)m * a.kcores * 2048;
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
+        for (int ks = 0; ks < nstage_k; ++ks) {
+          const int kc0 = ks * TC_KS;
+          const int nk = min(TC_KS, a.kcores - kc0);
+          mbar_wait(empty + stage, phase ^ 1);
+          mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + BN * 16));
+          bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
+          bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16_f32(128, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(acc_empty + buf, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
+        for (int ks = 0; ks < nstage_k; ++ks) {
+          const int nk = min(TC_KS, a.kcores - ks * TC_KS);
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sA + stage * a_stage_bytes);
+          const uint32_t sb = smem_u32(sB + stage * b_stage_bytes);
+          for (int j = 0; j < nk / 2; ++j) {
+            const uint64_t da = smem_desc_kb8(sa + j * 2 * 2048, 2048, 128);
+            const uint64_t db = smem_desc_kb8(sb + j * 2 * BN * 16, BN * 16, 128);
+            mma_f16_ss(d_tmem, da, db, idesc, (ks | j) != 0);
+          }
+          mma_commit(empty + stage);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(acc_full + buf);
+      }
+    }
+  } else {
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;               // row of the tile
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int m = t / a.n_tiles, n = t - m * a.n_tiles;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      long token = 0;
+      const bool row_ok = a.rows.map(m, r, &token);
+      float s_sum = 0.f, s_sq = 0.f;
+      mbar_wait(acc_full + buf, acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      int c0 = 0;
+      for (; c0 + 32 <= BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld_x32(t_addr + c0, acc);
+        tmem_ld_wait();
+        epilogue_chunk<EPI, 32>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq);
+      }
+      if (c0 < BN) {                           // BN % 32 == 16
+        uint32_t acc[16];
+        tmem_ld_x16(t_addr + c0, acc);
+        tmem_ld_wait();
+        epilogue_chunk<EPI, 16>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + buf);
+      if (EPI == EPI_RESID_F32 && a.stats) {
+        // rows of a warp are consecutive sequences: usually one sample, sometimes two or three
+        const long samp = row_ok ? token / a.tokens_per_sample : -1;
+        unsigned todo = __ballot_sync(0xffffffffu, row_ok);
+        while (todo) {
+          const int leader = __ffs(todo) - 1;
+          const long ls = __shfl_sync(0xffffffffu, samp, leader);
+          const bool mine = row_ok && samp == ls;
+          const float ps = warp_sum(mine ? s_sum : 0.f);
+          const float pq = warp_sum(mine ? s_sq : 0.f);
+          if (lane == leader) {
+            atomicAdd(a.stats + 2 * ls, (double)ps);
+            atomicAdd(a.stats + 2 * ls + 1, (double)pq);
+          }
+          todo &= ~__ballot_sync(0xffffffffu, mine);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * TC_ACC_COLS);
+  }
+}
+
+static size_t tc_smem_bytes(int BN) {
+  return (size_t)TC_STAGES * (TC_KS * 128 * 16 + TC_KS * BN * 16) + (2 * TC_STAGES + 4) * 8 + 16;
+}
+
+template <int EPI>
+static int launch_tc(const GemmTcArgs& a, cudaStream_t st) {
+  const size_t smem = tc_smem_bytes(a.BN);
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total = a.m_tiles * a.n_tiles;
+  const int grid = total < sms ? total : sms;
+  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace bsrnn
+using namespace bsrnn;
+
+extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, double* stats,
+                               int m_tiles, int n_tiles, int kcores, int BN, int epilogue, long ldo, int n_valid,
+                               int out_kcores, long tokens_per_sample, int tiles_per_step, int R, long seq_inner,
+                               long seq_outer, long seq_inner_stride, long step_stride, void* stream) {
+  BSRNN_CHECK_ARG(A && W && out, "gemm_tc: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && kcores > 0 && kcores % 2 == 0, "gemm_tc: bad tile counts (kcores=%d)", kcores);
+  BSRNN_CHECK_ARG(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc: BN=%d must be a multiple of 16 in [16,256]", BN);
+  BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && tokens_per_sample > 0, "gemm_tc: bad row map");
+  GemmTcArgs a;
+  a.A = reinterpret_cast<const __half*>(A);
+  a.W = reinterpret_cast<const __half*>(W);
+  a.bias = bias; a.out = out; a.stats = stats; a.ldo = ldo; a.tokens_per_sample = tokens_per_sample;
+  a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = kcores; a.BN = BN; a.n_valid = n_valid; a.out_kcores = out_kcores;
+  a.rows = RowMap{tiles_per_step, R, seq_inner, seq_outer, seq_inner_stride, step_stride};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (epilogue) {
+    case EPI_F16_ROWS: return launch_tc<EPI_F16_ROWS>(a, st);
+    case EPI_RESID_F32: return launch_tc<EPI_RESID_F32>(a, st);
+    case EPI_TANH_KB8: return launch_tc<EPI_TANH_KB8>(a, st);
+    case EPI_GLU_F32: return launch_tc<EPI_GLU_F32>(a, st);
+  }
+  set_error("gemm_tc: unknown epilogue %d", epilogue);
+  return 1;
+}

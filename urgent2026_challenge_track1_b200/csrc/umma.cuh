@@ -113,8 +113,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> f32, one thread issues for the CTA.
-__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T, 16-bit operands (type set by idesc) -> f32, one thread issues for the CTA.
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -167,6 +167,10 @@ __device__ __forceinline__ uint64_t smem_desc_kb8(uint32_t smem_addr, uint32_t l
 // [10,13)), both K-major (bits 15,16 = 0), N>>3 @[17,23), M>>4 @[24,29).
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// same with fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -1,0 +1,156 @@
+"""Tensor-core ("fp16") mode of the runtime: weight packing into the UMMA-native KB8 tiling and the sequencing of
+bsrnn_norm_cast_kb8 / bsrnn_gemm_tc / bsrnn_blstm_recurrence_tc (include/bsrnn_b200.h).  H = 2N = 392 only
+(BSRNN_baseline, N = 196): the recurrence kernel is specialised for that size (csrc/lstm_tc.cu).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .runtime import region, _f64
+
+BIG = 1 << 60
+CL, LU, LBN, LKC = 8, 49, 208, 50       # cluster size, units per CTA, gate columns per CTA, k-cores of h (K = 400)
+
+
+def to_kb8(w, rows_per_tile, kcores):
+    """(rows, K) -> fp16 [n_tiles][kcores][rows_per_tile][8]; rows / K zero padded."""
+    rows, K = w.shape
+    n_tiles = (rows + rows_per_tile - 1) // rows_per_tile
+    buf = torch.zeros(n_tiles * rows_per_tile, kcores * 8, dtype=torch.float32, device=w.device)
+    buf[:rows, :K] = w
+    return buf.view(n_tiles, rows_per_tile, kcores, 8).permute(0, 2, 1, 3).contiguous().to(torch.float16)
+
+
+def from_kb8(t, rows, K):
+    """inverse of to_kb8 (test helper): [n_tiles][kcores][rpt][8] -> (rows, K) f32."""
+    n_tiles, kcores, rpt, _ = t.shape
+    return t.permute(0, 2, 1, 3).reshape(n_tiles * rpt, kcores * 8)[:rows, :K].float()
+
+
+def _gate_perm(H, dev):
+    """row index into a (4H, .) LSTM matrix for packed position (q, c = 4*u + gate): gate*H + 49*q + u; -1 for pads."""
+    idx = torch.full((CL, LBN), -1, dtype=torch.long, device=dev)
+    for q in range(CL):
+        u = torch.arange(LU, device=dev)
+        for g in range(4):
+            idx[q, 4 * u + g] = g * H + LU * q + u
+    return idx
+
+
+def pack_lstm_tc(rnn):
+    """nn.LSTM(N, H=392, bidirectional) -> dict(wih [16][26][208][8], bih (16*208) f32, whh [2][8][50][208][8])."""
+    H, N = rnn.weight_hh_l0.shape[1], rnn.weight_ih_l0.shape[1]
+    if H != CL * LU:
+        raise NotImplementedError(f"tensor-core BLSTM kernel is specialised for H=392, got H={H}")
+    dev = rnn.weight_hh_l0.device
+    perm = _gate_perm(H, dev)
+    kc_in = (N + 15) // 16 * 2
+    wih_rows, bih_rows, whh = [], [], []
+    for sfx in ("", "_reverse"):
+        wi = getattr(rnn, "weight_ih_l0" + sfx).float()
+        wh = getattr(rnn, "weight_hh_l0" + sfx).float()
+        b = (getattr(rnn, "bias_ih_l0" + sfx) + getattr(rnn, "bias_hh_l0" + sfx)).float()
+        for q in range(CL):
+            sel = perm[q].clamp_min(0)
+            valid = (perm[q] >= 0).float()[:, None]
+            wih_rows.append(wi[sel] * valid)
+            bih_rows.append(b[sel] * valid[:, 0])
+            whh.append(to_kb8(wh[sel] * valid, LBN, LKC)[0])
+    wih = to_kb8(torch.cat(wih_rows, 0), LBN, kc_in)                # 16 tiles of 208 rows
+    return dict(wih=wih, bih=torch.cat(bih_rows).contiguous(), whh=torch.stack(whh).view(2, CL, LKC, LBN, 8).contiguous(),
+                kc_in=kc_in, H=H, N=N)
+
+
+def pack_fc_tc(fc, H):
+    """Linear(2H -> N): K re-indexed to the y tile's [dir][400] columns; one N tile of BN = ceil16(N)."""
+    N = fc.weight.shape[0]
+    BN = (N + 15) // 16 * 16
+    w = torch.zeros(N, 2 * LKC * 8, device=fc.weight.device)
+    w[:, :H] = fc.weight[:, :H]
+    w[:, LKC * 8: LKC * 8 + H] = fc.weight[:, H:]
+    bias = torch.zeros(BN, device=w.device)
+    bias[:N] = fc.bias
+    return dict(w=to_kb8(w, BN, 2 * LKC), b=bias, BN=BN, N=N)
+
+
+def pack_dual_path_tc(mod):
+    layers = []
+    for i in range(mod.num_layer):
+        e = {}
+        for axis in ("time", "freq"):
+            norm, rnn, fc = getattr(mod, f"norm_{axis}")[i], getattr(mod, f"rnn_{axis}")[i], getattr(mod, f"fc_{axis}")[i]
+            p = pack_lstm_tc(rnn)
+            p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(), fc=pack_fc_tc(fc, p["H"]))
+            e[axis] = p
+        layers.append(e)
+    return layers
+
+
+class TcWorkspace:
+    """Per-shape buffers of the tensor-core dual path (kept across calls: y must stay zero in its padding)."""
+
+    def __init__(self, B, T, K, N, dev):
+        self.key = (B, T, K, N, str(dev))
+        M = B * T * K
+        self.m_tiles = (M + 127) // 128
+        self.tiles_time = (B * K + 127) // 128
+        self.tiles_freq = (B * T + 127) // 128
+        kc_in = (N + 15) // 16 * 2
+        self.xhat = torch.empty(self.m_tiles * kc_in * 128 * 8, dtype=torch.float16, device=dev)
+        self.gates = torch.empty(M, 2 * CL * LBN, dtype=torch.float16, device=dev)
+        ntile = max(T * self.tiles_time, K * self.tiles_freq)
+        self.y = torch.zeros(ntile * 2 * LKC * 128 * 8, dtype=torch.float16, device=dev)
+        self.stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        self.scale = torch.empty(B, N, dtype=torch.float32, device=dev)
+        self.shift = torch.empty(B, N, dtype=torch.float32, device=dev)
+        self.counts = _f64([float(T) * K * N], dev)
+
+
+_WS = {}
+
+
+def workspace(B, T, K, N, dev):
+    key = (B, T, K, N, str(dev))
+    ws = _WS.get(key)
+    if ws is None:
+        _WS.clear()                     # one live shape at a time keeps the footprint bounded
+        ws = _WS[key] = TcWorkspace(B, T, K, N, dev)
+    return ws
+
+
+def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
+    """In-place 2*num_layer residual blocks on skip (B,T,K,N) f32, tensor-core mode."""
+    B, T, K, N = skip.shape
+    dev = skip.device
+    st = L.stream_ptr()
+    ws = workspace(B, T, K, N, dev)
+    M = B * T * K
+    L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
+    for i, lay in enumerate(layers):
+        for axis in ("time", "freq"):
+            w = lay[axis]
+            extra = t_emb[i] if (t_emb is not None and axis == "time") else None
+            with region("norm"):
+                L.call("bsrnn_gn_finalize", ws.stats.data_ptr(), w["gamma"].data_ptr(), w["beta"].data_ptr(), L.ptr(extra),
+                       ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), 1e-5, 1, st)
+                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(), ws.xhat.data_ptr(),
+                       N, 0, N, w["kc_in"], ws.m_tiles, ws.m_tiles, M, BIG, 0, 1, 0, T * K, 1, st)
+            with region("inproj"):
+                L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(), w["bih"].data_ptr(), ws.gates.data_ptr(), None,
+                       ws.m_tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_ROWS, 2 * CL * LBN, 2 * CL * LBN, 0, T * K,
+                       ws.m_tiles, M, BIG, 0, 1, 0, st)
+            if axis == "time":
+                R, steps, tiles, addr = B * K, T, ws.tiles_time, (K, T * K, 1, K)
+            else:
+                R, steps, tiles, addr = B * T, K, ws.tiles_freq, (1, K, 0, 1)
+            with region(f"lstm_{axis}"):
+                L.call("bsrnn_blstm_recurrence_tc", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.y.data_ptr(), R, steps,
+                       tiles, *addr, max_clusters, st)
+            with region("fc"):
+                ws.stats.zero_()
+                fc = w["fc"]
+                L.call("bsrnn_gemm_tc", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
+                       ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], L.TC_RESID_F32, N, N, 0, T * K,
+                       tiles, R, *addr, st)
+    return skip
