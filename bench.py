@@ -94,7 +94,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("BSRNN_B200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("BSRNN_B200_PRECISION", "fp16"))
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU (BASELINE config 2: 64)")
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="length of the bounded CPU-baseline sample")
@@ -199,7 +199,7 @@ def main():
             "metric": "BSRNN audio-sec/sec enhanced at 48 kHz", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "dtype": "f32" if args.precision == "fp32" else "fp16", "data": "synthetic",
             "config": {"workload": workload, "precision": args.precision, "weights": "random-init seed 0",
                        "l2": "inputs and activations larger than L2 (no flush needed)", "sharding": "utterances, no collective"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * n * 4 + B * 4, "d2h_bytes_per_step": B * n * 4},

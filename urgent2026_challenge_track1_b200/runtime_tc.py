@@ -154,3 +154,66 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                        ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], L.TC_RESID_F32, N, N, 0, T * K,
                        tiles, R, *addr, st)
     return skip
+
+
+# ------------------------------------------------------------------------------------------------ mask decoder
+def pack_mask_decoder_tc(md):
+    """espnet2-style MaskDecoder for the tensor-core path: Conv1d(N,4N) as 208-column tiles, Conv1d(4N,4s) with rows
+    interleaved (value, gate) so the GLU pairs sit in adjacent accumulator columns."""
+    out = {}
+    for name in ("mlp_mask", "mlp_residual"):
+        mlps = getattr(md, name)
+        N = mlps[0][1].weight.shape[1]
+        kc1 = (N + 15) // 16 * 2
+        H4 = 4 * N
+        kc2 = (H4 + 15) // 16 * 2
+        nt1 = (H4 + LBN - 1) // LBN
+        w1, b1, w2, b2, bn2 = [], [], [], [], []
+        for k, m in enumerate(mlps):
+            w1.append(to_kb8(m[1].weight[:, :, 0].float(), LBN, kc1))
+            bb = torch.zeros(nt1 * LBN, device=m[1].bias.device); bb[:H4] = m[1].bias
+            b1.append(bb)
+            w = m[3].weight[:, :, 0].float()                     # (4s, 4N): first 2s rows = value, last 2s = gate
+            half = w.shape[0] // 2
+            order = torch.stack([torch.arange(half), torch.arange(half) + half], 1).reshape(-1).to(w.device)
+            BN = (w.shape[0] + 15) // 16 * 16
+            w2.append(to_kb8(w[order], BN, kc2))
+            bb = torch.zeros(BN, device=w.device); bb[: w.shape[0]] = m[3].bias[order]
+            b2.append(bb)
+            bn2.append(BN)
+        out[name] = dict(gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
+                         beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
+                         w1=w1, b1=b1, w2=w2, b2=b2, bn2=bn2, kc1=kc1, kc2=kc2, nt1=nt1, N=N)
+    return out
+
+
+def mask_decoder_tc(skip, plan, md_pack):
+    """skip (B,T,K',N) -> mask, resid (B,T,F,2) f32, tensor-core mode."""
+    from .runtime import _decoder_norm_tables
+    B, T, K, N = skip.shape
+    F = plan.F
+    dev = skip.device
+    st = L.stream_ptr()
+    tabs = _decoder_norm_tables(skip, md_pack)
+    tiles = (B * T + 127) // 128
+    outs = {}
+    p0 = md_pack["mlp_mask"]
+    xhat = torch.empty(K * tiles * p0["kc1"] * 1024, dtype=torch.float16, device=dev)
+    hidden = torch.empty(tiles * p0["kc2"] * 1024, dtype=torch.float16, device=dev)
+    for name in ("mlp_mask", "mlp_residual"):
+        p = md_pack[name]
+        scale, shift = tabs[name][0], tabs[name][1]
+        o = torch.empty(B, T, F, 2, dtype=torch.float32, device=dev)
+        with region("maskdec"):
+            # rows of tile (k, j) are the (b,t) tokens of band k: same row map as the band-axis BLSTM
+            L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
+                   p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, st)
+            for k in range(K):
+                L.call("bsrnn_gemm_tc", xhat.data_ptr() + 2 * k * tiles * p["kc1"] * 1024, p["w1"][k].data_ptr(),
+                       p["b1"][k].data_ptr(), hidden.data_ptr(), None, tiles, p["nt1"], p["kc1"], LBN, L.TC_TANH_KB8,
+                       0, 4 * N, p["kc2"], B * T, tiles, B * T, BIG, 0, 1, 0, st)
+                L.call("bsrnn_gemm_tc", hidden.data_ptr(), p["w2"][k].data_ptr(), p["b2"][k].data_ptr(),
+                       o.data_ptr() + 8 * plan.bin0[k], None, tiles, 1, p["kc2"], p["bn2"][k], L.TC_GLU_F32, 2 * F,
+                       2 * plan.width[k], 0, B * T, tiles, B * T, BIG, 0, 1, 0, st)
+        outs[name] = o
+    return outs["mlp_mask"], outs["mlp_residual"]
