@@ -110,7 +110,7 @@ def check_lstm(B, T, K, axis, N=196):
 def main():
     L.require_device()
     print("max co-resident clusters:", L.lib().bsrnn_blstm_tc_max_clusters())
-    for (M, K, Nn, BN) in [(128, 64, 208, 208), (300, 208, 3328, 208), (1000, 800, 196, 208), (513, 784, 240, 240), (257, 196, 784, 256)]:
+    for (M, K, Nn, BN) in [(128, 64, 208, 208), (300, 208, 3328, 208), (1000, 800, 196, 208), (513, 784, 240, 240), (257, 196, 784, 256), (5120, 196, 3328, 208), (9000, 196, 784, 208)]:
         print(f"gemm rows   M={M} K={K} N={Nn} BN={BN}:", check_gemm(M, K, Nn, BN, "rows"))
     print("gemm resid :", check_gemm(1000, 800, 196, 208, "resid"))
     print("gemm tanh  :", check_gemm(700, 196, 784, 256, "tanh"))

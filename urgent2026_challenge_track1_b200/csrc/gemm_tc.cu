@@ -50,6 +50,7 @@ struct GemmTcArgs {
   int m_tiles, n_tiles, kcores, BN;
   int n_valid;                      // logical output columns kept
   int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
+  int b_resident;                   // 1: each CTA keeps ONE weight tile in shared memory and streams A tiles only
   RowMap rows;
 };
 
@@ -128,6 +129,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
   }
 }
 
+// Static tile schedule.  Streaming mode: tile t = blockIdx + it*grid, N tile innermost (CTAs running together share
+// the A tile through L2).  Weight-resident mode: CTA i owns N tile i % n_tiles for the whole launch and walks the M
+// tiles g, g+G, ... of its group (g = i / n_tiles, G = grid / n_tiles): the weight tile is fetched once, and the
+// n_tiles CTAs of a group still consume the same A tile at the same time.
+__device__ __forceinline__ bool next_tile(const GemmTcArgs& a, int it, int& m, int& n) {
+  if (a.b_resident) {
+    n = blockIdx.x % a.n_tiles;
+    m = blockIdx.x / a.n_tiles + it * (gridDim.x / a.n_tiles);
+    return m < a.m_tiles;
+  }
+  const int t = blockIdx.x + it * gridDim.x;
+  if (t >= a.m_tiles * a.n_tiles) return false;
+  m = t / a.n_tiles;
+  n = t - m * a.n_tiles;
+  return true;
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -136,17 +154,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   const uint32_t b_stage_bytes = TC_KS * BN * 16;
   uint8_t* sA = smem;
   uint8_t* sB = smem + TC_STAGES * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + TC_STAGES * b_stage_bytes);
+  const uint32_t b_region = a.b_resident ? (uint32_t)a.kcores * BN * 16 : TC_STAGES * b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_region);
   uint64_t* full = bars;                     // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
   uint64_t* acc_full = bars + 2 * TC_STAGES;     // [2]
   uint64_t* acc_empty = bars + 2 * TC_STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+  uint64_t* b_full = bars + 2 * TC_STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 2 * TC_ACC_COLS);
@@ -155,23 +176,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total = a.m_tiles * a.n_tiles;
   const int nstage_k = (a.kcores + TC_KS - 1) / TC_KS;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int m = t / a.n_tiles, n = t - m * a.n_tiles;
+      int m, n;
+      if (a.b_resident && next_tile(a, 0, m, n)) {
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
+        const uint32_t bytes = (uint32_t)a.kcores * BN * 16;
+        mbar_expect_tx(b_full, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
+      }
+      for (int it = 0; next_tile(a, it, m, n); ++it) {
         const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)m * a.kcores * 2048;
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
         for (int ks = 0; ks < nstage_k; ++ks) {
           const int kc0 = ks * TC_KS;
           const int nk = min(TC_KS, a.kcores - kc0);
           mbar_wait(empty + stage, phase ^ 1);
-          mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + BN * 16));
+          mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
           bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
-          bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
+          if (!a.b_resident)
+            bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -180,8 +207,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     if (lane == 0) {
       const uint32_t idesc = idesc_f16_f32(128, BN);
       uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      int m, n;
+      if (a.b_resident && next_tile(a, 0, m, n)) mbar_wait(b_full, 0);
+      for (int it = 0; next_tile(a, it, m, n); ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(acc_empty + buf, acc_phase ^ 1);
@@ -192,7 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(sA + stage * a_stage_bytes);
-          const uint32_t sb = smem_u32(sB + stage * b_stage_bytes);
+          const uint32_t sb = a.b_resident ? smem_u32(sB) + (uint32_t)ks * TC_KS * BN * 16
+                                           : smem_u32(sB + stage * b_stage_bytes);
           for (int j = 0; j < nk / 2; ++j) {
             const uint64_t da = smem_desc_kb8(sa + j * 2 * 2048, 2048, 128);
             const uint64_t db = smem_desc_kb8(sb + j * 2 * BN * 16, BN * 16, 128);
@@ -207,9 +236,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   } else {
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;               // row of the tile
-    int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int m = t / a.n_tiles, n = t - m * a.n_tiles;
+    int m, n;
+    for (int it = 0; next_tile(a, it, m, n); ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       long token = 0;
@@ -261,19 +289,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   }
 }
 
-static size_t tc_smem_bytes(int BN) {
-  return (size_t)TC_STAGES * (TC_KS * 128 * 16 + TC_KS * BN * 16) + (2 * TC_STAGES + 4) * 8 + 16;
+static size_t tc_smem_bytes(int BN, int kcores, bool resident) {
+  const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)TC_STAGES * TC_KS * BN * 16;
+  return (size_t)TC_STAGES * TC_KS * 128 * 16 + b + (2 * TC_STAGES + 5) * 8 + 16;
 }
 
 template <int EPI>
-static int launch_tc(const GemmTcArgs& a, cudaStream_t st) {
-  const size_t smem = tc_smem_bytes(a.BN);
-  BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // weight-resident schedule when several N tiles exist, the tile fits beside the A ring, and there is enough M work
+  a.b_resident = (a.n_tiles > 1 && a.n_tiles <= sms && (size_t)a.kcores * a.BN * 16 <= 120 * 1024 &&
+                  a.m_tiles >= 2 * (sms / a.n_tiles)) ? 1 : 0;
+  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident);
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int total = a.m_tiles * a.n_tiles;
-  const int grid = total < sms ? total : sms;
+  int grid = total < sms ? total : sms;
+  if (a.b_resident) grid = (sms / a.n_tiles) * a.n_tiles;
   gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
   BSRNN_LAUNCH_OK();
   return 0;

@@ -36,7 +36,7 @@ constexpr int LKC = 50;            // k-cores of the recurrent operand (K = 400)
 constexpr int LKS = 10;            // k-cores per A stage
 constexpr int LNST = LKC / LKS;    // 5 stages per step
 constexpr int LSTAGES = 3;
-constexpr int LTHREADS = 192;
+constexpr int LTHREADS = 320;        // producer warp + MMA warp + 8 epilogue warps
 constexpr uint32_t L_W_BYTES = LKC * LBN * 16;          // 166400
 constexpr uint32_t L_A_STAGE = LKS * 128 * 16;          // 20480
 constexpr size_t L_SMEM = L_W_BYTES + LSTAGES * L_A_STAGE + 16 * 8 + 16;
@@ -48,7 +48,13 @@ struct LstmTcArgs {
   __half* y;
   int R, steps, seq_tiles;
   long seq_inner, seq_outer, seq_inner_stride, step_stride;
+  long long* trace;      // optional (debug): [step][8] SM-clock stamps written by cluster 0 / CTA 0
 };
+
+#define LSTM_TRACE(slot, step)                                                         \
+  do {                                                                                 \
+    if (a.trace && cid == 0 && q == 0 && (step) < 64) a.trace[(step) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -63,53 +69,70 @@ __device__ __forceinline__ void gate_update(float pi, float pf, float pg, float 
   h = og * tanh_fast(c);
 }
 
-// Writes the 49 h values of one row into the KB8 tile: unit i -> k = 49Q + i -> k-core 6Q + (Q+i)/8, slot (Q+i)%8.
-template <int Q>
-__device__ __forceinline__ void store_h(__half* ytile_row /* &y[...][kc=0][r][0] */, const float (&h)[LU]) {
+// Epilogue work split: 8 warps; warp (quadrant, half) owns 32 rows x units [U0, U0+NU) with
+//   half 0: units [0,24)  = accumulator columns [0,96)    (3 chunks of 32 columns)
+//   half 1: units [24,49) = accumulator columns [96,196)  (3 chunks of 32 + one of 4)
+// Unit i of CTA Q is h column k = 49Q + i -> k-core 6Q + (Q+i)/8, slot (Q+i)%8 of the y tile.
+template <int Q, int U0, int NU>
+__device__ __forceinline__ void store_h(__half* ytile_row /* &y[...][kc=0][r][0] */, const float (&h)[25]) {
 #pragma unroll
   for (int jj = 0; jj < 7; ++jj) {
     const int lo = 8 * jj - Q;                       // unit index sitting in slot 0 of this core
+    if (lo + 8 <= U0 || lo >= U0 + NU) continue;     // core holds none of our units
     __half* dst = ytile_row + (size_t)(6 * Q + jj) * 128 * 8;
-    if (lo >= 0 && lo + 8 <= LU) {
-      __half2 p0 = __floats2half2_rn(h[lo], h[lo + 1]), p1 = __floats2half2_rn(h[lo + 2], h[lo + 3]);
-      __half2 p2 = __floats2half2_rn(h[lo + 4], h[lo + 5]), p3 = __floats2half2_rn(h[lo + 6], h[lo + 7]);
+    if (lo >= U0 && lo + 8 <= U0 + NU) {
+      const int b = lo - U0;
+      __half2 p0 = __floats2half2_rn(h[b], h[b + 1]), p1 = __floats2half2_rn(h[b + 2], h[b + 3]);
+      __half2 p2 = __floats2half2_rn(h[b + 4], h[b + 5]), p3 = __floats2half2_rn(h[b + 6], h[b + 7]);
       uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
       *reinterpret_cast<uint4*>(dst) = pk;
     } else {
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const int i = lo + s;
-        if (i >= 0 && i < LU) dst[s] = __float2half_rn(h[i]);
+      for (int sl = 0; sl < 8; ++sl) {
+        const int i = lo + sl;
+        if (i >= U0 && i < U0 + NU) dst[sl] = __float2half_rn(h[i - U0]);
       }
     }
   }
 }
 
-template <int Q>
-__device__ __forceinline__ void epilogue_step(const LstmTcArgs& a, uint32_t t_addr, bool have_acc, const __half* gx,
-                                              bool row_ok, __half* ytile_row, float (&c)[LU]) {
-  float h[LU];
-  // 6 chunks of 8 units (32 accumulator columns) + 1 chunk of 1 unit
+struct GxRegs {            // this thread's slice of the precomputed input projection for one step (fp16)
+  uint4 v[12];
+  uint2 tail;
+};
+
+template <int HALF>
+__device__ __forceinline__ void load_gx(const __half* gx, bool row_ok, GxRegs& g) {
+  if (row_ok) {
+    const uint4* p = reinterpret_cast<const uint4*>(gx + HALF * 96);
 #pragma unroll
-  for (int ch = 0; ch < 6; ++ch) {
+    for (int i = 0; i < 12; ++i) g.v[i] = __ldg(p + i);
+    if (HALF == 1) g.tail = __ldg(reinterpret_cast<const uint2*>(gx + 192));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) g.v[i] = make_uint4(0, 0, 0, 0);
+    g.tail = make_uint2(0, 0);
+  }
+}
+
+template <int Q, int HALF>
+__device__ __forceinline__ void epilogue_step(uint32_t t_addr, bool have_acc, const GxRegs& g, __half* ytile_row,
+                                              float (&c)[25]) {
+  constexpr int U0 = HALF == 0 ? 0 : 24;
+  constexpr int NU = HALF == 0 ? 24 : 25;
+  float h[25];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
     uint32_t acc[32];
-    uint4 g4[4];
-    if (row_ok) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) g4[v] = __ldg(reinterpret_cast<const uint4*>(gx + ch * 32) + v);
-    } else {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) g4[v] = make_uint4(0, 0, 0, 0);
-    }
     if (have_acc) {
-      tmem_ld_x32(t_addr + ch * 32, acc);
+      tmem_ld_x32(t_addr + HALF * 96 + ch * 32, acc);
       tmem_ld_wait();
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0u;
     }
-    const __half2* gh = reinterpret_cast<const __half2*>(g4);
+    const __half2* gh = reinterpret_cast<const __half2*>(&g.v[ch * 4]);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float2 g01 = __half22float2(gh[2 * u]), g23 = __half22float2(gh[2 * u + 1]);
@@ -118,21 +141,82 @@ __device__ __forceinline__ void epilogue_step(const LstmTcArgs& a, uint32_t t_ad
                   h[ch * 8 + u]);
     }
   }
-  {
+  if (HALF == 1) {
     uint32_t acc[4];
-    uint2 g2 = row_ok ? __ldg(reinterpret_cast<const uint2*>(gx + 192)) : make_uint2(0, 0);
     if (have_acc) {
       tmem_ld_x4(t_addr + 192, acc);
       tmem_ld_wait();
     } else {
       acc[0] = acc[1] = acc[2] = acc[3] = 0u;
     }
-    const __half2* gh = reinterpret_cast<const __half2*>(&g2);
+    const __half2* gh = reinterpret_cast<const __half2*>(&g.tail);
     const float2 g01 = __half22float2(gh[0]), g23 = __half22float2(gh[1]);
     gate_update(__uint_as_float(acc[0]) + g01.x, __uint_as_float(acc[1]) + g01.y, __uint_as_float(acc[2]) + g23.x,
-                __uint_as_float(acc[3]) + g23.y, c[48], h[48]);
+                __uint_as_float(acc[3]) + g23.y, c[24], h[24]);
   }
-  store_h<Q>(ytile_row, h);
+  store_h<Q, U0, NU>(ytile_row, h);
+}
+
+// The epilogue role for one (Q, HALF): loops over this cluster's work units and steps.
+template <int Q, int HALF>
+__device__ __forceinline__ void epilogue_role(const LstmTcArgs& a, uint32_t tmem_base, int warp, int lane, int cid, int ncl,
+                                              uint64_t* acc_full, uint64_t* acc_empty, uint64_t* h_ready, uint64_t* w_free) {
+  const int quad = warp & 3;
+  const int q = Q;
+  const bool tracer = warp == 2 && lane == 0;
+  const int r = quad * 32 + lane;
+  const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const int units = 2 * a.seq_tiles;
+  const size_t tile_elems = (size_t)LKC * 128 * 8;
+  uint32_t fphase = 0;
+  for (int w = cid; w < units; w += ncl) {
+    const int d = w / a.seq_tiles, j = w - d * a.seq_tiles;
+    const long seq = (long)j * 128 + r;
+    const bool row_ok = seq < a.R;
+    const long tok0 = row_ok ? (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride : 0;
+    float c[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) c[i] = 0.f;
+    for (int s = 0; s < a.steps; ++s) {
+      const int p = d == 0 ? s : a.steps - 1 - s;
+      const long token = tok0 + (long)p * a.step_stride;
+      const __half* gx = a.gates_x + (token * 2 + d) * (LCL * LBN) + Q * LBN;
+      __half* ytile_row = a.y + (((size_t)p * a.seq_tiles + j) * 2 + d) * tile_elems + (size_t)r * 8;
+      GxRegs g;
+      load_gx<HALF>(gx, row_ok, g);                 // issued before the wait: HBM latency hides behind the MMAs
+      const bool have_acc = s > 0;
+      if (have_acc) {
+        mbar_wait(acc_full, fphase);
+        fphase ^= 1;
+        tc_fence_after();
+        if (tracer) LSTM_TRACE(5, s);
+      }
+      epilogue_step<Q, HALF>(t_addr, have_acc, g, ytile_row, c);
+      if (tracer) LSTM_TRACE(6, s);
+      if (have_acc) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+      }
+      if (s + 1 == a.steps) {
+        const int wn = w + ncl;                     // next unit of this cluster switches direction?
+        if (wn < units && wn / a.seq_tiles != d) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(w_free);
+        }
+      } else {
+        // publish h_t: all 128 rows x 49 units are written once every epilogue thread passed the named barrier;
+        // one fence (cumulative over the CTA's stores) then 8 relaxed remote arrives issued by 8 lanes in parallel.
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane < LCL) {
+          fence_proxy_async_global();
+          fence_acq_rel_cluster();
+          mbar_arrive_cluster_relaxed(h_ready, lane);
+          if (lane == 0) LSTM_TRACE(7, s);
+        }
+      }
+    }
+  }
 }
 
 __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
@@ -156,10 +240,10 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   if (threadIdx.x == 0) {
     for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 4);
+    mbar_init(acc_empty, 8);
     mbar_init(h_ready, LCL);
     mbar_init(w_full, 1);
-    mbar_init(w_free, 4);
+    mbar_init(w_free, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
@@ -170,7 +254,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   const uint32_t tmem_base = *tmem_slot;
 
   const int units = 2 * a.seq_tiles;
-  const size_t tile_elems = (size_t)LKC * 128 * 8;     // halves per (dir, step, tile)
+  const size_t tile_elems = (size_t)LKC * 128 * 8;     // halves per (step, tile, dir)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: W slice + h tiles
@@ -196,6 +280,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
           const int p_prev = d == 0 ? s - 1 : a.steps - s;        // position whose h feeds this step
           mbar_wait_cluster(h_ready, hphase);
           hphase ^= 1;
+          LSTM_TRACE(0, s);
           fence_proxy_async_global();
           const uint8_t* src = reinterpret_cast<const uint8_t*>(
               a.y + (((size_t)p_prev * a.seq_tiles + j) * 2 + d) * tile_elems);
@@ -205,6 +290,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
             bulk_g2s(sA + stage * L_A_STAGE, src + (size_t)ks * L_A_STAGE, L_A_STAGE, full + stage);
             if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
           }
+          LSTM_TRACE(1, s);
         }
       }
     }
@@ -228,6 +314,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
           tc_fence_after();
           for (int ks = 0; ks < LNST; ++ks) {
             mbar_wait(full + stage, phase);
+            if (ks == 0) LSTM_TRACE(2, s);
+            if (ks == LNST - 1) LSTM_TRACE(3, s);
             tc_fence_after();
             const uint32_t sa = smem_u32(sA + stage * L_A_STAGE);
 #pragma unroll
@@ -240,67 +328,23 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
             if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
           }
           mma_commit(acc_full);
+          LSTM_TRACE(4, s);
         }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: 4 warps, thread = sequence row
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;
-    const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint32_t fphase = 0;
-    for (int w = cid; w < units; w += ncl) {
-      const int d = w / a.seq_tiles, j = w - d * a.seq_tiles;
-      const long seq = (long)j * 128 + r;
-      const bool row_ok = seq < a.R;
-      const long tok0 = row_ok ? (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride : 0;
-      float c[LU];
-#pragma unroll
-      for (int i = 0; i < LU; ++i) c[i] = 0.f;
-      for (int s = 0; s < a.steps; ++s) {
-        const int p = d == 0 ? s : a.steps - 1 - s;
-        const long token = tok0 + (long)p * a.step_stride;
-        const __half* gx = a.gates_x + (token * 2 + d) * (LCL * LBN) + q * LBN;
-        __half* ytile_row = a.y + (((size_t)p * a.seq_tiles + j) * 2 + d) * tile_elems + (size_t)r * 8;
-        const bool have_acc = s > 0;
-        if (have_acc) {
-          mbar_wait(acc_full, fphase);
-          fphase ^= 1;
-          tc_fence_after();
-        }
-        switch (q) {
-          case 0: epilogue_step<0>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          case 1: epilogue_step<1>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          case 2: epilogue_step<2>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          case 3: epilogue_step<3>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          case 4: epilogue_step<4>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          case 5: epilogue_step<5>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          case 6: epilogue_step<6>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-          default: epilogue_step<7>(a, t_addr, have_acc, gx, row_ok, ytile_row, c); break;
-        }
-        if (have_acc) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty);
-        }
-        if (s + 1 == a.steps) {
-          const int wn = w + ncl;                       // next unit of this cluster switches direction?
-          if (wn < units && wn / a.seq_tiles != d) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(w_free);
-          }
-        }
-        if (s + 1 < a.steps) {
-          // publish h_t: all 128 rows written -> one thread releases to the 8 CTAs of the cluster
-          fence_proxy_async_global();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (warp == 2 && lane == 0) {
-#pragma unroll
-            for (uint32_t p2 = 0; p2 < LCL; ++p2) mbar_arrive_cluster(h_ready, p2);
-          }
-        }
-      }
+    // ------------------------------------------------------------------ epilogue: 8 warps (see epilogue_role)
+    const int half = (warp - 2) >> 2;
+#define BSRNN_EPI_CASE(QQ)                                                                                        \
+  case QQ:                                                                                                        \
+    if (half == 0) epilogue_role<QQ, 0>(a, tmem_base, warp, lane, cid, ncl, acc_full, acc_empty, h_ready, w_free); \
+    else epilogue_role<QQ, 1>(a, tmem_base, warp, lane, cid, ncl, acc_full, acc_empty, h_ready, w_free);           \
+    break;
+    switch (q) {
+      BSRNN_EPI_CASE(0) BSRNN_EPI_CASE(1) BSRNN_EPI_CASE(2) BSRNN_EPI_CASE(3)
+      BSRNN_EPI_CASE(4) BSRNN_EPI_CASE(5) BSRNN_EPI_CASE(6) BSRNN_EPI_CASE(7)
     }
+#undef BSRNN_EPI_CASE
   }
   tc_fence_before();
   __syncthreads();
@@ -314,13 +358,17 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
 }  // namespace bsrnn
 using namespace bsrnn;
 
+static long long* g_lstm_trace = nullptr;
+extern "C" void bsrnn_debug_set_lstm_trace(void* p) { g_lstm_trace = reinterpret_cast<long long*>(p); }
+
 extern "C" int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, void* y, int R, int steps,
                                          int seq_tiles, long seq_inner, long seq_outer, long seq_inner_stride,
                                          long step_stride, int max_clusters, void* stream) {
   BSRNN_CHECK_ARG(gates_x && w_pack && y, "blstm_recurrence_tc: null pointer");
   BSRNN_CHECK_ARG(R > 0 && steps > 0 && seq_tiles * 128 >= R && seq_inner > 0, "blstm_recurrence_tc: bad dims");
   LstmTcArgs a{reinterpret_cast<const __half*>(gates_x), reinterpret_cast<const __half*>(w_pack),
-               reinterpret_cast<__half*>(y), R, steps, seq_tiles, seq_inner, seq_outer, seq_inner_stride, step_stride};
+               reinterpret_cast<__half*>(y), R, steps, seq_tiles, seq_inner, seq_outer, seq_inner_stride, step_stride,
+               g_lstm_trace};
   cudaStream_t st = (cudaStream_t)stream;
   BSRNN_CUDA_OK(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM));
   static int max_active = -1;
