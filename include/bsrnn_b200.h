@@ -164,6 +164,10 @@ int bsrnn_conv5x5_glu(const float* g, const float* weight, const float* bias, fl
                       int F, void* stream);
 int bsrnn_euler_step(float* x, const float* mask, const float* resid, float step, long n_complex, void* stream);
 int bsrnn_axpy_complex(float* out, const float* y, const float* z, float sigma, long n_complex, void* stream);
+/* out = sign * (mask*x + resid): the network output g = m*x_t + r [bsrnn_flowse.py:313-316]; sign=-1 gives the
+ * vector field FlowSEModel.forward returns [flow_model.py:203-209]. */
+int bsrnn_complex_mask(float* out, const float* x, const float* mask, const float* resid, float sign, long n_complex,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -118,3 +118,55 @@ def test_bsrnn_se_tensorcore_vs_oracle(fs, secs, B):
     assert e_w < 1e-2 and e_s < 1e-2
     out2, _ = m(x, lens, fs)                       # workspaces are reused across calls: result must not drift
     assert rel_l2(out2.cpu(), out.cpu()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ FlowSE
+def _flow_model(g):
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    cfg = Config(model_type="flowse", ema_decay=0.999, sigma_max=0.5, sigma_min=0.05, t_eps=0.03, T_rev=1.0,
+                 loss_type="mse", loss_abs_exponent=0.5, n_fft=1536, hop_length=384, spec_transform_type="exponent",
+                 spec_abs_exponent=0.667, spec_factor=0.065, bsrnn_hidden=16, num_layer=1, learning_rate=1e-4)
+    m = FlowSEModel(cfg)
+    m.load_state_dict(golden_sd(g))
+    return m.cuda().eval(no_ema=True)
+
+
+@pytest.mark.parametrize("fs", (16000, 22050, 48000))
+def test_flowse_vs_golden(fs):
+    """Vector field, fused Euler sampler and the literal registry loop against the verbatim reference's outputs."""
+    g = golden("flowse_n16_l1.npz")
+    m = _flow_model(g)
+    y, lens = torch.from_numpy(g[f"in/{fs}/wav"]), torch.from_numpy(g[f"in/{fs}/lens"])
+    z, t = torch.from_numpy(g[f"in/{fs}/z"]), torch.from_numpy(g[f"in/{fs}/t"])
+    Y = m.speech_to_feature(y, fs, lens)
+    assert rel_l2(Y.cpu(), g[f"out/{fs}/feature"]) < 2e-5
+    vf = m(Y + 0.5 * z.cuda(), t.cuda(), Y)
+    assert vf.shape == Y.shape and rel_l2(vf.cpu(), g[f"out/{fs}/vf"]) < 1e-4
+    enh = m.enhance(y, fs, lens, N=3, z=z)
+    assert rel_l2(enh.cpu(), g[f"out/{fs}/enhanced"]) < 1e-3           # f32 bar (north_star)
+    torch.manual_seed(11)                                              # same draw as make_golden.py -> same z
+    enh2 = m.enhance(y, fs, lens, N=3, solver="euler")
+    assert rel_l2(enh2.cpu(), g[f"out/{fs}/enhanced"]) < 1e-3
+
+
+def test_flowse_solver_registry_errors():
+    from urgent2026_challenge_track1_b200.sampling import ODEsolverRegistry
+    assert set(ODEsolverRegistry.get_all_names()) >= {"euler", "midpoint", "heun"}
+    with pytest.raises(ValueError):
+        ODEsolverRegistry.get_by_name("rk45")
+
+
+def test_flowse_midpoint_heun_vs_oracle():
+    g = golden("flowse_n16_l1.npz")
+    m = _flow_model(g)
+    sd = golden_sd(g)
+    fs = 16000
+    y, lens = torch.from_numpy(g[f"in/{fs}/wav"]), torch.from_numpy(g[f"in/{fs}/lens"])
+    z = torch.from_numpy(g[f"in/{fs}/z"])
+    for solver in ("midpoint", "heun"):
+        with torch.no_grad():
+            ref = R.flowse_enhance(sd, y, fs, lens, N=2, z=z, num_layer=1, solver=solver)
+        torch.manual_seed(11)
+        out = m.enhance(y, fs, lens, N=2, solver=solver)
+        assert rel_l2(out.cpu(), ref) < 1e-3

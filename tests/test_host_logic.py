@@ -1,0 +1,152 @@
+"""CPU tests of the host-side logic: band plans, STFT sizes, state_dict layout (against the golden fixtures, i.e. the
+reference's own key names), config / registry behaviour, KB8 packing, multi-rank sharding (gloo, world_size 2)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import golden, golden_sd
+from oracle import restated as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_band_plan_matches_reference_table():
+    from urgent2026_challenge_track1_b200.runtime import BandPlan, subbands_for, stft_dims
+    want = {8000: (81, 20), 16000: (161, 27), 22050: (221, 28), 24000: (241, 29), 32000: (321, 31), 44100: (442, 34),
+            48000: (481, 34)}
+    for fs, (F, K) in want.items():
+        n_fft, hop = stft_dims(fs, 960, 480)
+        assert (n_fft, hop) == R.stft_dims(fs, 960, 480) and n_fft // 2 + 1 == F
+        plan = BandPlan.make(subbands_for(481), F)
+        assert plan.K == K and sum(plan.width) == F
+    plan = BandPlan.make(subbands_for(481), 161)
+    assert plan.width[-1] == 20 and plan.subbands[plan.K - 1] == 40               # 20 real + 20 padded bins @16 kHz
+    assert BandPlan.make(subbands_for(769), 769).K == 48
+    with pytest.raises(NotImplementedError):
+        subbands_for(513)
+
+
+def test_state_dict_layout_is_the_references():
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    g = golden("bsrnn_se_n16_l2.npz")
+    m = BSRNN_SE(16, 2)
+    ref = golden_sd(g)
+    assert set(m.state_dict()) == set(ref)
+    assert all(m.state_dict()[k].shape == ref[k].shape for k in ref)
+    m.load_state_dict(ref)
+    full = BSRNN_SE(196, 6)
+    assert sum(p.numel() for p in full.parameters()) == 37_800_844 and len(full.state_dict()) == 688
+    g = golden("flowse_n16_l1.npz")
+    cfg = Config(model_type="flowse", ema_decay=0.999, sigma_max=0.5, sigma_min=0.05, t_eps=0.03, T_rev=1.0,
+                 loss_type="mse", n_fft=1536, hop_length=384, spec_transform_type="exponent", spec_abs_exponent=0.667,
+                 spec_factor=0.065, bsrnn_hidden=16, num_layer=1)
+    fm = FlowSEModel(cfg)
+    ref = golden_sd(g)
+    assert set(fm.state_dict()) == set(ref)
+    fm.load_state_dict(ref)
+    assert fm.dnn.t_cond[0].W.requires_grad is False
+
+
+def test_flowse_eval_swaps_ema_weights():
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    cfg = Config(model_type="flowse", ema_decay=0.5, sigma_max=0.5, sigma_min=0.05, t_eps=0.03, T_rev=1.0,
+                 loss_type="mse", n_fft=1536, hop_length=384, spec_transform_type="exponent", spec_abs_exponent=0.667,
+                 spec_factor=0.065, bsrnn_hidden=16, num_layer=1)
+    fm = FlowSEModel(cfg)
+    p = fm.dnn.condition_fc.bias
+    before = p.detach().clone()
+    with torch.no_grad():
+        p.add_(1.0)
+    fm.ema.update(fm.parameters())
+    fm.eval()                                   # reference flow_model.py:98-109: EMA weights swapped in place
+    assert not torch.allclose(p, before + 1.0)
+    fm.train()
+    assert torch.allclose(p, before + 1.0)
+    ck = {}
+    fm.on_save_checkpoint(ck)
+    assert set(ck["ema"]) == {"decay", "num_updates", "shadow_params", "collected_params"}
+
+
+def test_config_yaml_and_flags(tmp_path):
+    from urgent2026_challenge_track1_b200.config import Config, config_parser
+    y = tmp_path / "BSRNN_baseline.yaml"
+    y.write_text("batch_size: 4\nse_model: bsrnn\nmodel_configs:\n  num_channel: 196\n  num_layer: 6\nnew_key: 7\n")
+    args = config_parser(["--config_file", str(y), "--resume", "no", "--learning_rate", "2e-3"])
+    cfg = Config(**vars(args))
+    cfg.read_yaml()
+    assert cfg.batch_size == 4 and cfg.model_configs == {"num_channel": 196, "num_layer": 6} and cfg.new_key == 7
+    assert cfg.train_tag == "BSRNN_baseline" and cfg.resume is False and cfg.learning_rate == 2e-3
+
+
+def test_semodel_selector():
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.d_model import SEModel
+    m = SEModel(Config(se_model="bsrnn", model_configs={"num_channel": 16, "num_layer": 1}))
+    assert all(k.startswith("se_model.bsrnn.bsrnn.") for k in m.state_dict())
+    with pytest.raises(TypeError):
+        SEModel(Config(se_model="tfgridnet", model_configs={}))
+
+
+def test_euler_schedule_and_registry():
+    from urgent2026_challenge_track1_b200.sampling import ODEsolverRegistry, euler_schedule
+    ts, steps = euler_schedule(1.0, 0.03, 15)
+    rts, rsteps = R.euler_schedule(1.0, 0.03, 15)
+    assert torch.equal(ts, rts) and torch.equal(steps, rsteps)
+    with pytest.raises(ValueError):
+        ODEsolverRegistry.get_by_name("nope")
+
+
+def test_kb8_roundtrip_and_lstm_pack():
+    from urgent2026_challenge_track1_b200 import runtime_tc as tc
+    w = torch.randn(300, 196)
+    t = tc.to_kb8(w, 208, 26)
+    assert t.shape == (2, 26, 208, 8) and torch.equal(tc.from_kb8(t, 300, 196), w.half().float())
+    rnn = torch.nn.LSTM(196, 392, batch_first=True, bidirectional=True)
+    p = tc.pack_lstm_tc(rnn)
+    assert p["wih"].shape == (16, 26, 208, 8) and p["whh"].shape == (2, 8, 50, 208, 8)
+    # packed column c = 4*u + gate of CTA q is LSTM row gate*H + 49*q + u
+    q, u, gate = 3, 17, 2
+    row = tc.from_kb8(p["whh"][0, q][None], 208, 392)[4 * u + gate]
+    assert torch.equal(row, rnn.weight_hh_l0[gate * 392 + 49 * q + u].half().float())
+    with pytest.raises(NotImplementedError):
+        tc.pack_lstm_tc(torch.nn.LSTM(16, 32, batch_first=True, bidirectional=True))
+
+
+def _shard_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from urgent2026_challenge_track1_b200.sharding import shard_utterances, gather_max_ms
+    lengths = [480000, 120000, 480000, 96000, 240000, 240000, 64000]
+    fss = [48000, 16000, 48000, 16000, 48000, 48000, 8000]
+    mine = shard_utterances(lengths, fss, rank, world)
+    ms = gather_max_ms(10.0 + rank)
+    flat = sorted(i for _, idx in mine for i in idx)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, flat)
+    if rank == 0:
+        out.put((gathered, ms, [fs for fs, _ in mine]))
+    dist.destroy_process_group()
+
+
+def test_utterance_sharding_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, ms, _ = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(gathered[0] + gathered[1]) == list(range(7))            # every utterance exactly once
+    assert not set(gathered[0]) & set(gathered[1])
+    assert ms == 11.0                                                      # max over ranks

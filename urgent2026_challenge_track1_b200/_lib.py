@@ -44,6 +44,7 @@ PROTOTYPES = {
     "bsrnn_conv5x5_glu": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_long, c_void_p],
     "bsrnn_axpy_complex": [c_void_p, c_void_p, c_void_p, c_float, c_long, c_void_p],
+    "bsrnn_complex_mask": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_long, c_void_p],
 }
 
 # mirrors `bsrnn_gemm_desc` (include/bsrnn_b200.h); 144 bytes

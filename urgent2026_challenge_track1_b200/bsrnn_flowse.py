@@ -1,0 +1,105 @@
+"""Flow-matching BSRNN backbone — drop-in for ``baseline_code/models/bsrnn_flowse.py::BSRNN`` (reference
+bsrnn_flowse.py:171-318) with the same constructor, ``forward(dnn_input, t, fs=None)`` signature, ``current_fs``
+attribute and state_dict keys (band_split_x/y, condition_fc, norm/rnn/fc_{time,freq}, t_cond.{i}.W, grad_decoder.*).
+
+All arithmetic runs in libbsrnn_b200 kernels (f32 mode; the H=768 recurrence has no tensor-core kernel yet).  Besides
+the reference API the class exposes ``mask_resid(x, y_embed, t)`` working on the (B,T,F,2) layout so the sampler can
+fuse the Euler update with the network output and hoist the loop-invariant ``band_split_y``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import runtime as R
+from .layers import BandSplitParams, GradDecoderParams, add_dual_path
+
+
+class GaussianFourierProjection(nn.Module):
+    """Parameter container of the Gaussian Fourier time embedding (reference bsrnn_flowse.py:90-99);
+    W is in the state_dict with requires_grad=False, exactly as in the reference."""
+
+    def __init__(self, embedding_size=256, scale=1.0):
+        super().__init__()
+        self.W = nn.Parameter(torch.randn(embedding_size) * scale, requires_grad=False)
+
+    def forward(self, x):
+        out = torch.empty(x.shape[0], 2 * self.W.numel(), dtype=torch.float32, device=self.W.device)
+        t = x.to(device=self.W.device, dtype=torch.float32).contiguous()
+        L.call("bsrnn_time_embed", t.data_ptr(), self.W.data_ptr(), out.data_ptr(), t.shape[0], self.W.numel(), L.stream_ptr())
+        return out
+
+
+BandSplit = BandSplitParams          # reference names kept importable
+GradDecoder = GradDecoderParams
+
+
+class BSRNN(nn.Module):
+    def __init__(self, input_dim=481, num_channel=16, num_layer=6, target_fs=48000, causal=True, num_spk=1,
+                 norm_type="GN"):
+        super().__init__()
+        if causal:
+            raise NotImplementedError("the B200 path implements the non-causal (BLSTM) configuration the reference "
+                                      "instantiates (flow_model.py:44-49)")
+        if norm_type != "GN":
+            raise NotImplementedError("only norm_type='GN' (the reference default) is implemented")
+        self.num_layer, self.num_channel, self.input_dim = num_layer, num_channel, input_dim
+        self.band_split_y = BandSplitParams(input_dim, target_fs=target_fs, channels=num_channel)
+        self.band_split_x = BandSplitParams(input_dim, target_fs=target_fs, channels=num_channel)
+        self.condition_fc = nn.Linear(2 * num_channel, num_channel)
+        self.target_fs, self.causal, self.num_spk = target_fs, causal, num_spk
+        add_dual_path(self, num_channel, num_layer, with_t_cond=True, t_cond_cls=GaussianFourierProjection)
+        self.grad_decoder = GradDecoderParams(input_dim, self.band_split_x.subbands, channels=num_channel, num_spk=1)
+        self.current_fs = None
+        self._dual = R.PackedCache(self, R.pack_dual_path)
+        self._bsx = R.PackedCache(self.band_split_x, R.pack_band_split)
+        self._bsy = R.PackedCache(self.band_split_y, R.pack_band_split)
+        self._gd = R.PackedCache(self.grad_decoder, R.pack_grad_decoder)
+
+    # ------------------------------------------------------------------------------------------------ (B,T,F,2) core
+    def embed_y(self, y_btf):
+        """band_split_y(y) -> (B,T,K',2N) buffer with columns [N,2N) filled; loop-invariant across ODE steps."""
+        B, T, F, _ = y_btf.shape
+        plan = R.BandPlan.make(self.band_split_x.subbands, F)
+        N = self.num_channel
+        zz = torch.empty(B, T, plan.K, 2 * N, dtype=torch.float32, device=y_btf.device)
+        R.band_split_f32(y_btf, plan, self._bsy.get(), N, out=zz, out_col=N, out_width=2 * N)
+        return zz, plan
+
+    @torch.no_grad()
+    def mask_resid(self, x_btf, zz, plan, t):
+        """One network evaluation on the (B,T,F,2) layout -> (mask, resid) with g = mask*x + resid."""
+        B, T, F, _ = x_btf.shape
+        N = self.num_channel
+        dev = x_btf.device
+        st = L.stream_ptr()
+        R.band_split_f32(x_btf, plan, self._bsx.get(), N, out=zz, out_col=0, out_width=2 * N)
+        skip = torch.empty(B, T, plan.K, N, dtype=torch.float32, device=dev)
+        M = B * T * plan.K
+        dl = R.DescList()
+        w, b = self.condition_fc.weight, self.condition_fc.bias               # bsrnn_flowse.py:284-285
+        dl.add(**R._rows_desc(zz.data_ptr(), w.data_ptr(), b.data_ptr(), skip.data_ptr(), M, N, 2 * N,
+                              a_stride=2 * N, c_stride=N))
+        dl.upload(dev)
+        L.call("bsrnn_gemm_f32", dl.ptr(0), 1, M, N, st)
+        t = t.to(device=dev, dtype=torch.float32)
+        t_emb = [self.t_cond[i](t) for i in range(self.num_layer)]          # bsrnn_flowse.py:293
+        R.dual_path_f32(skip, self._dual.get(), t_emb=t_emb)
+        return R.grad_decoder_f32(skip, plan, self._gd.get(), self.grad_decoder.sub_channel)
+
+    # ------------------------------------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def forward(self, dnn_input, t=None, fs=None):
+        """dnn_input complex (B,2,F,T), t (B,) -> g complex (B,1,F,T)   [reference bsrnn_flowse.py:255-318]."""
+        L.require_device()
+        assert t is not None                                                  # bsrnn_flowse.py:280
+        dev = self.condition_fc.weight.device
+        d = dnn_input.to(dev)
+        x = torch.view_as_real(d[:, 0].permute(0, 2, 1).contiguous()).contiguous()
+        y = torch.view_as_real(d[:, 1].permute(0, 2, 1).contiguous()).contiguous()
+        zz, plan = self.embed_y(y)
+        m, r = self.mask_resid(x, zz, plan, t)
+        g = torch.empty_like(x)
+        L.call("bsrnn_complex_mask", g.data_ptr(), x.data_ptr(), m.data_ptr(), r.data_ptr(), 1.0, x.numel() // 2, L.stream_ptr())
+        return torch.view_as_complex(g).permute(0, 2, 1).unsqueeze(1)

@@ -76,6 +76,14 @@ __global__ void euler_step_kernel(float2* __restrict__ x, const float2* __restri
   }
 }
 
+__global__ void complex_mask_kernel(float2* __restrict__ out, const float2* __restrict__ x, const float2* __restrict__ m,
+                                    const float2* __restrict__ r, float sign, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float2 xv = x[i], mv = m[i], rv = r[i];
+    out[i] = make_float2(sign * (mv.x * xv.x - mv.y * xv.y + rv.x), sign * (mv.x * xv.y + mv.y * xv.x + rv.y));
+  }
+}
+
 __global__ void axpy_complex_kernel(float2* __restrict__ out, const float2* __restrict__ y, const float2* __restrict__ z,
                                     float sigma, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -119,6 +127,16 @@ extern "C" int bsrnn_axpy_complex(float* out, const float* y, const float* z, fl
   axpy_complex_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<float2*>(out), reinterpret_cast<const float2*>(y), reinterpret_cast<const float2*>(z), sigma,
       n_complex);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int bsrnn_complex_mask(float* out, const float* x, const float* mask, const float* resid, float sign,
+                                  long n_complex, void* stream) {
+  BSRNN_CHECK_ARG(out && x && mask && resid && n_complex > 0, "complex_mask: bad arguments");
+  complex_mask_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float2*>(out), reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(mask),
+      reinterpret_cast<const float2*>(resid), sign, n_complex);
   BSRNN_LAUNCH_OK();
   return 0;
 }
