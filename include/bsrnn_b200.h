@@ -148,6 +148,14 @@ int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, do
 int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, void* y, int R, int steps, int seq_tiles,
                               long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
                               int max_clusters, void* stream);
+/* Same with an explicit schedule: `slots` = sequence tiles one cluster advances in an interleaved fashion (their
+ * dependency chains overlap on the cluster's copy ring / tensor pipe / epilogue warps; <= 0 = default), `variant`
+ * 0 = uniform register budget (slots 1..3), 1 = setmaxnreg register split (slots 3..4).
+ * bsrnn_blstm_tc_configure sets the (slots, variant) bsrnn_blstm_recurrence_tc uses. */
+int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, void* y, int R, int steps, int seq_tiles,
+                                 long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
+                                 int max_clusters, int slots, int variant, void* stream);
+int bsrnn_blstm_tc_configure(int slots, int variant);
 int bsrnn_blstm_tc_max_clusters(void);
 
 /* ---------------------------------------------------------------------------------------------- FlowSE pieces

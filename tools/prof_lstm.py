@@ -1,49 +1,95 @@
-"""Runs the tensor-core BLSTM recurrence alone (for ncu / timing).  python tools/prof_lstm.py [B T K axis reps maxcl]"""
-import os, sys, time
+"""Runs the tensor-core BLSTM recurrence alone (timing / ncu / parity vs torch CPU).
+
+  python tools/prof_lstm.py --B 64 --T 1001 --K 34 --axis time --slots 3 --variant 0 [--check] [--trace] [--v2]
+"""
+import argparse, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from urgent2026_challenge_track1_b200 import runtime_tc as tc, _lib as L
 
-B, T, K = (int(a) for a in sys.argv[1:4]) if len(sys.argv) > 3 else (16, 401, 34)
-axis = sys.argv[4] if len(sys.argv) > 4 else "time"
-reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-maxcl = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+ap = argparse.ArgumentParser()
+ap.add_argument("--B", type=int, default=16); ap.add_argument("--T", type=int, default=401); ap.add_argument("--K", type=int, default=34)
+ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, default=3); ap.add_argument("--maxcl", type=int, default=0)
+ap.add_argument("--slots", type=int, default=0); ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
+a = ap.parse_args()
+B, T, K, axis = a.B, a.T, a.K, a.axis
 torch.manual_seed(0)
 N, H = 196, 392
-rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True).cuda()
-p = tc.pack_lstm_tc(rnn)
-M = B * T * K
+rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
 if axis == "time":
     R, steps, addr = B * K, T, (K, T * K, 1, K)
 else:
     R, steps, addr = B * T, K, (1, K, 0, 1)
+M = B * T * K
 tiles = (R + 127) // 128
-gates = (torch.randn(M, 3328, device="cuda") * 0.5).half()
-y = torch.zeros(steps * tiles * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
+ref = None
+if a.check:
+    x = torch.randn(B, T, K, N) * 0.7
+    with torch.no_grad():
+        if axis == "time":
+            ref = rnn(x.permute(0, 2, 1, 3).reshape(B * K, T, N))[0].reshape(B, K, T, 2 * H).permute(0, 2, 1, 3)
+        else:
+            ref = rnn(x.reshape(B * T, K, N))[0].reshape(B, T, K, 2 * H)
+rnn = rnn.cuda()
+p = tc.pack_lstm_tc(rnn)
 st = L.stream_ptr()
-for _ in range(reps):
+if a.check:
+    m_tiles = (M + 127) // 128
+    xg = x.cuda().reshape(M, N).contiguous()
+    xhat = torch.empty(m_tiles * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
+    L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], m_tiles, m_tiles, M,
+           tc.BIG, 0, 1, 0, M, 1, st)
+    gates = torch.empty(M, 3328, dtype=torch.float16, device="cuda")
+    L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bih"].data_ptr(), gates.data_ptr(), None, m_tiles, 16,
+           p["kc_in"], 208, L.TC_F16_ROWS, 3328, 3328, 0, M, m_tiles, M, tc.BIG, 0, 1, 0, st)
+else:
+    gates = torch.empty(M, 3328, dtype=torch.float16, device="cuda")
+    chunk = 1 << 16
+    for i in range(0, M, chunk):
+        gates[i:i + chunk] = (torch.randn(min(chunk, M - i), 3328, device="cuda") * 0.5).half()
+y = torch.zeros(steps * tiles * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
+
+
+def run():
+    if a.v2:
+        import ctypes as C
+        f = L.lib().bsrnn_blstm_recurrence_tc_v2
+        f.argtypes = L.PROTOTYPES["bsrnn_blstm_recurrence_tc"]; f.restype = C.c_int
+        L.check(f(gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), R, steps, tiles, *addr, a.maxcl, st), "v2")
+    else:
+        L.call("bsrnn_blstm_recurrence_tc_ex", gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), R, steps, tiles, *addr,
+               a.maxcl, a.slots, a.variant, st)
+
+
+tag = "v2" if a.v2 else f"v3 slots={a.slots} variant={a.variant}"
+for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    L.call("bsrnn_blstm_recurrence_tc", gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), R, steps, tiles, *addr, maxcl, st)
-    e1.record()
+    e0.record(); run(); e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    ncl = min(2 * tiles, 15 if maxcl <= 0 else maxcl)
-    waves = -(-2 * tiles // ncl)
-    print(f"B={B} T={T} K={K} {axis}: {ms:.3f} ms, units={2*tiles}, clusters={ncl}, waves={waves}, "
-          f"us/step={1e3*ms/(waves*steps):.2f}, TFLOP/s={2*R*steps*2*H*4*H/ms/1e9:.1f}")
+    print(f"[{tag}] B={B} T={T} K={K} {axis}: {ms:.3f} ms, units={2*tiles}, us per unit-step={1e3*ms*15/(2*tiles*steps):.2f} (x15 clusters), "
+          f"TFLOP/s={2*R*steps*2*H*4*H/ms/1e9:.1f}", flush=True)
 
-if os.environ.get("LSTM_TRACE"):
+if a.check:
+    yv = y.view(steps, tiles, 2, 50, 128, 8).permute(0, 1, 4, 2, 3, 5).reshape(steps, tiles * 128, 2, 400)[:, :R, :, :H]
+    yv = yv.reshape(steps, R, 2 * H).float().cpu()
+    mine = yv.reshape(T, B, K, 2 * H).permute(1, 0, 2, 3) if axis == "time" else yv.reshape(K, B, T, 2 * H).permute(1, 2, 0, 3)
+    err = float((mine.double() - ref.double()).norm() / ref.double().norm())
+    pad = y.view(steps, tiles, 2, 50, 128, 8)[:, :, :, 49].abs().max().item()
+    print(f"[{tag}] CHECK {axis} B={B} T={T} K={K}: rel_l2={err:.3e} pad_core_max={pad}  {'OK' if err < 3e-3 and pad == 0 else 'FAIL'}", flush=True)
+
+if a.trace and not a.v2:
     import ctypes
     tr = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
     L.lib().bsrnn_debug_set_lstm_trace.argtypes = [ctypes.c_void_p]
     L.lib().bsrnn_debug_set_lstm_trace(tr.data_ptr())
-    L.call("bsrnn_blstm_recurrence_tc", gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), R, steps, tiles, *addr, maxcl, st)
-    torch.cuda.synchronize()
+    run(); torch.cuda.synchronize()
     L.lib().bsrnn_debug_set_lstm_trace(None)
     t = tr.view(64, 8).cpu()
-    names = ["hready_seen", "loads_issued", "first_full", "last_full", "mma_committed", "acc_full_seen", "epi_done", "arrived"]
-    print("step " + " ".join(f"{n:>14s}" for n in names) + "   (cycles relative to hready_seen of the step)")
+    names = ["hready_seen", "loads_issued", "first_full", "last_full", "mma_committed", "-", "epi_done", "published"]
+    print("slot-0 chain, cycles relative to hready_seen of the step")
+    print("step " + " ".join(f"{n:>13s}" for n in names))
     for s_ in range(2, 12):
         base = int(t[s_, 0])
-        print(f"{s_:4d} " + " ".join(f"{int(t[s_, i]) - base:14d}" for i in range(8)) + f"   step period {int(t[s_+1,0]) - base}")
+        print(f"{s_:4d} " + " ".join(f"{int(t[s_, i]) - base:13d}" for i in range(8)) + f"   round period {int(t[s_+1,0]) - base}")

@@ -39,6 +39,11 @@ PROTOTYPES = {
                       c_int, c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
     "bsrnn_blstm_recurrence_tc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_long,
                                   c_int, c_void_p],
+    "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long,
+                                     c_long, c_int, c_int, c_int, c_void_p],
+    "bsrnn_blstm_tc_configure": [c_int, c_int],
+    "bsrnn_blstm_recurrence_tc_v2": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_long,
+                                     c_int, c_void_p],          # previous single-slot kernel, kept for A/B timing
     "bsrnn_blstm_tc_max_clusters": [],
     "bsrnn_time_embed": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "bsrnn_conv5x5_glu": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -9,7 +9,16 @@ import torch
 from . import _lib as L
 from .runtime import region, _f64
 
+import os
+
 BIG = 1 << 60
+# recurrence schedule per axis: (interleaved slots, variant) of bsrnn_blstm_recurrence_tc_ex; "time=3:0,freq=4:1"
+_LSTM_V2 = os.environ.get("BSRNN_LSTM_V2", "0") == "1"
+_LSTM_SCHED = {"time": (3, 0), "freq": (3, 0)}
+for _kv in os.environ.get("BSRNN_LSTM_SCHED", "").split(","):
+    if "=" in _kv:
+        _ax, _sv = _kv.split("=")
+        _LSTM_SCHED[_ax] = tuple(int(v) for v in _sv.split(":"))
 CL, LU, LBN, LKC = 8, 49, 208, 50       # cluster size, units per CTA, gate columns per CTA, k-cores of h (K = 400)
 
 
@@ -145,8 +154,13 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
             else:
                 R, steps, tiles, addr = B * T, K, ws.tiles_freq, (1, K, 0, 1)
             with region(f"lstm_{axis}"):
-                L.call("bsrnn_blstm_recurrence_tc", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.y.data_ptr(), R, steps,
-                       tiles, *addr, max_clusters, st)
+                if _LSTM_V2:
+                    L.call("bsrnn_blstm_recurrence_tc_v2", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.y.data_ptr(), R,
+                           steps, tiles, *addr, max_clusters, st)
+                else:
+                    slots, variant = _LSTM_SCHED[axis]
+                    L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.y.data_ptr(), R,
+                           steps, tiles, *addr, max_clusters, slots, variant, st)
             with region("fc"):
                 ws.stats.zero_()
                 fc = w["fc"]
