@@ -135,8 +135,17 @@ int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y
  *                       statistics of the next GroupNorm)
  *     2: tanh -> fp16 KB8 operand with out_kcores k-cores                 (MaskDecoder Conv1d(N->4N)+Tanh)
  *     3: GLU on (value,gate)-interleaved columns -> f32 out[token*ldo + col/2], col/2 < n_valid
- * bsrnn_blstm_recurrence_tc: persistent cluster kernel, H = 392 only (see csrc/lstm_tc.cu for the layouts of
- *     gates_x, w_pack and y).  max_clusters <= 0: use every co-resident cluster.
+ *     4: fp16 KB8 tiles out[m_tile][out_kcores][128][8], core = global column / 8 (LSTM input projection in the
+ *        layout the recurrence kernel reads with coalesced 16-byte loads)
+ * bsrnn_blstm_recurrence_tc: persistent cluster kernel, H = 392 only (csrc/lstm_tc.cu).  Sequences are grouped in
+ *     tiles of 128 (seq = j*128 + r, valid iff seq < R); all operands are (step, seq_tile)-major:
+ *       gates_x [step][seq_tile][dir][q][26][128][8] fp16 — epilogue 4 of bsrnn_gemm_tc over A tiles built with the
+ *               axis' row map (m_tile = step*seq_tiles + j) and the packed W_ih of 16 column tiles (dir, q);
+ *       w_pack  [dir][q][50][208][8] fp16; zero_tile: 50*128*8 fp16 zeros (h before the first step);
+ *       y       [step][seq_tile][dir][50][128][8] fp16 (k-core 49 must stay zero).
+ *     The i, f, o gate rows of W_ih / W_hh / bias are pre-multiplied by 0.5 by the packer.
+ *     max_clusters <= 0: use every co-resident cluster.  _ex: `slots` = sequence tiles one cluster interleaves
+ *     (1..3; <= 0 = 3).
  */
 int bsrnn_norm_cast_kb8(const float* x, const float* scale, const float* shift, void* out, long ldx, int col0, int C,
                         int kcores, int m_tiles, int tiles_per_step, int R, long seq_inner, long seq_outer,
@@ -145,17 +154,10 @@ int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, do
                   int kcores, int BN, int epilogue, long ldo, int n_valid, int out_kcores, long tokens_per_sample,
                   int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
                   void* stream);
-int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, void* y, int R, int steps, int seq_tiles,
-                              long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
-                              int max_clusters, void* stream);
-/* Same with an explicit schedule: `slots` = sequence tiles one cluster advances in an interleaved fashion (their
- * dependency chains overlap on the cluster's copy ring / tensor pipe / epilogue warps; <= 0 = default), `variant`
- * 0 = uniform register budget (slots 1..3), 1 = setmaxnreg register split (slots 3..4).
- * bsrnn_blstm_tc_configure sets the (slots, variant) bsrnn_blstm_recurrence_tc uses. */
-int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, void* y, int R, int steps, int seq_tiles,
-                                 long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
-                                 int max_clusters, int slots, int variant, void* stream);
-int bsrnn_blstm_tc_configure(int slots, int variant);
+int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R, int steps,
+                              int seq_tiles, int max_clusters, void* stream);
+int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
+                                 int steps, int seq_tiles, int max_clusters, int slots, void* stream);
 int bsrnn_blstm_tc_max_clusters(void);
 
 /* ---------------------------------------------------------------------------------------------- FlowSE pieces

@@ -60,51 +60,13 @@ def check_gemm(M, K, Nout, BN, epi="rows"):
         return rel(out, ref[:, :half] * torch.sigmoid(ref[:, half:]))
 
 
-def check_lstm(B, T, K, axis, N=196):
-    torch.manual_seed(1)
-    rnn = torch.nn.LSTM(N, 2 * N, batch_first=True, bidirectional=True)
-    H = 2 * N
-    x = torch.randn(B, T, K, N) * 0.7
-    if axis == "time":
-        xs = x.permute(0, 2, 1, 3).reshape(B * K, T, N)
-        ref = rnn(xs)[0].reshape(B, K, T, 2 * H).permute(0, 2, 1, 3)
-        Rr, steps, addr = B * K, T, (K, T * K, 1, K)
-    else:
-        xs = x.reshape(B * T, K, N)
-        ref = rnn(xs)[0].reshape(B, T, K, 2 * H)
-        Rr, steps, addr = B * T, K, (1, K, 0, 1)
-    rnn = rnn.cuda()
-    p = tc.pack_lstm_tc(rnn)
-    M = B * T * K
-    m_tiles = (M + 127) // 128
-    tiles = (Rr + 127) // 128
-    xg = x.cuda().reshape(M, N).contiguous()
-    st = L.stream_ptr()
-    xhat = torch.empty(m_tiles * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
-    L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], m_tiles, m_tiles, M,
-           tc.BIG, 0, 1, 0, M, 1, st)
-    gates = torch.empty(M, 2 * 8 * 208, dtype=torch.float16, device="cuda")
-    L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bih"].data_ptr(), gates.data_ptr(), None, m_tiles, 16,
-           p["kc_in"], 208, L.TC_F16_ROWS, 3328, 3328, 0, M, m_tiles, M, tc.BIG, 0, 1, 0, st)
-    torch.cuda.synchronize()
-    # check the input projection against torch
-    with torch.no_grad():
-        gi = xg.half().float() @ rnn.weight_ih_l0.half().float().t() + rnn.bias_ih_l0 + rnn.bias_hh_l0
-    perm = tc._gate_perm(H, "cuda")
-    got = gates.view(M, 2, 8, 208)[:, 0].float()
-    e_in = rel(got[:, perm >= 0], gi[:, perm[perm >= 0]])
-    y = torch.zeros(steps * tiles * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
-    t0 = time.time()
-    L.call("bsrnn_blstm_recurrence_tc", gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), Rr, steps, tiles, *addr, 0, st)
-    torch.cuda.synchronize()
-    dt = time.time() - t0
-    yv = y.view(steps, tiles, 2, 50, 128, 8).permute(0, 1, 4, 2, 3, 5).reshape(steps, tiles * 128, 2, 400)[:, :Rr, :, :H]
-    yv = yv.reshape(steps, Rr, 2 * H).float().cpu()            # (steps, seq, 2H)
-    if axis == "time":
-        mine = yv.reshape(T, B, K, 2 * H).permute(1, 0, 2, 3)
-    else:
-        mine = yv.reshape(K, B, T, 2 * H).permute(1, 2, 0, 3)
-    return e_in, rel(mine, ref), dt
+def check_lstm(B, T, K, axis, slots=0):
+    """recurrence + input projection vs torch: delegated to tools/prof_lstm.py --check (same layouts as the runtime)."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "prof_lstm.py"), "--B", str(B),
+                        "--T", str(T), "--K", str(K), "--axis", axis, "--slots", str(slots), "--check", "--reps", "1"],
+                       capture_output=True, text=True, timeout=300)
+    return [l for l in (r.stdout + r.stderr).splitlines() if "CHECK" in l or "rror" in l]
 
 
 def main():
@@ -116,9 +78,10 @@ def main():
     print("gemm tanh  :", check_gemm(700, 196, 784, 256, "tanh"))
     print("gemm glu   :", check_gemm(700, 784, 240, 240, "glu"))
     sys.stdout.flush()
-    for (B, T, K, axis) in [(1, 9, 20, "time"), (2, 33, 34, "time"), (2, 33, 34, "freq"), (5, 40, 34, "time")]:
-        print(f"lstm B={B} T={T} K={K} {axis}: inproj/rec rel err, secs =", check_lstm(B, T, K, axis))
-        sys.stdout.flush()
+    for (B, T, K, axis) in [(1, 9, 20, "time"), (2, 33, 34, "time"), (2, 33, 34, "freq"), (12, 40, 34, "time"), (3, 300, 34, "freq")]:
+        for slots in (1, 3):
+            print(f"lstm B={B} T={T} K={K} {axis} slots={slots}:", check_lstm(B, T, K, axis, slots))
+            sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--B", type=int, default=16); ap.add_argument("--T", type=int, default=401); ap.add_argument("--K", type=int, default=34)
 ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, default=3); ap.add_argument("--maxcl", type=int, default=0)
 ap.add_argument("--slots", type=int, default=0); ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--trace-cid", type=int, default=0); ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 B, T, K, axis = a.B, a.T, a.K, a.axis
@@ -34,35 +35,30 @@ if a.check:
 rnn = rnn.cuda()
 p = tc.pack_lstm_tc(rnn)
 st = L.stream_ptr()
+ntile = steps * tiles
+gates = torch.empty(ntile * 416 * 1024, dtype=torch.float16, device="cuda")
+zero_tile = torch.zeros(50 * 1024, dtype=torch.float16, device="cuda")
 if a.check:
-    m_tiles = (M + 127) // 128
     xg = x.cuda().reshape(M, N).contiguous()
-    xhat = torch.empty(m_tiles * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
-    L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], m_tiles, m_tiles, M,
-           tc.BIG, 0, 1, 0, M, 1, st)
-    gates = torch.empty(M, 3328, dtype=torch.float16, device="cuda")
-    L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bih"].data_ptr(), gates.data_ptr(), None, m_tiles, 16,
-           p["kc_in"], 208, L.TC_F16_ROWS, 3328, 3328, 0, M, m_tiles, M, tc.BIG, 0, 1, 0, st)
+    xhat = torch.empty(ntile * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
+    L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], ntile, tiles, R,
+           *addr, M, 1, st)
+    L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bih"].data_ptr(), gates.data_ptr(), None, ntile, 16,
+           p["kc_in"], 208, L.TC_F16_KB8, 0, 3328, 416, M, tiles, R, *addr, st)
 else:
-    gates = torch.empty(M, 3328, dtype=torch.float16, device="cuda")
-    chunk = 1 << 16
-    for i in range(0, M, chunk):
-        gates[i:i + chunk] = (torch.randn(min(chunk, M - i), 3328, device="cuda") * 0.5).half()
+    chunk = 1 << 26
+    for i in range(0, gates.numel(), chunk):
+        n = min(chunk, gates.numel() - i)
+        gates[i:i + n] = (torch.randn(n, device="cuda") * 0.5).half()
 y = torch.zeros(steps * tiles * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
 
 
 def run():
-    if a.v2:
-        import ctypes as C
-        f = L.lib().bsrnn_blstm_recurrence_tc_v2
-        f.argtypes = L.PROTOTYPES["bsrnn_blstm_recurrence_tc"]; f.restype = C.c_int
-        L.check(f(gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), R, steps, tiles, *addr, a.maxcl, st), "v2")
-    else:
-        L.call("bsrnn_blstm_recurrence_tc_ex", gates.data_ptr(), p["whh"].data_ptr(), y.data_ptr(), R, steps, tiles, *addr,
-               a.maxcl, a.slots, a.variant, st)
+    L.call("bsrnn_blstm_recurrence_tc_ex", gates.data_ptr(), p["whh"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
+           tiles, a.maxcl, a.slots, st)
 
 
-tag = "v2" if a.v2 else f"v3 slots={a.slots} variant={a.variant}"
+tag = f"v4 slots={a.slots} maxcl={a.maxcl}"
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record()
@@ -79,17 +75,15 @@ if a.check:
     pad = y.view(steps, tiles, 2, 50, 128, 8)[:, :, :, 49].abs().max().item()
     print(f"[{tag}] CHECK {axis} B={B} T={T} K={K}: rel_l2={err:.3e} pad_core_max={pad}  {'OK' if err < 3e-3 and pad == 0 else 'FAIL'}", flush=True)
 
-if a.trace and not a.v2:
+if a.trace:
     import ctypes
-    tr = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
-    L.lib().bsrnn_debug_set_lstm_trace.argtypes = [ctypes.c_void_p]
-    L.lib().bsrnn_debug_set_lstm_trace(tr.data_ptr())
+    tr = torch.zeros(32, dtype=torch.int64, device="cuda")
+    L.lib().bsrnn_debug_set_lstm_probe.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.lib().bsrnn_debug_set_lstm_probe(tr.data_ptr(), a.trace_cid)
     run(); torch.cuda.synchronize()
-    L.lib().bsrnn_debug_set_lstm_trace(None)
-    t = tr.view(64, 8).cpu()
-    names = ["hready_seen", "loads_issued", "first_full", "last_full", "mma_committed", "-", "epi_done", "published"]
-    print("slot-0 chain, cycles relative to hready_seen of the step")
-    print("step " + " ".join(f"{n:>13s}" for n in names))
-    for s_ in range(2, 12):
-        base = int(t[s_, 0])
-        print(f"{s_:4d} " + " ".join(f"{int(t[s_, i]) - base:13d}" for i in range(8)) + f"   round period {int(t[s_+1,0]) - base}")
+    L.lib().bsrnn_debug_set_lstm_probe(None, 0)
+    acc = tr.cpu().tolist()
+    print(f"[{tag}] cluster {a.trace_cid} CTA 0 whole-launch cycles:")
+    print(f"  producer : wait h_ready {acc[0]:>12d}  wait ring-empty {acc[1]:>12d}  other {acc[2]:>12d}   total {acc[0]+acc[1]+acc[2]}")
+    print(f"  mma      : wait acc_empty {acc[4]:>10d}  wait ring-full {acc[5]:>13d}  other {acc[6]:>12d}")
+    print(f"  epilogue (slot 0, quadrant 0): wait acc_full {acc[12]:>11d}  busy {acc[13]:>12d}")

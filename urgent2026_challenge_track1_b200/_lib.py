@@ -37,13 +37,9 @@ PROTOTYPES = {
                             c_long, c_long, c_long, c_long, c_long, c_int, c_void_p],
     "bsrnn_gemm_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long,
                       c_int, c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
-    "bsrnn_blstm_recurrence_tc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_long,
-                                  c_int, c_void_p],
-    "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long,
-                                     c_long, c_int, c_int, c_int, c_void_p],
-    "bsrnn_blstm_tc_configure": [c_int, c_int],
-    "bsrnn_blstm_recurrence_tc_v2": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_long,
-                                     c_int, c_void_p],          # previous single-slot kernel, kept for A/B timing
+    "bsrnn_blstm_recurrence_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p],
     "bsrnn_blstm_tc_max_clusters": [],
     "bsrnn_time_embed": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "bsrnn_conv5x5_glu": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
@@ -64,7 +60,7 @@ GEMM_DESC = np.dtype([
 assert GEMM_DESC.itemsize == 144
 
 EPI_STORE, EPI_TANH, EPI_RESIDUAL, EPI_GLU = 0, 1, 2, 3
-TC_F16_ROWS, TC_RESID_F32, TC_TANH_KB8, TC_GLU_F32 = 0, 1, 2, 3      # bsrnn_gemm_tc epilogues
+TC_F16_ROWS, TC_RESID_F32, TC_TANH_KB8, TC_GLU_F32, TC_F16_KB8 = 0, 1, 2, 3, 4      # bsrnn_gemm_tc epilogues
 
 _lib = None
 

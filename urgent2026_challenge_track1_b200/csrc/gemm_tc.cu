@@ -54,7 +54,7 @@ struct GemmTcArgs {
   RowMap rows;
 };
 
-enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3 };
+enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4 };
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -106,6 +106,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
             s_sum += nv; s_sq += nv * nv;
           }
       }
+    }
+  } else if (EPI == EPI_F16_KB8) {
+    // a warp stores 32 rows x 16 B = 512 contiguous bytes per instruction
+    __half* o = reinterpret_cast<__half*>(a.out) + (((long)m * a.out_kcores + (gc0 >> 3)) * 128 + r) * 8;
+#pragma unroll
+    for (int i = 0; i < NC; i += 8) {
+      uint4 pk = make_uint4(pack_h2(v[i], v[i + 1]), pack_h2(v[i + 2], v[i + 3]), pack_h2(v[i + 4], v[i + 5]),
+                            pack_h2(v[i + 6], v[i + 7]));
+      *reinterpret_cast<uint4*>(o + (long)(i >> 3) * 1024) = pk;
     }
   } else if (EPI == EPI_TANH_KB8) {
     __half* o = reinterpret_cast<__half*>(a.out);
@@ -335,6 +344,7 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
     case EPI_RESID_F32: return launch_tc<EPI_RESID_F32>(a, st);
     case EPI_TANH_KB8: return launch_tc<EPI_TANH_KB8>(a, st);
     case EPI_GLU_F32: return launch_tc<EPI_GLU_F32>(a, st);
+    case EPI_F16_KB8: return launch_tc<EPI_F16_KB8>(a, st);
   }
   set_error("gemm_tc: unknown epilogue %d", epilogue);
   return 1;

@@ -4,27 +4,37 @@
 // :296-297 (time axis: 2176 sequences x 1001 steps at BASELINE config 2) and :303-304 (band axis: 64064 x 34)].
 //
 // Decomposition.  A work unit is (direction d, tile j of 128 sequences).  A thread-block CLUSTER of 8 CTAs owns a
-// GROUP of up to NS units of one direction and advances them in lock step, slot after slot ("interleaved"): the
-// dependency chain of one unit (h published -> peers wake -> 100 KB h tile fetched from L2 -> 25 MMAs -> gates ->
-// h stored -> published) is ~10 us long but occupies each resource (copy ring, tensor pipe, epilogue warps) for a
-// fraction of that, so NS independent chains overlap on the same CTAs.  CTA q of the cluster owns hidden units
-// [49q, 49q+49) i.e. 196 of the 1568 gate columns, and keeps that slice of W_hh (208 x 400 fp16, 166 KB, UMMA KB8
-// layout) resident in shared memory for the whole launch.  Per (step, slot) every CTA
-//   (1) producer warp: acquires the slot's cluster-scope h_ready mbarrier, bulk-copies the full h_{t-1} tile
-//       (128 x 400 fp16 = 100 KB) from the y buffer in L2 through a 3-stage ring,
-//   (2) MMA warp: 25 tcgen05.mma (M=128, N=208, K=16) into one of two TMEM accumulators,
-//   (3) 8 epilogue warps: tcgen05.ld, add the precomputed input projection (fp16, prefetched into L2 one round
-//       ahead), gates with MUFU tanh, c kept in REGISTERS (25 f32 per thread per slot), h_t slice stored to y (which
-//       is at once the layer output consumed by the Linear GEMM and the exchange buffer for the other 7 CTAs),
-//       then a non-blocking named-barrier arrive,
-//   (4) publisher warp: completes that named barrier, one fence, 8 relaxed remote arrives on the slot's h_ready
-//       barrier of every CTA of the cluster.  The epilogue warps never wait for the publication.
+// GROUP of up to 3 units of one direction and advances them in lock step, slot after slot: the dependency chain of
+// one unit (h published -> peers wake -> 100 KB h tile fetched from L2 -> 25 MMAs -> gates -> h stored -> published)
+// is ~10 us long but occupies each resource (copy ring, tensor pipe, MUFU) for a fraction of that, so the chains of
+// the slots overlap on the same CTAs.  CTA q of the cluster owns hidden units [49q, 49q+49) i.e. 196 of the 1568
+// gate columns, and keeps that slice of W_hh (208 x 400 fp16, 166 KB, UMMA KB8 layout) resident in shared memory
+// for the whole launch.  16 warps per CTA:
+//   warp 0      producer : acquires the slot's cluster-scope h_ready mbarrier, bulk-copies the h_{t-1} tile
+//                          (128 x 400 fp16 = 100 KB, from the y buffer in L2; a zero tile at step 0) through a
+//                          3-stage ring,
+//   warp 1      MMA      : 25 tcgen05.mma (M=128, N=208, K=16) per (step, slot) into one of two TMEM accumulators,
+//   warp 2      publisher: completes the slot's named barrier, one fence, 8 relaxed remote arrives on the slot's
+//                          h_ready barrier of every CTA of the cluster,
+//   warps 4..15 epilogue : SLOT-SPECIALISED — slot k is served by warps 4+4k..7+4k (one per TMEM lane quadrant);
+//                          a thread owns one sequence row of its slot for the whole launch: tcgen05.ld, add the
+//                          precomputed input projection (fp16 tiles, coalesced, prefetched into L2 a step ahead),
+//                          gates with MUFU tanh, c in 49 REGISTERS, h_t stored to y (at once the layer output the
+//                          Linear GEMM consumes and the exchange buffer for the other 7 CTAs), then a
+//                          non-blocking named-barrier arrive.  All slots execute the SAME code (the slot is a
+//                          run-time offset), which keeps the hot loop inside the instruction cache: the previous
+//                          version unrolled the slots and lost 43 % of its issue slots to instruction-fetch
+//                          stalls (profiles/r01/call10_*).
+// Control warps give their registers to the epilogue warps (setmaxnreg 40 / 152).
 // No grid-wide synchronisation exists: clusters are independent, rows never mix.
 //
 // y layout (fp16): [step][seq_tile][dir][50 k-cores][128 rows][8]   (k-core 49 = zero padding, K = 400 per dir);
 //                  a (step, seq_tile) block is therefore a 128 x 800 KB8 operand tile for the Linear(4N->N) GEMM.
-// gates_x (fp16) : [token][dir][q][208]  column c = 4*u_local + gate (i,f,g,o), 196 real + 12 pad
+// gates_x (fp16) : [step][seq_tile][dir][q][26 cores][128 rows][8]: column c = 4*u_local + gate (i,f,g,o) of CTA q,
+//                  196 real + 12 pad — the KB8 tile the input-projection GEMM writes (epilogue 4).
 // w_hh pack      : [dir][q][50 k-cores][208][8]
+// The i, f, o gate rows of W_ih, W_hh and the bias are pre-multiplied by 0.5 at pack time: sigmoid(x) =
+// 0.5*tanh(x/2) + 0.5 then costs one MUFU and one FMA.
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
@@ -32,29 +42,32 @@
 namespace bsrnn {
 using namespace umma;
 
-constexpr int LH = 392;            // hidden size
 constexpr int LCL = 8;             // cluster size
+constexpr int LUN = 49;            // hidden units per CTA
 constexpr int LBN = 208;           // gate columns per CTA (4*49 = 196, padded to a multiple of 16)
+constexpr int LGC = LBN / 8;       // 26 gates_x cores per CTA
 constexpr int LKC = 50;            // k-cores of the recurrent operand (K = 400)
 constexpr int LKS = 10;            // k-cores per A stage
 constexpr int LNST = LKC / LKS;    // 5 stages per (step, slot)
 constexpr int LSTAGES = 3;
-constexpr int LMAXS = 4;           // most slots any instantiation uses
+constexpr int LNS = 3;             // slots (interleaved units per cluster)
 constexpr int LACC = 256;          // TMEM columns per accumulator buffer
+constexpr int LTHREADS = 512;      // 4 control warps + 3 slots x 4 epilogue warps
 constexpr uint32_t L_W_BYTES = LKC * LBN * 16;          // 166400
 constexpr uint32_t L_A_STAGE = LKS * 128 * 16;          // 20480
-constexpr int L_NBARS = 2 * LSTAGES + 2 + 2 + LMAXS + 2;
+constexpr int L_NBARS = 2 * LSTAGES + 2 + 2 + LNS + 2;
 constexpr size_t L_SMEM = L_W_BYTES + LSTAGES * L_A_STAGE + L_NBARS * 8 + 16;
 static_assert(L_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct LstmTcArgs {
   const __half* gates_x;
   const __half* w_pack;
+  const __half* zero_tile;   // 50*128*8 zeros: h_{-1}
   __half* y;
   int R, steps, seq_tiles;
-  int gpd;               // groups per direction (each group = up to NS consecutive sequence tiles)
-  long seq_inner, seq_outer, seq_inner_stride, step_stride;
-  long long* trace;      // optional (debug): [step][8] SM-clock stamps written by cluster 0 / CTA 0 / slot 0
+  int gpd;                   // groups per direction (each group = up to `slots` consecutive sequence tiles)
+  long long* probe;          // optional (debug): per-role wait/busy cycle totals of cluster probe_cid / CTA 0
+  int probe_cid;
 };
 
 struct Group {
@@ -69,9 +82,15 @@ __device__ __forceinline__ Group group_of(const LstmTcArgs& a, int g) {
   return r;
 }
 
-#define LSTM_TRACE(slot, step)                                                                   \
-  do {                                                                                           \
-    if (a.trace && cid == 0 && q == 0 && (step) < 64) a.trace[(step) * 8 + (slot)] = clock64();  \
+// whole-launch accumulators (debug): P_MARK(v) adds the cycles since the previous mark to v
+#define P_DECL(cond) const bool prb_ = a.probe && cid == a.probe_cid && q == 0 && (cond); long long pt_ = prb_ ? clock64() : 0
+#define P_MARK(v)                      \
+  do {                                 \
+    if (prb_) {                        \
+      const long long n_ = clock64();  \
+      (v) += n_ - pt_;                 \
+      pt_ = n_;                        \
+    }                                  \
   } while (0)
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -79,37 +98,32 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigm_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
-
+// pi, pf, po arrive pre-halved (see header): sigmoid = 0.5*tanh(.)+0.5
 __device__ __forceinline__ void gate_update(float pi, float pf, float pg, float po, float& c, float& h) {
-  const float ig = sigm_fast(pi), fg = sigm_fast(pf), gg = tanh_fast(pg), og = sigm_fast(po);
+  const float ig = fmaf(tanh_fast(pi), 0.5f, 0.5f), fg = fmaf(tanh_fast(pf), 0.5f, 0.5f);
+  const float gg = tanh_fast(pg), og = fmaf(tanh_fast(po), 0.5f, 0.5f);
   c = fmaf(fg, c, ig * gg);
   h = og * tanh_fast(c);
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Epilogue work split: 8 warps; warp (quadrant, half) owns 32 rows x units [U0, U0+NU) with
-//   half 0: units [0,24)  = accumulator columns [0,96)    (3 chunks of 32 columns)
-//   half 1: units [24,49) = accumulator columns [96,196)  (3 chunks of 32 + one of 4)
 // Unit i of CTA Q is h column k = 49Q + i -> k-core 6Q + (Q+i)/8, slot (Q+i)%8 of the y tile.
-// store_ready writes every 16-byte core (or the part of it this thread owns) that became complete when the local
-// units [D0, D1) were produced, so h values live in registers only until their core is full.
-template <int Q, int U0, int NU, int D0, int D1>
-__device__ __forceinline__ void store_ready(__half* ytile_row /* &y[...][kc=0][r][0] */, const float (&h)[25]) {
+// store_ready writes every 16-byte core (or the part of it this CTA owns) that became complete when the local units
+// [D0, D1) were produced, so h values live in registers only until their core is full.
+template <int Q, int D0, int D1>
+__device__ __forceinline__ void store_ready(__half* ytile_row /* &y[...][kc=0][r][0] */, const float (&h)[LUN]) {
 #pragma unroll
   for (int jj = 0; jj < 7; ++jj) {
     const int lo = 8 * jj - Q;                       // unit index sitting in slot 0 of this core
-    const int a0 = lo > U0 ? lo : U0;
-    const int b0 = (lo + 8) < (U0 + NU) ? (lo + 8) : (U0 + NU);
+    const int a0 = lo > 0 ? lo : 0;
+    const int b0 = (lo + 8) < LUN ? (lo + 8) : LUN;
     if (a0 >= b0) continue;                          // core holds none of our units
-    const int bl = b0 - U0;                          // local index one past the last of our units in the core
-    if (!(bl > D0 && bl <= D1)) continue;            // completed earlier / not complete yet
+    if (!(b0 > D0 && b0 <= D1)) continue;            // completed earlier / not complete yet
     __half* dst = ytile_row + (size_t)(6 * Q + jj) * 128 * 8;
     if (a0 == lo && b0 == lo + 8) {
-      const int b = lo - U0;
-      __half2 p0 = __floats2half2_rn(h[b], h[b + 1]), p1 = __floats2half2_rn(h[b + 2], h[b + 3]);
-      __half2 p2 = __floats2half2_rn(h[b + 4], h[b + 5]), p3 = __floats2half2_rn(h[b + 6], h[b + 7]);
+      __half2 p0 = __floats2half2_rn(h[lo], h[lo + 1]), p1 = __floats2half2_rn(h[lo + 2], h[lo + 3]);
+      __half2 p2 = __floats2half2_rn(h[lo + 4], h[lo + 5]), p3 = __floats2half2_rn(h[lo + 6], h[lo + 7]);
       uint4 pk = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                             *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
       *reinterpret_cast<uint4*>(dst) = pk;
@@ -117,146 +131,124 @@ __device__ __forceinline__ void store_ready(__half* ytile_row /* &y[...][kc=0][r
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {
         const int i = lo + sl;
-        if (i >= a0 && i < b0) dst[sl] = __float2half_rn(h[i - U0]);
+        if (i >= a0 && i < b0) dst[sl] = __float2half_rn(h[i]);
       }
     }
   }
 }
 
-__device__ __forceinline__ void load_g4(const uint4* p, bool ok, uint4 (&g)[4]) {
-  if (ok) {
+__device__ __forceinline__ void load_g4(const uint4* p, uint4 (&g)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) g[i] = __ldg(p + i);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) g[i] = make_uint4(0, 0, 0, 0);
-  }
+  for (int i = 0; i < 4; ++i) g[i] = __ldg(p + i * 128);             // cores are 128 rows x 16 B apart
 }
 
-// One (step, slot) item of the epilogue for a thread: row r of the tile, units [U0, U0+NU) of CTA Q.
-template <int Q, int HALF>
-__device__ __forceinline__ void epilogue_item(uint32_t t_addr, bool have_acc, uint64_t* acc_full, uint32_t acc_phase,
-                                              const __half* gx, bool row_ok, __half* ytile_row, float (&c)[25]) {
-  constexpr int U0 = HALF == 0 ? 0 : 24;
-  constexpr int NU = HALF == 0 ? 24 : 25;
-  const uint4* gp = reinterpret_cast<const uint4*>(gx + HALF * 96);
-  uint4 g[2][4];
-  uint2 gt = make_uint2(0, 0);
-  load_g4(gp, row_ok, g[0]);                         // issued before the wait
-  if (have_acc) {
-    mbar_wait(acc_full, acc_phase);
-    tc_fence_after();
+template <int Q, int CH>
+__device__ __forceinline__ void epilogue_chunk(uint32_t t_addr, const uint4 (&g)[4], __half* ytile_row, float (&c)[LUN],
+                                               float (&h)[LUN]) {
+  uint32_t acc[32];
+  tmem_ld_x32(t_addr + CH * 32, acc);
+  tmem_ld_wait();
+  const __half2* gh = reinterpret_cast<const __half2*>(&g[0]);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float2 g01 = __half22float2(gh[2 * u]), g23 = __half22float2(gh[2 * u + 1]);
+    gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
+                __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[CH * 8 + u],
+                h[CH * 8 + u]);
   }
-  float h[25];
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch) {
-    if (ch < 2) load_g4(gp + 4 * (ch + 1), row_ok, g[(ch + 1) & 1]);
-    else if (HALF == 1 && row_ok) gt = __ldg(reinterpret_cast<const uint2*>(gx + 192));
-    uint32_t acc[32];
-    if (have_acc) {
-      tmem_ld_x32(t_addr + HALF * 96 + ch * 32, acc);
-      tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = 0u;
-    }
-    const __half2* gh = reinterpret_cast<const __half2*>(&g[ch & 1][0]);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float2 g01 = __half22float2(gh[2 * u]), g23 = __half22float2(gh[2 * u + 1]);
-      gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
-                  __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[ch * 8 + u],
-                  h[ch * 8 + u]);
-    }
-    if (ch == 0) store_ready<Q, U0, NU, 0, 8>(ytile_row, h);
-    if (ch == 1) store_ready<Q, U0, NU, 8, 16>(ytile_row, h);
-    if (ch == 2) store_ready<Q, U0, NU, 16, 24>(ytile_row, h);
-  }
-  if (HALF == 1) {
+  store_ready<Q, CH * 8, CH * 8 + 8>(ytile_row, h);
+}
+
+// One (step, slot) item for a thread: row r of the tile, all 49 units of CTA Q.  gp -> this row's 16 bytes of core 0.
+// Rows beyond R (padding of the last sequence tile) are computed like any other: their gates_x rows hold the bias
+// (the GEMM ran on zero operand rows), rows never mix, and nothing downstream reads them.
+template <int Q>
+__device__ __forceinline__ void epilogue_item(uint32_t t_addr, const uint4* gp, __half* ytile_row, float (&c)[LUN]) {
+  float h[LUN];
+  uint4 ga[4], gb[4];
+  load_g4(gp, ga);
+  load_g4(gp + 4 * 128, gb);
+  epilogue_chunk<Q, 0>(t_addr, ga, ytile_row, c, h);
+  load_g4(gp + 8 * 128, ga);
+  epilogue_chunk<Q, 1>(t_addr, gb, ytile_row, c, h);
+  load_g4(gp + 12 * 128, gb);
+  epilogue_chunk<Q, 2>(t_addr, ga, ytile_row, c, h);
+  load_g4(gp + 16 * 128, ga);
+  epilogue_chunk<Q, 3>(t_addr, gb, ytile_row, c, h);
+  load_g4(gp + 20 * 128, gb);
+  epilogue_chunk<Q, 4>(t_addr, ga, ytile_row, c, h);
+  const uint2 gt = __ldg(reinterpret_cast<const uint2*>(gp + 24 * 128));
+  epilogue_chunk<Q, 5>(t_addr, gb, ytile_row, c, h);
+  {
     uint32_t acc[4];
-    if (have_acc) {
-      tmem_ld_x4(t_addr + 192, acc);
-      tmem_ld_wait();
-    } else {
-      acc[0] = acc[1] = acc[2] = acc[3] = 0u;
-    }
+    tmem_ld_x4(t_addr + 192, acc);
+    tmem_ld_wait();
     const __half2* gh = reinterpret_cast<const __half2*>(&gt);
     const float2 g01 = __half22float2(gh[0]), g23 = __half22float2(gh[1]);
     gate_update(__uint_as_float(acc[0]) + g01.x, __uint_as_float(acc[1]) + g01.y, __uint_as_float(acc[2]) + g23.x,
-                __uint_as_float(acc[3]) + g23.y, c[24], h[24]);
-    store_ready<Q, U0, NU, 24, 25>(ytile_row, h);
+                __uint_as_float(acc[3]) + g23.y, c[48], h[48]);
+    store_ready<Q, 48, 49>(ytile_row, h);
   }
 }
 
-// The epilogue role for one (Q, HALF): loops over this cluster's groups, steps and slots.
-template <int Q, int HALF, int NS, int NTHR_PUB>
-__device__ __forceinline__ void epilogue_role(const LstmTcArgs& a, uint32_t tmem_base, int warp, int lane, int cid, int ncl,
-                                              bool tracer, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free) {
-  const int quad = warp & 3;
+// The epilogue role of one warp: slot k, TMEM lane quadrant `quad`; loops over this cluster's groups and steps.
+template <int Q>
+__device__ __forceinline__ void epilogue_role(const LstmTcArgs& a, uint32_t tmem_base, int k, int quad, int lane, int cid,
+                                              int ncl, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free) {
   const int q = Q;
   const int r = quad * 32 + lane;
   const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
   const int ngroups = 2 * a.gpd;
-  const size_t tile_elems = (size_t)LKC * 128 * 8;
-  const long gx_step = a.step_stride * 2 * (LCL * LBN);      // halves between consecutive positions of a sequence
-  uint32_t it = 0;                                            // accumulator items consumed so far (all groups)
-  float c[NS][25];
+  const size_t y_tile = (size_t)LKC * 128 * 8;                 // halves per (step, tile, dir) of y
+  const size_t g_tile = (size_t)2 * LCL * LGC * 128 * 8;       // halves per (step, tile) of gates_x
+  uint32_t it0 = 0;                                            // accumulator items of the groups done so far
+  long long w_acc = 0, w_busy = 0;
+  P_DECL(k == 0 && quad == 0 && lane == 0);
+  float c[LUN];
   for (int g = cid; g < ngroups; g += ncl) {
     const Group G = group_of(a, g);
-    long tok0[NS];
-    bool row_ok[NS];
+    if (k < G.nact) {
+      const int j = G.j0 + k;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-      const long seq = (long)(G.j0 + k) * 128 + r;
-      row_ok[k] = k < G.nact && seq < a.R;
-      tok0[k] = row_ok[k] ? (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride : 0;
+      for (int i = 0; i < LUN; ++i) c[i] = 0.f;
+      for (int s = 0; s < a.steps; ++s) {
+        const int p = G.d == 0 ? s : a.steps - 1 - s;
+        const size_t tile = (size_t)p * a.seq_tiles + j;
+        const __half* gbase = a.gates_x + tile * g_tile + (size_t)(G.d * LCL + Q) * (LGC * 128 * 8);
+        __half* ytile_row = a.y + (tile * 2 + G.d) * y_tile + (size_t)r * 8;
+        if (s + 1 < a.steps) {                       // next step's input projection (53 KB) -> L2
+          const long step_off = (G.d == 0 ? 1 : -1) * (long)a.seq_tiles * (long)g_tile;
+          const char* nx = reinterpret_cast<const char*>(gbase + step_off) + r * 128;
 #pragma unroll
-      for (int i = 0; i < 25; ++i) c[k][i] = 0.f;
-    }
-    for (int s = 0; s < a.steps; ++s) {
-      const int p = G.d == 0 ? s : a.steps - 1 - s;
-      const bool have_acc = s > 0;
-      const bool more = s + 1 < a.steps;
-#pragma unroll
-      for (int k = 0; k < NS; ++k) {
-        if (k < G.nact) {
-          const long token = tok0[k] + (long)p * a.step_stride;
-          const __half* gx = a.gates_x + (token * 2 + G.d) * (LCL * LBN) + Q * LBN;
-          __half* ytile_row = a.y + (((size_t)p * a.seq_tiles + (G.j0 + k)) * 2 + G.d) * tile_elems + (size_t)r * 8;
-          if (more && row_ok[k]) {                   // next step's input projection -> L2, one full round ahead
-            const char* nx = reinterpret_cast<const char*>(gx + (G.d == 0 ? gx_step : -gx_step) + HALF * 96);
-            prefetch_l2(nx);
-            prefetch_l2(nx + 100);
-            prefetch_l2(nx + 199);
-          }
-          const uint32_t buf = it & 1;
-          epilogue_item<Q, HALF>(t_lane + buf * LACC, have_acc, acc_full + buf, (it >> 1) & 1, gx, row_ok[k], ytile_row,
-                                 c[k]);
-          if (tracer && k == 0) LSTM_TRACE(6, s);
-          if (have_acc) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + buf);
-            ++it;
-          }
-          // h_t slice of this warp is stored: tell the publisher (non-blocking)
-          if (more) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(256 + NTHR_PUB) : "memory");
+          for (int i = 0; i < 4; ++i)
+            if (i * 128 + r < LGC * 16) prefetch_l2(nx + i * 128 * 128);
         }
+        const uint32_t it = it0 + (uint32_t)(s * G.nact + k);
+        const uint32_t buf = it & 1;
+        P_MARK(w_busy);
+        mbar_wait(acc_full + buf, (it >> 1) & 1);
+        tc_fence_after();
+        P_MARK(w_acc);
+        epilogue_item<Q>(t_lane + buf * LACC, reinterpret_cast<const uint4*>(gbase) + r, ytile_row, c);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);
+        // h_t slice of this warp is stored: tell the publisher (non-blocking)
+        if (s + 1 < a.steps) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(128 + 32) : "memory");
+      }
+      const int gn = g + ncl;                        // next group of this cluster switches direction?
+      if (k == G.nact - 1 && gn < ngroups && gn / a.gpd != G.d) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(w_free);          // the last slot's last accumulator is consumed: W may go
       }
     }
-    const int gn = g + ncl;                          // next group of this cluster switches direction?
-    if (gn < ngroups && gn / a.gpd != G.d) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(w_free);
-    }
+    it0 += (uint32_t)(a.steps * G.nact);
   }
+  P_MARK(w_busy);
+  if (prb_) { a.probe[12] = w_acc; a.probe[13] = w_busy; }
 }
 
-// NS = interleaved slots; REGSPLIT: 12 warps with setmaxnreg (producer/MMA/publisher/idle give registers to the 8
-// epilogue warps) instead of 11 warps with a uniform budget.
-template <int NS, bool REGSPLIT>
-__global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 352, 1) lstm_tc_kernel(const LstmTcArgs a) {
-  constexpr int EW0 = REGSPLIT ? 4 : 3;              // first epilogue warp
+__global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + L_W_BYTES;
@@ -265,8 +257,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 3
   uint64_t* empty = bars + LSTAGES;            // [3]
   uint64_t* acc_full = bars + 2 * LSTAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint64_t* h_ready = acc_empty + 2;           // [LMAXS]
-  uint64_t* w_full = h_ready + LMAXS;
+  uint64_t* h_ready = acc_empty + 2;           // [LNS]
+  uint64_t* w_full = h_ready + LNS;
   uint64_t* w_free = w_full + 1;               // epilogue -> producer: the resident W slice may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_free + 1);
 
@@ -276,10 +268,10 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 3
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 8); }
-    for (int i = 0; i < LMAXS; ++i) mbar_init(h_ready + i, LCL);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < LNS; ++i) mbar_init(h_ready + i, LCL);
     mbar_init(w_full, 1);
-    mbar_init(w_free, 8);
+    mbar_init(w_free, 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 2 * LACC);
@@ -290,19 +282,21 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 3
   const uint32_t tmem_base = *tmem_slot;
 
   const int ngroups = 2 * a.gpd;
-  const size_t tile_elems = (size_t)LKC * 128 * 8;     // halves per (step, tile, dir)
+  const size_t y_tile = (size_t)LKC * 128 * 8;         // halves per (step, tile, dir)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: W slice + h tiles
-    if (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, hphase = 0, wfphase = 0;
       int cur_dir = -1;
+      long long w_h = 0, w_e = 0, w_o = 0;
+      P_DECL(true);
       for (int g = cid; g < ngroups; g += ncl) {
         const Group G = group_of(a, g);
         if (G.d != cur_dir) {
-          // The epilogue warps signal w_free after consuming the last accumulator of the previous direction, i.e.
-          // after every MMA that read the old slice has retired.
+          // the epilogue warps of the last slot signal w_free after consuming the last accumulator of the previous
+          // direction, i.e. after every MMA that read the old slice has retired.
           if (cur_dir >= 0) {
             mbar_wait(w_free, wfphase);
             wfphase ^= 1;
@@ -312,34 +306,42 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 3
           for (uint32_t off = 0; off < L_W_BYTES; off += 33280) bulk_g2s(sW + off, src + off, 33280, w_full);
           cur_dir = G.d;
         }
-        for (int s = 1; s < a.steps; ++s) {
+        for (int s = 0; s < a.steps; ++s) {
           const int p_prev = G.d == 0 ? s - 1 : a.steps - s;        // position whose h feeds this step
           for (int k = 0; k < G.nact; ++k) {
-            mbar_wait_cluster(h_ready + k, (hphase >> k) & 1);
-            hphase ^= 1u << k;
-            if (k == 0) LSTM_TRACE(0, s);
-            fence_proxy_async_global();
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(
-                a.y + (((size_t)p_prev * a.seq_tiles + (G.j0 + k)) * 2 + G.d) * tile_elems);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(a.zero_tile);
+            if (s > 0) {
+              P_MARK(w_o);
+              mbar_wait_cluster(h_ready + k, (hphase >> k) & 1);
+              P_MARK(w_h);
+              hphase ^= 1u << k;
+              fence_proxy_async_global();
+              src = reinterpret_cast<const uint8_t*>(a.y + (((size_t)p_prev * a.seq_tiles + (G.j0 + k)) * 2 + G.d) * y_tile);
+            }
             for (int ks = 0; ks < LNST; ++ks) {
+              P_MARK(w_o);
               mbar_wait(empty + stage, phase ^ 1);
+              P_MARK(w_e);
               mbar_expect_tx(full + stage, L_A_STAGE);
               bulk_g2s(sA + stage * L_A_STAGE, src + (size_t)ks * L_A_STAGE, L_A_STAGE, full + stage);
               if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
             }
-            if (k == 0) LSTM_TRACE(1, s);
           }
         }
       }
+      P_MARK(w_o);
+      if (prb_) { a.probe[0] = w_h; a.probe[1] = w_e; a.probe[2] = w_o; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0) {
       const uint32_t idesc = idesc_f16_f32(128, LBN);
       uint32_t stage = 0, phase = 0, it = 0, wphase = 0;
       int cur_dir = -1;
       const uint32_t sw = smem_u32(sW);
+      long long w_a = 0, w_f = 0, w_o = 0;
+      P_DECL(true);
       for (int g = cid; g < ngroups; g += ncl) {
         const Group G = group_of(a, g);
         if (G.d != cur_dir) {
@@ -347,69 +349,66 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 3
           wphase ^= 1;
           cur_dir = G.d;
         }
-        for (int s = 1; s < a.steps; ++s) {
-          for (int k = 0; k < G.nact; ++k, ++it) {
-            const uint32_t buf = it & 1;
-            mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+        const int nitems = a.steps * G.nact;
+        for (int i = 0; i < nitems; ++i, ++it) {
+          const uint32_t buf = it & 1;
+          P_MARK(w_o);
+          mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+          P_MARK(w_a);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * LACC;
+          for (int ks = 0; ks < LNST; ++ks) {
+            P_MARK(w_o);
+            mbar_wait(full + stage, phase);
+            P_MARK(w_f);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * LACC;
-            for (int ks = 0; ks < LNST; ++ks) {
-              mbar_wait(full + stage, phase);
-              if (k == 0 && ks == 0) LSTM_TRACE(2, s);
-              if (k == 0 && ks == LNST - 1) LSTM_TRACE(3, s);
-              tc_fence_after();
-              const uint32_t sa = smem_u32(sA + stage * L_A_STAGE);
+            const uint32_t sa = smem_u32(sA + stage * L_A_STAGE);
 #pragma unroll
-              for (int jk = 0; jk < LKS / 2; ++jk) {
-                const uint64_t da = smem_desc_kb8(sa + jk * 2 * 2048, 2048, 128);
-                const uint64_t db = smem_desc_kb8(sw + (ks * LKS + jk * 2) * (LBN * 16), LBN * 16, 128);
-                mma_f16_ss(d_tmem, da, db, idesc, (ks | jk) != 0);
-              }
-              mma_commit(empty + stage);
-              if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+            for (int jk = 0; jk < LKS / 2; ++jk) {
+              const uint64_t da = smem_desc_kb8(sa + jk * 2 * 2048, 2048, 128);
+              const uint64_t db = smem_desc_kb8(sw + (ks * LKS + jk * 2) * (LBN * 16), LBN * 16, 128);
+              mma_f16_ss(d_tmem, da, db, idesc, (ks | jk) != 0);
             }
-            mma_commit(acc_full + buf);
-            if (k == 0) LSTM_TRACE(4, s);
+            mma_commit(empty + stage);
+            if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
           }
+          mma_commit(acc_full + buf);
         }
       }
+      P_MARK(w_o);
+      if (prb_) { a.probe[4] = w_a; a.probe[5] = w_f; a.probe[6] = w_o; }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ publisher
-    if (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     for (int g = cid; g < ngroups; g += ncl) {
       const Group G = group_of(a, g);
       for (int s = 0; s + 1 < a.steps; ++s) {
         for (int k = 0; k < G.nact; ++k) {
-          // completes once the 8 epilogue warps have stored their h_t slices of slot k
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(256 + 32) : "memory");
+          // completes once the 4 epilogue warps of slot k have stored their h_t slices
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(128 + 32) : "memory");
           if (lane < LCL) {
             fence_proxy_async_global();
             fence_acq_rel_cluster();
             mbar_arrive_cluster_relaxed(h_ready + k, lane);
-            if (lane == 0 && k == 0) LSTM_TRACE(7, s);
           }
           __syncwarp();
         }
       }
     }
-  } else if (warp >= EW0) {
-    // ------------------------------------------------------------------ epilogue: 8 warps (see epilogue_role)
-    if (REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int half = (warp - EW0) >> 2;
-    const bool tracer = warp == EW0 && lane == 0;
-#define BSRNN_EPI_CASE(QQ)                                                                                               \
-  case QQ:                                                                                                               \
-    if (half == 0) epilogue_role<QQ, 0, NS, 32>(a, tmem_base, warp, lane, cid, ncl, tracer, acc_full, acc_empty, w_free); \
-    else epilogue_role<QQ, 1, NS, 32>(a, tmem_base, warp, lane, cid, ncl, tracer, acc_full, acc_empty, w_free);          \
-    break;
+  } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // idle 4th warp of warpgroup 0
+  } else {
+    // ------------------------------------------------------------------ epilogue: 3 slots x 4 warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int k = (warp - 4) >> 2, quad = warp & 3;
+#define BSRNN_EPI_CASE(QQ) \
+  case QQ: epilogue_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free); break;
     switch (q) {
       BSRNN_EPI_CASE(0) BSRNN_EPI_CASE(1) BSRNN_EPI_CASE(2) BSRNN_EPI_CASE(3)
       BSRNN_EPI_CASE(4) BSRNN_EPI_CASE(5) BSRNN_EPI_CASE(6) BSRNN_EPI_CASE(7)
     }
 #undef BSRNN_EPI_CASE
-  } else {
-    if (REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // idle 4th warp of warpgroup 0
   }
   tc_fence_before();
   __syncthreads();
@@ -420,91 +419,62 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(REGSPLIT ? 384 : 3
   }
 }
 
-template <int NS, bool REGSPLIT>
 static int max_active_clusters() {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(LCL * 64);
-  cfg.blockDim = dim3(REGSPLIT ? 384 : 352);
+  cfg.blockDim = dim3(LTHREADS);
   cfg.dynamicSmemBytes = L_SMEM;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = LCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaFuncSetAttribute(lstm_tc_kernel<NS, REGSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM) != cudaSuccess)
-    return -1;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<NS, REGSPLIT>, &cfg) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel, &cfg) != cudaSuccess) return -1;
   return n;
-}
-
-template <int NS, bool REGSPLIT>
-static int launch_lstm(LstmTcArgs a, int max_clusters, cudaStream_t st) {
-  static int max_active = -1;
-  if (max_active < 0) {
-    int n = max_active_clusters<NS, REGSPLIT>();
-    if (n <= 0) {
-      cudaGetLastError();
-      set_error("blstm_recurrence_tc: no co-resident 8-CTA cluster for slots=%d regsplit=%d", NS, (int)REGSPLIT);
-      return 2;
-    }
-    max_active = n;
-  }
-  a.gpd = (a.seq_tiles + NS - 1) / NS;
-  int ncl = 2 * a.gpd;
-  if (ncl > max_active) ncl = max_active;
-  if (max_clusters > 0 && ncl > max_clusters) ncl = max_clusters;
-  lstm_tc_kernel<NS, REGSPLIT><<<ncl * LCL, REGSPLIT ? 384 : 352, L_SMEM, st>>>(a);
-  BSRNN_LAUNCH_OK();
-  return 0;
 }
 
 }  // namespace bsrnn
 using namespace bsrnn;
 
-static long long* g_lstm_trace = nullptr;
-extern "C" void bsrnn_debug_set_lstm_trace(void* p) { g_lstm_trace = reinterpret_cast<long long*>(p); }
-
-// slots: interleaved sequence tiles per cluster (1..4; <= 0 = automatic); variant 0 = uniform register budget
-// (slots <= 3), 1 = setmaxnreg register split (slots <= 4).
-extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, void* y, int R, int steps,
-                                            int seq_tiles, long seq_inner, long seq_outer, long seq_inner_stride,
-                                            long step_stride, int max_clusters, int slots, int variant, void* stream) {
-  BSRNN_CHECK_ARG(gates_x && w_pack && y, "blstm_recurrence_tc: null pointer");
-  BSRNN_CHECK_ARG(R > 0 && steps > 0 && seq_tiles * 128 >= R && seq_inner > 0, "blstm_recurrence_tc: bad dims");
-  LstmTcArgs a{reinterpret_cast<const __half*>(gates_x), reinterpret_cast<const __half*>(w_pack),
-               reinterpret_cast<__half*>(y), R, steps, seq_tiles, 0, seq_inner, seq_outer, seq_inner_stride, step_stride,
-               g_lstm_trace};
-  cudaStream_t st = (cudaStream_t)stream;
-  if (slots <= 0) slots = 3;
-  if (slots > seq_tiles) slots = seq_tiles;
-  if (variant == 0) {
-    switch (slots) {
-      case 1: return launch_lstm<1, false>(a, max_clusters, st);
-      case 2: return launch_lstm<2, false>(a, max_clusters, st);
-      case 3: return launch_lstm<3, false>(a, max_clusters, st);
-    }
-  } else if (variant == 1) {
-    switch (slots) {
-      case 3: return launch_lstm<3, true>(a, max_clusters, st);
-      case 4: return launch_lstm<4, true>(a, max_clusters, st);
-    }
-  }
-  set_error("blstm_recurrence_tc: unsupported slots=%d variant=%d", slots, variant);
-  return 1;
+static long long* g_lstm_probe = nullptr;
+static int g_lstm_probe_cid = 0;
+extern "C" void bsrnn_debug_set_lstm_probe(void* p, int cid) {
+  g_lstm_probe = reinterpret_cast<long long*>(p);
+  g_lstm_probe_cid = cid;
 }
 
-static int g_slots = 0, g_variant = 0;
-extern "C" int bsrnn_blstm_tc_configure(int slots, int variant) {
-  g_slots = slots;
-  g_variant = variant;
+// slots: sequence tiles a cluster interleaves (1..3; <= 0 = 3).
+extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
+                                            int steps, int seq_tiles, int max_clusters, int slots, void* stream) {
+  BSRNN_CHECK_ARG(gates_x && w_pack && zero_tile && y, "blstm_recurrence_tc: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_recurrence_tc: bad dims");
+  if (slots <= 0 || slots > LNS) slots = LNS;
+  if (slots > seq_tiles) slots = seq_tiles;
+  LstmTcArgs a{reinterpret_cast<const __half*>(gates_x), reinterpret_cast<const __half*>(w_pack),
+               reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y), R, steps, seq_tiles,
+               (seq_tiles + slots - 1) / slots, g_lstm_probe, g_lstm_probe_cid};
+  static int max_active = -1;
+  if (max_active < 0) {
+    const int n = max_active_clusters();
+    if (n <= 0) {
+      cudaGetLastError();
+      set_error("blstm_recurrence_tc: no co-resident 8-CTA cluster (512 threads, %zu B shared memory)", L_SMEM);
+      return 2;
+    }
+    max_active = n;
+  }
+  int ncl = 2 * a.gpd;
+  if (ncl > max_active) ncl = max_active;
+  if (max_clusters > 0 && ncl > max_clusters) ncl = max_clusters;
+  lstm_tc_kernel<<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  BSRNN_LAUNCH_OK();
   return 0;
 }
 
-extern "C" int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, void* y, int R, int steps,
-                                         int seq_tiles, long seq_inner, long seq_outer, long seq_inner_stride,
-                                         long step_stride, int max_clusters, void* stream) {
-  return bsrnn_blstm_recurrence_tc_ex(gates_x, w_pack, y, R, steps, seq_tiles, seq_inner, seq_outer, seq_inner_stride,
-                                      step_stride, max_clusters, g_slots, g_variant, stream);
+extern "C" int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
+                                         int steps, int seq_tiles, int max_clusters, void* stream) {
+  return bsrnn_blstm_recurrence_tc_ex(gates_x, w_pack, zero_tile, y, R, steps, seq_tiles, max_clusters, 0, stream);
 }
 
-extern "C" int bsrnn_blstm_tc_max_clusters(void) { return max_active_clusters<3, false>(); }
+extern "C" int bsrnn_blstm_tc_max_clusters(void) { return max_active_clusters(); }

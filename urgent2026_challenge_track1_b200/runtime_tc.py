@@ -12,14 +12,15 @@ from .runtime import region, _f64
 import os
 
 BIG = 1 << 60
-# recurrence schedule per axis: (interleaved slots, variant) of bsrnn_blstm_recurrence_tc_ex; "time=3:0,freq=4:1"
-_LSTM_V2 = os.environ.get("BSRNN_LSTM_V2", "0") == "1"
-_LSTM_SCHED = {"time": (3, 0), "freq": (3, 0)}
-for _kv in os.environ.get("BSRNN_LSTM_SCHED", "").split(","):
+# recurrence schedule per axis: interleaved slots of bsrnn_blstm_recurrence_tc_ex, e.g. BSRNN_LSTM_SLOTS="time=3,freq=2"
+_LSTM_SLOTS = {"time": 3, "freq": 3}
+for _kv in os.environ.get("BSRNN_LSTM_SLOTS", "").split(","):
     if "=" in _kv:
         _ax, _sv = _kv.split("=")
-        _LSTM_SCHED[_ax] = tuple(int(v) for v in _sv.split(":"))
+        _LSTM_SLOTS[_ax] = int(_sv)
 CL, LU, LBN, LKC = 8, 49, 208, 50       # cluster size, units per CTA, gate columns per CTA, k-cores of h (K = 400)
+LGC = LBN // 8                           # gates_x cores per CTA
+GATE_SCALE = (0.5, 0.5, 1.0, 0.5)       # i, f, o rows pre-halved: sigmoid(x) = 0.5*tanh(x/2) + 0.5 in the kernel
 
 
 def to_kb8(w, rows_per_tile, kcores):
@@ -54,6 +55,8 @@ def pack_lstm_tc(rnn):
         raise NotImplementedError(f"tensor-core BLSTM kernel is specialised for H=392, got H={H}")
     dev = rnn.weight_hh_l0.device
     perm = _gate_perm(H, dev)
+    gsc = torch.tensor(GATE_SCALE, device=dev).repeat(LU)           # packed column c = 4*u + gate
+    gsc = torch.cat([gsc, torch.zeros(LBN - 4 * LU, device=dev)])
     kc_in = (N + 15) // 16 * 2
     wih_rows, bih_rows, whh = [], [], []
     for sfx in ("", "_reverse"):
@@ -62,7 +65,7 @@ def pack_lstm_tc(rnn):
         b = (getattr(rnn, "bias_ih_l0" + sfx) + getattr(rnn, "bias_hh_l0" + sfx)).float()
         for q in range(CL):
             sel = perm[q].clamp_min(0)
-            valid = (perm[q] >= 0).float()[:, None]
+            valid = ((perm[q] >= 0).float() * gsc)[:, None]
             wih_rows.append(wi[sel] * valid)
             bih_rows.append(b[sel] * valid[:, 0])
             whh.append(to_kb8(wh[sel] * valid, LBN, LKC)[0])
@@ -106,9 +109,10 @@ class TcWorkspace:
         self.tiles_time = (B * K + 127) // 128
         self.tiles_freq = (B * T + 127) // 128
         kc_in = (N + 15) // 16 * 2
-        self.xhat = torch.empty(self.m_tiles * kc_in * 128 * 8, dtype=torch.float16, device=dev)
-        self.gates = torch.empty(M, 2 * CL * LBN, dtype=torch.float16, device=dev)
-        ntile = max(T * self.tiles_time, K * self.tiles_freq)
+        ntile = max(T * self.tiles_time, K * self.tiles_freq)     # (step, sequence tile) pairs of either axis
+        self.xhat = torch.empty(ntile * kc_in * 128 * 8, dtype=torch.float16, device=dev)
+        self.gates = torch.empty(ntile * 2 * CL * LGC * 128 * 8, dtype=torch.float16, device=dev)
+        self.zero_tile = torch.zeros(LKC * 128 * 8, dtype=torch.float16, device=dev)
         self.y = torch.zeros(ntile * 2 * LKC * 128 * 8, dtype=torch.float16, device=dev)
         self.stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
         self.scale = torch.empty(B, N, dtype=torch.float32, device=dev)
@@ -140,27 +144,24 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
         for axis in ("time", "freq"):
             w = lay[axis]
             extra = t_emb[i] if (t_emb is not None and axis == "time") else None
-            with region("norm"):
-                L.call("bsrnn_gn_finalize", ws.stats.data_ptr(), w["gamma"].data_ptr(), w["beta"].data_ptr(), L.ptr(extra),
-                       ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), 1e-5, 1, st)
-                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(), ws.xhat.data_ptr(),
-                       N, 0, N, w["kc_in"], ws.m_tiles, ws.m_tiles, M, BIG, 0, 1, 0, T * K, 1, st)
-            with region("inproj"):
-                L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(), w["bih"].data_ptr(), ws.gates.data_ptr(), None,
-                       ws.m_tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_ROWS, 2 * CL * LBN, 2 * CL * LBN, 0, T * K,
-                       ws.m_tiles, M, BIG, 0, 1, 0, st)
             if axis == "time":
                 R, steps, tiles, addr = B * K, T, ws.tiles_time, (K, T * K, 1, K)
             else:
                 R, steps, tiles, addr = B * T, K, ws.tiles_freq, (1, K, 0, 1)
+            with region("norm"):
+                L.call("bsrnn_gn_finalize", ws.stats.data_ptr(), w["gamma"].data_ptr(), w["beta"].data_ptr(), L.ptr(extra),
+                       ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), 1e-5, 1, st)
+                # operand tiles in the axis' (step, sequence tile) order: the GEMM output tiles are then the
+                # recurrence kernel's gates_x tiles
+                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(), ws.xhat.data_ptr(),
+                       N, 0, N, w["kc_in"], steps * tiles, tiles, R, *addr, T * K, 1, st)
+            with region("inproj"):
+                L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(), w["bih"].data_ptr(), ws.gates.data_ptr(), None,
+                       steps * tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_KB8, 0, 2 * CL * LBN, 2 * CL * LGC, T * K,
+                       tiles, R, *addr, st)
             with region(f"lstm_{axis}"):
-                if _LSTM_V2:
-                    L.call("bsrnn_blstm_recurrence_tc_v2", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.y.data_ptr(), R,
-                           steps, tiles, *addr, max_clusters, st)
-                else:
-                    slots, variant = _LSTM_SCHED[axis]
-                    L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.y.data_ptr(), R,
-                           steps, tiles, *addr, max_clusters, slots, variant, st)
+                L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.zero_tile.data_ptr(),
+                       ws.y.data_ptr(), R, steps, tiles, max_clusters, _LSTM_SLOTS[axis], st)
             with region("fc"):
                 ws.stats.zero_()
                 fc = w["fc"]
