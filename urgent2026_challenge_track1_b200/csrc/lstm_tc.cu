@@ -55,7 +55,7 @@ constexpr int LACC = 256;          // TMEM columns per accumulator buffer
 constexpr int LTHREADS = 512;      // 4 control warps + 3 slots x 4 epilogue warps
 constexpr uint32_t L_W_BYTES = LKC * LBN * 16;          // 166400
 constexpr uint32_t L_A_STAGE = LKS * 128 * 16;          // 20480
-constexpr int L_NBARS = 2 * LSTAGES + 2 + 2 + LNS + 2;
+constexpr int L_NBARS = 2 * LSTAGES + LNS + 2 + LNS + 2;
 constexpr size_t L_SMEM = L_W_BYTES + LSTAGES * L_A_STAGE + L_NBARS * 8 + 16;
 static_assert(L_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
@@ -202,6 +202,7 @@ __device__ __forceinline__ void epilogue_role(const LstmTcArgs& a, uint32_t tmem
   const size_t y_tile = (size_t)LKC * 128 * 8;                 // halves per (step, tile, dir) of y
   const size_t g_tile = (size_t)2 * LCL * LGC * 128 * 8;       // halves per (step, tile) of gates_x
   uint32_t it0 = 0;                                            // accumulator items of the groups done so far
+  uint32_t nfull = 0;                                          // items this slot has consumed (phase of acc_full[k])
   long long w_acc = 0, w_busy = 0;
   P_DECL(k == 0 && quad == 0 && lane == 0);
   float c[LUN];
@@ -226,7 +227,8 @@ __device__ __forceinline__ void epilogue_role(const LstmTcArgs& a, uint32_t tmem
         const uint32_t it = it0 + (uint32_t)(s * G.nact + k);
         const uint32_t buf = it & 1;
         P_MARK(w_busy);
-        mbar_wait(acc_full + buf, (it >> 1) & 1);
+        mbar_wait(acc_full + k, nfull & 1);
+        ++nfull;
         tc_fence_after();
         P_MARK(w_acc);
         epilogue_item<Q>(t_lane + buf * LACC, reinterpret_cast<const uint4*>(gbase) + r, ytile_row, c);
@@ -255,8 +257,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + LSTAGES * L_A_STAGE);
   uint64_t* full = bars;                       // [3]
   uint64_t* empty = bars + LSTAGES;            // [3]
-  uint64_t* acc_full = bars + 2 * LSTAGES;     // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint64_t* acc_full = bars + 2 * LSTAGES;     // [LNS]: one per SLOT — each slot's warps see every phase of theirs
+  uint64_t* acc_empty = acc_full + LNS;        // [2]: one per TMEM buffer — the MMA thread sees every phase
   uint64_t* h_ready = acc_empty + 2;           // [LNS]
   uint64_t* w_full = h_ready + LNS;
   uint64_t* w_free = w_full + 1;               // epilogue -> producer: the resident W slice may be overwritten
@@ -268,7 +270,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, 4);
     for (int i = 0; i < LNS; ++i) mbar_init(h_ready + i, LCL);
     mbar_init(w_full, 1);
     mbar_init(w_free, 4);
@@ -372,7 +375,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
             mma_commit(empty + stage);
             if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
           }
-          mma_commit(acc_full + buf);
+          mma_commit(acc_full + (i % G.nact));
         }
       }
       P_MARK(w_o);
