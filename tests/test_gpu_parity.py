@@ -120,6 +120,31 @@ def test_bsrnn_se_tensorcore_vs_oracle(fs, secs, B):
     assert rel_l2(out2.cpu(), out.cpu()) < 1e-6
 
 
+@pytest.mark.parametrize("precision,width,layers", [("fp16", 196, 2), ("fp32", 32, 2)])
+def test_bsrnn_se_cuda_graph_replay_matches_eager(precision, width, layers):
+    """cuda_graph=True replays the captured launch sequence: same result as host launches, new inputs are honoured,
+    and an in-place parameter update invalidates the graph."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=width, num_layer=layers, precision=precision).cuda()
+    fs, n = 16000, 12000
+    lens = torch.tensor([n, n - 777])
+    x1, x2 = R.synth_noisy(2, n, fs, seed=1), R.synth_noisy(2, n, fs, seed=2)
+    e1, e2 = m(x1, lens, fs)[0].clone(), m(x2, lens, fs)[0].clone()
+    m.cuda_graph = True
+    g1 = m(x1, lens, fs)[0].clone()
+    g2 = m(x2.cuda(), lens, fs)[0].clone()          # second call = pure replay with a device-resident input
+    g1b = m(x1, lens, fs)[0].clone()
+    assert len(m._graphs) == 1
+    assert rel_l2(g1.cpu(), e1.cpu()) < 1e-5 and rel_l2(g2.cpu(), e2.cpu()) < 1e-5 and rel_l2(g1b.cpu(), g1.cpu()) < 1e-6
+    with torch.no_grad():
+        m.bsrnn.bsrnn.fc_time[0].weight.mul_(0.5)  # in-place update (optimizer / EMA swap): graph must be rebuilt
+    g3 = m(x1, lens, fs)[0].clone()
+    m.cuda_graph = False
+    e3 = m(x1, lens, fs)[0]
+    assert rel_l2(g3.cpu(), e3.cpu()) < 1e-5 and rel_l2(g3.cpu(), g1.cpu()) > 1e-4
+
+
 # ------------------------------------------------------------------------------------------------ FlowSE
 def _flow_model(g):
     from urgent2026_challenge_track1_b200.config import Config

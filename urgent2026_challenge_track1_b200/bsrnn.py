@@ -40,8 +40,12 @@ class _Separator(nn.Module):
 class BSRNN_SE(nn.Module):
     N_FFT, HOP, DEFAULT_FS = 960, 480, 48000          # reference bsrnn.py:14-25
 
-    def __init__(self, num_channel=192, num_layer=6, precision=None):
+    def __init__(self, num_channel=192, num_layer=6, precision=None, cuda_graph=None):
         super().__init__()
+        # cuda_graph: replay the fixed-shape launch sequence from a captured CUDA graph (one graph per
+        # (B, L, fs, lengths) signature, invalidated when parameters change).  Default from BSRNN_B200_GRAPH (off).
+        self.cuda_graph = (os.environ.get("BSRNN_B200_GRAPH", "0") == "1") if cuda_graph is None else bool(cuda_graph)
+        self._graphs = {}
         self.bsrnn = _Separator(self.N_FFT // 2 + 1, num_channel, num_layer, self.DEFAULT_FS)
         self.num_channel, self.num_layer = num_channel, num_layer
         # "fp32": CUDA-core kernels, parity bar 1e-3.  "fp16" (alias "bf16"): tcgen05 tensor cores with 16-bit
@@ -69,12 +73,31 @@ class BSRNN_SE(nn.Module):
         if dev.type != "cuda":
             raise L.NativeLibraryError("BSRNN_SE parameters must live on a CUDA device (no CPU fallback)")
         fs = int(fs)
-        wav = speech_mix.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        if wav.dim() != 2:
-            raise ValueError(f"speech_mix must be (B, L), got {tuple(wav.shape)}")
+        if speech_mix.dim() != 2:
+            raise ValueError(f"speech_mix must be (B, L), got {tuple(speech_mix.shape)}")
         lens_host = speech_lengths.detach().to("cpu") if torch.is_tensor(speech_lengths) else torch.as_tensor(speech_lengths)
         L_out = int(lens_host.max())
-        lens = lens_host.to(device=dev, dtype=torch.int32, non_blocking=True)
+        if not self.cuda_graph:
+            wav = speech_mix.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            lens = lens_host.to(device=dev, dtype=torch.int32, non_blocking=True)
+            return self._forward_device(wav, lens, L_out, fs)
+        # ---- CUDA-graph path: one captured launch sequence per input signature and parameter version
+        params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (tuple(speech_mix.shape), fs, tuple(int(v) for v in lens_host.tolist()), self.precision)
+        entry = self._graphs.get(key)
+        if entry is None or entry[1] != params:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()                       # graphs pin their workspaces: keep only a few alive
+            x_static = torch.empty(tuple(speech_mix.shape), dtype=torch.float32, device=dev)
+            x_static.copy_(speech_mix)
+            lens = lens_host.to(device=dev, dtype=torch.int32)
+            g = R.GraphedForward(lambda x: self._forward_device(x, lens, L_out, fs), [x_static])
+            entry = self._graphs[key] = (g, params)
+        wav_out, est = entry[0].run(speech_mix)
+        return wav_out.clone(), est.clone()               # the graph's own output buffers are reused by the next replay
+
+    def _forward_device(self, wav, lens, L_out, fs):
+        """The launch sequence on device-resident inputs (everything stream-ordered on the current stream)."""
         n_fft, hop = R.stft_dims(fs, self.N_FFT, self.HOP, self.DEFAULT_FS)
         core = self.bsrnn.bsrnn
         plan = R.BandPlan.make(core.band_split.subbands, n_fft // 2 + 1)

@@ -5,9 +5,12 @@
 //   C[128*m_tiles, BN*n_tiles] = A_kb8 * W_kb8^T   (+ fused epilogue)
 //
 // Operands live in HBM in the UMMA-native "KB8" layout (umma.cuh), so each pipeline stage is filled by two plain
-// cp.async.bulk copies.  Roles: warp 0 = bulk-copy producer, warp 1 = single-thread tcgen05.mma issuer, warps 2-5 =
-// epilogue (tcgen05.ld -> registers -> fused op -> global).  Two 256-column TMEM accumulators let the epilogue of
-// tile i overlap the MMAs of tile i+1.  One CTA per SM, static round-robin tile schedule with the N tile innermost so
+// cp.async.bulk copies.  Roles: warp 0 = bulk-copy producer, warp 1 = single-thread tcgen05.mma issuer, warps 2-9 =
+// epilogue (tcgen05.ld -> registers -> fused op -> global): two warps per TMEM lane quadrant, each taking half of the
+// tile's column chunks (these GEMMs have K <= 800, so a 4-warp epilogue was the pacing stage).  Two 256-column TMEM
+// accumulators let the epilogue of tile i overlap the MMAs of tile i+1.  The residual epilogue transposes each
+// 32x32 chunk through a per-warp shared-memory scratch so that the f32 read-modify-write of the residual stream
+// moves whole 128-byte lines.  One CTA per SM, static round-robin tile schedule with the N tile innermost so
 // concurrently running CTAs share the same A tile through L2.
 //
 // Used for (fp16 tensor-core mode): LSTM input projections, Linear(4N->N)+skip (+GroupNorm statistics of the result),
@@ -22,7 +25,10 @@ using namespace umma;
 
 constexpr int TC_STAGES = 4;
 constexpr int TC_KS = 8;            // k-cores (8 halves each) per pipeline stage -> K = 64 per stage
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_SCR_LD = 36;                                   // floats per scratch row (32 + 4: conflict-free 16 B rows)
+constexpr int TC_SCR_BYTES = TC_EPI_WARPS * 32 * TC_SCR_LD * 4;  // residual epilogue only
 constexpr int TC_ACC_COLS = 256;
 
 struct RowMap {                     // global row (m_tile, r) -> token
@@ -71,7 +77,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // Epilogue for NC (16 or 32) accumulator columns [c0, c0+NC) of row r of tile (m, n).
 template <int EPI, int NC>
 __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n, int r, int c0, const uint32_t* acc,
-                                               bool row_ok, long token, float& s_sum, float& s_sq) {
+                                               bool row_ok, long token, float& s_sum, float& s_sq, float* scr, int lane) {
   const int gc0 = n * a.BN + c0;                      // global output column of acc[0]
   float v[NC];
 #pragma unroll
@@ -87,26 +93,49 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
       *reinterpret_cast<uint4*>(o + i) = pk;
     }
   } else if (EPI == EPI_RESID_F32) {
-    if (!row_ok) return;
-    float* o = reinterpret_cast<float*>(a.out) + token * a.ldo + gc0;
+    // out[token, gc0 + c] += v[c].  Thread r owns row r; the rows of a warp are 32 scattered tokens of ldo floats, so
+    // the chunk goes through the warp's scratch (row stride 36 floats): afterwards 8 lanes cover one row's 128
+    // bytes and a warp instruction touches 4 whole lines instead of 32 partial ones.
+    float* my = scr + (r & 31) * TC_SCR_LD;
 #pragma unroll
-    for (int i = 0; i < NC; i += 4) {
-      if (gc0 + i + 3 < a.n_valid) {
-        float4 old = *reinterpret_cast<float4*>(o + i);
-        old.x += v[i]; old.y += v[i + 1]; old.z += v[i + 2]; old.w += v[i + 3];
-        *reinterpret_cast<float4*>(o + i) = old;
-        s_sum += old.x + old.y + old.z + old.w;
-        s_sq += old.x * old.x + old.y * old.y + old.z * old.z + old.w * old.w;
-      } else {
+    for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(my + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    __syncwarp();
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (gc0 + i + j < a.n_valid) {
-            const float nv = o[i + j] + v[i + j];
-            o[i + j] = nv;
-            s_sum += nv; s_sq += nv * nv;
-          }
+    for (int i = 0; i < 8; ++i) {
+      const int rr = 4 * i + sub;
+      const long tok = __shfl_sync(0xffffffffu, token, rr);
+      if (((okmask >> rr) & 1u) && c4 < NC && gc0 + c4 < a.n_valid) {
+        float* sp = scr + rr * TC_SCR_LD + c4;
+        float* o = reinterpret_cast<float*>(a.out) + tok * a.ldo + gc0 + c4;
+        float4 nv = *reinterpret_cast<const float4*>(sp);
+        if (gc0 + c4 + 3 < a.n_valid) {
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          nv.x += old.x; nv.y += old.y; nv.z += old.z; nv.w += old.w;
+          *reinterpret_cast<float4*>(o) = nv;
+        } else {
+          float t[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gc0 + c4 + j < a.n_valid) { t[j] += o[j]; o[j] = t[j]; } else t[j] = 0.f;
+          nv = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(sp) = nv;           // new values back for the row owner's statistics
       }
     }
+    __syncwarp();
+    if (row_ok && a.stats) {
+#pragma unroll
+      for (int i = 0; i < NC; i += 4) {
+        if (gc0 + i < a.n_valid) {
+          const float4 nv = *reinterpret_cast<const float4*>(my + i);
+          s_sum += nv.x + nv.y + nv.z + nv.w;
+          s_sq += nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
+        }
+      }
+    }
+    __syncwarp();
   } else if (EPI == EPI_F16_KB8) {
     // a warp stores 32 rows x 16 B = 512 contiguous bytes per instruction
     __half* o = reinterpret_cast<__half*>(a.out) + (((long)m * a.out_kcores + (gc0 >> 3)) * 128 + r) * 8;
@@ -171,11 +200,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   uint64_t* acc_empty = bars + 2 * TC_STAGES + 2;  // [2]
   uint64_t* b_full = bars + 2 * TC_STAGES + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 5);
+  uint8_t* smem_scr = reinterpret_cast<uint8_t*>(bars + 2 * TC_STAGES + 8);     // 16-byte aligned (EPI_RESID_F32 only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -244,7 +274,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     }
   } else {
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // which half of the tile's column chunks
     const int r = q * 32 + lane;               // row of the tile
+    const int nch = (BN + 31) >> 5;            // 32-column chunks (the last one may be 16 wide)
+    const int ch0 = half == 0 ? 0 : (nch + 1) >> 1, ch1 = half == 0 ? (nch + 1) >> 1 : nch;
+    float* scr = reinterpret_cast<float*>(smem_scr) + (warp - 2) * 32 * TC_SCR_LD;
     int m, n;
     for (int it = 0; next_tile(a, it, m, n); ++it) {
       const int buf = it & 1;
@@ -255,18 +289,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       mbar_wait(acc_full + buf, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
-      int c0 = 0;
-      for (; c0 + 32 <= BN; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld_x32(t_addr + c0, acc);
-        tmem_ld_wait();
-        epilogue_chunk<EPI, 32>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq);
-      }
-      if (c0 < BN) {                           // BN % 32 == 16
-        uint32_t acc[16];
-        tmem_ld_x16(t_addr + c0, acc);
-        tmem_ld_wait();
-        epilogue_chunk<EPI, 16>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq);
+      for (int ch = ch0; ch < ch1; ++ch) {
+        const int c0 = ch * 32;
+        if (c0 + 32 <= BN) {
+          uint32_t acc[32];
+          tmem_ld_x32(t_addr + c0, acc);
+          tmem_ld_wait();
+          epilogue_chunk<EPI, 32>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane);
+        } else {                               // BN % 32 == 16
+          uint32_t acc[16];
+          tmem_ld_x16(t_addr + c0, acc);
+          tmem_ld_wait();
+          epilogue_chunk<EPI, 16>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -298,9 +333,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   }
 }
 
-static size_t tc_smem_bytes(int BN, int kcores, bool resident) {
+static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch) {
   const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)TC_STAGES * TC_KS * BN * 16;
-  return (size_t)TC_STAGES * TC_KS * 128 * 16 + b + (2 * TC_STAGES + 5) * 8 + 16;
+  return (size_t)TC_STAGES * TC_KS * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0);
 }
 
 template <int EPI>
@@ -311,7 +346,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   // weight-resident schedule when several N tiles exist, the tile fits beside the A ring, and there is enough M work
   a.b_resident = (a.n_tiles > 1 && a.n_tiles <= sms && (size_t)a.kcores * a.BN * 16 <= 120 * 1024 &&
                   a.m_tiles >= 2 * (sms / a.n_tiles)) ? 1 : 0;
-  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident);
+  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32);
   BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;

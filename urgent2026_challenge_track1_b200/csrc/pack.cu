@@ -20,36 +20,83 @@ struct PackArgs {
   int g_inner;
 };
 
-// grid (m_tiles), block 256, dynamic smem 128 * (kcores*8 + 8) halves
-__global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a) {
+// grid (m_tiles), block 256, dynamic smem 128 * (kcores*8 + 8) halves + 128 row descriptors.
+// Work item = (row, 4 consecutive channels): consecutive threads read consecutive float4 of a token row (coalesced
+// 16-byte loads, four in flight per thread), apply the affine, and drop 4 halves into the padded tile; the tile then
+// leaves as 16-byte KB8 cores.  Needs C % 4 == 0, col0 % 4 == 0 and 16-byte aligned rows; otherwise the scalar path.
+struct PackRow {
+  long tok;        // token index or -1
+  long grp;        // scale/shift row
+};
+
+__global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, int vec_ok) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half* tile = reinterpret_cast<__half*>(smem_raw);
   const int ld = a.kcores * 8 + 8;                 // +8 halves: rows land in different banks
+  __half* tile = reinterpret_cast<__half*>(smem_raw);
+  PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)128 * ld * 2);
   const int m = blockIdx.x;
   const int step = m / a.tiles_per_step, j = m - step * a.tiles_per_step;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kw = a.kcores * 8;
-  for (int r = warp; r < 128; r += 8) {
+  if (threadIdx.x < 128) {
+    const int r = threadIdx.x;
     const long seq = (long)j * 128 + r;
-    const bool ok = seq < a.R;
-    long token = 0;
-    const float *sc = nullptr, *sh = nullptr;
-    if (ok) {
-      token = (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride + (long)step * a.step_stride;
-      if (a.scale) {
-        const long g = (token / a.tokens_per_sample) * a.g_inner + (a.g_inner > 1 ? token % a.g_inner : 0);
-        sc = a.scale + g * a.C;
-        sh = a.shift + g * a.C;
+    PackRow pr{-1, 0};
+    if (seq < a.R) {
+      pr.tok = (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride + (long)step * a.step_stride;
+      if (a.scale) pr.grp = (pr.tok / a.tokens_per_sample) * a.g_inner + (a.g_inner > 1 ? pr.tok % a.g_inner : 0);
+    }
+    rows[r] = pr;
+  }
+  __syncthreads();
+  if (vec_ok) {
+    const int q4 = kw >> 2;                        // float4 slots per row (52 for N = 196)
+    const int items = 128 * q4;
+    for (int base = threadIdx.x; base < items; base += 256 * 4) {
+      float4 v[4];
+      int rr[4], cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * 256;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rr[u] = -1;
+        if (idx < items) {
+          rr[u] = idx / q4;
+          cc[u] = (idx - rr[u] * q4) * 4;
+          const long tok = rows[rr[u]].tok;
+          if (tok >= 0 && cc[u] < a.C) v[u] = __ldg(reinterpret_cast<const float4*>(a.x + tok * a.ldx + a.col0 + cc[u]));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (rr[u] < 0) continue;
+        const PackRow pr = rows[rr[u]];
+        if (a.scale && pr.tok >= 0 && cc[u] < a.C) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + pr.grp * a.C + cc[u]));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + pr.grp * a.C + cc[u]));
+          v[u].x = fmaf(v[u].x, sc.x, sh.x); v[u].y = fmaf(v[u].y, sc.y, sh.y);
+          v[u].z = fmaf(v[u].z, sc.z, sh.z); v[u].w = fmaf(v[u].w, sc.w, sh.w);
+        }
+        __half2 lo = __floats2half2_rn(v[u].x, v[u].y), hi = __floats2half2_rn(v[u].z, v[u].w);
+        *reinterpret_cast<uint2*>(tile + rr[u] * ld + cc[u]) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       }
     }
-    const float* row = a.x + token * a.ldx + a.col0;
-    for (int c = lane; c < kw; c += 32) {
-      float v = 0.f;
-      if (ok && c < a.C) {
-        v = row[c];
-        if (sc) v = fmaf(v, sc[c], sh[c]);
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < 128; r += 8) {
+      const PackRow pr = rows[r];
+      const bool ok = pr.tok >= 0;
+      const float* row = a.x + (ok ? pr.tok : 0) * a.ldx + a.col0;
+      const float* sc = a.scale ? a.scale + pr.grp * a.C : nullptr;
+      const float* sh = a.scale ? a.shift + pr.grp * a.C : nullptr;
+      for (int c = lane; c < kw; c += 32) {
+        float v = 0.f;
+        if (ok && c < a.C) {
+          v = row[c];
+          if (sc) v = fmaf(v, sc[c], sh[c]);
+        }
+        tile[r * ld + c] = __float2half_rn(v);
       }
-      tile[r * ld + c] = __float2half_rn(v);
     }
   }
   __syncthreads();
@@ -72,9 +119,12 @@ extern "C" int bsrnn_norm_cast_kb8(const float* x, const float* scale, const flo
   BSRNN_CHECK_ARG((scale == nullptr) == (shift == nullptr), "norm_cast_kb8: scale and shift come together");
   PackArgs a{x, scale, shift, reinterpret_cast<__half*>(out), ldx, col0, C, kcores, tiles_per_step, R,
              seq_inner, seq_outer, seq_inner_stride, step_stride, tokens_per_sample, g_inner};
-  const size_t smem = (size_t)128 * (kcores * 8 + 8) * 2;
+  const size_t smem = (size_t)128 * (kcores * 8 + 8) * 2 + 128 * sizeof(PackRow);
+  const int vec_ok = (C % 4 == 0 && col0 % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                      (!scale || ((reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0)))
+                         ? 1 : 0;
   BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  norm_cast_kb8_kernel<<<m_tiles, 256, smem, (cudaStream_t)stream>>>(a);
+  norm_cast_kb8_kernel<<<m_tiles, 256, smem, (cudaStream_t)stream>>>(a, vec_ok);
   BSRNN_LAUNCH_OK();
   return 0;
 }

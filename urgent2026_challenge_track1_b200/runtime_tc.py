@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
-from .runtime import region, _f64
+from .runtime import region, _f64, keepalive
 
 import os
 
@@ -138,6 +138,7 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
     dev = skip.device
     st = L.stream_ptr()
     ws = workspace(B, T, K, N, dev)
+    keepalive(ws)
     M = B * T * K
     L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
     for i, lay in enumerate(layers):
