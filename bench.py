@@ -99,7 +99,8 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="length of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying the "
+                    "per-step kernel sequence from a captured CUDA graph (BSRNN_SE cuda_graph=True)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

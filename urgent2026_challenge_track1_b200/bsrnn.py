@@ -91,7 +91,7 @@ class BSRNN_SE(nn.Module):
             x_static = torch.empty(tuple(speech_mix.shape), dtype=torch.float32, device=dev)
             x_static.copy_(speech_mix)
             lens = lens_host.to(device=dev, dtype=torch.int32)
-            g = R.GraphedForward(lambda x: self._forward_device(x, lens, L_out, fs), [x_static])
+            g = R.GraphedForward(lambda x: self._forward_device(x, lens, L_out, fs), [x_static], keep=[lens])
             entry = self._graphs[key] = (g, params)
         wav_out, est = entry[0].run(speech_mix)
         return wav_out.clone(), est.clone()               # the graph's own output buffers are reused by the next replay

@@ -102,33 +102,34 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
     __syncwarp();
     const int sub = lane >> 3, c4 = (lane & 7) * 4;
     const unsigned okmask = __ballot_sync(0xffffffffu, row_ok);
+    const bool col_ok = c4 < NC && gc0 + c4 + 3 < a.n_valid;     // n_valid % 4 == 0 is checked by the launcher
+    // all 8 reads of the residual stream are issued before the first store (the rows are scattered tokens: the
+    // compiler cannot prove the stores do not alias the later loads and would serialise 8 DRAM round trips)
+    float* optr[8];
+    float4 old[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rr = 4 * i + sub;
       const long tok = __shfl_sync(0xffffffffu, token, rr);
-      if (((okmask >> rr) & 1u) && c4 < NC && gc0 + c4 < a.n_valid) {
-        float* sp = scr + rr * TC_SCR_LD + c4;
-        float* o = reinterpret_cast<float*>(a.out) + tok * a.ldo + gc0 + c4;
-        float4 nv = *reinterpret_cast<const float4*>(sp);
-        if (gc0 + c4 + 3 < a.n_valid) {
-          const float4 old = *reinterpret_cast<const float4*>(o);
-          nv.x += old.x; nv.y += old.y; nv.z += old.z; nv.w += old.w;
-          *reinterpret_cast<float4*>(o) = nv;
-        } else {
-          float t[4] = {nv.x, nv.y, nv.z, nv.w};
+      optr[i] = (((okmask >> rr) & 1u) && col_ok) ? reinterpret_cast<float*>(a.out) + tok * a.ldo + gc0 + c4 : nullptr;
+      old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (optr[i]) old[i] = *reinterpret_cast<const float4*>(optr[i]);
+    }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (gc0 + c4 + j < a.n_valid) { t[j] += o[j]; o[j] = t[j]; } else t[j] = 0.f;
-          nv = make_float4(t[0], t[1], t[2], t[3]);
-        }
-        *reinterpret_cast<float4*>(sp) = nv;           // new values back for the row owner's statistics
+    for (int i = 0; i < 8; ++i) {
+      if (optr[i]) {
+        float* sp = scr + (4 * i + sub) * TC_SCR_LD + c4;
+        float4 nv = *reinterpret_cast<const float4*>(sp);
+        nv.x += old[i].x; nv.y += old[i].y; nv.z += old[i].z; nv.w += old[i].w;
+        *reinterpret_cast<float4*>(optr[i]) = nv;
+        *reinterpret_cast<float4*>(sp) = nv;             // new values back for the row owner's statistics
       }
     }
     __syncwarp();
     if (row_ok && a.stats) {
 #pragma unroll
       for (int i = 0; i < NC; i += 4) {
-        if (gc0 + i < a.n_valid) {
+        if (gc0 + i + 3 < a.n_valid) {
           const float4 nv = *reinterpret_cast<const float4*>(my + i);
           s_sum += nv.x + nv.y + nv.z + nv.w;
           s_sq += nv.x * nv.x + nv.y * nv.y + nv.z * nv.z + nv.w * nv.w;
@@ -286,6 +287,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       long token = 0;
       const bool row_ok = a.rows.map(m, r, &token);
       float s_sum = 0.f, s_sq = 0.f;
+      if (EPI == EPI_RESID_F32) {                      // next tile's residual rows -> L2 while this tile is processed
+        int m2, n2;
+        long tok2 = 0;
+        if (next_tile(a, it + 1, m2, n2) && a.rows.map(m2, r, &tok2)) {
+          const char* p = reinterpret_cast<const char*>(reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + n2 * a.BN);
+          const int nbytes = (a.n_valid - n2 * a.BN < a.BN ? a.n_valid - n2 * a.BN : a.BN) * 4;
+          for (int off = half * 128; off < nbytes; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+        }
+      }
       mbar_wait(acc_full + buf, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -367,6 +377,8 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && kcores > 0 && kcores % 2 == 0, "gemm_tc: bad tile counts (kcores=%d)", kcores);
   BSRNN_CHECK_ARG(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc: BN=%d must be a multiple of 16 in [16,256]", BN);
   BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && tokens_per_sample > 0, "gemm_tc: bad row map");
+  BSRNN_CHECK_ARG(epilogue != EPI_RESID_F32 || (n_valid % 4 == 0 && ldo % 4 == 0),
+                  "gemm_tc: the residual epilogue needs n_valid and ldo to be multiples of 4 (got %d, %ld)", n_valid, ldo);
   GemmTcArgs a;
   a.A = reinterpret_cast<const __half*>(A);
   a.W = reinterpret_cast<const __half*>(W);

@@ -92,24 +92,50 @@ class region:
 # Host -> device traffic of the launch sequence.  Descriptor arrays embed raw device pointers; with a warm caching
 # allocator the same forward produces the same bytes, so uploads are content-addressed and a steady-state forward
 # issues no H2D copy at all.  Under CUDA-graph capture (GraphedForward) nothing may be copied from pageable memory:
-# the device buffer is allocated inside the capture and its bytes are written once, right after the capture ends
-# (the buffer stays alive, at a fixed address, as long as the graph does).
+# descriptors are carved out of an arena that was allocated BEFORE the capture (ordinary memory owned by the graph
+# object, so no captured allocation can ever alias it) and their bytes are written once, right after the capture.
 _DESC_CACHE = {}
 _DESC_CACHE_MAX = 512
-_CAPTURE_PENDING = None          # list of (device uint8 tensor, host bytes) while a capture is being recorded
+_CAPTURE = None                  # _CaptureState while a capture is being recorded
+
+
+class _CaptureState:
+    ARENA_BYTES = 4 << 20
+
+    def __init__(self, device):
+        self.arena = torch.zeros(self.ARENA_BYTES, dtype=torch.uint8, device=device)
+        self.used = 0
+        self.writes = []         # (offset, bytes)
+        self.keep = []           # objects allocated outside the capture but referenced by captured kernels
+
+    def carve(self, raw):
+        off = (self.used + 255) // 256 * 256
+        if off + len(raw) > self.ARENA_BYTES:
+            raise RuntimeError("descriptor arena exhausted during CUDA-graph capture")
+        self.used = off + len(raw)
+        self.writes.append((off, raw))
+        return self.arena[off:off + len(raw)]
+
+    def flush(self):
+        host = torch.zeros(self.used, dtype=torch.uint8)
+        for off, raw in self.writes:
+            host[off:off + len(raw)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        self.arena[: self.used].copy_(host)
+
+
+def _capturing():
+    return _CAPTURE is not None and torch.cuda.is_current_stream_capturing()
 
 
 def keepalive(obj):
     """Objects allocated OUTSIDE a capture but referenced by captured kernels (workspaces) must outlive the graph."""
-    if _CAPTURE_PENDING is not None and torch.cuda.is_current_stream_capturing():
-        _CAPTURE_PENDING.append((obj, None))
+    if _capturing():
+        _CAPTURE.keep.append(obj)
 
 
 def _upload_bytes(raw: bytes, device):
-    if _CAPTURE_PENDING is not None and torch.cuda.is_current_stream_capturing():
-        dev = torch.empty(len(raw), dtype=torch.uint8, device=device)
-        _CAPTURE_PENDING.append((dev, raw))
-        return dev
+    if _capturing():
+        return _CAPTURE.carve(raw)
     key = (raw, str(device))
     dev = _DESC_CACHE.get(key)
     if dev is None:
@@ -307,22 +333,21 @@ class GraphedForward:
     uploads requested during the capture are performed once after it.  `run` copies new inputs into the static
     input tensors and replays.  Outputs are the capture's own tensors: valid until the next `run`."""
 
-    def __init__(self, fn, static_inputs):
-        global _CAPTURE_PENDING
+    def __init__(self, fn, static_inputs, keep=()):
+        global _CAPTURE
         self.inputs = static_inputs
+        self.keep = list(keep)                              # e.g. device-resident constants the closure captured
         fn(*static_inputs)                                  # eager warm-up
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        _CAPTURE_PENDING = []
+        self.state = _CaptureState(static_inputs[0].device)
+        _CAPTURE = self.state
         try:
             with torch.cuda.graph(self.graph):
                 self.outputs = fn(*static_inputs)
-            self.keep = _CAPTURE_PENDING                    # device buffers referenced by captured kernels
         finally:
-            _CAPTURE_PENDING = None
-        for dev, raw in self.keep:
-            if raw is not None:
-                dev.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+            _CAPTURE = None
+        self.state.flush()
         torch.cuda.synchronize()
 
     def run(self, *inputs):
