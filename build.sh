@@ -8,7 +8,7 @@ mkdir -p $OUT
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --use_fast_math"
 # fast-math is NOT applied to the f32-mode kernels' transcendental calls: they use expf/tanhf explicitly... see per-file flags
-for f in api fft norm gemm_f32 lstm_f32 flow pack gemm_tc lstm_tc $EXTRA; do
+for f in api fft norm gemm_f32 lstm_f32 flow pack gemm_tc lstm_tc optim $EXTRA; do
   FF="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
   $NVCC $FF -c $SRC/$f.cu -o $OUT/$f.o 2> $OUT/$f.ptxas.log || { cat $OUT/$f.ptxas.log; exit 1; }
 done

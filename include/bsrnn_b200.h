@@ -160,6 +160,31 @@ int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const 
                                  int steps, int seq_tiles, int max_clusters, int slots, void* stream);
 int bsrnn_blstm_tc_max_clusters(void);
 
+/* ---------------------------------------------------------------------------------------------- training (f32)
+ * The sequential parts of the BLSTM forward/backward for train_se.py [reference d_model.py:61-95 -> autograd through
+ * nn.LSTM at bsrnn_flowse.py:296-297,303-304]; the batched GEMMs around them (input projection, dW, dx) are plain
+ * library GEMMs issued by the host side (training.py).
+ * bsrnn_blstm_train_fwd_f32: bsrnn_blstm_recurrence_f32 that also stores saved (tokens, 2, 5, H) = sigmoid(i),
+ *     sigmoid(f), tanh(g), sigmoid(o), c per (token, direction).
+ * bsrnn_blstm_train_bwd_f32: back-propagation through time.  dy (tokens, 2H) = dL/dy -> dgates (tokens, 2, 4H) =
+ *     dL/d gates_x (pre-activations, gate order i,f,g,o).  dh_rec, dc_carry: (2, R, H) f32 scratch.
+ * bsrnn_grad_sumsq / bsrnn_adamw_step: the optimizer tail on one flat buffer — stats = {sum g^2, non-finite flag};
+ *     gradients are scaled by grad_scale (1/world after a summed allreduce), clipped to max_norm like
+ *     torch.nn.utils.clip_grad_norm_ [train_se.py:78], the step is skipped when a non-finite gradient was seen
+ *     [d_model.py:48-57], then AdamW with decoupled weight decay [d_model.py:102-109] and, if ema != NULL,
+ *     ema -= (1-ema_decay)*(ema - param) [torch_ema, flow_model.py:84].
+ */
+int bsrnn_blstm_train_fwd_f32(const float* gates_x, const float* w_hh, float* y, float* c_state, float* saved, int R,
+                              int steps, int H, long seq_inner, long seq_outer, long seq_inner_stride,
+                              long step_stride, void* stream);
+int bsrnn_blstm_train_bwd_f32(const float* dy, const float* saved, const float* w_hh, float* dgates, float* dh_rec,
+                              float* dc_carry, int R, int steps, int H, long seq_inner, long seq_outer,
+                              long seq_inner_stride, long step_stride, void* stream);
+int bsrnn_grad_sumsq(const float* grad, long n, double* stats, void* stream);
+int bsrnn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, long n,
+                     const double* stats, float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, int step, float ema_decay, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- FlowSE pieces
  * bsrnn_time_embed: GaussianFourierProjection [bsrnn_flowse.py:90-99]: out (B, 2*E) = [sin(2*pi*t*W), cos(...)].
  * bsrnn_conv5x5_glu: GradDecoder.conv_after_* = Conv2d(16->4, 5x5, pad 2) + GLU(dim=1) [bsrnn_flowse.py:114-117,

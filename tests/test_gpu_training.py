@@ -1,0 +1,127 @@
+"""GPU tests (-m gpu) of the training path: BLSTM forward/backward kernels against torch autograd, the full
+differentiable forward and its gradients against the CPU oracle, the fused clip+AdamW(+EMA) kernels against
+torch.optim.AdamW + clip_grad_norm_, and a few optimisation steps on a fixed batch."""
+import copy
+
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import restated as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("axis,B,T,K,N", [("time", 2, 19, 5, 12), ("freq", 3, 7, 11, 12), ("time", 1, 70, 3, 20)])
+def test_blstm_function_matches_torch_autograd(axis, B, T, K, N):
+    from urgent2026_challenge_track1_b200.training import blstm
+    torch.manual_seed(0)
+    H = 2 * N
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, K, N, dtype=torch.float64)
+    wgt = torch.randn(B, T, K, 2 * H, dtype=torch.float64)
+    ref_rnn = copy.deepcopy(rnn).double()
+    xr = x.clone().requires_grad_(True)
+    if axis == "time":
+        yr = ref_rnn(xr.permute(0, 2, 1, 3).reshape(B * K, T, N))[0].reshape(B, K, T, 2 * H).permute(0, 2, 1, 3)
+    else:
+        yr = ref_rnn(xr.reshape(B * T, K, N))[0].reshape(B, T, K, 2 * H)
+    (yr * wgt).sum().backward()
+    rnn = rnn.cuda()
+    xg = x.float().cuda().requires_grad_(True)
+    y = blstm(xg, rnn, axis)
+    (y * wgt.float().cuda()).sum().backward()
+    assert rel_l2(y.detach().cpu().double(), yr.detach()) < 2e-6
+    assert rel_l2(xg.grad.cpu().double(), xr.grad) < 2e-5
+    for name, p in rnn.named_parameters():
+        assert rel_l2(p.grad.cpu().double(), getattr(ref_rnn, name).grad) < 2e-5, name
+
+
+def _tiny(fs=16000, n=6000, B=2, width=16, layers=2):
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=width, num_layer=layers, precision="fp32")
+    x = R.synth_noisy(B, n, fs, seed=1)
+    clean = R.synth_noisy(B, n, fs, seed=7)
+    lens = torch.tensor([n] + [n - 517 * (i + 1) for i in range(B - 1)])
+    return m, x, clean, lens
+
+
+@pytest.mark.parametrize("fs", (16000, 48000))
+def test_train_forward_and_gradients_match_oracle(fs):
+    from urgent2026_challenge_track1_b200.losses import multires_l1_spec_loss
+    from urgent2026_challenge_track1_b200.training import bsrnn_se_train_forward
+    m, x, clean, lens = _tiny(fs=fs, n=fs * 3 // 8)
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref_wav, _ = R.bsrnn_se_forward(sd, x.double(), lens, fs, num_layer=2)
+    multires_l1_spec_loss(clean.double(), ref_wav).mean().backward()
+    m.cuda()
+    wav, spec = bsrnn_se_train_forward(m, x.cuda(), lens, fs)
+    loss = multires_l1_spec_loss(clean.cuda(), wav).mean()
+    loss.backward()
+    assert rel_l2(wav.detach().cpu().double(), ref_wav.detach()) < 1e-4
+    inf_wav, _ = m(x, lens, fs)                                  # inference kernels (f32 mode) on the same weights
+    assert rel_l2(inf_wav.cpu(), wav.detach().cpu()) < 1e-4
+    worst = 0.0
+    for k, p in m.named_parameters():
+        g_ref = sd[k].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k       # unused bands at low sample rates
+            continue
+        e = rel_l2(p.grad.cpu().double(), g_ref)
+        worst = max(worst, e)
+        assert e < 5e-3, (k, e)
+    print(f"fs={fs}: worst parameter-gradient rel_l2 = {worst:.2e}")
+
+
+def test_fused_adamw_matches_torch():
+    from urgent2026_challenge_track1_b200 import _lib as L
+    torch.manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, device="cuda")
+    ref_p = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, eps=1e-8, weight_decay=1e-2)
+    npad = n + (-n) % 4
+    p, m, v = torch.zeros(npad, device="cuda"), torch.zeros(npad, device="cuda"), torch.zeros(npad, device="cuda")
+    p[:n] = p0
+    ema = p.clone()
+    ema_ref = p0.clone()
+    stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+    st = L.stream_ptr()
+    for step in range(1, 6):
+        g = torch.randn(n, device="cuda") * (10.0 if step % 2 else 0.001)      # clipped and unclipped steps
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 0.5)
+        opt.step()
+        ema_ref -= (1 - 0.9) * (ema_ref - ref_p.detach())
+        gp = torch.zeros(npad, device="cuda"); gp[:n] = g * 2.0                # "summed over 2 ranks"
+        L.call("bsrnn_grad_sumsq", gp.data_ptr(), npad, stats.data_ptr(), st)
+        L.call("bsrnn_adamw_step", p.data_ptr(), gp.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), npad,
+               stats.data_ptr(), 0.5, 0.5, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 0.9, st)
+        assert rel_l2(p[:n].cpu(), ref_p.detach().cpu()) < 1e-6, step
+        assert rel_l2(ema[:n].cpu(), ema_ref.cpu()) < 1e-6, step
+    # a non-finite gradient skips the update
+    before = p.clone()
+    gp[5] = float("nan")
+    L.call("bsrnn_grad_sumsq", gp.data_ptr(), npad, stats.data_ptr(), st)
+    L.call("bsrnn_adamw_step", p.data_ptr(), gp.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), npad,
+           stats.data_ptr(), 0.5, 0.5, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 6, 0.9, st)
+    assert torch.equal(p, before) and float(stats[1]) == 1.0
+
+
+def test_trainer_steps_reduce_the_loss():
+    from urgent2026_challenge_track1_b200.training import SETrainer
+    m, x, clean, lens = _tiny(fs=16000, n=8000, B=2, width=16, layers=1)
+    m.cuda()
+    tr = SETrainer(m, lr=2e-3, ema_decay=0.999)
+    noisy, clean = x.cuda().view(2, 1, -1), clean.cuda().view(2, 1, -1)        # dataset contract: (B, 1, T)
+    losses = [float(tr.step(noisy, clean, lens, torch.tensor(16000, dtype=torch.int32))[0]) for _ in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    assert tr.grad_norm() > 0
+    # the flat buffer is what the module's parameters alias, and the EMA trails it
+    p = m.bsrnn.bsrnn.fc_time[0].weight
+    off = tr.flat.offsets[[id(q) for q in tr.flat.params].index(id(p))]
+    assert torch.equal(tr.flat.flat[off:off + p.numel()].view_as(p), p)
+    assert 0 < float((tr.ema - tr.flat.flat).abs().max())
+    out, _ = m(x, lens, 16000)                                                  # inference kernels see the updated weights
+    assert torch.isfinite(out).all()

@@ -41,6 +41,13 @@ PROTOTYPES = {
     "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p],
     "bsrnn_blstm_tc_max_clusters": [],
+    "bsrnn_blstm_train_fwd_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long,
+                                  c_long, c_long, c_void_p],
+    "bsrnn_blstm_train_bwd_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_long, c_long, c_long, c_long, c_void_p],
+    "bsrnn_grad_sumsq": [c_void_p, c_long, c_void_p, c_void_p],
+    "bsrnn_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float,
+                         c_float, c_float, c_float, c_float, c_int, c_float, c_void_p],
     "bsrnn_time_embed": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "bsrnn_conv5x5_glu": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_long, c_void_p],

@@ -1,0 +1,276 @@
+"""Training path of BSRNN_SE (reference train_se.py -> SEModel.training_step d_model.py:61-113, SURVEY.md §8a rows
+a15-a17, §8e): differentiable forward, loss, backward, gradient allreduce, clip + AdamW.
+
+What runs where (round-1 state):
+  * the 12 BLSTMs (91 % of the FLOPs): the sequential recurrence, forward AND back-propagation through time, are the
+    hand-written kernels bsrnn_blstm_train_fwd_f32 / bsrnn_blstm_train_bwd_f32 (csrc/lstm_f32.cu) behind
+    `BLSTMFunction`; the batched GEMMs around them (x W_ih^T, dG W_ih, dG^T x, dG^T h_prev) are plain library GEMMs
+    (torch.matmul -> cuBLAS);
+  * the input STFT is bsrnn_stft_fwd (no gradient flows into the noisy input);
+  * BandSplit, GroupNorms, Linear+residual, MaskDecoder, complex mask, iSTFT and the loss are torch autograd ops over
+    the SAME nn.Parameters (the reference's names/shapes), so `state_dict()` stays checkpoint-compatible;
+  * the optimizer tail is two kernels on one flat buffer (csrc/optim.cu): global grad-norm + non-finite flag, then
+    clip(0.5) + AdamW (+ EMA).  Data parallelism = ONE allreduce of that flat gradient buffer (NCCL on GPUs, gloo in
+    the CPU tests); parameters unused on a rank (bands beyond K' at low sample rates) contribute zeros, which is what
+    the reference's `ddp_find_unused_parameters_true` does (train_se.py:82).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import runtime as R
+from .losses import multires_l1_spec_loss, si_snr_loss
+
+
+# ------------------------------------------------------------------------------------------------ BLSTM
+class BLSTMFunction(torch.autograd.Function):
+    """nn.LSTM(N, H, batch_first, bidirectional) over one axis of a token-major (B,T,K,N) tensor -> (B,T,K,2H)."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, axis):
+        B, T, K, N = x.shape
+        H = w_hh.shape[1]
+        M = B * T * K
+        dev = x.device
+        st = L.stream_ptr()
+        x2 = x.reshape(M, N).contiguous()
+        wih = torch.cat([w_ih, w_ih_r], 0).contiguous()                      # (8H, N)
+        bias = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r], 0)
+        whh = torch.stack([w_hh, w_hh_r], 0).contiguous()                    # (2, 4H, H)
+        gates = torch.addmm(bias, x2, wih.t())                               # (M, 8H) = (tokens, 2, 4H)
+        if axis == "time":
+            Rr, steps, addr = B * K, T, (K, T * K, 1, K)
+        else:
+            Rr, steps, addr = B * T, K, (1, K, 0, 1)
+        y = torch.empty(M, 2 * H, dtype=torch.float32, device=dev)
+        saved = torch.empty(M, 2, 5, H, dtype=torch.float32, device=dev)
+        cst = torch.empty(2 * Rr * H, dtype=torch.float32, device=dev)
+        L.call("bsrnn_blstm_train_fwd_f32", gates.data_ptr(), whh.data_ptr(), y.data_ptr(), cst.data_ptr(), saved.data_ptr(),
+               Rr, steps, H, *addr, st)
+        ctx.save_for_backward(x2, wih, whh, y, saved)
+        ctx.dims = (B, T, K, N, H, Rr, steps, addr, axis)
+        return y.view(B, T, K, 2 * H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wih, whh, y, saved = ctx.saved_tensors
+        B, T, K, N, H, Rr, steps, addr, axis = ctx.dims
+        M = B * T * K
+        dev = dy.device
+        st = L.stream_ptr()
+        dy = dy.reshape(M, 2 * H).contiguous().float()
+        dG = torch.empty(M, 2, 4 * H, dtype=torch.float32, device=dev)
+        dh = torch.empty(2 * Rr * H, dtype=torch.float32, device=dev)
+        dc = torch.empty(2 * Rr * H, dtype=torch.float32, device=dev)
+        L.call("bsrnn_blstm_train_bwd_f32", dy.data_ptr(), saved.data_ptr(), whh.data_ptr(), dG.data_ptr(), dh.data_ptr(),
+               dc.data_ptr(), Rr, steps, H, *addr, st)
+        dG2 = dG.view(M, 8 * H)
+        dx = (dG2 @ wih).view(B, T, K, N)
+        dwih = dG2.t() @ x2                                                   # (8H, N)
+        dbias = dG2.sum(0)
+        # h_{t-1} per direction: y shifted by one step along the recurrence axis (zeros at the sequence start)
+        y5 = y.view(B, T, K, 2, H)
+        hp_f, hp_b = torch.zeros_like(y5[..., 0, :]), torch.zeros_like(y5[..., 1, :])
+        if axis == "time":
+            hp_f[:, 1:] = y5[:, :-1, :, 0]
+            hp_b[:, :-1] = y5[:, 1:, :, 1]
+        else:
+            hp_f[:, :, 1:] = y5[:, :, :-1, 0]
+            hp_b[:, :, :-1] = y5[:, :, 1:, 1]
+        dwhh_f = dG[:, 0].t() @ hp_f.reshape(M, H)
+        dwhh_b = dG[:, 1].t() @ hp_b.reshape(M, H)
+        h4 = 4 * H
+        return (dx, dwih[:h4], dwhh_f, dbias[:h4], dbias[:h4], dwih[h4:], dwhh_b, dbias[h4:], dbias[h4:], None)
+
+
+def blstm(x, rnn, axis):
+    return BLSTMFunction.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
+                               rnn.weight_ih_l0_reverse, rnn.weight_hh_l0_reverse, rnn.bias_ih_l0_reverse,
+                               rnn.bias_hh_l0_reverse, axis)
+
+
+# ------------------------------------------------------------------------------------------------ differentiable forward
+def _gn(x, dims, weight, bias, eps=1e-5):
+    """GroupNorm(1, C) with the channel axis last: statistics over `dims` per sample, affine over the last axis."""
+    mean = x.mean(dim=dims, keepdim=True)
+    var = x.var(dim=dims, unbiased=False, keepdim=True)
+    return (x - mean) * torch.rsqrt(var + eps) * weight + bias
+
+
+def bsrnn_se_train_forward(model, wav, lens, fs):
+    """Differentiable BSRNN_SE.forward on CUDA tensors: wav (B,L) f32, lens (B,) int -> (enhanced (B, max len),
+    enhanced spectrum (B,T,F) complex64).  Same arithmetic as the inference kernels / the reference
+    (bsrnn.py:36-41; espnet2 BSRNN.forward), zeros of padded frames and truncated bands
+    included in every GroupNorm statistic (§8g.1)."""
+    core = model.bsrnn.bsrnn
+    fs = int(fs)
+    n_fft, hop = R.stft_dims(fs, model.N_FFT, model.HOP, model.DEFAULT_FS)
+    F_bins = n_fft // 2 + 1
+    plan = R.BandPlan.make(core.band_split.subbands, F_bins)
+    lens_dev = lens.to(device=wav.device, dtype=torch.int32)
+    with torch.no_grad():
+        spec = R.stft(wav.contiguous().float(), lens_dev, n_fft, hop)           # (B,T,F,2), frames >= olens are zeros
+    B, T = spec.shape[0], spec.shape[1]
+
+    # BandSplit [bsrnn_flowse.py:65-86 / espnet2 BandSplit]
+    zs = []
+    for k in range(plan.K):
+        s, b0, w = plan.subbands[k], plan.bin0[k], plan.width[k]
+        xk = spec[:, :, b0:b0 + w, :]
+        if w < s:
+            xk = F.pad(xk, (0, 0, 0, s - w))
+        xk = xk.reshape(B, T, 2 * s)
+        xk = _gn(xk, (1, 2), core.band_split.norm[k].weight, core.band_split.norm[k].bias)
+        zs.append(F.linear(xk, core.band_split.fc[k].weight[:, :, 0], core.band_split.fc[k].bias))
+    skip = torch.stack(zs, dim=2)                                               # (B,T,K',N)
+
+    for i in range(core.num_layer):
+        for axis, norm, rnn, fc in (("time", core.norm_time[i], core.rnn_time[i], core.fc_time[i]),
+                                    ("freq", core.norm_freq[i], core.rnn_freq[i], core.fc_freq[i])):
+            out = _gn(skip, (1, 2, 3), norm.weight, norm.bias)
+            out = blstm(out, rnn, axis)
+            skip = skip + F.linear(out, fc.weight, fc.bias)
+
+    # MaskDecoder (espnet2): per band GN -> Conv1d(N,4N) -> tanh -> Conv1d(4N,4s) -> GLU
+    outs = []
+    for mlps in (core.mask_decoder.mlp_mask, core.mask_decoder.mlp_residual):
+        parts = []
+        for k in range(plan.K):
+            m = mlps[k]
+            xk = _gn(skip[:, :, k, :], (1, 2), m[0].weight, m[0].bias)
+            hk = torch.tanh(F.linear(xk, m[1].weight[:, :, 0], m[1].bias))
+            ok = F.glu(F.linear(hk, m[3].weight[:, :, 0], m[3].bias), dim=-1)   # (B,T,2s)
+            parts.append(ok.reshape(B, T, plan.subbands[k], 2))
+        outs.append(torch.cat(parts, dim=2)[:, :, :F_bins, :])
+    m_c, r_c = torch.view_as_complex(outs[0].contiguous()), torch.view_as_complex(outs[1].contiguous())
+    est = m_c * torch.view_as_complex(spec) + r_c                               # (B,T,F)
+
+    window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32, device=wav.device)
+    L_out = int(lens.max())
+    wav_out = torch.istft(est.transpose(1, 2), n_fft, hop, n_fft, window, center=True, normalized=False, onesided=True,
+                          length=L_out)
+    return wav_out, est
+
+
+# ------------------------------------------------------------------------------------------------ flat parameters + step
+class FlatParams:
+    """All trainable parameters of a module re-pointed into ONE contiguous f32 buffer (and their .grad into another),
+    so the allreduce is a single collective and the optimizer tail a single pair of kernels."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.numel = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        pad = (-self.numel) % 4
+        self.flat = torch.zeros(self.numel + pad, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros_like(self.flat)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)
+            p.grad = self.grad[off:off + n].view_as(p)
+            self.offsets.append(off)
+            off += n
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, off in zip(self.params, self.offsets):           # autograd may have replaced .grad: re-attach the views
+            n = p.numel()
+            view = self.grad[off:off + n].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+
+    def gather_grads(self):
+        """Make sure every gradient autograd produced lives in the flat buffer (it normally accumulates in place)."""
+        for p, off in zip(self.params, self.offsets):
+            n = p.numel()
+            view = self.grad[off:off + n].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
+
+class SETrainer:
+    """One optimisation step of the reference's SEModel [d_model.py:61-113 + Trainer(gradient_clip_val=0.5),
+    train_se.py:74-83]:  forward -> MultiResL1SpecLoss.mean() (NaN loss -> zero loss, d_model.py:75-77) -> backward ->
+    allreduce(avg) -> clip-by-norm -> AdamW(lr, eps=adam_epsilon, weight_decay) -> optional EMA; StepLR via set_lr()."""
+
+    def __init__(self, se_model, lr=1e-3, weight_decay=1e-6, eps=1e-8, betas=(0.9, 0.999), gradient_clip=0.5,
+                 ema_decay=None, process_group=None, forward_fn=None):
+        self.model = se_model
+        self.flat = FlatParams(se_model)
+        self.lr, self.weight_decay, self.eps, self.betas, self.clip = lr, weight_decay, eps, betas, gradient_clip
+        self.exp_avg = torch.zeros_like(self.flat.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat.flat)
+        self.ema = self.flat.flat.clone() if ema_decay else None
+        self.ema_decay, self.ema_updates = ema_decay, 0
+        self.stats = torch.zeros(2, dtype=torch.float64, device=self.flat.flat.device)
+        self.step_count = 0
+        self.group = process_group
+        self.forward_fn = forward_fn or bsrnn_se_train_forward
+
+    def set_lr(self, lr):
+        self.lr = lr
+
+    def world_size(self):
+        import torch.distributed as dist
+        return dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def loss(self, noisy, clean, lengths, fs):
+        """SEModel.forward_step [d_model.py:61-89]: returns (loss scalar, SI-SNR in dB averaged over the batch)."""
+        Bn = clean.shape[0]
+        clean, noisy = clean.reshape(Bn, -1).float(), noisy.reshape(Bn, -1).float()
+        est = self.forward_fn(self.model, noisy, lengths, fs)[0]
+        loss = multires_l1_spec_loss(clean, est).mean()
+        if torch.isnan(loss):
+            loss = est.mean() * 0
+        with torch.no_grad():
+            sisnr = -si_snr_loss(clean, est).mean()
+        return loss, sisnr
+
+    def step(self, noisy, clean, lengths, fs):
+        self.flat.zero_grad()
+        loss, sisnr = self.loss(noisy, clean, lengths, fs)
+        loss.backward()
+        self.flat.gather_grads()
+        self.apply_gradients()
+        return loss.detach(), sisnr
+
+    def allreduce_gradients(self):
+        """ONE collective over the flat gradient buffer (sum; the 1/world factor is folded into the optimizer kernel).
+        Parameters that received no gradient on this rank hold zeros, so ranks with different sample rates (different
+        K') still agree on what is reduced — the semantics of ddp_find_unused_parameters_true (train_se.py:82)."""
+        import torch.distributed as dist
+        world = self.world_size()
+        if world > 1:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
+        return world
+
+    def apply_gradients(self):
+        """allreduce (sum) of the flat gradient buffer, then the fused clip + AdamW (+EMA) tail."""
+        world = self.allreduce_gradients()
+        self.step_count += 1
+        ema_d = 0.0
+        if self.ema is not None:                                   # torch_ema: d = min(decay, (1+n)/(10+n))
+            self.ema_updates += 1
+            ema_d = min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
+        g = self.flat.grad
+        if g.is_cuda:
+            st = L.stream_ptr()
+            L.call("bsrnn_grad_sumsq", g.data_ptr(), g.numel(), self.stats.data_ptr(), st)
+            L.call("bsrnn_adamw_step", self.flat.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
+                   self.exp_avg_sq.data_ptr(), L.ptr(self.ema), g.numel(), self.stats.data_ptr(), 1.0 / world,
+                   float(self.clip or 0.0), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                   self.step_count, ema_d, st)
+        else:
+            raise L.NativeLibraryError("SETrainer.apply_gradients needs CUDA parameters (no CPU fallback)")
+
+    def grad_norm(self):
+        """Global L2 norm of the (averaged) gradients of the last step — the reference logs it as `Grad_norm`."""
+        return math.sqrt(float(self.stats[0])) / self.world_size()
