@@ -19,11 +19,12 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace bsrnn {
 using namespace umma;
 
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 8;       // barrier slots; a launch uses a.stages (4 or 8) of them
 constexpr int TC_KS = 8;            // k-cores (8 halves each) per pipeline stage -> K = 64 per stage
 constexpr int TC_THREADS = 320;
 constexpr int TC_EPI_WARPS = 8;
@@ -57,6 +58,8 @@ struct GemmTcArgs {
   int n_valid;                      // logical output columns kept
   int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
   int b_resident;                   // 1: each CTA keeps ONE weight tile in shared memory and streams A tiles only
+  int stages;                       // pipeline depth: 8 when the shared memory allows (short-K GEMMs: one tile is 4 stages,
+                                    // and a ring of one tile exposes the HBM latency of every A tile), else 4
   RowMap rows;
 };
 
@@ -192,8 +195,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   const uint32_t a_stage_bytes = TC_KS * 128 * 16;
   const uint32_t b_stage_bytes = TC_KS * BN * 16;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + TC_STAGES * a_stage_bytes;
-  const uint32_t b_region = a.b_resident ? (uint32_t)a.kcores * BN * 16 : TC_STAGES * b_stage_bytes;
+  const uint32_t NST = (uint32_t)a.stages;
+  uint8_t* sB = smem + NST * a_stage_bytes;
+  const uint32_t b_region = a.b_resident ? (uint32_t)a.kcores * BN * 16 : NST * b_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_region);
   uint64_t* full = bars;                     // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;        // [TC_STAGES]
@@ -231,6 +235,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       for (int it = 0; next_tile(a, it, m, n); ++it) {
         const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)m * a.kcores * 2048;
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
+        {                                          // the A tile three tiles ahead -> L2 (one bulk prefetch)
+          int m3, n3;
+          if (next_tile(a, it + 3, m3, n3) && (a.b_resident ? (blockIdx.x % a.n_tiles) == (m3 % a.n_tiles) : n3 == 0))
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.A) + (size_t)m3 * a.kcores * 2048, (uint32_t)a.kcores * 2048);
+        }
         for (int ks = 0; ks < nstage_k; ++ks) {
           const int kc0 = ks * TC_KS;
           const int nk = min(TC_KS, a.kcores - kc0);
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
           if (!a.b_resident)
             bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
             mma_f16_ss(d_tmem, da, db, idesc, (ks | j) != 0);
           }
           mma_commit(empty + stage);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         mma_commit(acc_full + buf);
       }
@@ -343,9 +352,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   }
 }
 
-static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch) {
-  const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)TC_STAGES * TC_KS * BN * 16;
-  return (size_t)TC_STAGES * TC_KS * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0);
+static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch, int stages) {
+  const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)stages * TC_KS * BN * 16;
+  return (size_t)stages * TC_KS * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0);
 }
 
 template <int EPI>
@@ -356,7 +365,11 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   // weight-resident schedule when several N tiles exist, the tile fits beside the A ring, and there is enough M work
   a.b_resident = (a.n_tiles > 1 && a.n_tiles <= sms && (size_t)a.kcores * a.BN * 16 <= 120 * 1024 &&
                   a.m_tiles >= 2 * (sms / a.n_tiles)) ? 1 : 0;
-  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32);
+  a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8) <= 227 * 1024 ? 8 : 4;
+  static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
+  if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
+  if (force4) a.stages = 4;
+  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages);
   BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;

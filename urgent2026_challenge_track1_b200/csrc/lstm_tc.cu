@@ -38,6 +38,7 @@
 #include "common.cuh"
 #include "umma.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace bsrnn {
 using namespace umma;
@@ -250,6 +251,156 @@ __device__ __forceinline__ void epilogue_role(const LstmTcArgs& a, uint32_t tmem
   if (prb_) { a.probe[12] = w_acc; a.probe[13] = w_busy; }
 }
 
+
+// ------------------------------------------------------------------------------------------------ v5 epilogue
+// All 12 epilogue warps serve EVERY accumulator item: thread = (row r, third T); third T owns the local units
+// [16T, 16T+16) (third 2 also unit 48).  One item then costs a warp 16-17 units instead of 49, the three warps of
+// an SM sub-partition run the same instructions at the same time (one instruction-cache stream instead of three),
+// and the item's input-projection row segment (8 x 16 B) is already in registers when the accumulator arrives
+// because the loads are issued BEFORE the wait.  profiles/r01/call19 (v4): 34 % of the epilogue's issue slots
+// were lost to instruction fetch and 23 % to L2 latency of those loads.
+//
+// Unit j of third T is h column 49Q + 16T + j -> k-core 6Q + 2T + (Q+j)/8, slot (Q+j)%8: the store pattern of a
+// third depends on Q only (compile time); T is a run-time offset.
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 p = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+// slots [S0, S1) of one 16-byte core <- h[J0 ...]; 4-byte stores for aligned pairs, 2-byte for the edges
+template <int S0, int S1, int J0>
+__device__ __forceinline__ void store_partial(__half* core, const float (&h)[16]) {
+#pragma unroll
+  for (int sl = S0; sl < S1; ++sl) {
+    const int j = J0 + (sl - S0);
+    if ((sl & 1) == 0 && sl + 1 < S1) {
+      *reinterpret_cast<uint32_t*>(core + sl) = pack_h2(h[j], h[j + 1]);
+    } else if ((sl & 1) == 1 && sl > S0) {
+      // upper half of a pair already written
+    } else {
+      core[sl] = __float2half_rn(h[j]);
+    }
+  }
+}
+template <int J0>
+__device__ __forceinline__ void store_full(__half* core, const float (&h)[16]) {
+  *reinterpret_cast<uint4*>(core) = make_uint4(pack_h2(h[J0], h[J0 + 1]), pack_h2(h[J0 + 2], h[J0 + 3]),
+                                               pack_h2(h[J0 + 4], h[J0 + 5]), pack_h2(h[J0 + 6], h[J0 + 7]));
+}
+
+// One item for one thread.  t_col: TMEM address of this thread's lane, accumulator column 64T.  g: the row's 8
+// gates_x cores of this third.  ycore: &y[..][k-core 6Q + 2T][r][0].
+template <int Q>
+__device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint32_t t_col48, const uint4 (&g)[8],
+                                          const uint2 g48, __half* ycore, float (&c)[17]) {
+  constexpr size_t CORE = 128 * 8;                  // halves between consecutive k-cores of a y tile
+  float h[16];
+  uint32_t acc[32];
+  const __half2* gh = reinterpret_cast<const __half2*>(&g[0]);
+  tmem_ld_x32(t_col, acc);
+  tmem_ld_wait();
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float2 g01 = __half22float2(gh[2 * u]), g23 = __half22float2(gh[2 * u + 1]);
+    gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
+                __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[u], h[u]);
+  }
+  tmem_ld_x32(t_col + 32, acc);
+  if (Q == 0) store_full<0>(ycore, h);
+  else store_partial<Q, 8, 0>(ycore, h);            // core A: slots Q..7 <- j = 0..7-Q
+  tmem_ld_wait();
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float2 g01 = __half22float2(gh[16 + 2 * u]), g23 = __half22float2(gh[16 + 2 * u + 1]);
+    gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
+                __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[8 + u], h[8 + u]);
+  }
+  store_full<8 - Q>(ycore + CORE, h);               // core B: j = 8-Q .. 15-Q
+  if (Q > 0) store_partial<0, Q, 16 - Q>(ycore + 2 * CORE, h);   // core C: slots 0..Q-1 <- j = 16-Q .. 15
+  if (last_third) {                                 // local unit 48 -> slot Q of core C
+    uint32_t a4[4];
+    tmem_ld_x4(t_col48, a4);
+    tmem_ld_wait();
+    const __half2* g4 = reinterpret_cast<const __half2*>(&g48);
+    const float2 g01 = __half22float2(g4[0]), g23 = __half22float2(g4[1]);
+    float h48;
+    gate_update(__uint_as_float(a4[0]) + g01.x, __uint_as_float(a4[1]) + g01.y, __uint_as_float(a4[2]) + g23.x,
+                __uint_as_float(a4[3]) + g23.y, c[16], h48);
+    ycore[2 * CORE + Q] = __float2half_rn(h48);
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
+                                               int ncl, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free) {
+  const int q = Q;
+  const int r = quad * 32 + lane;
+  const bool last_third = T == 2;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + 64 * T;
+  const uint32_t t_lane48 = tmem_base + ((uint32_t)(quad * 32) << 16) + 192;
+  const int ngroups = 2 * a.gpd;
+  const size_t y_tile = (size_t)LKC * 128 * 8;                 // halves per (step, tile, dir) of y
+  const size_t g_tile = (size_t)2 * LCL * LGC * 128 * 8;       // halves per (step, tile) of gates_x
+  const int pf_idx = (T * 4 + quad) * 32 + lane;               // 0..383: share of the next step's L2 prefetch
+  uint32_t it0 = 0;                                            // accumulator items of the groups done so far
+  uint32_t nfull = 0;                                          // bit k: parity of the next wait on acc_full[k]
+  long long w_acc = 0, w_busy = 0;
+  P_DECL(T == 0 && quad == 0 && lane == 0);
+  float c0[17], c1[17], c2[17];
+  for (int g = cid; g < ngroups; g += ncl) {
+    const Group G = group_of(a, g);
+#pragma unroll
+    for (int i = 0; i < 17; ++i) c0[i] = c1[i] = c2[i] = 0.f;
+    for (int s = 0; s < a.steps; ++s) {
+      const int p = G.d == 0 ? s : a.steps - 1 - s;
+#pragma unroll
+      for (int k = 0; k < LNS; ++k) {
+        if (k < G.nact) {
+          const size_t tile = (size_t)p * a.seq_tiles + (G.j0 + k);
+          const __half* gbase = a.gates_x + tile * g_tile + (size_t)(G.d * LCL + Q) * (LGC * 128 * 8);
+          __half* ycore = a.y + (tile * 2 + G.d) * y_tile + (size_t)(6 * Q + 2 * T) * (128 * 8) + (size_t)r * 8;
+          const uint4* gp = reinterpret_cast<const uint4*>(gbase) + (size_t)(8 * T) * 128 + r;
+          uint4 gg[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gg[i] = __ldg(gp + i * 128);
+          uint2 g48 = make_uint2(0u, 0u);
+          if (last_third) g48 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(gbase) + 24 * 128 + r));
+          if (s + 1 < a.steps) {                       // next step's input projection (53 KB = 416 lines) -> L2
+            const long step_off = (G.d == 0 ? 1 : -1) * (long)a.seq_tiles * (long)g_tile;
+            const char* nx = reinterpret_cast<const char*>(gbase + step_off);
+            prefetch_l2(nx + pf_idx * 128);
+            if (pf_idx < LGC * 16 - 384) prefetch_l2(nx + (384 + pf_idx) * 128);
+          }
+          const uint32_t it = it0 + (uint32_t)(s * G.nact + k);
+          const uint32_t buf = it & 1;
+          P_MARK(w_busy);
+          mbar_wait(acc_full + k, (nfull >> k) & 1);
+          nfull ^= 1u << k;
+          tc_fence_after();
+          P_MARK(w_acc);
+          if (k == 0) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c0);
+          else if (k == 1) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c1);
+          else epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c2);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + buf);
+          // h_t slice of this warp is stored: tell the publisher (non-blocking)
+          if (s + 1 < a.steps) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+        }
+      }
+    }
+    const int gn = g + ncl;                          // next group of this cluster switches direction?
+    if (gn < ngroups && gn / a.gpd != G.d) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_free);            // this warp consumed the last accumulator: W may go
+    }
+    it0 += (uint32_t)(a.steps * G.nact);
+  }
+  P_MARK(w_busy);
+  if (prb_) { a.probe[12] = w_acc; a.probe[13] = w_busy; }
+  (void)q;
+}
+
+template <bool V5>
 __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
@@ -271,10 +422,10 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   if (threadIdx.x == 0) {
     for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, 4);
+    for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, V5 ? 12 : 4);
     for (int i = 0; i < LNS; ++i) mbar_init(h_ready + i, LCL);
     mbar_init(w_full, 1);
-    mbar_init(w_free, 4);
+    mbar_init(w_free, V5 ? 12 : 4);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 2 * LACC);
@@ -389,7 +540,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
       for (int s = 0; s + 1 < a.steps; ++s) {
         for (int k = 0; k < G.nact; ++k) {
           // completes once the 4 epilogue warps of slot k have stored their h_t slices
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(128 + 32) : "memory");
+          if (V5) asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+          else asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(128 + 32) : "memory");
           if (lane < LCL) {
             fence_proxy_async_global();
             fence_acq_rel_cluster();
@@ -405,8 +557,11 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
     // ------------------------------------------------------------------ epilogue: 3 slots x 4 warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int k = (warp - 4) >> 2, quad = warp & 3;
-#define BSRNN_EPI_CASE(QQ) \
-  case QQ: epilogue_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free); break;
+#define BSRNN_EPI_CASE(QQ)                                                                                   \
+  case QQ:                                                                                                   \
+    if (V5) epilogue5_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);          \
+    else epilogue_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);              \
+    break;
     switch (q) {
       BSRNN_EPI_CASE(0) BSRNN_EPI_CASE(1) BSRNN_EPI_CASE(2) BSRNN_EPI_CASE(3)
       BSRNN_EPI_CASE(4) BSRNN_EPI_CASE(5) BSRNN_EPI_CASE(6) BSRNN_EPI_CASE(7)
@@ -422,7 +577,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   }
 }
 
-static int max_active_clusters() {
+template <bool V5>
+static int max_active_clusters_t() {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(LCL * 64);
   cfg.blockDim = dim3(LTHREADS);
@@ -432,9 +588,13 @@ static int max_active_clusters() {
   at[0].val.clusterDim.x = LCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM) != cudaSuccess) return -1;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel, &cfg) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(lstm_tc_kernel<V5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<V5>, &cfg) != cudaSuccess) return -1;
   return n;
+}
+static int max_active_clusters() {
+  const int a5 = max_active_clusters_t<true>(), a4 = max_active_clusters_t<false>();
+  return a5 < a4 ? a5 : a4;
 }
 
 }  // namespace bsrnn
@@ -470,7 +630,10 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
   int ncl = 2 * a.gpd;
   if (ncl > max_active) ncl = max_active;
   if (max_clusters > 0 && ncl > max_clusters) ncl = max_clusters;
-  lstm_tc_kernel<<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  static int use_v4 = -1;                 // BSRNN_LSTM_V4=1: the slot-specialised epilogue of the previous version (A/B)
+  if (use_v4 < 0) { const char* e = getenv("BSRNN_LSTM_V4"); use_v4 = (e && e[0] == '1') ? 1 : 0; }
+  if (use_v4) lstm_tc_kernel<false><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  else lstm_tc_kernel<true><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
   BSRNN_LAUNCH_OK();
   return 0;
 }
