@@ -205,6 +205,24 @@ def main():
         calls = max(1, rec_calls + rec_calls_b)
         flops_per_call = fl["lstm_rec"] / (2 * NUM_LAYER)
         achieved = flops_per_call / ((rec_ms + rec_ms_b) / calls / 1e3) / 1e12 if rec_ms + rec_ms_b > 0 else 0.0
+        # ncu --set full capture of the recurrence kernel at this workload (time axis): dram__bytes_read.sum +
+        # dram__bytes_write.sum per launch, committed under profiles/ (profiles/r01/traffic.json names the source file)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+        if os.path.exists(tp) and B == 64 and args.seconds == 10.0:
+            traffic = json.load(open(tp)).get("blstm_recurrence", {}).get("dram_bytes_per_launch")
+        # memory-bound kernel families: algorithmic bytes per call at this workload / measured time
+        hbm_peak = peaks.get("hbm_gbs", 6500.0)
+        tok = B * T * K
+        kb = lambda kc: tok * kc * 16                                   # bytes of a KB8 fp16 operand with kc k-cores
+        alg = {"inproj": kb(26) + kb(416), "fc": kb(100) + 2 * tok * NUM_CHANNEL * 4, "norm": tok * NUM_CHANNEL * 4 + kb(26)}
+        others = {}
+        for name, nbytes in alg.items():
+            ms_r, n_r = regions.get(name, (0.0, 0))
+            if ms_r > 0:
+                gbs = nbytes * n_r / (ms_r / 1e3) / 1e9
+                others[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                "algorithmic_bytes_per_call": nbytes, "calls": n_r}
         line = {
             "metric": "BSRNN audio-sec/sec enhanced at 48 kHz", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -217,11 +235,13 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "blstm_recurrence", "achieved": achieved, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                         "algorithmic_flops_per_launch": flops_per_call, "launches_per_step": calls,
+                         "other_kernels": others,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                          "regions_ms_per_step": {k: v[0] for k, v in regions.items()}},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:              # reported at N=1 only (bounded sample, rank 0)
             v, c, sample = cpu_reference_throughput(args.cpu_seconds, cores)
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": c, "kind": "port", "sample": sample}
         print(json.dumps(line))

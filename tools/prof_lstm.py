@@ -58,7 +58,7 @@ def run():
            tiles, a.maxcl, a.slots, st)
 
 
-tag = f"{'v4' if os.environ.get('BSRNN_LSTM_V4') == '1' else 'v5'} slots={a.slots} maxcl={a.maxcl}"
+tag = f"v{os.environ.get('BSRNN_LSTM_VER', '5')} slots={a.slots} maxcl={a.maxcl}"
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record()

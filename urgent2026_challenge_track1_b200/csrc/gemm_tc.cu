@@ -80,11 +80,14 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // Epilogue for NC (16 or 32) accumulator columns [c0, c0+NC) of row r of tile (m, n).
 template <int EPI, int NC>
 __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n, int r, int c0, const uint32_t* acc,
-                                               bool row_ok, long token, float& s_sum, float& s_sq, float* scr, int lane) {
+                                               bool row_ok, long token, float& s_sum, float& s_sq, float* scr, int lane,
+                                               float bias_lane) {
   const int gc0 = n * a.BN + c0;                      // global output column of acc[0]
+  // bias_lane = bias[gc0 + lane]: ONE coalesced load per chunk (issued before the accumulator wait), broadcast by
+  // shuffles.  32 dependent uniform loads per chunk were 60 % of the epilogue's stall samples (profiles/r01/call21).
   float v[NC];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) + (a.bias ? __ldg(a.bias + gc0 + i) : 0.f);
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
 
   if (EPI == EPI_F16_ROWS) {
     if (!row_ok) return;
@@ -305,21 +308,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           for (int off = half * 128; off < nbytes; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
         }
       }
+      float bl[4] = {0.f, 0.f, 0.f, 0.f};          // this lane's bias column of each of the warp's (<= 4) chunks
+      if (a.bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = (ch0 + i) * 32 + lane;
+          if (ch0 + i < ch1 && c < BN) bl[i] = __ldg(a.bias + n * BN + c);
+        }
+      }
       mbar_wait(acc_full + buf, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
-      for (int ch = ch0; ch < ch1; ++ch) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = ch0 + i;
+        if (ch >= ch1) break;
         const int c0 = ch * 32;
         if (c0 + 32 <= BN) {
           uint32_t acc[32];
           tmem_ld_x32(t_addr + c0, acc);
           tmem_ld_wait();
-          epilogue_chunk<EPI, 32>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane);
+          epilogue_chunk<EPI, 32>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
         } else {                               // BN % 32 == 16
           uint32_t acc[16];
           tmem_ld_x16(t_addr + c0, acc);
           tmem_ld_wait();
-          epilogue_chunk<EPI, 16>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane);
+          epilogue_chunk<EPI, 16>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
         }
       }
       tc_fence_before();

@@ -329,7 +329,52 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
   }
 }
 
+// Pipelined variant (v6): 4 chunks of 4 units (16 accumulator columns each, so 16 instead of 32 registers hold the
+// accumulator), and the gates registers of a chunk are refilled with the NEXT item's values as soon as they are consumed.
 template <int Q>
+__device__ __forceinline__ void epi6_item(uint32_t t_col, bool last_third, uint32_t t_col48, uint4 (&g)[8], uint2& g48,
+                                          const uint4* gnext, bool have_next, __half* ycore, float (&c)[17]) {
+  constexpr size_t CORE = 128 * 8;
+  float h[16];
+  uint32_t acc[16];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    tmem_ld_x16(t_col + 16 * ch, acc);
+    tmem_ld_wait();
+    const __half2* gh = reinterpret_cast<const __half2*>(&g[2 * ch]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 g01 = __half22float2(gh[2 * u]), g23 = __half22float2(gh[2 * u + 1]);
+      gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
+                  __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[4 * ch + u],
+                  h[4 * ch + u]);
+    }
+    if (have_next) {
+      g[2 * ch] = __ldg(gnext + (2 * ch) * 128);
+      g[2 * ch + 1] = __ldg(gnext + (2 * ch + 1) * 128);
+    }
+    if (ch == 1) {
+      if (Q == 0) store_full<0>(ycore, h);
+      else store_partial<Q, 8, 0>(ycore, h);          // core A: slots Q..7 <- j = 0..7-Q
+    }
+  }
+  store_full<8 - Q>(ycore + CORE, h);                 // core B: j = 8-Q .. 15-Q
+  if (Q > 0) store_partial<0, Q, 16 - Q>(ycore + 2 * CORE, h);   // core C: slots 0..Q-1 <- j = 16-Q .. 15
+  if (last_third) {                                   // local unit 48 -> slot Q of core C
+    uint32_t a4[4];
+    tmem_ld_x4(t_col48, a4);
+    tmem_ld_wait();
+    const __half2* g4 = reinterpret_cast<const __half2*>(&g48);
+    const float2 g01 = __half22float2(g4[0]), g23 = __half22float2(g4[1]);
+    float h48;
+    gate_update(__uint_as_float(a4[0]) + g01.x, __uint_as_float(a4[1]) + g01.y, __uint_as_float(a4[2]) + g23.x,
+                __uint_as_float(a4[3]) + g23.y, c[16], h48);
+    if (have_next) g48 = __ldg(reinterpret_cast<const uint2*>(gnext + (24 - 8 * 2) * 128));   // core 24 (T = 2: gnext -> core 16)
+    ycore[2 * CORE + Q] = __float2half_rn(h48);
+  }
+}
+
+template <int Q, bool PIPE>
 __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
                                                int ncl, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free) {
   const int q = Q;
@@ -350,6 +395,15 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
     const Group G = group_of(a, g);
 #pragma unroll
     for (int i = 0; i < 17; ++i) c0[i] = c1[i] = c2[i] = 0.f;
+    uint4 gg[8];
+    uint2 g48 = make_uint2(0u, 0u);
+    if (PIPE) {                                      // first item of the group: (step 0, slot 0)
+      const size_t tile = (size_t)(G.d == 0 ? 0 : a.steps - 1) * a.seq_tiles + G.j0;
+      const uint4* gb4 = reinterpret_cast<const uint4*>(a.gates_x + tile * g_tile + (size_t)(G.d * LCL + Q) * (LGC * 128 * 8));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gg[i] = __ldg(gb4 + (size_t)(8 * T + i) * 128 + r);
+      if (last_third) g48 = __ldg(reinterpret_cast<const uint2*>(gb4 + 24 * 128 + r));
+    }
     for (int s = 0; s < a.steps; ++s) {
       const int p = G.d == 0 ? s : a.steps - 1 - s;
 #pragma unroll
@@ -359,11 +413,19 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
           const __half* gbase = a.gates_x + tile * g_tile + (size_t)(G.d * LCL + Q) * (LGC * 128 * 8);
           __half* ycore = a.y + (tile * 2 + G.d) * y_tile + (size_t)(6 * Q + 2 * T) * (128 * 8) + (size_t)r * 8;
           const uint4* gp = reinterpret_cast<const uint4*>(gbase) + (size_t)(8 * T) * 128 + r;
-          uint4 gg[8];
+          const uint4* gnext = gp;                   // PIPE: this thread's segment of the next item it will serve
+          bool have_next = false;
+          if (PIPE) {
+            const bool wrap = k + 1 >= G.nact;
+            have_next = !wrap || s + 1 < a.steps;
+            // tiles of one step are consecutive; the next step is seq_tiles tiles further (forward) or back (reverse)
+            const long dt = wrap ? (long)(G.d == 0 ? a.seq_tiles : -a.seq_tiles) - (G.nact - 1) : 1;
+            gnext = gp + dt * (long)(g_tile / 8);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gg[i] = __ldg(gp + i * 128);
-          uint2 g48 = make_uint2(0u, 0u);
-          if (last_third) g48 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(gbase) + 24 * 128 + r));
+            for (int i = 0; i < 8; ++i) gg[i] = __ldg(gp + i * 128);
+            if (last_third) g48 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(gbase) + 24 * 128 + r));
+          }
           if (s + 1 < a.steps) {                       // next step's input projection (53 KB = 416 lines) -> L2
             const long step_off = (G.d == 0 ? 1 : -1) * (long)a.seq_tiles * (long)g_tile;
             const char* nx = reinterpret_cast<const char*>(gbase + step_off);
@@ -377,9 +439,15 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
           nfull ^= 1u << k;
           tc_fence_after();
           P_MARK(w_acc);
-          if (k == 0) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c0);
-          else if (k == 1) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c1);
-          else epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c2);
+          if (PIPE) {
+            if (k == 0) epi6_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c0);
+            else if (k == 1) epi6_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c1);
+            else epi6_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c2);
+          } else {
+            if (k == 0) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c0);
+            else if (k == 1) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c1);
+            else epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c2);
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + buf);
@@ -400,8 +468,10 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
   (void)q;
 }
 
-template <bool V5>
+template <int VER>   // 4: slot-specialised epilogue; 5: all-warps epilogue; 6: 5 + multicast h loads + pipelined gate loads
 __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
+  constexpr bool V5 = VER >= 5;
+  constexpr bool MC = VER >= 6;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + L_W_BYTES;
@@ -420,7 +490,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   const int cid = cluster_id_x(), ncl = num_clusters_x();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, MC ? LCL : 1); }
     for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
     for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, V5 ? 12 : 4);
     for (int i = 0; i < LNS; ++i) mbar_init(h_ready + i, LCL);
@@ -477,7 +547,15 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
               mbar_wait(empty + stage, phase ^ 1);
               P_MARK(w_e);
               mbar_expect_tx(full + stage, L_A_STAGE);
-              bulk_g2s(sA + stage * L_A_STAGE, src + (size_t)ks * L_A_STAGE, L_A_STAGE, full + stage);
+              if (MC) {
+                // every CTA of the cluster needs the same h tile: each fetches 1/8 of the stage and multicasts it into
+                // the same ring slot of all 8 (empty[stage] counts the 8 MMA commits, so the slot is free everywhere)
+                constexpr uint32_t SL = L_A_STAGE / LCL;
+                bulk_g2s_multicast(sA + stage * L_A_STAGE + q * SL, src + (size_t)ks * L_A_STAGE + q * SL, SL, full + stage,
+                                   (uint16_t)((1u << LCL) - 1));
+              } else {
+                bulk_g2s(sA + stage * L_A_STAGE, src + (size_t)ks * L_A_STAGE, L_A_STAGE, full + stage);
+              }
               if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -523,7 +601,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
               const uint64_t db = smem_desc_kb8(sw + (ks * LKS + jk * 2) * (LBN * 16), LBN * 16, 128);
               mma_f16_ss(d_tmem, da, db, idesc, (ks | jk) != 0);
             }
-            mma_commit(empty + stage);
+            if (MC) mma_commit_multicast(empty + stage, (uint16_t)((1u << LCL) - 1));
+            else mma_commit(empty + stage);
             if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
           }
           mma_commit(acc_full + (i % G.nact));
@@ -559,7 +638,8 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
     const int k = (warp - 4) >> 2, quad = warp & 3;
 #define BSRNN_EPI_CASE(QQ)                                                                                   \
   case QQ:                                                                                                   \
-    if (V5) epilogue5_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);          \
+    if (MC) epilogue5_role<QQ, true>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);    \
+    else if (V5) epilogue5_role<QQ, false>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free); \
     else epilogue_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);              \
     break;
     switch (q) {
@@ -577,7 +657,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   }
 }
 
-template <bool V5>
+template <int V5>
 static int max_active_clusters_t() {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(LCL * 64);
@@ -593,8 +673,9 @@ static int max_active_clusters_t() {
   return n;
 }
 static int max_active_clusters() {
-  const int a5 = max_active_clusters_t<true>(), a4 = max_active_clusters_t<false>();
-  return a5 < a4 ? a5 : a4;
+  const int a6 = max_active_clusters_t<6>(), a5 = max_active_clusters_t<5>(), a4 = max_active_clusters_t<4>();
+  const int m = a5 < a4 ? a5 : a4;
+  return a6 < m ? a6 : m;
 }
 
 }  // namespace bsrnn
@@ -630,10 +711,14 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
   int ncl = 2 * a.gpd;
   if (ncl > max_active) ncl = max_active;
   if (max_clusters > 0 && ncl > max_clusters) ncl = max_clusters;
-  static int use_v4 = -1;                 // BSRNN_LSTM_V4=1: the slot-specialised epilogue of the previous version (A/B)
-  if (use_v4 < 0) { const char* e = getenv("BSRNN_LSTM_V4"); use_v4 = (e && e[0] == '1') ? 1 : 0; }
-  if (use_v4) lstm_tc_kernel<false><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
-  else lstm_tc_kernel<true><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  // BSRNN_LSTM_VER=4|5|6 selects the schedule for A/B timing.  Default 5: the multicast / pipelined-gates variant (6)
+  // measured 8.17 vs 8.01 ms (time axis) and 6.85 vs 6.81 ms (band axis) at BASELINE config 2 (profiles/r01/call22):
+  // the kernel is bound by the 60 KB h ring (ring bytes / L2 latency), not by L2 traffic or the gate loads.
+  static int ver = -1;
+  if (ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); ver = (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 5; }
+  if (ver == 4) lstm_tc_kernel<4><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  else if (ver == 5) lstm_tc_kernel<5><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  else lstm_tc_kernel<6><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
   BSRNN_LAUNCH_OK();
   return 0;
 }
