@@ -162,7 +162,8 @@ def main():
         model(x_dev, lens, FS)
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if os.environ.get("BSRNN_BENCH_NO_NVML", "0") != "1":     # A/B switch: NVML polling off (clocks then read null)
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -182,12 +183,17 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler.is_alive():
+        sampler.join(timeout=2)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    clk = sampler.summary()
+    mine = torch.tensor([ms, ms_e2e, float(clk["sm_mhz"] or 0)], dtype=torch.float64, device=dev)
+    per_rank = [mine]
+    if world > 1:                                            # the only exchange: every rank's own device time
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(per_rank, mine)
+    per_rank = torch.stack(per_rank).cpu()
+    ms, ms_e2e = float(per_rank[:, 0].max()), float(per_rank[:, 1].max())      # max over ranks
     audio_s = world * B * args.seconds * args.steps
     value, e2e = audio_s / (ms / 1e3), audio_s / (ms_e2e / 1e3)
 
@@ -233,7 +239,10 @@ def main():
                        "launch": "host launches" if args.no_graph else "CUDA graph replay of the per-step kernel sequence"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * n * 4 + B * 4, "d2h_bytes_per_step": B * n * 4},
             "gpu_launches": int(launches),
-            "clocks": sampler.summary(),
+            "clocks": clk,
+            "per_rank": {"ms_per_step": [round(float(v) / args.steps, 3) for v in per_rank[:, 0]],
+                         "e2e_ms_per_step": [round(float(v) / args.steps, 3) for v in per_rank[:, 1]],
+                         "sm_mhz": [int(v) for v in per_rank[:, 2]]},
             "roofline": {"bound": "tensor", "kernel": "blstm_recurrence", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                          "algorithmic_flops_per_launch": flops_per_call, "launches_per_step": calls,

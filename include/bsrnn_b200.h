@@ -159,6 +159,12 @@ int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, const voi
 int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
                                  int steps, int seq_tiles, int max_clusters, int slots, void* stream);
 int bsrnn_blstm_tc_max_clusters(void);
+/* Co-resident 16-CTA clusters of the CTA-pair schedule (BSRNN_LSTM_VER=7: cta_group::2 MMAs, half of the W_hh slice
+ * per CTA); <= 0 when the device cannot host one. */
+int bsrnn_blstm_tc_max_pair_clusters(void);
+/* Debug / A-B timing: selects the recurrence schedule (4, 5, 6: 8-CTA clusters; 7: CTA pairs); any other value
+ * returns to the BSRNN_LSTM_VER environment default. */
+void bsrnn_debug_set_lstm_schedule(int ver);
 
 /* ---------------------------------------------------------------------------------------------- training (f32)
  * The sequential parts of the BLSTM forward/backward for train_se.py [reference d_model.py:61-95 -> autograd through

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p],
     "bsrnn_blstm_tc_max_clusters": [],
+    "bsrnn_blstm_tc_max_pair_clusters": [],
+    "bsrnn_debug_set_lstm_schedule": [c_int],
     "bsrnn_blstm_train_fwd_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long,
                                   c_long, c_long, c_void_p],
     "bsrnn_blstm_train_bwd_f32": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

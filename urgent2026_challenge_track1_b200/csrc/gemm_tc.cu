@@ -58,6 +58,7 @@ struct GemmTcArgs {
   int n_valid;                      // logical output columns kept
   int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
   int b_resident;                   // 1: each CTA keeps ONE weight tile in shared memory and streams A tiles only
+  int pf_dist;                      // A tile this many tiles ahead is bulk-prefetched into L2 (0 = off)
   int stages;                       // pipeline depth: 8 when the shared memory allows (short-K GEMMs: one tile is 4 stages,
                                     // and a ring of one tile exposes the HBM latency of every A tile), else 4
   RowMap rows;
@@ -238,9 +239,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       for (int it = 0; next_tile(a, it, m, n); ++it) {
         const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)m * a.kcores * 2048;
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
-        {                                          // the A tile three tiles ahead -> L2 (one bulk prefetch)
+        if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
           int m3, n3;
-          if (next_tile(a, it + 3, m3, n3) && (a.b_resident ? (blockIdx.x % a.n_tiles) == (m3 % a.n_tiles) : n3 == 0))
+          if (next_tile(a, it + a.pf_dist, m3, n3) && (a.b_resident ? (blockIdx.x % a.n_tiles) == (m3 % a.n_tiles) : n3 == 0))
             bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.A) + (size_t)m3 * a.kcores * 2048, (uint32_t)a.kcores * 2048);
         }
         for (int ks = 0; ks < nstage_k; ++ks) {
@@ -383,6 +384,15 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
   if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
   if (force4) a.stages = 4;
+  // L2 prefetch distance of the A tiles.  Streaming mode has one prefetcher per CTA: at K = 800 (Linear 4N->N, A tile
+  // 205 KB) three tiles ahead on 148 CTAs is 91 MB of prefetched lines in a 126 MB L2 that also carries the residual
+  // stream -- they were evicted before use and fetched twice (ncu: 9.3 GB read for 5.2 GB algorithmic,
+  // profiles/r01/call21_ncu_full_gemm_fc_raw.csv).  Keep the prefetched set under ~32 MB.
+  a.pf_dist = 3;
+  if (!a.b_resident && (size_t)a.kcores * 2048 * sms * 3 > ((size_t)32 << 20)) a.pf_dist = 1;
+  static int pfd = -2;                    // BSRNN_GEMM_PFDIST=0..3 overrides (A/B timing)
+  if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
+  if (pfd >= 0) a.pf_dist = pfd;
   const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages);
   BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int total = a.m_tiles * a.n_tiles;

@@ -291,7 +291,7 @@ __device__ __forceinline__ void store_full(__half* core, const float (&h)[16]) {
 // gates_x cores of this third.  ycore: &y[..][k-core 6Q + 2T][r][0].
 template <int Q>
 __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint32_t t_col48, const uint4 (&g)[8],
-                                          const uint2 g48, __half* ycore, float (&c)[17]) {
+                                          const uint2 g48, __half* ycore, float (&c)[17], bool st = true) {
   constexpr size_t CORE = 128 * 8;                  // halves between consecutive k-cores of a y tile
   float h[16];
   uint32_t acc[32];
@@ -305,8 +305,10 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
                 __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[u], h[u]);
   }
   tmem_ld_x32(t_col + 32, acc);
-  if (Q == 0) store_full<0>(ycore, h);
-  else store_partial<Q, 8, 0>(ycore, h);            // core A: slots Q..7 <- j = 0..7-Q
+  if (st) {
+    if (Q == 0) store_full<0>(ycore, h);
+    else store_partial<Q, 8, 0>(ycore, h);          // core A: slots Q..7 <- j = 0..7-Q
+  }
   tmem_ld_wait();
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
@@ -314,8 +316,10 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
     gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
                 __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[8 + u], h[8 + u]);
   }
-  store_full<8 - Q>(ycore + CORE, h);               // core B: j = 8-Q .. 15-Q
-  if (Q > 0) store_partial<0, Q, 16 - Q>(ycore + 2 * CORE, h);   // core C: slots 0..Q-1 <- j = 16-Q .. 15
+  if (st) {
+    store_full<8 - Q>(ycore + CORE, h);             // core B: j = 8-Q .. 15-Q
+    if (Q > 0) store_partial<0, Q, 16 - Q>(ycore + 2 * CORE, h);   // core C: slots 0..Q-1 <- j = 16-Q .. 15
+  }
   if (last_third) {                                 // local unit 48 -> slot Q of core C
     uint32_t a4[4];
     tmem_ld_x4(t_col48, a4);
@@ -325,7 +329,7 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
     float h48;
     gate_update(__uint_as_float(a4[0]) + g01.x, __uint_as_float(a4[1]) + g01.y, __uint_as_float(a4[2]) + g23.x,
                 __uint_as_float(a4[3]) + g23.y, c[16], h48);
-    ycore[2 * CORE + Q] = __float2half_rn(h48);
+    if (st) ycore[2 * CORE + Q] = __float2half_rn(h48);
   }
 }
 
@@ -657,6 +661,331 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   }
 }
 
+// ================================================================================================ v7: CTA pairs
+// Same decomposition as v5, but the cluster has 16 CTAs = 8 CTA PAIRS and every MMA is a cta_group::2 instruction
+// (M = 256, N = 208): pair P = rank/2 owns hidden units [49P, 49P+49); its even CTA serves sequence tile 2j, its odd
+// CTA tile 2j+1 of the slot's tile pair j, and each keeps only HALF of the pair's W_hh slice (104 x 400 fp16 = 83 KB)
+// in shared memory.  What that buys over v5 (profiles/r01/call20 ncu: tensor pipe 53 % of active cycles, shared-memory
+// tensor wavefronts at 81 % of the tensor-active share, producer blocked on a 60 KB ring):
+//   * the tensor core of each SM reads A (4 KB) + half of B (3.3 KB) per MMA instead of 4 + 6.6 KB,
+//   * the h ring grows from 3 to 6 stages (120 KB > one whole 100 KB tile), so the next item's tile streams in while
+//     the current one is consumed and the L2 latency of a refill is no longer exposed.
+// Protocol differences: the even CTA (leader) issues all MMAs and needs BOTH CTAs' ring stages — warp 1 of the odd CTA
+// relays its `full` completions to the leader's `pfull` barriers (remote arrive); tcgen05.commit multicasts to both
+// CTAs' `empty` / `acc_full`; both CTAs' epilogue warps arrive on the LEADER's acc_empty (count 24); h_ready counts the
+// 8 CTAs of the same parity (they exchange the h of the same sequence tile).  An odd tile count leaves the odd CTAs of
+// the last pair without a tile: they feed zeros, skip loads and stores, and keep the barrier protocol.
+constexpr int PCL = 16;
+constexpr int PBH = LBN / 2;                               // 104 rows of B per CTA
+constexpr int PSTAGES = 6;
+constexpr uint32_t P_W_BYTES = LKC * PBH * 16;             // 83200
+constexpr int P_NBARS = 3 * PSTAGES + LNS + 2 + LNS + 3;
+constexpr size_t P_SMEM = P_W_BYTES + PSTAGES * L_A_STAGE + P_NBARS * 8 + 16;
+static_assert(P_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+
+__device__ __forceinline__ Group group_of_p(const LstmTcArgs& a, int g) {      // j0 / nact in tile PAIRS
+  const int ptiles = (a.seq_tiles + 1) >> 1;
+  Group r;
+  r.d = g / a.gpd;
+  const int gi = g - r.d * a.gpd;
+  r.j0 = (int)(((long)gi * ptiles) / a.gpd);
+  r.nact = (int)(((long)(gi + 1) * ptiles) / a.gpd) - r.j0;
+  return r;
+}
+
+template <int Q>
+__device__ __forceinline__ void epilogue7_role(const LstmTcArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
+                                               int ncl, int e, uint32_t leader, uint64_t* acc_full, uint64_t* acc_empty,
+                                               uint64_t* w_free) {
+  const int r = quad * 32 + lane;
+  const bool last_third = T == 2;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + 64 * T;
+  const uint32_t t_lane48 = tmem_base + ((uint32_t)(quad * 32) << 16) + 192;
+  const int ngroups = 2 * a.gpd;
+  const size_t y_tile = (size_t)LKC * 128 * 8;                 // halves per (step, tile, dir) of y
+  const size_t g_tile = (size_t)2 * LCL * LGC * 128 * 8;       // halves per (step, tile) of gates_x
+  const int pf_idx = (T * 4 + quad) * 32 + lane;               // 0..383: share of the next step's L2 prefetch
+  uint32_t it0 = 0, nfull = 0;
+  float c0[17], c1[17], c2[17];
+  for (int g = cid; g < ngroups; g += ncl) {
+    const Group G = group_of_p(a, g);
+#pragma unroll
+    for (int i = 0; i < 17; ++i) c0[i] = c1[i] = c2[i] = 0.f;
+    for (int s = 0; s < a.steps; ++s) {
+      const int p = G.d == 0 ? s : a.steps - 1 - s;
+#pragma unroll
+      for (int k = 0; k < LNS; ++k) {
+        if (k < G.nact) {
+          const int j = 2 * (G.j0 + k) + e;
+          const bool valid = j < a.seq_tiles;
+          const size_t tile = (size_t)p * a.seq_tiles + (valid ? j : 0);
+          const __half* gbase = a.gates_x + tile * g_tile + (size_t)(G.d * LCL + Q) * (LGC * 128 * 8);
+          __half* ycore = a.y + (tile * 2 + G.d) * y_tile + (size_t)(6 * Q + 2 * T) * (128 * 8) + (size_t)r * 8;
+          // a missing tile (odd tile count) is computed on tile 0's input projection and never stored
+          uint4 gg[8];
+          uint2 g48 = make_uint2(0u, 0u);
+          const uint4* gp = reinterpret_cast<const uint4*>(gbase) + (size_t)(8 * T) * 128 + r;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gg[i] = __ldg(gp + i * 128);
+          if (last_third) g48 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(gbase) + 24 * 128 + r));
+          if (s + 1 < a.steps) {                         // next step's input projection (53 KB = 416 lines) -> L2
+            const long step_off = (G.d == 0 ? 1 : -1) * (long)a.seq_tiles * (long)g_tile;
+            const char* nx = reinterpret_cast<const char*>(gbase + step_off);
+            prefetch_l2(nx + pf_idx * 128);
+            if (pf_idx < LGC * 16 - 384) prefetch_l2(nx + (384 + pf_idx) * 128);
+          }
+          const uint32_t it = it0 + (uint32_t)(s * G.nact + k);
+          const uint32_t buf = it & 1;
+          mbar_wait(acc_full + k, (nfull >> k) & 1);
+          nfull ^= 1u << k;
+          tc_fence_after();
+          if (k == 0) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c0, valid);
+          else if (k == 1) epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c1, valid);
+          else epi5_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, ycore, c2, valid);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty + buf, leader);   // the pair's MMA issuer counts both CTAs' warps
+          if (s + 1 < a.steps) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+        }
+      }
+    }
+    const int gn = g + ncl;                          // next group of this cluster switches direction?
+    if (gn < ngroups && gn / a.gpd != G.d) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_free);            // this warp consumed the last accumulator: W may go
+    }
+    it0 += (uint32_t)(a.steps * G.nact);
+  }
+}
+
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_tc2_kernel(const LstmTcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + P_W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + PSTAGES * L_A_STAGE);
+  uint64_t* full = bars;                       // [PSTAGES] this CTA's ring stage landed
+  uint64_t* empty = full + PSTAGES;            // [PSTAGES] MMAs that read the stage retired (multicast commit)
+  uint64_t* pfull = empty + PSTAGES;           // [PSTAGES] leader only: the odd CTA's stage landed (relayed)
+  uint64_t* acc_full = pfull + PSTAGES;        // [LNS]
+  uint64_t* acc_empty = acc_full + LNS;        // [2]   leader only: 24 epilogue warps of the pair
+  uint64_t* h_ready = acc_empty + 2;           // [LNS] 8 arrivals: the CTAs of this parity
+  uint64_t* w_full = h_ready + LNS;
+  uint64_t* w_free = w_full + 1;
+  uint64_t* pw_full = w_free + 1;              // leader only: the odd CTA's W half landed (relayed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pw_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t q = rank >> 1;                // pair = unit slice
+  const int e = (int)(rank & 1u);              // tile parity served by this CTA
+  const uint32_t leader = rank & ~1u;
+  const int cid = cluster_id_x(), ncl = num_clusters_x();
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < PSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(pfull + i, 1); }
+    for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, 24);
+    for (int i = 0; i < LNS; ++i) mbar_init(h_ready + i, PCL / 2);
+    mbar_init(w_full, 1);
+    mbar_init(w_free, 12);
+    mbar_init(pw_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 2 * LACC);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                       // every CTA's barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int ngroups = 2 * a.gpd;
+  const size_t y_tile = (size_t)LKC * 128 * 8;         // halves per (step, tile, dir)
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: W half + this CTA's h tiles
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, hphase = 0, wfphase = 0;
+      int cur_dir = -1;
+      long long w_h = 0, w_e = 0, w_o = 0;
+      P_DECL(e == 0);
+      for (int g = cid; g < ngroups; g += ncl) {
+        const Group G = group_of_p(a, g);
+        if (G.d != cur_dir) {
+          if (cur_dir >= 0) {
+            mbar_wait(w_free, wfphase);
+            wfphase ^= 1;
+          }
+          mbar_expect_tx(w_full, P_W_BYTES);
+          // rows [104e, 104e+104) of every k-core of the pair's packed slice [50][208][8]
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_pack) + ((size_t)G.d * LCL + q) * L_W_BYTES + (size_t)e * (PBH * 16);
+          for (int kc = 0; kc < LKC; ++kc) bulk_g2s(sW + kc * (PBH * 16), src + (size_t)kc * (LBN * 16), PBH * 16, w_full);
+          cur_dir = G.d;
+        }
+        for (int s = 0; s < a.steps; ++s) {
+          const int p_prev = G.d == 0 ? s - 1 : a.steps - s;        // position whose h feeds this step
+          for (int k = 0; k < G.nact; ++k) {
+            const int j = 2 * (G.j0 + k) + e;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(a.zero_tile);
+            if (s > 0) {
+              P_MARK(w_o);
+              mbar_wait_cluster(h_ready + k, (hphase >> k) & 1);
+              P_MARK(w_h);
+              hphase ^= 1u << k;
+              fence_proxy_async_global();
+              if (j < a.seq_tiles)
+                src = reinterpret_cast<const uint8_t*>(a.y + (((size_t)p_prev * a.seq_tiles + j) * 2 + G.d) * y_tile);
+            }
+            for (int ks = 0; ks < LNST; ++ks) {
+              P_MARK(w_o);
+              mbar_wait(empty + stage, phase ^ 1);
+              P_MARK(w_e);
+              mbar_expect_tx(full + stage, L_A_STAGE);
+              bulk_g2s(sA + stage * L_A_STAGE, src + (size_t)ks * L_A_STAGE, L_A_STAGE, full + stage);
+              if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+      P_MARK(w_o);
+      if (prb_) { a.probe[0] = w_h; a.probe[1] = w_e; a.probe[2] = w_o; }
+    }
+  } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (lane == 0 && e == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA of the pair)
+      const uint32_t idesc = idesc_f16_f32(256, LBN);
+      const uint16_t pair_mask = (uint16_t)(3u << rank);
+      uint32_t stage = 0, phase = 0, it = 0, wphase = 0;
+      int cur_dir = -1;
+      const uint32_t sw = smem_u32(sW);
+      long long w_a = 0, w_f = 0, w_o = 0;
+      P_DECL(e == 0);
+      for (int g = cid; g < ngroups; g += ncl) {
+        const Group G = group_of_p(a, g);
+        if (G.d != cur_dir) {
+          mbar_wait(w_full, wphase);
+          mbar_wait_cluster(pw_full, wphase);
+          wphase ^= 1;
+          cur_dir = G.d;
+        }
+        const int nitems = a.steps * G.nact;
+        for (int i = 0; i < nitems; ++i, ++it) {
+          const uint32_t buf = it & 1;
+          P_MARK(w_o);
+          mbar_wait_cluster(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+          P_MARK(w_a);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * LACC;
+          for (int ks = 0; ks < LNST; ++ks) {
+            P_MARK(w_o);
+            mbar_wait(full + stage, phase);
+            mbar_wait_cluster(pfull + stage, phase);
+            P_MARK(w_f);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(sA + stage * L_A_STAGE);
+#pragma unroll
+            for (int jk = 0; jk < LKS / 2; ++jk) {
+              const uint64_t da = smem_desc_kb8(sa + jk * 2 * 2048, 2048, 128);
+              const uint64_t db = smem_desc_kb8(sw + (ks * LKS + jk * 2) * (PBH * 16), PBH * 16, 128);
+              mma_f16_ss_2cta(d_tmem, da, db, idesc, (ks | jk) != 0);
+            }
+            mma_commit2_multicast(empty + stage, pair_mask);
+            if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+          }
+          mma_commit2_multicast(acc_full + (i % G.nact), pair_mask);
+        }
+      }
+      P_MARK(w_o);
+      if (prb_) { a.probe[4] = w_a; a.probe[5] = w_f; a.probe[6] = w_o; }
+    } else if (lane == 0) {
+      // ---------------------------------------------------------------- relay (odd CTA): my stages -> leader's pfull
+      uint32_t stage = 0, phase = 0, wphase = 0;
+      int cur_dir = -1;
+      for (int g = cid; g < ngroups; g += ncl) {
+        const Group G = group_of_p(a, g);
+        if (G.d != cur_dir) {
+          mbar_wait(w_full, wphase);
+          wphase ^= 1;
+          mbar_arrive_cluster(pw_full, leader);
+          cur_dir = G.d;
+        }
+        const int nfills = a.steps * G.nact * LNST;
+        for (int i = 0; i < nfills; ++i) {
+          mbar_wait(full + stage, phase);
+          mbar_arrive_cluster(pfull + stage, leader);
+          if (++stage == PSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ publisher
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    for (int g = cid; g < ngroups; g += ncl) {
+      const Group G = group_of_p(a, g);
+      for (int s = 0; s + 1 < a.steps; ++s) {
+        for (int k = 0; k < G.nact; ++k) {
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+          if (lane < PCL / 2) {
+            fence_proxy_async_global();
+            fence_acq_rel_cluster();
+            mbar_arrive_cluster_relaxed(h_ready + k, 2 * lane + e);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // idle 4th warp of warpgroup 0
+  } else {
+    // ------------------------------------------------------------------ epilogue: 12 warps, every item
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int k = (warp - 4) >> 2, quad = warp & 3;
+#define BSRNN_EPI7_CASE(QQ) \
+  case QQ: epilogue7_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, e, leader, acc_full, acc_empty, w_free); break;
+    switch (q) {
+      BSRNN_EPI7_CASE(0) BSRNN_EPI7_CASE(1) BSRNN_EPI7_CASE(2) BSRNN_EPI7_CASE(3)
+      BSRNN_EPI7_CASE(4) BSRNN_EPI7_CASE(5) BSRNN_EPI7_CASE(6) BSRNN_EPI7_CASE(7)
+    }
+#undef BSRNN_EPI7_CASE
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                       // no CTA exits (or frees TMEM) while peers may still arrive / read
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * LACC);
+  }
+}
+
+static cudaError_t launch_v7(const LstmTcArgs& a, int ncl, cudaStream_t st, int* occupancy) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(lstm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
+    if (e1 != cudaSuccess) return e1;
+    e1 = cudaFuncSetAttribute(lstm_tc2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e1 != cudaSuccess) return e1;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((occupancy ? 16 : ncl) * PCL);
+  cfg.blockDim = dim3(LTHREADS);
+  cfg.dynamicSmemBytes = P_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = PCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (occupancy) return cudaOccupancyMaxActiveClusters(occupancy, lstm_tc2_kernel, &cfg);
+  return cudaLaunchKernelEx(&cfg, lstm_tc2_kernel, a);
+}
+static int max_active_clusters_v7() {
+  int n = 0;
+  LstmTcArgs dummy{};
+  if (launch_v7(dummy, 0, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
 template <int V5>
 static int max_active_clusters_t() {
   cudaLaunchConfig_t cfg = {};
@@ -688,6 +1017,11 @@ extern "C" void bsrnn_debug_set_lstm_probe(void* p, int cid) {
   g_lstm_probe_cid = cid;
 }
 
+// Recurrence schedule: 4 / 5 / 6 (8-CTA clusters, see lstm_tc_kernel) or 7 (CTA pairs, lstm_tc2_kernel); < 0 = take
+// BSRNN_LSTM_VER from the environment at the next call (default 5).
+static int g_lstm_ver = -1;
+extern "C" void bsrnn_debug_set_lstm_schedule(int ver) { g_lstm_ver = (ver >= 4 && ver <= 7) ? ver : -1; }
+
 // slots: sequence tiles a cluster interleaves (1..3; <= 0 = 3).
 extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
                                             int steps, int seq_tiles, int max_clusters, int slots, void* stream) {
@@ -708,14 +1042,35 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
     }
     max_active = n;
   }
+  if (g_lstm_ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); g_lstm_ver = (e && e[0] >= '4' && e[0] <= '7') ? e[0] - '0' : 5; }
+  const int ver = g_lstm_ver;
+  if (ver == 7) {
+    // CTA-pair schedule: units are (direction, PAIR of sequence tiles); 16-CTA clusters
+    static int max7 = -2;
+    if (max7 == -2) max7 = max_active_clusters_v7();
+    if (max7 <= 0) {
+      set_error("blstm_recurrence_tc: no co-resident 16-CTA cluster (512 threads, %zu B shared memory)", P_SMEM);
+      return 2;
+    }
+    const int ptiles = (seq_tiles + 1) / 2;
+    int sl = slots > ptiles ? ptiles : slots;
+    a.gpd = (ptiles + sl - 1) / sl;
+    int want = max7;                                 // spread over all co-resident clusters when there are few units
+    if (max_clusters > 0 && want > max_clusters) want = max_clusters;
+    if (2 * a.gpd < want) { a.gpd = want / 2 < ptiles ? want / 2 : ptiles; if (a.gpd < 1) a.gpd = 1; }
+    int ncl7 = 2 * a.gpd;
+    if (ncl7 > want) ncl7 = want;
+    cudaError_t le = launch_v7(a, ncl7, (cudaStream_t)stream, nullptr);
+    if (le != cudaSuccess) { set_error("blstm_recurrence_tc (pair schedule): %s", cudaGetErrorString(le)); return 3; }
+    BSRNN_LAUNCH_OK();
+    return 0;
+  }
   int ncl = 2 * a.gpd;
   if (ncl > max_active) ncl = max_active;
   if (max_clusters > 0 && ncl > max_clusters) ncl = max_clusters;
   // BSRNN_LSTM_VER=4|5|6 selects the schedule for A/B timing.  Default 5: the multicast / pipelined-gates variant (6)
   // measured 8.17 vs 8.01 ms (time axis) and 6.85 vs 6.81 ms (band axis) at BASELINE config 2 (profiles/r01/call22):
   // the kernel is bound by the 60 KB h ring (ring bytes / L2 latency), not by L2 traffic or the gate loads.
-  static int ver = -1;
-  if (ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); ver = (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 5; }
   if (ver == 4) lstm_tc_kernel<4><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
   else if (ver == 5) lstm_tc_kernel<5><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
   else lstm_tc_kernel<6><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
@@ -729,3 +1084,4 @@ extern "C" int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack
 }
 
 extern "C" int bsrnn_blstm_tc_max_clusters(void) { return max_active_clusters(); }
+extern "C" int bsrnn_blstm_tc_max_pair_clusters(void) { return max_active_clusters_v7(); }

@@ -152,6 +152,33 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta
                ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: CTAs 2i and 2i+1 of a cluster (same TPC) execute ONE M=256 MMA; each supplies
+// its own 128 rows of A and HALF of the B rows (N/2) from its own shared memory at the same offsets, and receives
+// its 128 rows x N columns of D in its own TMEM.  Only the even (leader) CTA issues mma / commit; alloc and dealloc
+// are executed by the same warp index of BOTH CTAs with the same shared-memory slot offset.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive(1) on the same-offset mbarrier of every CTA in cta_mask (cluster ranks) when all previously issued
+// cta_group::2 MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit2_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // TMEM -> registers: warp w may touch lanes [32*(w%4), +32); thread l gets lane base+l, N consecutive columns.
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
