@@ -128,7 +128,9 @@ int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y
  * bsrnn_norm_cast_kb8: out_kb8 = fp16( x[token, col0:col0+C] * scale[g] + shift[g] ), zero padded to kcores*8 columns;
  *     g = (token / tokens_per_sample)*g_inner + (g_inner > 1 ? token % g_inner : 0).  The apply half of
  *     nn.GroupNorm(1,N) [bsrnn_flowse.py:291,302,146-152] fused with the operand re-tiling.
- * bsrnn_gemm_tc: C = A_kb8 * W_kb8^T + bias with epilogue
+ *     _ones: additionally writes the constant 1 into padding column one_col (C <= one_col < kcores*8, multiple of 4;
+ *     -1 = none) so that a bias stored as weight column one_col is added by the GEMM itself (bias = NULL there).
+ * bsrnn_gemm_tc: C = A_kb8 * W_kb8^T + bias (bias may be NULL) with epilogue
  *     0: fp16 rows      out[token*ldo + col]                              (LSTM input projection, :296,:303)
  *     1: f32 residual   out[token*ldo + col] += .., col < n_valid; optional per-sample {sum,sumsq} of the new
  *                       values added into stats (samples,2) double        (Linear + skip :298-300,:305-307 and the
@@ -150,6 +152,10 @@ int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y
 int bsrnn_norm_cast_kb8(const float* x, const float* scale, const float* shift, void* out, long ldx, int col0, int C,
                         int kcores, int m_tiles, int tiles_per_step, int R, long seq_inner, long seq_outer,
                         long seq_inner_stride, long step_stride, long tokens_per_sample, int g_inner, void* stream);
+int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, const float* shift, void* out, long ldx, int col0,
+                             int C, int kcores, int m_tiles, int tiles_per_step, int R, long seq_inner, long seq_outer,
+                             long seq_inner_stride, long step_stride, long tokens_per_sample, int g_inner, int one_col,
+                             void* stream);
 int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, double* stats, int m_tiles, int n_tiles,
                   int kcores, int BN, int epilogue, long ldo, int n_valid, int out_kcores, long tokens_per_sample,
                   int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,

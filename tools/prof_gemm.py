@@ -10,6 +10,7 @@ from urgent2026_challenge_track1_b200 import runtime_tc as tc, _lib as L
 ap = argparse.ArgumentParser()
 ap.add_argument("--which", default="inproj", choices=["inproj", "fc"])
 ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--nobias", action="store_true", help="inproj: bias folded into the weights (bias pointer NULL)")
 ap.add_argument("--B", type=int, default=64); ap.add_argument("--T", type=int, default=1001); ap.add_argument("--K", type=int, default=34)
 a = ap.parse_args()
 B, T, K, N = a.B, a.T, a.K, 196
@@ -29,7 +30,7 @@ if a.which == "inproj":
     W = (torch.randn(16 * kc * 208 * 8, device=dev) * 0.05).half()
     bias = torch.randn(16 * 208, device=dev)
     out = torch.empty(ntile * 416 * 1024, dtype=torch.float16, device=dev)
-    run = lambda: L.call("bsrnn_gemm_tc", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), None, ntile, 16, kc, 208,
+    run = lambda: L.call("bsrnn_gemm_tc", A.data_ptr(), W.data_ptr(), None if a.nobias else bias.data_ptr(), out.data_ptr(), None, ntile, 16, kc, 208,
                          L.TC_F16_KB8, 0, 3328, 416, T * K, tiles, R, *addr, st)
     bytes_alg = A.numel() * 2 + out.numel() * 2
     flops = 2.0 * ntile * 128 * 208 * 3328
@@ -52,4 +53,4 @@ for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"[gemm {a.which} {a.axis} stages={os.environ.get('BSRNN_GEMM_STAGES', '8')}] {ms:.3f} ms  {bytes_alg / ms / 1e6:.0f} GB/s algorithmic  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
+    print(f"[gemm {a.which} {a.axis}{' nobias' if a.nobias else ''} stages={os.environ.get('BSRNN_GEMM_STAGES', '8')}] {ms:.3f} ms  {bytes_alg / ms / 1e6:.0f} GB/s algorithmic  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)

@@ -35,6 +35,8 @@ PROTOTYPES = {
                                    c_long, c_long, c_void_p],
     "bsrnn_norm_cast_kb8": [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_long, c_long, c_long, c_long, c_long, c_int, c_void_p],
+    "bsrnn_norm_cast_kb8_ones": [c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_long, c_long, c_long, c_long, c_long, c_int, c_int, c_void_p],
     "bsrnn_gemm_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long,
                       c_int, c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
     "bsrnn_blstm_recurrence_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

@@ -87,8 +87,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
   // bias_lane = bias[gc0 + lane]: ONE coalesced load per chunk (issued before the accumulator wait), broadcast by
   // shuffles.  32 dependent uniform loads per chunk were 60 % of the epilogue's stall samples (profiles/r01/call21).
   float v[NC];
+  if (a.bias) {
 #pragma unroll
-  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
+    for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]) + __shfl_sync(0xffffffffu, bias_lane, i);
+  } else {               // bias folded into the weights (constant-one operand column): nothing to add
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
+  }
 
   if (EPI == EPI_F16_ROWS) {
     if (!row_ok) return;
@@ -320,21 +325,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       mbar_wait(acc_full + buf, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      // software pipeline over the warp's (<= 4) chunks: the TMEM load of chunk i+1 is in flight while chunk i is
+      // converted and stored (two register buffers; tcgen05.wait::ld covers every load issued before it)
+      uint32_t acc0[32], acc1[32];
+      auto issue = [&](int ch, uint32_t (&dst)[32]) {
+        const int c0 = ch * 32;
+        if (c0 + 32 <= BN) tmem_ld_x32(t_addr + c0, dst);
+        else tmem_ld_x16(t_addr + c0, reinterpret_cast<uint32_t(&)[16]>(dst));      // BN % 32 == 16
+      };
+      auto consume = [&](int ch, int i, uint32_t (&src)[32]) {
+        const int c0 = ch * 32;
+        tmem_ld_pin(src);
+        if (c0 + 32 <= BN) epilogue_chunk<EPI, 32>(a, m, n, r, c0, src, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
+        else epilogue_chunk<EPI, 16>(a, m, n, r, c0, src, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
+      };
+      if (ch0 < ch1) issue(ch0, acc0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int ch = ch0 + i;
         if (ch >= ch1) break;
-        const int c0 = ch * 32;
-        if (c0 + 32 <= BN) {
-          uint32_t acc[32];
-          tmem_ld_x32(t_addr + c0, acc);
-          tmem_ld_wait();
-          epilogue_chunk<EPI, 32>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
-        } else {                               // BN % 32 == 16
-          uint32_t acc[16];
-          tmem_ld_x16(t_addr + c0, acc);
-          tmem_ld_wait();
-          epilogue_chunk<EPI, 16>(a, m, n, r, c0, acc, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
+        tmem_ld_wait();
+        if ((i & 1) == 0) {
+          if (ch + 1 < ch1) issue(ch + 1, acc1);
+          consume(ch, i, acc0);
+        } else {
+          if (ch + 1 < ch1) issue(ch + 1, acc0);
+          consume(ch, i, acc1);
         }
       }
       tc_fence_before();
@@ -388,8 +404,10 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   // 205 KB) three tiles ahead on 148 CTAs is 91 MB of prefetched lines in a 126 MB L2 that also carries the residual
   // stream -- they were evicted before use and fetched twice (ncu: 9.3 GB read for 5.2 GB algorithmic,
   // profiles/r01/call21_ncu_full_gemm_fc_raw.csv).  Keep the prefetched set under ~32 MB.
-  a.pf_dist = 3;
-  if (!a.b_resident && (size_t)a.kcores * 2048 * sms * 3 > ((size_t)32 << 20)) a.pf_dist = 1;
+  // Measured (profiles/r01/call24_gemm_fc.log, Linear 4N->N at BASELINE config 2): distance 3 / 1 / 0 = 2.09 / 2.01 /
+  // 1.60 ms -- with an 8-stage ring the bulk copies already run a full tile ahead, and the extra L2 prefetch only
+  // competes with the residual stream.  Streaming mode: off.  Weight-resident mode (short K): 3 tiles ahead.
+  a.pf_dist = a.b_resident ? 3 : 0;
   static int pfd = -2;                    // BSRNN_GEMM_PFDIST=0..3 overrides (A/B timing)
   if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
   if (pfd >= 0) a.pf_dist = pfd;

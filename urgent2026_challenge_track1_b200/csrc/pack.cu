@@ -18,6 +18,7 @@ struct PackArgs {
   long seq_inner, seq_outer, seq_inner_stride, step_stride;
   long tokens_per_sample;  // scale row = (token / tokens_per_sample) * g_inner + (g_inner > 1 ? token % g_inner : 0)
   int g_inner;
+  int one_col;           // >= C: this operand column is the constant 1 (bias row of the weights); -1 = none
 };
 
 // grid (m_tiles), block 256, dynamic smem 128 * (kcores*8 + 8) halves + 128 row descriptors.
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
           cc[u] = (idx - rr[u] * q4) * 4;
           const long tok = rows[rr[u]].tok;
           if (tok >= 0 && cc[u] < a.C) v[u] = __ldg(reinterpret_cast<const float4*>(a.x + tok * a.ldx + a.col0 + cc[u]));
+          if (cc[u] == a.one_col) v[u].x = 1.f;
         }
       }
 #pragma unroll
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
           v = row[c];
           if (sc) v = fmaf(v, sc[c], sh[c]);
         }
+        if (c == a.one_col) v = 1.f;
         tile[r * ld + c] = __float2half_rn(v);
       }
     }
@@ -110,15 +113,17 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
 }  // namespace bsrnn
 using namespace bsrnn;
 
-extern "C" int bsrnn_norm_cast_kb8(const float* x, const float* scale, const float* shift, void* out, long ldx,
+extern "C" int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, const float* shift, void* out, long ldx,
                                    int col0, int C, int kcores, int m_tiles, int tiles_per_step, int R,
                                    long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
-                                   long tokens_per_sample, int g_inner, void* stream) {
+                                   long tokens_per_sample, int g_inner, int one_col, void* stream) {
   BSRNN_CHECK_ARG(x && out && C > 0 && kcores * 8 >= C && m_tiles > 0 && tiles_per_step > 0 && seq_inner > 0 &&
                   tokens_per_sample > 0 && g_inner > 0, "norm_cast_kb8: bad arguments");
   BSRNN_CHECK_ARG((scale == nullptr) == (shift == nullptr), "norm_cast_kb8: scale and shift come together");
+  BSRNN_CHECK_ARG(one_col < 0 || (one_col >= C && one_col < kcores * 8 && one_col % 4 == 0),
+                  "norm_cast_kb8: the constant-one column must be a padding column (multiple of 4)");
   PackArgs a{x, scale, shift, reinterpret_cast<__half*>(out), ldx, col0, C, kcores, tiles_per_step, R,
-             seq_inner, seq_outer, seq_inner_stride, step_stride, tokens_per_sample, g_inner};
+             seq_inner, seq_outer, seq_inner_stride, step_stride, tokens_per_sample, g_inner, one_col};
   const size_t smem = (size_t)128 * (kcores * 8 + 8) * 2 + 128 * sizeof(PackRow);
   const int vec_ok = (C % 4 == 0 && col0 % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (!scale || ((reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0)))
@@ -127,4 +132,12 @@ extern "C" int bsrnn_norm_cast_kb8(const float* x, const float* scale, const flo
   norm_cast_kb8_kernel<<<m_tiles, 256, smem, (cudaStream_t)stream>>>(a, vec_ok);
   BSRNN_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int bsrnn_norm_cast_kb8(const float* x, const float* scale, const float* shift, void* out, long ldx,
+                                   int col0, int C, int kcores, int m_tiles, int tiles_per_step, int R,
+                                   long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
+                                   long tokens_per_sample, int g_inner, void* stream) {
+  return bsrnn_norm_cast_kb8_ones(x, scale, shift, out, ldx, col0, C, kcores, m_tiles, tiles_per_step, R, seq_inner,
+                                  seq_outer, seq_inner_stride, step_stride, tokens_per_sample, g_inner, -1, stream);
 }

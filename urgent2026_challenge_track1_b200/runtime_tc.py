@@ -49,7 +49,11 @@ def _gate_perm(H, dev):
 
 
 def pack_lstm_tc(rnn):
-    """nn.LSTM(N, H=392, bidirectional) -> dict(wih [16][26][208][8], bih (16*208) f32, whh [2][8][50][208][8])."""
+    """nn.LSTM(N, H=392, bidirectional) -> dict(wih [16][26][208][8], bih (16*208) f32, whh [2][8][50][208][8]).
+
+    When the operand has a padding column (N < kc_in*8) the bias b_ih + b_hh is ALSO stored as weight column N
+    (`one_col`): norm_cast_kb8_ones writes the constant 1 there and the input-projection GEMM runs without a bias
+    epilogue (its epilogue is then a pure convert-and-store at HBM write speed)."""
     H, N = rnn.weight_hh_l0.shape[1], rnn.weight_ih_l0.shape[1]
     if H != CL * LU:
         raise NotImplementedError(f"tensor-core BLSTM kernel is specialised for H=392, got H={H}")
@@ -58,6 +62,7 @@ def pack_lstm_tc(rnn):
     gsc = torch.tensor(GATE_SCALE, device=dev).repeat(LU)           # packed column c = 4*u + gate
     gsc = torch.cat([gsc, torch.zeros(LBN - 4 * LU, device=dev)])
     kc_in = (N + 15) // 16 * 2
+    one_col = N if (N % 4 == 0 and N < kc_in * 8) else -1
     wih_rows, bih_rows, whh = [], [], []
     for sfx in ("", "_reverse"):
         wi = getattr(rnn, "weight_ih_l0" + sfx).float()
@@ -66,12 +71,17 @@ def pack_lstm_tc(rnn):
         for q in range(CL):
             sel = perm[q].clamp_min(0)
             valid = ((perm[q] >= 0).float() * gsc)[:, None]
-            wih_rows.append(wi[sel] * valid)
-            bih_rows.append(b[sel] * valid[:, 0])
+            wrow = wi[sel] * valid
+            brow = b[sel] * valid[:, 0]
+            if one_col >= 0:
+                wrow = torch.cat([wrow, torch.zeros(wrow.shape[0], kc_in * 8 - N, device=dev)], 1)
+                wrow[:, one_col] = brow
+            wih_rows.append(wrow)
+            bih_rows.append(brow)
             whh.append(to_kb8(wh[sel] * valid, LBN, LKC)[0])
     wih = to_kb8(torch.cat(wih_rows, 0), LBN, kc_in)                # 16 tiles of 208 rows
     return dict(wih=wih, bih=torch.cat(bih_rows).contiguous(), whh=torch.stack(whh).view(2, CL, LKC, LBN, 8).contiguous(),
-                kc_in=kc_in, H=H, N=N)
+                kc_in=kc_in, H=H, N=N, one_col=one_col)
 
 
 def pack_fc_tc(fc, H):
@@ -154,10 +164,11 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                        ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), 1e-5, 1, st)
                 # operand tiles in the axis' (step, sequence tile) order: the GEMM output tiles are then the
                 # recurrence kernel's gates_x tiles
-                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(), ws.xhat.data_ptr(),
-                       N, 0, N, w["kc_in"], steps * tiles, tiles, R, *addr, T * K, 1, st)
+                L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(),
+                       ws.xhat.data_ptr(), N, 0, N, w["kc_in"], steps * tiles, tiles, R, *addr, T * K, 1, w["one_col"], st)
             with region("inproj"):
-                L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(), w["bih"].data_ptr(), ws.gates.data_ptr(), None,
+                L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(),
+                       None if w["one_col"] >= 0 else w["bih"].data_ptr(), ws.gates.data_ptr(), None,
                        steps * tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_KB8, 0, 2 * CL * LBN, 2 * CL * LGC, T * K,
                        tiles, R, *addr, st)
             with region(f"lstm_{axis}"):
