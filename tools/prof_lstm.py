@@ -12,7 +12,7 @@ ap.add_argument("--B", type=int, default=16); ap.add_argument("--T", type=int, d
 ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, default=3); ap.add_argument("--maxcl", type=int, default=0)
 ap.add_argument("--slots", type=int, default=0); ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--trace-cid", type=int, default=0); ap.add_argument("--flags", type=int, default=0)
-ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..7 (0 = BSRNN_LSTM_VER / default)")
+ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..8 (0 = BSRNN_LSTM_VER / default)")
 ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 B, T, K, axis = a.B, a.T, a.K, a.axis
@@ -61,8 +61,8 @@ def run():
 
 if a.ver:
     L.lib().bsrnn_debug_set_lstm_schedule(a.ver)
-tag = f"v{a.ver or os.environ.get('BSRNN_LSTM_VER', '5')} slots={a.slots} maxcl={a.maxcl}"
-if (a.ver or int(os.environ.get('BSRNN_LSTM_VER', '5'))) == 7:
+tag = f"v{a.ver or os.environ.get('BSRNN_LSTM_VER', '8')} slots={a.slots} maxcl={a.maxcl}"
+if (a.ver or int(os.environ.get('BSRNN_LSTM_VER', '8'))) == 7:
     print(f"[{tag}] co-resident 16-CTA clusters: {L.lib().bsrnn_blstm_tc_max_pair_clusters()}  (8-CTA: {L.lib().bsrnn_blstm_tc_max_clusters()})", flush=True)
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -197,7 +197,23 @@ __device__ __forceinline__ bool next_tile(const GemmTcArgs& a, int it, int& m, i
   return true;
 }
 
-template <int EPI>
+// 32 accumulator columns of one row -> 4 consecutive KB8 cores (16 bytes each, 128 rows x 16 B apart)
+template <int NCORES>
+__device__ __forceinline__ void store_kb8_cores(__half* o, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < NCORES; ++i) {
+    const uint4 pk = make_uint4(pack_h2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                                pack_h2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                                pack_h2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                                pack_h2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+    *reinterpret_cast<uint4*>(o + (size_t)i * 1024) = pk;
+  }
+}
+
+// BNC > 0: BN is the compile-time constant BNC and the launch is the bias-free, weight-resident LSTM input
+// projection (EPI_F16_KB8): its epilogue is then straight-line code (profiles/r01/call26: the generic epilogue spent
+// ~440 instructions per tile and warp on 70 useful ones and paced the kernel at 2.8x the MMA time).
+template <int EPI, int BNC = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int BN = a.BN;
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, BNC ? TC_EPI_WARPS / 2 : TC_EPI_WARPS); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -231,42 +247,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
 
   const int nstage_k = (a.kcores + TC_KS - 1) / TC_KS;
 
+  // Control warps run CONVERGED (all 32 lanes walk the schedule and wait on the barriers); the asynchronous
+  // operations are issued inside `if (elect_one())`.  With the roles under `if (lane == 0)` the compiler cannot
+  // prove single-thread execution and wraps every UTCHMMA / UBLKCP / UTCBAR in an elect-and-retry loop with the
+  // descriptors rebuilt in vector registers: ~15 dependent instructions = ~250 cycles per MMA issued, 2.4x the
+  // 104-cycle MMA itself (profiles/r01/call26: MMA warp 87 % busy issuing, tensor pipe 40 % active).
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       int m, n;
       if (a.b_resident && next_tile(a, 0, m, n)) {
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
         const uint32_t bytes = (uint32_t)a.kcores * BN * 16;
-        mbar_expect_tx(b_full, bytes);
-        for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
+        if (elect_one()) {
+          mbar_expect_tx(b_full, bytes);
+          for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
+        }
+        __syncwarp();
       }
       for (int it = 0; next_tile(a, it, m, n); ++it) {
         const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)m * a.kcores * 2048;
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
         if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
           int m3, n3;
-          if (next_tile(a, it + a.pf_dist, m3, n3) && (a.b_resident ? (blockIdx.x % a.n_tiles) == (m3 % a.n_tiles) : n3 == 0))
-            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.A) + (size_t)m3 * a.kcores * 2048, (uint32_t)a.kcores * 2048);
+          if (next_tile(a, it + a.pf_dist, m3, n3) && (a.b_resident ? (blockIdx.x % a.n_tiles) == (m3 % a.n_tiles) : n3 == 0)) {
+            if (elect_one())
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.A) + (size_t)m3 * a.kcores * 2048, (uint32_t)a.kcores * 2048);
+            __syncwarp();
+          }
         }
         for (int ks = 0; ks < nstage_k; ++ks) {
           const int kc0 = ks * TC_KS;
           const int nk = min(TC_KS, a.kcores - kc0);
           mbar_wait(empty + stage, phase ^ 1);
-          mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
-          bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
-          if (!a.b_resident)
-            bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
+          if (elect_one()) {
+            mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
+            bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
+            if (!a.b_resident)
+              bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
+          }
+          __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = idesc_f16_f32(128, BN);
       uint32_t stage = 0, phase = 0;
       int m, n;
       if (a.b_resident && next_tile(a, 0, m, n)) mbar_wait(b_full, 0);
+      // descriptors advance by adding to the 14-bit (address >> 4) field: shared memory is < 256 KB, no carry out
+      const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
+      const uint64_t db0 = smem_desc_kb8(smem_u32(sB), BN * 16, 128);
+      const uint32_t a_step = (2 * 2048) >> 4, b_step = (uint32_t)(2 * BN * 16) >> 4;    // one K = 16 step
       for (int it = 0; next_tile(a, it, m, n); ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -277,24 +311,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           const int nk = min(TC_KS, a.kcores - ks * TC_KS);
           mbar_wait(full + stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(sA + stage * a_stage_bytes);
-          const uint32_t sb = a.b_resident ? smem_u32(sB) + (uint32_t)ks * TC_KS * BN * 16
-                                           : smem_u32(sB + stage * b_stage_bytes);
-          for (int j = 0; j < nk / 2; ++j) {
-            const uint64_t da = smem_desc_kb8(sa + j * 2 * 2048, 2048, 128);
-            const uint64_t db = smem_desc_kb8(sb + j * 2 * BN * 16, BN * 16, 128);
-            mma_f16_ss(d_tmem, da, db, idesc, (ks | j) != 0);
+          if (elect_one()) {
+            const uint64_t da = da0 + (uint64_t)(stage * (a_stage_bytes >> 4));
+            const uint64_t db = db0 + (uint64_t)(a.b_resident ? (uint32_t)ks * (TC_KS / 2) * b_step : stage * (b_stage_bytes >> 4));
+            for (int j = 0; j < nk / 2; ++j) mma_f16_ss(d_tmem, da + (uint64_t)(j * a_step), db + (uint64_t)(j * b_step), idesc, (ks | j) != 0);
+            mma_commit(empty + stage);
+            if (ks == nstage_k - 1) mma_commit(acc_full + buf);
           }
-          mma_commit(empty + stage);
+          __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        mma_commit(acc_full + buf);
       }
     }
   } else {
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // which half of the tile's column chunks
     const int r = q * 32 + lane;               // row of the tile
+    if constexpr (EPI == EPI_F16_KB8 && BNC == 208) {
+      // The two 4-warp groups take ALTERNATE tiles (group g <-> TMEM buffer g), each warp the whole 208-column row
+      // of its lane quadrant in two passes ([0,112) and [112,208)): one group is reading TMEM while the other is
+      // storing, so the TMEM read port and the store path are both busy all the time instead of in turns
+      // (all 8 warps in the same phase paced the kernel at TMEM-read + store time, 2.4x the MMA time).  The
+      // accumulator goes back to the MMA warp as soon as the second pass sits in registers.
+      const int n = blockIdx.x % a.n_tiles;
+      const int mstep = gridDim.x / a.n_tiles;
+      __half* obase = reinterpret_cast<__half*>(a.out) + ((size_t)(n * (BNC / 8)) * 128 + r) * 8;
+      const size_t o_tile = (size_t)a.out_kcores * 1024;
+      const uint32_t t_row = tmem_base + half * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      uint32_t acc_phase = 0;
+      for (int m = blockIdx.x / a.n_tiles + half * mstep; m < a.m_tiles; m += 2 * mstep, acc_phase ^= 1) {
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        __half* o = obase + (size_t)m * o_tile;
+        mbar_wait(acc_full + half, acc_phase);
+        tc_fence_after();
+        tmem_ld_x32(t_row, v0);
+        tmem_ld_x32(t_row + 32, v1);
+        tmem_ld_x32(t_row + 64, v2);
+        tmem_ld_x16(t_row + 96, reinterpret_cast<uint32_t(&)[16]>(v3));
+        tmem_ld_wait();
+        tmem_ld_pin(v0); tmem_ld_pin(v1); tmem_ld_pin(v2); tmem_ld_pin(v3);
+        store_kb8_cores<4>(o, v0);
+        store_kb8_cores<4>(o + 4 * 1024, v1);
+        store_kb8_cores<4>(o + 8 * 1024, v2);
+        store_kb8_cores<2>(o + 12 * 1024, v3);
+        tmem_ld_x32(t_row + 112, v0);
+        tmem_ld_x32(t_row + 144, v1);
+        tmem_ld_x32(t_row + 176, v2);
+        tmem_ld_wait();
+        tmem_ld_pin(v0); tmem_ld_pin(v1); tmem_ld_pin(v2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + half);
+        store_kb8_cores<4>(o + 14 * 1024, v0);
+        store_kb8_cores<4>(o + 18 * 1024, v1);
+        store_kb8_cores<4>(o + 22 * 1024, v2);
+      }
+    } else {
     const int nch = (BN + 31) >> 5;            // 32-column chunks (the last one may be 16 wide)
     const int ch0 = half == 0 ? 0 : (nch + 1) >> 1, ch1 = half == 0 ? (nch + 1) >> 1 : nch;
     float* scr = reinterpret_cast<float*>(smem_scr) + (warp - 2) * 32 * TC_SCR_LD;
@@ -374,6 +446,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -416,7 +489,12 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;
   if (a.b_resident) grid = (sms / a.n_tiles) * a.n_tiles;
-  gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
+  if (EPI == EPI_F16_KB8 && a.BN == 208 && a.bias == nullptr && a.b_resident && a.out_kcores >= a.n_tiles * 26) {
+    BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F16_KB8, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, TC_THREADS, smem, st>>>(a);
+  } else {
+    gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
+  }
   BSRNN_LAUNCH_OK();
   return 0;
 }

@@ -59,6 +59,18 @@ constexpr uint32_t L_A_STAGE = LKS * 128 * 16;          // 20480
 constexpr int L_NBARS = 2 * LSTAGES + LNS + 2 + LNS + 2;
 constexpr size_t L_SMEM = L_W_BYTES + LSTAGES * L_A_STAGE + L_NBARS * 8 + 16;
 static_assert(L_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+// Ring geometry of lstm_tc_kernel (v4..v8): FKS k-cores per stage, FSTAGES stages.  Measured (profiles/r01/call31): a
+// FINE ring (FKS = 2: one 4 KB stage per MMA, 15 stages, meant to keep ~56 KB in flight instead of ~40) is much
+// SLOWER -- 13.3 / 10.4 ms against 7.2 / 6.3 ms: the producer then issues 25 bulk copies per item and each
+// wait + expect_tx + cp.async.bulk round costs it ~400 cycles, i.e. 4 KB copies are issue-bound at ~10 B/clk.  The
+// coarse ring (10 k-cores = 20 KB per copy, 3 stages) stays.
+constexpr int FKS = 10;
+constexpr int FNST = LKC / FKS;           // 5 stages per (step, slot)
+constexpr int FSTAGES = 3;
+constexpr uint32_t F_A_STAGE = FKS * 128 * 16;          // 20480
+constexpr int F_NBARS = 2 * FSTAGES + LNS + 2 + LNS + 2;
+constexpr size_t F_SMEM = L_W_BYTES + FSTAGES * F_A_STAGE + F_NBARS * 8 + 16;
+static_assert(F_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 
 struct LstmTcArgs {
   const __half* gates_x;
@@ -105,6 +117,15 @@ __device__ __forceinline__ void gate_update(float pi, float pf, float pg, float 
   const float gg = tanh_fast(pg), og = fmaf(tanh_fast(po), 0.5f, 0.5f);
   c = fmaf(fg, c, ig * gg);
   h = og * tanh_fast(c);
+}
+
+// (f32 accumulator pair) + (fp16 pair packed in one register): sm_100a mixed-precision FHADD takes the fp16 operand
+// (either half of the register) directly -- one instruction per gate instead of a convert and an add.
+__device__ __forceinline__ float2 add_h2_f32(uint32_t g, uint32_t a0, uint32_t a1) {
+  float2 d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %3;\n\tadd.rn.f32.f16 %1, hi, %4;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "r"(g), "f"(__uint_as_float(a0)), "f"(__uint_as_float(a1)));
+  return d;
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -295,14 +316,14 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
   constexpr size_t CORE = 128 * 8;                  // halves between consecutive k-cores of a y tile
   float h[16];
   uint32_t acc[32];
-  const __half2* gh = reinterpret_cast<const __half2*>(&g[0]);
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g[0]);
   tmem_ld_x32(t_col, acc);
   tmem_ld_wait();
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const float2 g01 = __half22float2(gh[2 * u]), g23 = __half22float2(gh[2 * u + 1]);
-    gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
-                __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[u], h[u]);
+    const float2 p01 = add_h2_f32(gw[2 * u], acc[4 * u], acc[4 * u + 1]);
+    const float2 p23 = add_h2_f32(gw[2 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+    gate_update(p01.x, p01.y, p23.x, p23.y, c[u], h[u]);
   }
   tmem_ld_x32(t_col + 32, acc);
   if (st) {
@@ -312,9 +333,9 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
   tmem_ld_wait();
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const float2 g01 = __half22float2(gh[16 + 2 * u]), g23 = __half22float2(gh[16 + 2 * u + 1]);
-    gate_update(__uint_as_float(acc[4 * u]) + g01.x, __uint_as_float(acc[4 * u + 1]) + g01.y,
-                __uint_as_float(acc[4 * u + 2]) + g23.x, __uint_as_float(acc[4 * u + 3]) + g23.y, c[8 + u], h[8 + u]);
+    const float2 p01 = add_h2_f32(gw[16 + 2 * u], acc[4 * u], acc[4 * u + 1]);
+    const float2 p23 = add_h2_f32(gw[16 + 2 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+    gate_update(p01.x, p01.y, p23.x, p23.y, c[8 + u], h[8 + u]);
   }
   if (st) {
     store_full<8 - Q>(ycore + CORE, h);             // core B: j = 8-Q .. 15-Q
@@ -324,11 +345,9 @@ __device__ __forceinline__ void epi5_item(uint32_t t_col, bool last_third, uint3
     uint32_t a4[4];
     tmem_ld_x4(t_col48, a4);
     tmem_ld_wait();
-    const __half2* g4 = reinterpret_cast<const __half2*>(&g48);
-    const float2 g01 = __half22float2(g4[0]), g23 = __half22float2(g4[1]);
+    const float2 p01 = add_h2_f32(g48.x, a4[0], a4[1]), p23 = add_h2_f32(g48.y, a4[2], a4[3]);
     float h48;
-    gate_update(__uint_as_float(a4[0]) + g01.x, __uint_as_float(a4[1]) + g01.y, __uint_as_float(a4[2]) + g23.x,
-                __uint_as_float(a4[3]) + g23.y, c[16], h48);
+    gate_update(p01.x, p01.y, p23.x, p23.y, c[16], h48);
     if (st) ycore[2 * CORE + Q] = __float2half_rn(h48);
   }
 }
@@ -378,9 +397,76 @@ __device__ __forceinline__ void epi6_item(uint32_t t_col, bool last_third, uint3
   }
 }
 
-template <int Q, bool PIPE>
+// v8 item: v6's register-refilled gates_x (the NEXT item's input projection replaces each pair of cores as soon as it
+// is consumed, so no global-load latency is exposed after the accumulator wait) + FHADD gate adds + software-pipelined
+// TMEM loads: 4 chunks of 4 units (16 columns), the load of chunk j+1 in flight while chunk j runs through the MUFU
+// pipe.  profiles/r01/call25 (v5, ncu source page): the epilogue paces both axes (~4 700 cycles per item against 2 600
+// of MMA and a 1 960-cycle MUFU floor = 5 tanh x 49 units x 128 rows / 16 per clock); its MUFU pipe idles while all 12
+// warps sit in the same TMEM-load / gate-load / store phases.
+__device__ __forceinline__ void tmem_ld_pin16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+template <int CH>
+__device__ __forceinline__ void epi8_chunk(const uint32_t (&acc)[16], uint4 (&g)[8], const uint4* gnext, bool have_next,
+                                           float (&c)[17], float (&h)[16]) {
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g[2 * CH]);
+  float2 p01[4], p23[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    p01[u] = add_h2_f32(gw[2 * u], acc[4 * u], acc[4 * u + 1]);
+    p23[u] = add_h2_f32(gw[2 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+  }
+  if (have_next) {                                   // the two cores are consumed: fetch the next item's
+    g[2 * CH] = __ldg(gnext + (2 * CH) * 128);
+    g[2 * CH + 1] = __ldg(gnext + (2 * CH + 1) * 128);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) gate_update(p01[u].x, p01[u].y, p23[u].x, p23[u].y, c[4 * CH + u], h[4 * CH + u]);
+}
+template <int Q>
+__device__ __forceinline__ void epi8_item(uint32_t t_col, bool last_third, uint32_t t_col48, uint4 (&g)[8], uint2& g48,
+                                          const uint4* gnext, bool have_next, __half* ycore, float (&c)[17]) {
+  constexpr size_t CORE = 128 * 8;
+  float h[16];
+  uint32_t accA[16], accB[16];
+  tmem_ld_x16(t_col, accA);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 16, accB);
+  tmem_ld_pin16(accA);
+  epi8_chunk<0>(accA, g, gnext, have_next, c, h);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 32, accA);
+  tmem_ld_pin16(accB);
+  epi8_chunk<1>(accB, g, gnext, have_next, c, h);
+  if (Q == 0) store_full<0>(ycore, h);
+  else store_partial<Q, 8, 0>(ycore, h);              // core A: slots Q..7 <- j = 0..7-Q
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 48, accB);
+  tmem_ld_pin16(accA);
+  epi8_chunk<2>(accA, g, gnext, have_next, c, h);
+  uint32_t a4[4] = {0u, 0u, 0u, 0u};
+  tmem_ld_wait();
+  if (last_third) tmem_ld_x4(t_col48, a4);
+  tmem_ld_pin16(accB);
+  epi8_chunk<3>(accB, g, gnext, have_next, c, h);
+  store_full<8 - Q>(ycore + CORE, h);                 // core B: j = 8-Q .. 15-Q
+  if (Q > 0) store_partial<0, Q, 16 - Q>(ycore + 2 * CORE, h);   // core C: slots 0..Q-1 <- j = 16-Q .. 15
+  if (last_third) {                                   // local unit 48 -> slot Q of core C
+    tmem_ld_wait();
+    asm volatile("" : "+r"(a4[0]), "+r"(a4[1]), "+r"(a4[2]), "+r"(a4[3]));
+    const float2 p01 = add_h2_f32(g48.x, a4[0], a4[1]), p23 = add_h2_f32(g48.y, a4[2], a4[3]);
+    float h48;
+    gate_update(p01.x, p01.y, p23.x, p23.y, c[16], h48);
+    if (have_next) g48 = __ldg(reinterpret_cast<const uint2*>(gnext + (24 - 8 * 2) * 128));   // core 24 (T = 2: gnext -> core 16)
+    ycore[2 * CORE + Q] = __float2half_rn(h48);
+  }
+}
+
+template <int Q, int MODE>   // 0: v5 item, 1: v6 item (gates refilled in registers), 2: v8 item
 __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
                                                int ncl, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free) {
+  constexpr bool PIPE = MODE != 0;
   const int q = Q;
   const int r = quad * 32 + lane;
   const bool last_third = T == 2;
@@ -443,7 +529,11 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
           nfull ^= 1u << k;
           tc_fence_after();
           P_MARK(w_acc);
-          if (PIPE) {
+          if (MODE == 2) {
+            if (k == 0) epi8_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c0);
+            else if (k == 1) epi8_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c1);
+            else epi8_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c2);
+          } else if (PIPE) {
             if (k == 0) epi6_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c0);
             else if (k == 1) epi6_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c1);
             else epi6_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, gg, g48, gnext, have_next, ycore, c2);
@@ -472,17 +562,18 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
   (void)q;
 }
 
-template <int VER>   // 4: slot-specialised epilogue; 5: all-warps epilogue; 6: 5 + multicast h loads + pipelined gate loads
+template <int VER>   // 4: slot-specialised epilogue; 5: all-warps epilogue; 6: 5 + multicast h loads + pipelined gate loads;
+                     // 8: 5 + register-refilled gates, FHADD, software-pipelined TMEM loads (epi8_item)
 __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
   constexpr bool V5 = VER >= 5;
-  constexpr bool MC = VER >= 6;
+  constexpr bool MC = VER == 6;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + L_W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + LSTAGES * L_A_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + FSTAGES * F_A_STAGE);
   uint64_t* full = bars;                       // [3]
-  uint64_t* empty = bars + LSTAGES;            // [3]
-  uint64_t* acc_full = bars + 2 * LSTAGES;     // [LNS]: one per SLOT — each slot's warps see every phase of theirs
+  uint64_t* empty = bars + FSTAGES;            // [3]
+  uint64_t* acc_full = bars + 2 * FSTAGES;     // [LNS]: one per SLOT — each slot's warps see every phase of theirs
   uint64_t* acc_empty = acc_full + LNS;        // [2]: one per TMEM buffer — the MMA thread sees every phase
   uint64_t* h_ready = acc_empty + 2;           // [LNS]
   uint64_t* w_full = h_ready + LNS;
@@ -494,7 +585,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   const int cid = cluster_id_x(), ncl = num_clusters_x();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < LSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, MC ? LCL : 1); }
+    for (int i = 0; i < FSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, MC ? LCL : 1); }
     for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
     for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, V5 ? 12 : 4);
     for (int i = 0; i < LNS; ++i) mbar_init(h_ready + i, LCL);
@@ -512,10 +603,15 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   const int ngroups = 2 * a.gpd;
   const size_t y_tile = (size_t)LKC * 128 * 8;         // halves per (step, tile, dir)
 
+  // The producer and MMA warps run CONVERGED: all 32 lanes walk the schedule and wait on the barriers, the bulk
+  // copies / MMAs / commits are issued inside `if (elect_one())`.  Under `if (lane == 0)` the compiler wraps each
+  // UTCHMMA / UBLKCP / UTCBAR in an elect-and-retry loop with descriptors rebuilt in vector registers (~15
+  // dependent instructions per MMA): the issue thread, not the tensor pipe, then paces the kernel
+  // (profiles/r01/call26, same pattern in the GEMM).
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: W slice + h tiles
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0, hphase = 0, wfphase = 0;
       int cur_dir = -1;
       long long w_h = 0, w_e = 0, w_o = 0;
@@ -529,9 +625,12 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
             mbar_wait(w_free, wfphase);
             wfphase ^= 1;
           }
-          mbar_expect_tx(w_full, L_W_BYTES);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_pack) + ((size_t)G.d * LCL + q) * L_W_BYTES;
-          for (uint32_t off = 0; off < L_W_BYTES; off += 33280) bulk_g2s(sW + off, src + off, 33280, w_full);
+          if (elect_one()) {
+            mbar_expect_tx(w_full, L_W_BYTES);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_pack) + ((size_t)G.d * LCL + q) * L_W_BYTES;
+            for (uint32_t off = 0; off < L_W_BYTES; off += 33280) bulk_g2s(sW + off, src + off, 33280, w_full);
+          }
+          __syncwarp();
           cur_dir = G.d;
         }
         for (int s = 0; s < a.steps; ++s) {
@@ -543,39 +642,44 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
               mbar_wait_cluster(h_ready + k, (hphase >> k) & 1);
               P_MARK(w_h);
               hphase ^= 1u << k;
-              fence_proxy_async_global();
               src = reinterpret_cast<const uint8_t*>(a.y + (((size_t)p_prev * a.seq_tiles + (G.j0 + k)) * 2 + G.d) * y_tile);
             }
-            for (int ks = 0; ks < LNST; ++ks) {
+            for (int ks = 0; ks < FNST; ++ks) {
               P_MARK(w_o);
               mbar_wait(empty + stage, phase ^ 1);
               P_MARK(w_e);
-              mbar_expect_tx(full + stage, L_A_STAGE);
-              if (MC) {
-                // every CTA of the cluster needs the same h tile: each fetches 1/8 of the stage and multicasts it into
-                // the same ring slot of all 8 (empty[stage] counts the 8 MMA commits, so the slot is free everywhere)
-                constexpr uint32_t SL = L_A_STAGE / LCL;
-                bulk_g2s_multicast(sA + stage * L_A_STAGE + q * SL, src + (size_t)ks * L_A_STAGE + q * SL, SL, full + stage,
-                                   (uint16_t)((1u << LCL) - 1));
-              } else {
-                bulk_g2s(sA + stage * L_A_STAGE, src + (size_t)ks * L_A_STAGE, L_A_STAGE, full + stage);
+              if (elect_one()) {
+                if (s > 0 && ks == 0) fence_proxy_async_global();      // peers' generic-proxy h stores -> this thread's async-proxy reads
+                mbar_expect_tx(full + stage, F_A_STAGE);
+                if (MC) {
+                  // every CTA of the cluster needs the same h tile: each fetches 1/8 of the stage and multicasts it into
+                  // the same ring slot of all 8 (empty[stage] counts the 8 MMA commits, so the slot is free everywhere)
+                  constexpr uint32_t SL = F_A_STAGE / LCL;
+                  bulk_g2s_multicast(sA + stage * F_A_STAGE + q * SL, src + (size_t)ks * F_A_STAGE + q * SL, SL, full + stage,
+                                     (uint16_t)((1u << LCL) - 1));
+                } else {
+                  bulk_g2s(sA + stage * F_A_STAGE, src + (size_t)ks * F_A_STAGE, F_A_STAGE, full + stage);
+                }
               }
-              if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+              __syncwarp();
+              if (++stage == FSTAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
       P_MARK(w_o);
-      if (prb_) { a.probe[0] = w_h; a.probe[1] = w_e; a.probe[2] = w_o; }
+      if (prb_ && lane == 0) { a.probe[0] = w_h; a.probe[1] = w_e; a.probe[2] = w_o; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0) {
+    {
       const uint32_t idesc = idesc_f16_f32(128, LBN);
       uint32_t stage = 0, phase = 0, it = 0, wphase = 0;
       int cur_dir = -1;
-      const uint32_t sw = smem_u32(sW);
+      // descriptors advance by adding to the 14-bit (address >> 4) field: shared memory is < 256 KB, no carry out
+      const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
+      const uint64_t db0 = smem_desc_kb8(smem_u32(sW), LBN * 16, 128);
       long long w_a = 0, w_f = 0, w_o = 0;
       P_DECL(true);
       for (int g = cid; g < ngroups; g += ncl) {
@@ -586,6 +690,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
           cur_dir = G.d;
         }
         const int nitems = a.steps * G.nact;
+        int slot = 0;
         for (int i = 0; i < nitems; ++i, ++it) {
           const uint32_t buf = it & 1;
           P_MARK(w_o);
@@ -593,27 +698,31 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
           P_MARK(w_a);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * LACC;
-          for (int ks = 0; ks < LNST; ++ks) {
+#pragma unroll
+          for (int ks = 0; ks < FNST; ++ks) {
             P_MARK(w_o);
             mbar_wait(full + stage, phase);
             P_MARK(w_f);
             tc_fence_after();
-            const uint32_t sa = smem_u32(sA + stage * L_A_STAGE);
+            if (elect_one()) {
+              const uint64_t da = da0 + (uint64_t)(stage * (F_A_STAGE >> 4));
+              const uint64_t db = db0 + (uint64_t)(ks * FKS * ((LBN * 16) >> 4));
 #pragma unroll
-            for (int jk = 0; jk < LKS / 2; ++jk) {
-              const uint64_t da = smem_desc_kb8(sa + jk * 2 * 2048, 2048, 128);
-              const uint64_t db = smem_desc_kb8(sw + (ks * LKS + jk * 2) * (LBN * 16), LBN * 16, 128);
-              mma_f16_ss(d_tmem, da, db, idesc, (ks | jk) != 0);
+              for (int jk = 0; jk < FKS / 2; ++jk)
+                mma_f16_ss(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * LBN * 16) >> 4)), idesc,
+                           (ks | jk) != 0);
+              if (MC) mma_commit_multicast(empty + stage, (uint16_t)((1u << LCL) - 1));
+              else mma_commit(empty + stage);
+              if (ks == FNST - 1) mma_commit(acc_full + slot);
             }
-            if (MC) mma_commit_multicast(empty + stage, (uint16_t)((1u << LCL) - 1));
-            else mma_commit(empty + stage);
-            if (++stage == LSTAGES) { stage = 0; phase ^= 1; }
+            __syncwarp();
+            if (++stage == FSTAGES) { stage = 0; phase ^= 1; }
           }
-          mma_commit(acc_full + (i % G.nact));
+          if (++slot == G.nact) slot = 0;
         }
       }
       P_MARK(w_o);
-      if (prb_) { a.probe[4] = w_a; a.probe[5] = w_f; a.probe[6] = w_o; }
+      if (prb_ && lane == 0) { a.probe[4] = w_a; a.probe[5] = w_f; a.probe[6] = w_o; }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ publisher
@@ -642,8 +751,9 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
     const int k = (warp - 4) >> 2, quad = warp & 3;
 #define BSRNN_EPI_CASE(QQ)                                                                                   \
   case QQ:                                                                                                   \
-    if (MC) epilogue5_role<QQ, true>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);    \
-    else if (V5) epilogue5_role<QQ, false>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free); \
+    if (VER == 8) epilogue5_role<QQ, 2>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
+    else if (MC) epilogue5_role<QQ, 1>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
+    else if (V5) epilogue5_role<QQ, 0>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
     else epilogue_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);              \
     break;
     switch (q) {
@@ -991,19 +1101,20 @@ static int max_active_clusters_t() {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(LCL * 64);
   cfg.blockDim = dim3(LTHREADS);
-  cfg.dynamicSmemBytes = L_SMEM;
+  cfg.dynamicSmemBytes = F_SMEM;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = LCL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaFuncSetAttribute(lstm_tc_kernel<V5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L_SMEM) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(lstm_tc_kernel<V5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) != cudaSuccess) return -1;
   if (cudaOccupancyMaxActiveClusters(&n, lstm_tc_kernel<V5>, &cfg) != cudaSuccess) return -1;
   return n;
 }
 static int max_active_clusters() {
   const int a6 = max_active_clusters_t<6>(), a5 = max_active_clusters_t<5>(), a4 = max_active_clusters_t<4>();
-  const int m = a5 < a4 ? a5 : a4;
+  const int a8 = max_active_clusters_t<8>();
+  const int m = (a5 < a4 ? a5 : a4) < a8 ? (a5 < a4 ? a5 : a4) : a8;
   return a6 < m ? a6 : m;
 }
 
@@ -1017,10 +1128,10 @@ extern "C" void bsrnn_debug_set_lstm_probe(void* p, int cid) {
   g_lstm_probe_cid = cid;
 }
 
-// Recurrence schedule: 4 / 5 / 6 (8-CTA clusters, see lstm_tc_kernel) or 7 (CTA pairs, lstm_tc2_kernel); < 0 = take
-// BSRNN_LSTM_VER from the environment at the next call (default 5).
+// Recurrence schedule: 4 / 5 / 6 / 8 (8-CTA clusters, see lstm_tc_kernel) or 7 (CTA pairs, lstm_tc2_kernel); < 0 = take
+// BSRNN_LSTM_VER from the environment at the next call (default 8).
 static int g_lstm_ver = -1;
-extern "C" void bsrnn_debug_set_lstm_schedule(int ver) { g_lstm_ver = (ver >= 4 && ver <= 7) ? ver : -1; }
+extern "C" void bsrnn_debug_set_lstm_schedule(int ver) { g_lstm_ver = (ver >= 4 && ver <= 8) ? ver : -1; }
 
 // slots: sequence tiles a cluster interleaves (1..3; <= 0 = 3).
 extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
@@ -1037,12 +1148,12 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
     const int n = max_active_clusters();
     if (n <= 0) {
       cudaGetLastError();
-      set_error("blstm_recurrence_tc: no co-resident 8-CTA cluster (512 threads, %zu B shared memory)", L_SMEM);
+      set_error("blstm_recurrence_tc: no co-resident 8-CTA cluster (512 threads, %zu B shared memory)", F_SMEM);
       return 2;
     }
     max_active = n;
   }
-  if (g_lstm_ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); g_lstm_ver = (e && e[0] >= '4' && e[0] <= '7') ? e[0] - '0' : 5; }
+  if (g_lstm_ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); g_lstm_ver = (e && e[0] >= '4' && e[0] <= '8') ? e[0] - '0' : 8; }
   const int ver = g_lstm_ver;
   if (ver == 7) {
     // CTA-pair schedule: units are (direction, PAIR of sequence tiles); 16-CTA clusters
@@ -1068,12 +1179,13 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
   int ncl = 2 * a.gpd;
   if (ncl > max_active) ncl = max_active;
   if (max_clusters > 0 && ncl > max_clusters) ncl = max_clusters;
-  // BSRNN_LSTM_VER=4|5|6 selects the schedule for A/B timing.  Default 5: the multicast / pipelined-gates variant (6)
-  // measured 8.17 vs 8.01 ms (time axis) and 6.85 vs 6.81 ms (band axis) at BASELINE config 2 (profiles/r01/call22):
-  // the kernel is bound by the 60 KB h ring (ring bytes / L2 latency), not by L2 traffic or the gate loads.
-  if (ver == 4) lstm_tc_kernel<4><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
-  else if (ver == 5) lstm_tc_kernel<5><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
-  else lstm_tc_kernel<6><<<ncl * LCL, LTHREADS, L_SMEM, (cudaStream_t)stream>>>(a);
+  // BSRNN_LSTM_VER=4|5|6|8 selects the schedule for A/B timing.  Default 8 (profiles/r01/call30, BASELINE config 2):
+  // v5 7.49 / 6.51 ms (time / band axis), v8 7.16 / 6.31 ms.  The multicast variant (6) gained nothing over 5
+  // (call22): the h ring (60 KB in flight / L2 latency) and the MUFU-heavy epilogue pace the kernel, not L2 traffic.
+  if (ver == 4) lstm_tc_kernel<4><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
+  else if (ver == 5) lstm_tc_kernel<5><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
+  else if (ver == 8) lstm_tc_kernel<8><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
+  else lstm_tc_kernel<6><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
   BSRNN_LAUNCH_OK();
   return 0;
 }

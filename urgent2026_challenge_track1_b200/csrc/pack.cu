@@ -23,8 +23,10 @@ struct PackArgs {
 
 // grid (m_tiles), block 256, dynamic smem 128 * (kcores*8 + 8) halves + 128 row descriptors.
 // Work item = (row, 4 consecutive channels): consecutive threads read consecutive float4 of a token row (coalesced
-// 16-byte loads, four in flight per thread), apply the affine, and drop 4 halves into the padded tile; the tile then
+// 16-byte loads, PK_U in flight per thread), apply the affine, and drop 4 halves into the padded tile; the tile then
 // leaves as 16-byte KB8 cores.  Needs C % 4 == 0, col0 % 4 == 0 and 16-byte aligned rows; otherwise the scalar path.
+// 16-byte loads each thread keeps in flight (profiles/r01/call26: with 4 the kernel sat on the load latency at 2.9 TB/s)
+constexpr int PK_U = 8;
 struct PackRow {
   long tok;        // token index or -1
   long grp;        // scale/shift row
@@ -52,11 +54,11 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
   if (vec_ok) {
     const int q4 = kw >> 2;                        // float4 slots per row (52 for N = 196)
     const int items = 128 * q4;
-    for (int base = threadIdx.x; base < items; base += 256 * 4) {
-      float4 v[4];
-      int rr[4], cc[4];
+    for (int base = threadIdx.x; base < items; base += 256 * PK_U) {
+      float4 v[PK_U];
+      int rr[PK_U], cc[PK_U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < PK_U; ++u) {
         const int idx = base + u * 256;
         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         rr[u] = -1;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < PK_U; ++u) {
         if (rr[u] < 0) continue;
         const PackRow pr = rows[rr[u]];
         if (a.scale && pr.tok >= 0 && cc[u] < a.C) {
