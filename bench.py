@@ -139,7 +139,6 @@ def main():
     host = (host * (1.0 + 0.01 * torch.arange(B)[:, None])).pin_memory()      # distinct utterances
     lens = torch.full((B,), n, dtype=torch.int32)
     x_dev = host.to(dev)
-    out_host = torch.empty(B, n, dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
@@ -175,12 +174,18 @@ def main():
     # ---- end to end through the public call with host buffers
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the package's batched front-end (pipeline.StreamedEnhancer, used by inference.py): every step copies its own
+    # input batch from pinned host memory and its enhanced waveforms back to pinned host memory; the copies of
+    # neighbouring steps run on their own streams under the current step's compute
+    from urgent2026_challenge_track1_b200.pipeline import StreamedEnhancer
+    enh = StreamedEnhancer(model)
     f0.record()
-    for _ in range(args.steps):
-        wav, _ = model(host, lens, FS)                       # H2D inside (pinned, non_blocking)
-        out_host.copy_(wav, non_blocking=True)               # D2H of the enhanced waveforms
+    n_out = 0
+    for out, _, _ in enh.run((host, lens, FS) for _ in range(args.steps)):
+        n_out += out.shape[0]                                # result is complete in pinned host memory here
     f1.record()
     barrier()
+    assert n_out == B * args.steps
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop_flag = True
     if sampler.is_alive():
@@ -237,7 +242,7 @@ def main():
             "config": {"workload": workload, "precision": args.precision, "weights": "random-init seed 0",
                        "l2": "inputs and activations larger than L2 (no flush needed)", "sharding": "utterances, no collective",
                        "launch": "host launches" if args.no_graph else "CUDA graph replay of the per-step kernel sequence"},
-            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * n * 4 + B * 4, "d2h_bytes_per_step": B * n * 4},
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": enh.h2d_bytes // args.steps, "d2h_bytes_per_step": enh.d2h_bytes // args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
             "per_rank": {"ms_per_step": [round(float(v) / args.steps, 3) for v in per_rank[:, 0]],

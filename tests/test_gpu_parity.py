@@ -145,6 +145,28 @@ def test_bsrnn_se_cuda_graph_replay_matches_eager(precision, width, layers):
     assert rel_l2(g3.cpu(), e3.cpu()) < 1e-5 and rel_l2(g3.cpu(), g1.cpu()) > 1e-4
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_streamed_enhancer_matches_direct_calls(graph):
+    """pipeline.StreamedEnhancer (H2D / D2H on their own streams around the forward) returns, batch by batch and in
+    order, what direct calls return -- including ragged batches, changing shapes and reused staging buffers."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    from urgent2026_challenge_track1_b200.pipeline import StreamedEnhancer
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=32, num_layer=1, precision="fp32", cuda_graph=graph).cuda()
+    fs = 16000
+    batches = []
+    for i, n in enumerate([9000, 9000, 7000, 9000, 9000]):
+        x = R.synth_noisy(2, n, fs, seed=10 + i).pin_memory()
+        batches.append((x, torch.tensor([n, n - 500 * (i + 1)]), fs))
+    direct = [m(x, lens, fs)[0].cpu().clone() for x, lens, fs in batches]
+    enh = StreamedEnhancer(m)
+    got = [out.clone() for out, _, _ in enh.run(iter(batches))]
+    assert len(got) == len(direct)
+    for g, d in zip(got, direct):
+        assert g.shape == d.shape and rel_l2(g, d) < 1e-6
+    assert enh.h2d_bytes == sum(x.numel() * 4 for x, _, _ in batches)
+
+
 # ------------------------------------------------------------------------------------------------ FlowSE
 def _flow_model(g):
     from urgent2026_challenge_track1_b200.config import Config

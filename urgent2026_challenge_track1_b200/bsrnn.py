@@ -86,6 +86,10 @@ class BSRNN_SE(nn.Module):
         key = (tuple(speech_mix.shape), fs, tuple(int(v) for v in lens_host.tolist()), self.precision)
         entry = self._graphs.get(key)
         if entry is None or entry[1] != params:
+            # A replay may still be running (callers such as pipeline.StreamedEnhancer do not synchronise between
+            # batches): destroying or replacing its graph would hand its private memory pool to the next capture, so
+            # drain the device before touching the cache (a capture is a slow path anyway).
+            torch.cuda.synchronize(dev)
             if len(self._graphs) >= 4:
                 self._graphs.clear()                       # graphs pin their workspaces: keep only a few alive
             x_static = torch.empty(tuple(speech_mix.shape), dtype=torch.float32, device=dev)

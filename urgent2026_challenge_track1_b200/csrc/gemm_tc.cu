@@ -59,6 +59,8 @@ struct GemmTcArgs {
   int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
   int b_resident;                   // 1: each CTA keeps ONE weight tile in shared memory and streams A tiles only
   int pf_dist;                      // A tile this many tiles ahead is bulk-prefetched into L2 (0 = off)
+  int debug;                        // BSRNN_GEMM_DEBUG (A/B experiments on the input projection): 1 = every tile
+                                    // writes the first tile's output block (stores stay in L2), 2 = no stores
   int stages;                       // pipeline depth: 8 when the shared memory allows (short-K GEMMs: one tile is 4 stages,
                                     // and a ring of one tile exposes the HBM latency of every A tile), else 4
   RowMap rows;
@@ -184,18 +186,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
 // the A tile through L2).  Weight-resident mode: CTA i owns N tile i % n_tiles for the whole launch and walks the M
 // tiles g, g+G, ... of its group (g = i / n_tiles, G = grid / n_tiles): the weight tile is fetched once, and the
 // n_tiles CTAs of a group still consume the same A tile at the same time.
-__device__ __forceinline__ bool next_tile(const GemmTcArgs& a, int it, int& m, int& n) {
-  if (a.b_resident) {
-    n = blockIdx.x % a.n_tiles;
-    m = blockIdx.x / a.n_tiles + it * (gridDim.x / a.n_tiles);
-    return m < a.m_tiles;
+// The schedule above as an iterator without a division per tile: the control warps have ~1 350 cycles of MMA per tile at
+// K = 208 and every dependent integer division costs them ~150 (profiles/r01/call32: the MMA warp spent more time
+// between tiles than issuing).
+struct TileIter {
+  int m, n;
+  int dm, dn, n_tiles, m_tiles;
+  bool resident;
+  __device__ __forceinline__ TileIter(const GemmTcArgs& a) {
+    n_tiles = a.n_tiles; m_tiles = a.m_tiles; resident = a.b_resident != 0;
+    n = (int)blockIdx.x % n_tiles;
+    m = (int)blockIdx.x / n_tiles;
+    dm = (int)gridDim.x / n_tiles;
+    dn = resident ? 0 : (int)gridDim.x - dm * n_tiles;
   }
-  const int t = blockIdx.x + it * gridDim.x;
-  if (t >= a.m_tiles * a.n_tiles) return false;
-  m = t / a.n_tiles;
-  n = t - m * a.n_tiles;
-  return true;
-}
+  __device__ __forceinline__ bool valid() const { return m < m_tiles; }
+  __device__ __forceinline__ void next() {
+    m += dm; n += dn;
+    if (n >= n_tiles) { n -= n_tiles; ++m; }
+  }
+  __device__ __forceinline__ TileIter ahead(int k) const {       // k small (prefetch distance / next tile)
+    TileIter t = *this;
+    for (int i = 0; i < k; ++i) t.next();
+    return t;
+  }
+};
 
 // 32 accumulator columns of one row -> 4 consecutive KB8 cores (16 bytes each, 128 rows x 16 B apart)
 template <int NCORES>
@@ -247,79 +262,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
 
   const int nstage_k = (a.kcores + TC_KS - 1) / TC_KS;
 
-  // Control warps run CONVERGED (all 32 lanes walk the schedule and wait on the barriers); the asynchronous
-  // operations are issued inside `if (elect_one())`.  With the roles under `if (lane == 0)` the compiler cannot
-  // prove single-thread execution and wraps every UTCHMMA / UBLKCP / UTCBAR in an elect-and-retry loop with the
+  // Control warps: the whole role runs inside ONE `if (elect_one())` region.  The compiler then knows a single
+  // thread executes it and emits back-to-back UTCHMMA / UBLKCP / UTCBAR with descriptors in uniform registers.  Under
+  // `if (lane == 0)` it cannot prove that and wraps every such instruction in an elect-and-retry loop with the
   // descriptors rebuilt in vector registers: ~15 dependent instructions = ~250 cycles per MMA issued, 2.4x the
   // 104-cycle MMA itself (profiles/r01/call26: MMA warp 87 % busy issuing, tensor pipe 40 % active).
   if (warp == 0) {
-    {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0;
-      int m, n;
-      if (a.b_resident && next_tile(a, 0, m, n)) {
-        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
-        const uint32_t bytes = (uint32_t)a.kcores * BN * 16;
-        if (elect_one()) {
-          mbar_expect_tx(b_full, bytes);
-          for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
-        }
-        __syncwarp();
+      TileIter ti(a);
+      // weight-resident mode: the CTA of the group whose N tile equals (m mod n_tiles) prefetches A tile m
+      int pf_mod = 0, pf_dmod = 0;
+      if (a.b_resident && a.pf_dist > 0) {
+        const TileIter t3 = ti.ahead(a.pf_dist);
+        pf_mod = t3.m % a.n_tiles; pf_dmod = ti.dm % a.n_tiles;
       }
-      for (int it = 0; next_tile(a, it, m, n); ++it) {
-        const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)m * a.kcores * 2048;
-        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)n * a.kcores * BN * 16;
+      if (a.b_resident && ti.valid()) {
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)ti.n * a.kcores * BN * 16;
+        const uint32_t bytes = (uint32_t)a.kcores * BN * 16;
+        mbar_expect_tx(b_full, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
+      }
+      for (; ti.valid(); ti.next()) {
+        const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)ti.m * a.kcores * 2048;
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)ti.n * a.kcores * BN * 16;
         if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
-          int m3, n3;
-          if (next_tile(a, it + a.pf_dist, m3, n3) && (a.b_resident ? (blockIdx.x % a.n_tiles) == (m3 % a.n_tiles) : n3 == 0)) {
-            if (elect_one())
-              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.A) + (size_t)m3 * a.kcores * 2048, (uint32_t)a.kcores * 2048);
-            __syncwarp();
-          }
+          const TileIter t3 = ti.ahead(a.pf_dist);
+          if (t3.valid() && (a.b_resident ? ti.n == pf_mod : t3.n == 0))
+            bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.A) + (size_t)t3.m * a.kcores * 2048, (uint32_t)a.kcores * 2048);
+          pf_mod += pf_dmod;
+          if (pf_mod >= a.n_tiles) pf_mod -= a.n_tiles;
         }
         for (int ks = 0; ks < nstage_k; ++ks) {
           const int kc0 = ks * TC_KS;
           const int nk = min(TC_KS, a.kcores - kc0);
           mbar_wait(empty + stage, phase ^ 1);
-          if (elect_one()) {
-            mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
-            bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
-            if (!a.b_resident)
-              bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
-          }
-          __syncwarp();
+          mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
+          bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
+          if (!a.b_resident)
+            bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    {
+    if (elect_one()) {
       const uint32_t idesc = idesc_f16_f32(128, BN);
-      uint32_t stage = 0, phase = 0;
-      int m, n;
-      if (a.b_resident && next_tile(a, 0, m, n)) mbar_wait(b_full, 0);
+      TileIter ti(a);
+      if (a.b_resident && ti.valid()) mbar_wait(b_full, 0);
       // descriptors advance by adding to the 14-bit (address >> 4) field: shared memory is < 256 KB, no carry out
       const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
       const uint64_t db0 = smem_desc_kb8(smem_u32(sB), BN * 16, 128);
       const uint32_t a_step = (2 * 2048) >> 4, b_step = (uint32_t)(2 * BN * 16) >> 4;    // one K = 16 step
-      for (int it = 0; next_tile(a, it, m, n); ++it) {
-        const int buf = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(acc_empty + buf, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
-        for (int ks = 0; ks < nstage_k; ++ks) {
-          const int nk = min(TC_KS, a.kcores - ks * TC_KS);
-          mbar_wait(full + stage, phase);
+      if constexpr (BNC == 208) {
+        // K = 208, 8 ring stages, resident weights (checked by the launcher): a tile is 4 stages of 4+4+4+1 MMAs and
+        // tile `it` uses ring stages 4*(it&1)..+3 in phase (it>>1)&1 -- everything below unrolls to constants.
+        for (int it = 0; ti.valid(); ti.next(), ++it) {
+          const uint32_t buf = it & 1, par = (it >> 1) & 1;
+          mbar_wait(acc_empty + buf, par ^ 1);
           tc_fence_after();
-          if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
+          const uint64_t da_t = da0 + (uint64_t)(buf * 4 * (a_stage_bytes >> 4));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            mbar_wait(full + buf * 4 + ks, par);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < (ks < 3 ? 4 : 1); ++j)
+              mma_f16_ss(d_tmem, da_t + (uint64_t)(ks * (a_stage_bytes >> 4) + j * a_step),
+                         db0 + (uint64_t)((ks * 4 + j) * b_step), idesc, (ks | j) != 0);
+            mma_commit(empty + buf * 4 + ks);
+          }
+          mma_commit(acc_full + buf);
+        }
+      } else {
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; ti.valid(); ti.next(), ++it) {
+          const int buf = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(acc_empty + buf, acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
+          for (int ks = 0; ks < nstage_k; ++ks) {
+            const int nk = min(TC_KS, a.kcores - ks * TC_KS);
+            mbar_wait(full + stage, phase);
+            tc_fence_after();
             const uint64_t da = da0 + (uint64_t)(stage * (a_stage_bytes >> 4));
             const uint64_t db = db0 + (uint64_t)(a.b_resident ? (uint32_t)ks * (TC_KS / 2) * b_step : stage * (b_stage_bytes >> 4));
             for (int j = 0; j < nk / 2; ++j) mma_f16_ss(d_tmem, da + (uint64_t)(j * a_step), db + (uint64_t)(j * b_step), idesc, (ks | j) != 0);
             mma_commit(empty + stage);
-            if (ks == nstage_k - 1) mma_commit(acc_full + buf);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == NST) { stage = 0; phase ^= 1; }
+          mma_commit(acc_full + buf);
         }
       }
     }
@@ -336,7 +370,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       const int n = blockIdx.x % a.n_tiles;
       const int mstep = gridDim.x / a.n_tiles;
       __half* obase = reinterpret_cast<__half*>(a.out) + ((size_t)(n * (BNC / 8)) * 128 + r) * 8;
-      const size_t o_tile = (size_t)a.out_kcores * 1024;
+      const size_t o_tile = (a.debug & 1) ? 0 : (size_t)a.out_kcores * 1024;
+      const bool do_store = !(a.debug & 2);
       const uint32_t t_row = tmem_base + half * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
       uint32_t acc_phase = 0;
       for (int m = blockIdx.x / a.n_tiles + half * mstep; m < a.m_tiles; m += 2 * mstep, acc_phase ^= 1) {
@@ -350,10 +385,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         tmem_ld_x16(t_row + 96, reinterpret_cast<uint32_t(&)[16]>(v3));
         tmem_ld_wait();
         tmem_ld_pin(v0); tmem_ld_pin(v1); tmem_ld_pin(v2); tmem_ld_pin(v3);
-        store_kb8_cores<4>(o, v0);
-        store_kb8_cores<4>(o + 4 * 1024, v1);
-        store_kb8_cores<4>(o + 8 * 1024, v2);
-        store_kb8_cores<2>(o + 12 * 1024, v3);
+        if (do_store) {
+          store_kb8_cores<4>(o, v0);
+          store_kb8_cores<4>(o + 4 * 1024, v1);
+          store_kb8_cores<4>(o + 8 * 1024, v2);
+          store_kb8_cores<2>(o + 12 * 1024, v3);
+        }
         tmem_ld_x32(t_row + 112, v0);
         tmem_ld_x32(t_row + 144, v1);
         tmem_ld_x32(t_row + 176, v2);
@@ -362,25 +399,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + half);
-        store_kb8_cores<4>(o + 14 * 1024, v0);
-        store_kb8_cores<4>(o + 18 * 1024, v1);
-        store_kb8_cores<4>(o + 22 * 1024, v2);
+        if (do_store) {
+          store_kb8_cores<4>(o + 14 * 1024, v0);
+          store_kb8_cores<4>(o + 18 * 1024, v1);
+          store_kb8_cores<4>(o + 22 * 1024, v2);
+        }
       }
     } else {
     const int nch = (BN + 31) >> 5;            // 32-column chunks (the last one may be 16 wide)
     const int ch0 = half == 0 ? 0 : (nch + 1) >> 1, ch1 = half == 0 ? (nch + 1) >> 1 : nch;
     float* scr = reinterpret_cast<float*>(smem_scr) + (warp - 2) * 32 * TC_SCR_LD;
-    int m, n;
-    for (int it = 0; next_tile(a, it, m, n); ++it) {
+    TileIter ti(a);
+    for (int it = 0; ti.valid(); ti.next(), ++it) {
+      const int m = ti.m, n = ti.n;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       long token = 0;
       const bool row_ok = a.rows.map(m, r, &token);
       float s_sum = 0.f, s_sq = 0.f;
       if (EPI == EPI_RESID_F32) {                      // next tile's residual rows -> L2 while this tile is processed
-        int m2, n2;
+        const TileIter t2 = ti.ahead(1);
+        const int m2 = t2.m, n2 = t2.n;
         long tok2 = 0;
-        if (next_tile(a, it + 1, m2, n2) && a.rows.map(m2, r, &tok2)) {
+        if (t2.valid() && a.rows.map(m2, r, &tok2)) {
           const char* p = reinterpret_cast<const char*>(reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + n2 * a.BN);
           const int nbytes = (a.n_valid - n2 * a.BN < a.BN ? a.n_valid - n2 * a.BN : a.BN) * 4;
           for (int off = half * 128; off < nbytes; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
@@ -481,6 +522,9 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   // 1.60 ms -- with an 8-stage ring the bulk copies already run a full tile ahead, and the extra L2 prefetch only
   // competes with the residual stream.  Streaming mode: off.  Weight-resident mode (short K): 3 tiles ahead.
   a.pf_dist = a.b_resident ? 3 : 0;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("BSRNN_GEMM_DEBUG"); dbg = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0; }
+  a.debug = dbg;
   static int pfd = -2;                    // BSRNN_GEMM_PFDIST=0..3 overrides (A/B timing)
   if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
   if (pfd >= 0) a.pf_dist = pfd;
@@ -489,7 +533,8 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;
   if (a.b_resident) grid = (sms / a.n_tiles) * a.n_tiles;
-  if (EPI == EPI_F16_KB8 && a.BN == 208 && a.bias == nullptr && a.b_resident && a.out_kcores >= a.n_tiles * 26) {
+  if (EPI == EPI_F16_KB8 && a.BN == 208 && a.kcores == 26 && a.stages == 8 && a.bias == nullptr && a.b_resident &&
+      a.out_kcores >= a.n_tiles * 26) {
     BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F16_KB8, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, TC_THREADS, smem, st>>>(a);
   } else {

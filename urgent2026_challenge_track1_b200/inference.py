@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from .d_model import SEModel
+from .pipeline import StreamedEnhancer
 from .sharding import shard_utterances
 
 
@@ -44,15 +45,18 @@ def main(args):
     audio = [_read_wav(p) for _, p in utts]
     batches = shard_utterances([len(a) for a, _ in audio], [sr for _, sr in audio], rank, world, args.max_batch)
     with open(os.path.join(args.output_dir, f"inf.{rank}.scp" if world > 1 else "inf.scp"), "w") as f:
-        for fs, idx in batches:
-            lens = torch.tensor([len(audio[i][0]) for i in idx], dtype=torch.int32)
-            batch = torch.zeros(len(idx), int(lens.max()), dtype=torch.float32).pin_memory()
+        def host_batches():
+            for fs, idx in batches:
+                lens = torch.tensor([len(audio[i][0]) for i in idx], dtype=torch.int32)
+                batch = torch.zeros(len(idx), int(lens.max()), dtype=torch.float32).pin_memory()
+                for row, i in enumerate(idx):
+                    batch[row, : lens[row]] = torch.from_numpy(audio[i][0])      # right zero-pad (dataset.py:404-441)
+                yield batch, lens, fs
+
+        # H2D of the next batch and D2H of the previous one overlap the current batch's kernels
+        for (fs, idx), (enhanced, lens, _) in zip(batches, StreamedEnhancer(model.se_model).run(host_batches())):
             for row, i in enumerate(idx):
-                batch[row, : lens[row]] = torch.from_numpy(audio[i][0])          # right zero-pad (dataset.py:404-441)
-            enhanced, _ = model.se_model(batch, lens, fs)
-            enhanced = enhanced.cpu()
-            for row, i in enumerate(idx):
-                y = enhanced[row, : lens[row]]
+                y = enhanced[row, : lens[row]].clone()
                 y = y / y.abs().max().clamp_min(1e-12) * 0.9                    # inference.py:60
                 out = os.path.join(args.output_dir, "wav", f"{utts[i][0]}.wav")
                 _write_wav(out, y.numpy(), fs)
