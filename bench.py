@@ -42,6 +42,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.times = []
 
     def run(self):
         try:
@@ -54,6 +55,7 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
             while not self.stop_flag:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.times.append(time.monotonic())
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 for bit, name in names.items():
                     if r & bit:
@@ -62,9 +64,14 @@ class ClockSampler(threading.Thread):
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_error:{type(e).__name__}")
 
-    def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+    def median(self, t0=None, t1=None):
+        s = sorted(v for v, t in zip(self.samples, self.times) if (t0 is None or t >= t0) and (t1 is None or t <= t1))
+        return s[len(s) // 2] if s else None
+
+    def summary(self, t0=None, t1=None, t2=None):
+        """sm_mhz: median over [t0, t1] (the device-resident timed loop); sm_mhz_e2e: over [t1, t2]."""
+        return {"sm_mhz": self.median(t0, t1), "sm_mhz_e2e": self.median(t1, t2), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
 
 
 def cpu_reference_throughput(seconds, threads, steps=1, warmup=0):
@@ -146,16 +153,28 @@ def main():
         torch.cuda.synchronize()
 
     lib = _lib.lib()
-    # one eager pass with per-region CUDA events (roofline leg) and the kernel count of one forward
+    # setup, in this order so that the GPU is under continuous load from the region passes to the timed loop (a 1 kW
+    # part that goes idle -> full load overshoots its power cap and clocks down for about a second; a graph capture
+    # placed between the eager passes and the warm-up left exactly that transient inside the timed region):
+    #   1. one eager forward (packs weights, sizes workspaces) and, for the product path, the CUDA-graph capture;
+    #   2. REGION_PASSES eager forwards with per-region CUDA events (roofline leg; averaged) + the kernel count;
+    #   3. W warm-up steps of the product path, barrier, K timed steps.
     model(x_dev, lens, FS)
     barrier()
+    if not args.no_graph:
+        model.cuda_graph = True
+        model(x_dev, lens, FS)                               # capture (+ first replay)
+        barrier()
+        model.cuda_graph = False
+    REGION_PASSES = 3
     lib.bsrnn_launch_count(1)
     with runtime.Profile() as prof:
-        model(x_dev, lens, FS)
+        for _ in range(REGION_PASSES):
+            model(x_dev, lens, FS)
         barrier()
-        regions = prof.totals_ms()
-    launches_per_step = lib.bsrnn_launch_count(0)
-    # the product path: the same launch sequence replayed from a captured CUDA graph
+        regions = {k: (v[0] / REGION_PASSES, v[1] // REGION_PASSES) for k, v in prof.totals_ms().items()}
+    launches_per_step = lib.bsrnn_launch_count(0) // REGION_PASSES
+    # the product path: the same launch sequence replayed from the captured CUDA graph
     model.cuda_graph = not args.no_graph
     for _ in range(args.warmup):
         model(x_dev, lens, FS)
@@ -164,11 +183,13 @@ def main():
     if os.environ.get("BSRNN_BENCH_NO_NVML", "0") != "1":     # A/B switch: NVML polling off (clocks then read null)
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.monotonic()
     e0.record()
     for _ in range(args.steps):
         model(x_dev, lens, FS)
     e1.record()
     barrier()
+    t_b = time.monotonic()
     launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
     # ---- end to end through the public call with host buffers
@@ -179,6 +200,10 @@ def main():
     # neighbouring steps run on their own streams under the current step's compute
     from urgent2026_challenge_track1_b200.pipeline import StreamedEnhancer
     enh = StreamedEnhancer(model)
+    for out, _, _ in enh.run((host, lens, FS) for _ in range(2)):      # untimed: allocates the two staging / pinned slots
+        pass
+    barrier()
+    enh.h2d_bytes = enh.d2h_bytes = 0
     f0.record()
     n_out = 0
     for out, _, _ in enh.run((host, lens, FS) for _ in range(args.steps)):
@@ -191,7 +216,7 @@ def main():
     if sampler.is_alive():
         sampler.join(timeout=2)
 
-    clk = sampler.summary()
+    clk = sampler.summary(t_a, t_b, time.monotonic())
     mine = torch.tensor([ms, ms_e2e, float(clk["sm_mhz"] or 0)], dtype=torch.float64, device=dev)
     per_rank = [mine]
     if world > 1:                                            # the only exchange: every rank's own device time

@@ -225,6 +225,21 @@ __device__ __forceinline__ void store_kb8_cores(__half* o, const uint32_t (&v)[3
   }
 }
 
+template <int NCORES>
+__device__ __forceinline__ void store_kb8_cores_smem(uint8_t* p, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < NCORES; ++i) {
+    const uint4 pk = make_uint4(pack_h2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                                pack_h2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                                pack_h2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                                pack_h2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+    *reinterpret_cast<uint4*>(p + (size_t)i * 2048) = pk;
+  }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // BNC > 0: BN is the compile-time constant BNC and the launch is the bias-free, weight-resident LSTM input
 // projection (EPI_F16_KB8): its epilogue is then straight-line code (profiles/r01/call26: the generic epilogue spent
 // ~440 instructions per tile and warp on 70 useful ones and paced the kernel at 2.8x the MMA time).
@@ -314,28 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
       const uint64_t db0 = smem_desc_kb8(smem_u32(sB), BN * 16, 128);
       const uint32_t a_step = (2 * 2048) >> 4, b_step = (uint32_t)(2 * BN * 16) >> 4;    // one K = 16 step
-      if constexpr (BNC == 208) {
-        // K = 208, 8 ring stages, resident weights (checked by the launcher): a tile is 4 stages of 4+4+4+1 MMAs and
-        // tile `it` uses ring stages 4*(it&1)..+3 in phase (it>>1)&1 -- everything below unrolls to constants.
-        for (int it = 0; ti.valid(); ti.next(), ++it) {
-          const uint32_t buf = it & 1, par = (it >> 1) & 1;
-          mbar_wait(acc_empty + buf, par ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
-          const uint64_t da_t = da0 + (uint64_t)(buf * 4 * (a_stage_bytes >> 4));
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mbar_wait(full + buf * 4 + ks, par);
-            tc_fence_after();
-#pragma unroll
-            for (int j = 0; j < (ks < 3 ? 4 : 1); ++j)
-              mma_f16_ss(d_tmem, da_t + (uint64_t)(ks * (a_stage_bytes >> 4) + j * a_step),
-                         db0 + (uint64_t)((ks * 4 + j) * b_step), idesc, (ks | j) != 0);
-            mma_commit(empty + buf * 4 + ks);
-          }
-          mma_commit(acc_full + buf);
-        }
-      } else {
+      {
         uint32_t stage = 0, phase = 0;
         for (int it = 0; ti.valid(); ti.next(), ++it) {
           const int buf = it & 1;
@@ -363,20 +357,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     const int r = q * 32 + lane;               // row of the tile
     if constexpr (EPI == EPI_F16_KB8 && BNC == 208) {
       // The two 4-warp groups take ALTERNATE tiles (group g <-> TMEM buffer g), each warp the whole 208-column row
-      // of its lane quadrant in two passes ([0,112) and [112,208)): one group is reading TMEM while the other is
-      // storing, so the TMEM read port and the store path are both busy all the time instead of in turns
-      // (all 8 warps in the same phase paced the kernel at TMEM-read + store time, 2.4x the MMA time).  The
-      // accumulator goes back to the MMA warp as soon as the second pass sits in registers.
+      // of its lane quadrant in two passes (cores [0,14) and [14,26) of the tile's 26 KB8 cores).  A pass is
+      // converted into the group's shared-memory staging block -- already in the global layout, a pass is ONE
+      // contiguous run of 2 KB cores -- and leaves as a single cp.async.bulk shared->global store.
+      // Why not st.global: measured (profiles/r01/call37) 1.95 ms without stores, 3.06 ms with st.global.v4 stores that
+      // never leave L2, 3.42 ms with DRAM behind them: the LSU store path (8 warps, 512 B per instruction) paced the
+      // kernel at ~19 B/clk/SM, not DRAM.  Bulk stores move the same bytes through the TMA unit.
       const int n = blockIdx.x % a.n_tiles;
       const int mstep = gridDim.x / a.n_tiles;
-      __half* obase = reinterpret_cast<__half*>(a.out) + ((size_t)(n * (BNC / 8)) * 128 + r) * 8;
-      const size_t o_tile = (a.debug & 1) ? 0 : (size_t)a.out_kcores * 1024;
+      constexpr uint32_t STG_BYTES = 14 * 2048;                         // staging block of one group (pass A: 14 cores)
+      uint8_t* stg = smem_scr + half * STG_BYTES;
+      uint8_t* my_stg = stg + r * 16;                                   // this row's 16 bytes of core 0
+      uint8_t* gbase = reinterpret_cast<uint8_t*>(a.out) + (size_t)(n * (BNC / 8)) * 2048;
+      const size_t o_tile = (a.debug & 1) ? 0 : (size_t)a.out_kcores * 2048;
       const bool do_store = !(a.debug & 2);
+      const bool leader = (warp == 2 + 4 * half) && lane == 0;          // issues and tracks the group's bulk stores
       const uint32_t t_row = tmem_base + half * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      const int bar_id = 1 + half;                                      // named barrier of the group (128 threads)
       uint32_t acc_phase = 0;
       for (int m = blockIdx.x / a.n_tiles + half * mstep; m < a.m_tiles; m += 2 * mstep, acc_phase ^= 1) {
         uint32_t v0[32], v1[32], v2[32], v3[32];
-        __half* o = obase + (size_t)m * o_tile;
+        uint8_t* gdst = gbase + (size_t)m * o_tile;
         mbar_wait(acc_full + half, acc_phase);
         tc_fence_after();
         tmem_ld_x32(t_row, v0);
@@ -385,12 +386,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         tmem_ld_x16(t_row + 96, reinterpret_cast<uint32_t(&)[16]>(v3));
         tmem_ld_wait();
         tmem_ld_pin(v0); tmem_ld_pin(v1); tmem_ld_pin(v2); tmem_ld_pin(v3);
-        if (do_store) {
-          store_kb8_cores<4>(o, v0);
-          store_kb8_cores<4>(o + 4 * 1024, v1);
-          store_kb8_cores<4>(o + 8 * 1024, v2);
-          store_kb8_cores<2>(o + 12 * 1024, v3);
-        }
+        if (leader) bulk_store_wait_read();                             // previous store has finished reading the staging block
+        named_bar_sync(bar_id, 128);
+        store_kb8_cores_smem<4>(my_stg, v0);
+        store_kb8_cores_smem<4>(my_stg + 4 * 2048, v1);
+        store_kb8_cores_smem<4>(my_stg + 8 * 2048, v2);
+        store_kb8_cores_smem<2>(my_stg + 12 * 2048, v3);
+        fence_proxy_async_shared();                                     // generic-proxy smem writes -> the bulk copy's reads
+        named_bar_sync(bar_id, 128);
+        if (leader && do_store) bulk_s2g(gdst, stg, 14 * 2048);
         tmem_ld_x32(t_row + 112, v0);
         tmem_ld_x32(t_row + 144, v1);
         tmem_ld_x32(t_row + 176, v2);
@@ -398,13 +402,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         tmem_ld_pin(v0); tmem_ld_pin(v1); tmem_ld_pin(v2);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + half);
-        if (do_store) {
-          store_kb8_cores<4>(o + 14 * 1024, v0);
-          store_kb8_cores<4>(o + 18 * 1024, v1);
-          store_kb8_cores<4>(o + 22 * 1024, v2);
-        }
+        if (lane == 0) mbar_arrive(acc_empty + half);                   // the accumulator sits in registers: back to the MMA warp
+        if (leader) bulk_store_wait_read();
+        named_bar_sync(bar_id, 128);
+        store_kb8_cores_smem<4>(my_stg, v0);
+        store_kb8_cores_smem<4>(my_stg + 4 * 2048, v1);
+        store_kb8_cores_smem<3>(my_stg + 8 * 2048, v2);                 // core 25 (columns 200..207) is padding nobody reads
+        fence_proxy_async_shared();
+        named_bar_sync(bar_id, 128);
+        if (leader && do_store) bulk_s2g(gdst + 14 * 2048, stg, 11 * 2048);
       }
+      if (leader) bulk_store_wait_all();
     } else {
     const int nch = (BN + 31) >> 5;            // 32-column chunks (the last one may be 16 wide)
     const int ch0 = half == 0 ? 0 : (nch + 1) >> 1, ch1 = half == 0 ? (nch + 1) >> 1 : nch;
@@ -533,10 +541,13 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;
   if (a.b_resident) grid = (sms / a.n_tiles) * a.n_tiles;
-  if (EPI == EPI_F16_KB8 && a.BN == 208 && a.kcores == 26 && a.stages == 8 && a.bias == nullptr && a.b_resident &&
+  if (EPI == EPI_F16_KB8 && a.BN == 208 && a.kcores == 26 && a.bias == nullptr && a.b_resident &&
       a.out_kcores >= a.n_tiles * 26) {
-    BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F16_KB8, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, TC_THREADS, smem, st>>>(a);
+    // specialised input-projection kernel: 5 ring stages + two 28 KB staging blocks for the bulk stores
+    a.stages = 5;
+    const size_t smem_ip = tc_smem_bytes(a.BN, a.kcores, true, false, a.stages) + 2 * 14 * 2048;
+    BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F16_KB8, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ip));
+    gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, TC_THREADS, smem_ip, st>>>(a);
   } else {
     gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
   }

@@ -4,6 +4,7 @@
 // the form the next GEMM's bulk copies fetch.
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace bsrnn {
 
@@ -112,6 +113,75 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
   }
 }
 
+
+// Asynchronous variant (vectorisable shapes): every thread fires its share of the tile's 16-byte global->shared
+// cp.async copies at once (no registers held, ~100 KB in flight per block, 2 blocks per SM), waits once, and then
+// converts from the f32 shared-memory tile: thread = (k-core, row) reads 8 floats, applies the affine and stores one
+// 16-byte KB8 core entry (a warp = 512 contiguous bytes).  The register-staged kernel above held at most 8 loads per
+// thread and measured 0.885 ms = 2.9 TB/s at BASELINE config 2 whatever that count (profiles/r01/call26, call42).
+// Row stride = C floats: for C % 8 == 4 (N = 196) consecutive rows start 4 banks apart, so the 8 rows of one
+// 16-byte-access phase cover all 32 banks.
+__global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                    // [128][C]
+  PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)128 * a.C * 4);
+  const int m = blockIdx.x;
+  const int step = m / a.tiles_per_step, j = m - step * a.tiles_per_step;
+  if (threadIdx.x < 128) {
+    const int r = threadIdx.x;
+    const long seq = (long)j * 128 + r;
+    PackRow pr{-1, 0};
+    if (seq < a.R) {
+      pr.tok = (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride + (long)step * a.step_stride;
+      if (a.scale) pr.grp = (pr.tok / a.tokens_per_sample) * a.g_inner + (a.g_inner > 1 ? pr.tok % a.g_inner : 0);
+    }
+    rows[r] = pr;
+  }
+  __syncthreads();
+  const int q4 = a.C >> 2;                                             // 16-byte pieces per row
+  const int items = 128 * q4;
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  for (int idx = threadIdx.x; idx < items; idx += 256) {
+    const int r = idx / q4, c4 = idx - r * q4;
+    const long tok = rows[r].tok;
+    if (tok >= 0) {
+      const float* src = a.x + tok * a.ldx + a.col0 + 4 * c4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (uint32_t)(r * a.C + 4 * c4) * 4), "l"(src) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  __half* dst = a.out + (size_t)m * a.kcores * 128 * 8;
+  for (int i = threadIdx.x; i < a.kcores * 128; i += 256) {
+    const int kc = i >> 7, r = i & 127;
+    const PackRow pr = rows[r];
+    const int c0 = kc * 8;
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + 4 * h;
+      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pr.tok >= 0 && c < a.C) {                                    // C % 4 == 0: a 4-group is all valid or all padding
+        x4 = *reinterpret_cast<const float4*>(tile + r * a.C + c);
+        if (a.scale) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + pr.grp * a.C + c));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + pr.grp * a.C + c));
+          x4.x = fmaf(x4.x, sc.x, sh.x); x4.y = fmaf(x4.y, sc.y, sh.y);
+          x4.z = fmaf(x4.z, sc.z, sh.z); x4.w = fmaf(x4.w, sc.w, sh.w);
+        }
+      }
+      if (c == a.one_col) x4.x = 1.f;
+      v[4 * h] = x4.x; v[4 * h + 1] = x4.y; v[4 * h + 2] = x4.z; v[4 * h + 3] = x4.w;
+    }
+    const __half2 p0 = __floats2half2_rn(v[0], v[1]), p1 = __floats2half2_rn(v[2], v[3]);
+    const __half2 p2 = __floats2half2_rn(v[4], v[5]), p3 = __floats2half2_rn(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) =
+        make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                   *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
+  }
+}
+
 }  // namespace bsrnn
 using namespace bsrnn;
 
@@ -130,6 +200,16 @@ extern "C" int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, cons
   const int vec_ok = (C % 4 == 0 && col0 % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                       (!scale || ((reinterpret_cast<uintptr_t>(scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(shift) & 15) == 0)))
                          ? 1 : 0;
+  // asynchronous kernel: vectorisable shapes whose f32 tile fits twice per SM and whose row stride is bank-friendly
+  static int force_old = -1;              // BSRNN_PACK_SYNC=1: the register-staged kernel (A/B timing)
+  if (force_old < 0) { const char* e = getenv("BSRNN_PACK_SYNC"); force_old = (e && e[0] == '1') ? 1 : 0; }
+  const size_t smem_async = (size_t)128 * C * 4 + 128 * sizeof(PackRow);
+  if (vec_ok && !force_old && C % 8 == 4 && smem_async <= 110 * 1024 && (one_col < 0 || one_col % 4 == 0)) {
+    BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_async));
+    norm_cast_kb8_async_kernel<<<m_tiles, 256, smem_async, (cudaStream_t)stream>>>(a);
+    BSRNN_LAUNCH_OK();
+    return 0;
+  }
   BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   norm_cast_kb8_kernel<<<m_tiles, 256, smem, (cudaStream_t)stream>>>(a, vec_ok);
   BSRNN_LAUNCH_OK();
