@@ -95,7 +95,29 @@ def cpu_reference_throughput(seconds, threads, steps=1, warmup=0):
     return seconds / dt, threads, f"1x{seconds:g}s@48kHz utterance, f32, {steps} run(s) after {warmup} warm-up"
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 when
+    the box sets NCCL_DEBUG): keep a private duplicate of the real stdout for the JSON line and point fd 1 at stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -120,7 +142,7 @@ def main():
         if rank != 0:
             return
         v, c, sample = cpu_reference_throughput(args.cpu_seconds, cores, steps=max(1, args.steps), warmup=min(args.warmup, 1))
-        print(json.dumps({
+        _emit(({
             "impl": "reference", "metric": "BSRNN audio-sec/sec enhanced at 48 kHz", "value": v, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.cpu_seconds / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -283,7 +305,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:              # reported at N=1 only (bounded sample, rank 0)
             v, c, sample = cpu_reference_throughput(args.cpu_seconds, cores)
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": c, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
