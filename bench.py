@@ -273,7 +273,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6500.0)
         tok = B * T * K
         kb = lambda kc: tok * kc * 16                                   # bytes of a KB8 fp16 operand with kc k-cores
-        alg = {"inproj": kb(26) + kb(416), "fc": kb(100) + 2 * tok * NUM_CHANNEL * 4, "norm": tok * NUM_CHANNEL * 4 + kb(26)}
+        alg = {"inproj": kb(26) + kb(400), "fc": kb(100) + 2 * tok * NUM_CHANNEL * 4, "norm": tok * NUM_CHANNEL * 4 + kb(26)}
         others = {}
         for name, nbytes in alg.items():
             ms_r, n_r = regions.get(name, (0.0, 0))

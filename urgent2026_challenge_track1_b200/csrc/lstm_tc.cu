@@ -95,7 +95,11 @@ __device__ __forceinline__ Group group_of(const LstmTcArgs& a, int g) {
   return r;
 }
 
-// whole-launch accumulators (debug): P_MARK(v) adds the cycles since the previous mark to v
+// whole-launch accumulators (debug): P_MARK(v) adds the cycles since the previous mark to v.  Compiled in only with
+// -DBSRNN_LSTM_PROBE (tools/prof_lstm.py --trace needs such a build): even predicated off, every mark left a clock
+// read and a dependent add in the hot loops, and the ncu source page of v8 (profiles/r01/call41) showed ~15 % of the
+// epilogue warps' stall samples on exactly those instructions.
+#ifdef BSRNN_LSTM_PROBE
 #define P_DECL(cond) const bool prb_ = a.probe && cid == a.probe_cid && q == 0 && (cond); long long pt_ = prb_ ? clock64() : 0
 #define P_MARK(v)                      \
   do {                                 \
@@ -105,6 +109,10 @@ __device__ __forceinline__ Group group_of(const LstmTcArgs& a, int g) {
       pt_ = n_;                        \
     }                                  \
   } while (0)
+#else
+#define P_DECL(cond) constexpr bool prb_ = false
+#define P_MARK(v) do { (void)(v); } while (0)
+#endif
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -516,7 +524,9 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
             for (int i = 0; i < 8; ++i) gg[i] = __ldg(gp + i * 128);
             if (last_third) g48 = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint4*>(gbase) + 24 * 128 + r));
           }
-          if (s + 1 < a.steps) {                       // next step's input projection (53 KB = 416 lines) -> L2
+          // next step's input projection (53 KB = 416 lines) -> L2.  Not in v8: its register refill already runs a
+          // whole item (> 4 000 cycles) ahead of use, which covers a DRAM round trip without the prefetch instructions.
+          if (MODE != 2 && s + 1 < a.steps) {
             const long step_off = (G.d == 0 ? 1 : -1) * (long)a.seq_tiles * (long)g_tile;
             const char* nx = reinterpret_cast<const char*>(gbase + step_off);
             prefetch_l2(nx + pf_idx * 128);
