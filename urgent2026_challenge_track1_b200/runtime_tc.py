@@ -142,6 +142,9 @@ def workspace(B, T, K, N, dev):
     return ws
 
 
+_EXACT_STATS = os.environ.get("BSRNN_TC_EXACT_STATS", "0") == "1"
+
+
 def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
     """In-place 2*num_layer residual blocks on skip (B,T,K,N) f32, tensor-core mode."""
     B, T, K, N = skip.shape
@@ -180,6 +183,9 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                 L.call("bsrnn_gemm_tc", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
                        ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], L.TC_RESID_F32, N, N, 0, T * K,
                        tiles, R, *addr, st)
+                if _EXACT_STATS:                       # diagnosis: statistics from a separate pass over skip
+                    ws.stats.zero_()
+                    L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
     return skip
 
 
