@@ -12,7 +12,7 @@ ap.add_argument("--B", type=int, default=16); ap.add_argument("--T", type=int, d
 ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, default=3); ap.add_argument("--maxcl", type=int, default=0)
 ap.add_argument("--slots", type=int, default=0); ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--trace-cid", type=int, default=0); ap.add_argument("--flags", type=int, default=0)
-ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..8 (0 = BSRNN_LSTM_VER / default)")
+ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..9 (0 = BSRNN_LSTM_VER / default)")
 ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 B, T, K, axis = a.B, a.T, a.K, a.axis

@@ -576,7 +576,7 @@ template <int VER>   // 4: slot-specialised epilogue; 5: all-warps epilogue; 6: 
                      // 8: 5 + register-refilled gates, FHADD, software-pipelined TMEM loads (epi8_item)
 __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
   constexpr bool V5 = VER >= 5;
-  constexpr bool MC = VER == 6;
+  constexpr bool MC = VER == 6 || VER == 9;          // 9: v8 epilogue + multicast h loads
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + L_W_BYTES;
@@ -761,7 +761,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
     const int k = (warp - 4) >> 2, quad = warp & 3;
 #define BSRNN_EPI_CASE(QQ)                                                                                   \
   case QQ:                                                                                                   \
-    if (VER == 8) epilogue5_role<QQ, 2>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
+    if (VER == 8 || VER == 9) epilogue5_role<QQ, 2>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
     else if (MC) epilogue5_role<QQ, 1>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
     else if (V5) epilogue5_role<QQ, 0>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);  \
     else epilogue_role<QQ>(a, tmem_base, k, quad, lane, cid, ncl, acc_full, acc_empty, w_free);              \
@@ -1123,7 +1123,7 @@ static int max_active_clusters_t() {
 }
 static int max_active_clusters() {
   const int a6 = max_active_clusters_t<6>(), a5 = max_active_clusters_t<5>(), a4 = max_active_clusters_t<4>();
-  const int a8 = max_active_clusters_t<8>();
+  const int a8 = max_active_clusters_t<8>() < max_active_clusters_t<9>() ? max_active_clusters_t<8>() : max_active_clusters_t<9>();
   const int m = (a5 < a4 ? a5 : a4) < a8 ? (a5 < a4 ? a5 : a4) : a8;
   return a6 < m ? a6 : m;
 }
@@ -1141,7 +1141,7 @@ extern "C" void bsrnn_debug_set_lstm_probe(void* p, int cid) {
 // Recurrence schedule: 4 / 5 / 6 / 8 (8-CTA clusters, see lstm_tc_kernel) or 7 (CTA pairs, lstm_tc2_kernel); < 0 = take
 // BSRNN_LSTM_VER from the environment at the next call (default 8).
 static int g_lstm_ver = -1;
-extern "C" void bsrnn_debug_set_lstm_schedule(int ver) { g_lstm_ver = (ver >= 4 && ver <= 8) ? ver : -1; }
+extern "C" void bsrnn_debug_set_lstm_schedule(int ver) { g_lstm_ver = (ver >= 4 && ver <= 9) ? ver : -1; }
 
 // slots: sequence tiles a cluster interleaves (1..3; <= 0 = 3).
 extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
@@ -1163,7 +1163,7 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
     }
     max_active = n;
   }
-  if (g_lstm_ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); g_lstm_ver = (e && e[0] >= '4' && e[0] <= '8') ? e[0] - '0' : 8; }
+  if (g_lstm_ver < 0) { const char* e = getenv("BSRNN_LSTM_VER"); g_lstm_ver = (e && e[0] >= '4' && e[0] <= '9') ? e[0] - '0' : 8; }
   const int ver = g_lstm_ver;
   if (ver == 7) {
     // CTA-pair schedule: units are (direction, PAIR of sequence tiles); 16-CTA clusters
@@ -1192,9 +1192,11 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
   // BSRNN_LSTM_VER=4|5|6|8 selects the schedule for A/B timing.  Default 8 (profiles/r01/call30, BASELINE config 2):
   // v5 7.49 / 6.51 ms (time / band axis), v8 7.16 / 6.31 ms.  The multicast variant (6) gained nothing over 5
   // (call22): the h ring (60 KB in flight / L2 latency) and the MUFU-heavy epilogue pace the kernel, not L2 traffic.
+  // 9 = 8 + multicast h loads: 7.08 / 5.99 ms against 6.84 / 6.02 ms for 8 in the same run (call59): still no gain.
   if (ver == 4) lstm_tc_kernel<4><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
   else if (ver == 5) lstm_tc_kernel<5><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
   else if (ver == 8) lstm_tc_kernel<8><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
+  else if (ver == 9) lstm_tc_kernel<9><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
   else lstm_tc_kernel<6><<<ncl * LCL, LTHREADS, F_SMEM, (cudaStream_t)stream>>>(a);
   BSRNN_LAUNCH_OK();
   return 0;
