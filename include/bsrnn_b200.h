@@ -160,6 +160,15 @@ int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, do
                   int kcores, int BN, int epilogue, long ldo, int n_valid, int out_kcores, long tokens_per_sample,
                   int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
                   void* stream);
+/* bsrnn_lstm_step_tc: ONE time step of one LSTM direction on tensor cores for any hidden size H % 16 == 0 (FlowSE: H = 768,
+ *     which does not fit the persistent kernel above) [nn.LSTM, bsrnn_flowse.py:226-238]: h_{t-1} * W_hh^T as a tcgen05 GEMM
+ *     whose epilogue adds the input projection, applies the gates, updates c in place and writes h_t as the KB8 tile that is
+ *     the next step's A operand and the layer output.  A / out_h: [m_tiles][H/8][128][8] fp16 (zero tiles for the first
+ *     step); W: [n_tiles][H/8][BN][8] fp16, rows reordered to 4u + gate, i/f/o rows pre-halved, BN % 32 == 0;
+ *     gx: rows [m*128 + r][ld_gx] fp16 of this step and direction (same column order, bias included);
+ *     cstate: [m_tiles*128][H] f32. */
+int bsrnn_lstm_step_tc(const void* A, const void* W, const void* gx, float* cstate, void* out_h, int m_tiles, int n_tiles,
+                       int BN, int H, long ld_gx, void* stream);
 int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R, int steps,
                               int seq_tiles, int max_clusters, void* stream);
 int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,

@@ -201,6 +201,49 @@ def test_flowse_vs_golden(fs):
     assert rel_l2(enh2.cpu(), enh3.cpu()) < 1e-4
 
 
+@pytest.mark.parametrize("fs", (16000, 48000))
+def test_flowse_tensorcore_steps_vs_golden(fs):
+    """FlowSE with the dual path on fp16 tensor-core GEMMs + the step-wise tensor-core BLSTM (runtime_tc_steps, any
+    H % 16 == 0): vector field and sampled waveform against the verbatim reference's outputs; bar 1e-2 (16-bit mode)."""
+    g = golden("flowse_n16_l1.npz")
+    m = _flow_model(g)
+    m.dnn.precision = "fp16"
+    y, lens = torch.from_numpy(g[f"in/{fs}/wav"]), torch.from_numpy(g[f"in/{fs}/lens"])
+    z, t = torch.from_numpy(g[f"in/{fs}/z"]), torch.from_numpy(g[f"in/{fs}/t"])
+    Y = m.speech_to_feature(y, fs, lens)
+    vf = m(Y + 0.5 * z.cuda(), t.cuda(), Y)
+    e_vf = rel_l2(vf.cpu(), g[f"out/{fs}/vf"])
+    enh = m.enhance(y, fs, lens, N=3, z=z)
+    e_enh = rel_l2(enh.cpu(), g[f"out/{fs}/enhanced"])
+    print(f"fs={fs} FlowSE tensor-core steps: vf rel_l2={e_vf:.3e} enhanced rel_l2={e_enh:.3e}")
+    assert e_vf < 1e-2 and e_enh < 1e-2
+
+
+def test_lstm_step_tc_vs_torch_h768():
+    """bsrnn_lstm_step_tc at the FlowSE width (N = 384, H = 768), ragged last tile: against torch.nn.LSTM on the CPU."""
+    from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L
+    torch.manual_seed(0)
+    N, H, Rr, steps = 384, 768, 150, 9
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
+    x = torch.randn(Rr, steps, N) * 0.7
+    with torch.no_grad():
+        ref = rnn(x)[0]
+    rnn = rnn.cuda()
+    p = S.pack_lstm_steps_tc(rnn)
+    tiles = (Rr + 127) // 128
+    ws = S.StepsWorkspace(steps, tiles, H, "cuda")
+    xhat = torch.empty(steps * tiles * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
+    xg = x.cuda().contiguous()
+    L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"],
+           steps * tiles, tiles, Rr, 1 << 40, 0, steps, 1, Rr * steps, 1, L.stream_ptr())
+    S.blstm_steps_tc(xhat, p, steps, tiles, ws)
+    outs = []
+    for d in (0, 1):
+        yd = ws.y[d].view(steps, tiles, H // 8, 128, 8).permute(0, 1, 3, 2, 4).reshape(steps, tiles * 128, H)[:, :Rr]
+        outs.append(yd.permute(1, 0, 2).float().cpu())
+    assert rel_l2(torch.cat(outs, 2), ref) < 3e-3
+
+
 def test_flowse_solver_registry_errors():
     from urgent2026_challenge_track1_b200.sampling import ODEsolverRegistry
     assert set(ODEsolverRegistry.get_all_names()) >= {"euler", "midpoint", "heun"}

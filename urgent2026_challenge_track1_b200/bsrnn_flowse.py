@@ -2,17 +2,21 @@
 bsrnn_flowse.py:171-318) with the same constructor, ``forward(dnn_input, t, fs=None)`` signature, ``current_fs``
 attribute and state_dict keys (band_split_x/y, condition_fc, norm/rnn/fc_{time,freq}, t_cond.{i}.W, grad_decoder.*).
 
-All arithmetic runs in libbsrnn_b200 kernels (f32 mode; the H=768 recurrence has no tensor-core kernel yet).  Besides
+All arithmetic runs in libbsrnn_b200 kernels: f32 mode by default; ``precision = "fp16"`` runs the dual path on fp16
+tensor-core GEMMs with the step-wise tensor-core BLSTM of runtime_tc_steps (any H % 16 == 0, so H = 768 too).  Besides
 the reference API the class exposes ``mask_resid(x, y_embed, t)`` working on the (B,T,F,2) layout so the sampler can
 fuse the Euler update with the network output and hoist the loop-invariant ``band_split_y``.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn as nn
 
 from . import _lib as L
 from . import runtime as R
+from . import runtime_tc_steps as TS
 from .layers import BandSplitParams, GradDecoderParams, add_dual_path
 
 
@@ -53,6 +57,10 @@ class BSRNN(nn.Module):
         self.grad_decoder = GradDecoderParams(input_dim, self.band_split_x.subbands, channels=num_channel, num_spk=1)
         self.current_fs = None
         self._dual = R.PackedCache(self, R.pack_dual_path)
+        # precision "fp16": fp16 tensor-core GEMMs + the step-wise tensor-core BLSTM (runtime_tc_steps) for the dual path;
+        # band split, condition_fc and GradDecoder stay f32.  Default f32 everywhere (BSRNN_FLOWSE_PRECISION overrides).
+        self.precision = os.environ.get("BSRNN_FLOWSE_PRECISION", "fp32")
+        self._dual_steps = R.PackedCache(self, TS.pack_dual_path_steps)
         self._bsx = R.PackedCache(self.band_split_x, R.pack_band_split)
         self._bsy = R.PackedCache(self.band_split_y, R.pack_band_split)
         self._gd = R.PackedCache(self.grad_decoder, R.pack_grad_decoder)
@@ -85,7 +93,10 @@ class BSRNN(nn.Module):
         L.call("bsrnn_gemm_f32", dl.ptr(0), 1, M, N, st)
         t = t.to(device=dev, dtype=torch.float32)
         t_emb = [self.t_cond[i](t) for i in range(self.num_layer)]          # bsrnn_flowse.py:293
-        R.dual_path_f32(skip, self._dual.get(), t_emb=t_emb)
+        if self.precision in ("fp16", "bf16"):
+            TS.dual_path_tc_steps(skip, self._dual_steps.get(), t_emb=t_emb)
+        else:
+            R.dual_path_f32(skip, self._dual.get(), t_emb=t_emb)
         return R.grad_decoder_f32(skip, plan, self._gd.get(), self.grad_decoder.sub_channel)
 
     # ------------------------------------------------------------------------------------------------ reference API

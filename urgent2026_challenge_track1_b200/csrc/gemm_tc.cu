@@ -59,6 +59,10 @@ struct GemmTcArgs {
   int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
   int b_resident;                   // 1: each CTA keeps ONE weight tile in shared memory and streams A tiles only
   int pf_dist;                      // A tile this many tiles ahead is bulk-prefetched into L2 (0 = off)
+  const __half* gx;                 // EPI_LSTM_STEP: input projection rows [m*128 + r][ld_gx] fp16 (this step, this direction)
+  float* cstate;                    // EPI_LSTM_STEP: cell state [m*128 + r][H] f32 (this direction), updated in place
+  long ld_gx;
+  int H;
   int debug;                        // BSRNN_GEMM_DEBUG (A/B experiments on the input projection): 1 = every tile
                                     // writes the first tile's output block (stores stay in L2), 2 = no stores
   int stages;                       // pipeline depth: 8 when the shared memory allows (short-K GEMMs: one tile is 4 stages,
@@ -66,7 +70,7 @@ struct GemmTcArgs {
   RowMap rows;
 };
 
-enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4 };
+enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4, EPI_LSTM_STEP = 5 };
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -159,6 +163,39 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
       uint4 pk = make_uint4(pack_h2(v[i], v[i + 1]), pack_h2(v[i + 2], v[i + 3]), pack_h2(v[i + 4], v[i + 5]),
                             pack_h2(v[i + 6], v[i + 7]));
       *reinterpret_cast<uint4*>(o + (long)(i >> 3) * 1024) = pk;
+    }
+  } else if (EPI == EPI_LSTM_STEP) {
+    // One LSTM step for any hidden size (FlowSE, H = 768): the GEMM is h_{t-1} * W_hh^T with gate-interleaved weight
+    // rows (column 4u + gate, i/f/o rows pre-halved like lstm_tc.cu), so a chunk of 32 accumulator columns holds the 4
+    // gates of 8 hidden units of this row: add the input projection (fp16, same column order), update c in place,
+    // and store h_t as ONE 16-byte KB8 core entry of the tile that is next step's A operand and the layer output.
+    // [reference nn.LSTM semantics: bsrnn_flowse.py:226-238; zero initial state = zero A tile and zero c]
+    if (NC == 32) {
+      const int u0 = gc0 >> 2;
+      if (u0 < a.H) {
+        const long grow = (long)m * 128 + r;
+        const uint4* gp = reinterpret_cast<const uint4*>(a.gx + grow * a.ld_gx + gc0);
+        float* cp = a.cstate + grow * a.H + u0;
+        uint4 g4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g4[i] = __ldg(gp + i);
+        float4 c4[2] = {*reinterpret_cast<const float4*>(cp), *reinterpret_cast<const float4*>(cp + 4)};
+        float* c = reinterpret_cast<float*>(c4);
+        const __half2* gh = reinterpret_cast<const __half2*>(g4);
+        float h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 g01 = __half22float2(gh[2 * j]), g23 = __half22float2(gh[2 * j + 1]);
+          const float ig = fmaf(fast_tanh(v[4 * j] + g01.x), 0.5f, 0.5f), fg = fmaf(fast_tanh(v[4 * j + 1] + g01.y), 0.5f, 0.5f);
+          const float gg = fast_tanh(v[4 * j + 2] + g23.x), og = fmaf(fast_tanh(v[4 * j + 3] + g23.y), 0.5f, 0.5f);
+          c[j] = fmaf(fg, c[j], ig * gg);
+          h[j] = og * fast_tanh(c[j]);
+        }
+        *reinterpret_cast<float4*>(cp) = c4[0];
+        *reinterpret_cast<float4*>(cp + 4) = c4[1];
+        __half* o = reinterpret_cast<__half*>(a.out) + (((long)m * (a.H >> 3) + (u0 >> 3)) * 128 + r) * 8;
+        *reinterpret_cast<uint4*>(o) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+      }
     }
   } else if (EPI == EPI_TANH_KB8) {
     __half* o = reinterpret_cast<__half*>(a.out);
@@ -568,7 +605,7 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && tokens_per_sample > 0, "gemm_tc: bad row map");
   BSRNN_CHECK_ARG(epilogue != EPI_RESID_F32 || (n_valid % 4 == 0 && ldo % 4 == 0),
                   "gemm_tc: the residual epilogue needs n_valid and ldo to be multiples of 4 (got %d, %ld)", n_valid, ldo);
-  GemmTcArgs a;
+  GemmTcArgs a{};
   a.A = reinterpret_cast<const __half*>(A);
   a.W = reinterpret_cast<const __half*>(W);
   a.bias = bias; a.out = out; a.stats = stats; a.ldo = ldo; a.tokens_per_sample = tokens_per_sample;
@@ -584,4 +621,24 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   }
   set_error("gemm_tc: unknown epilogue %d", epilogue);
   return 1;
+}
+
+// One time step of an LSTM direction on tensor cores, any H % 8 == 0 (csrc/gemm_tc.cu, EPI_LSTM_STEP):
+//   A      [m_tiles][H/8][128][8] fp16  h_{t-1} tiles (a zero tile set for the first step)
+//   W      [n_tiles][H/8][BN][8]  fp16  W_hh with rows reordered to 4u + gate and i/f/o rows pre-halved; BN % 32 == 0
+//   gx     rows [m*128 + r][ld_gx] fp16: input projection (+ bias) of THIS step and direction, same column order
+//   cstate [m_tiles*128][H] f32, updated in place;   out_h: h_t tiles, same layout as A
+extern "C" int bsrnn_lstm_step_tc(const void* A, const void* W, const void* gx, float* cstate, void* out_h, int m_tiles,
+                                  int n_tiles, int BN, int H, long ld_gx, void* stream) {
+  BSRNN_CHECK_ARG(A && W && gx && cstate && out_h, "lstm_step_tc: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 16 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
+                  (long)n_tiles * BN >= 4L * H && ld_gx >= 4L * H && ld_gx % 8 == 0, "lstm_step_tc: bad dims");
+  GemmTcArgs a{};
+  a.A = reinterpret_cast<const __half*>(A);
+  a.W = reinterpret_cast<const __half*>(W);
+  a.bias = nullptr; a.out = out_h; a.stats = nullptr; a.ldo = 0; a.tokens_per_sample = 1;
+  a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = H / 8; a.BN = BN; a.n_valid = 4 * H; a.out_kcores = H / 8;
+  a.gx = reinterpret_cast<const __half*>(gx); a.cstate = cstate; a.ld_gx = ld_gx; a.H = H;
+  a.rows = RowMap{m_tiles, m_tiles * 128, 1L << 40, 0, 1, 0};
+  return launch_tc<EPI_LSTM_STEP>(a, (cudaStream_t)stream);
 }

@@ -1,0 +1,145 @@
+"""Step-wise tensor-core BLSTM for hidden sizes the persistent cluster kernel does not cover (FlowSE: N = 384, H = 768;
+reference nn.LSTM(N, 2N, bidirectional), bsrnn_flowse.py:226-238, called at :296-297 / :303-304).
+
+One launch per (time step, direction): `bsrnn_lstm_step_tc` = tcgen05 GEMM h_{t-1} * W_hh^T whose epilogue adds the input
+projection, applies the gates (f32, MUFU tanh), updates c in place and writes h_t in the KB8 tile layout -- the tile is
+the next step's A operand and the layer output.  The input projection of ALL steps and both directions is one
+`bsrnn_gemm_tc` launch (fp16 rows, bias in its epilogue).  Gate columns are interleaved (4u + gate) and the i/f/o rows
+of W_ih / W_hh / bias pre-halved, exactly as in runtime_tc.pack_lstm_tc.
+
+Layouts (rows of an axis are grouped in tiles of 128 sequences; m = step*tiles + j):
+  xhat   [steps*tiles][kc_in][128][8] fp16          (bsrnn_norm_cast_kb8 with the axis' row map)
+  gates  rows [m*128 + r][2 * 4H] fp16              (direction-major columns)
+  y[d]   [steps*tiles][H/8][128][8] fp16            (per direction: the fc GEMM consumes the two as K halves)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .runtime_tc import GATE_SCALE, to_kb8
+
+
+def _bn_for(cols):
+    for bn in (256, 224, 192, 160, 128, 96, 64, 32):
+        if cols % bn == 0:
+            return bn
+    return 256
+
+
+def pack_lstm_steps_tc(rnn):
+    H, N = rnn.weight_hh_l0.shape[1], rnn.weight_ih_l0.shape[1]
+    if H % 16:
+        raise NotImplementedError(f"step-wise tensor-core LSTM needs H % 16 == 0, got {H}")
+    dev = rnn.weight_hh_l0.device
+    u = torch.arange(H, device=dev)
+    perm = (torch.arange(4, device=dev)[None, :] * H + u[:, None]).reshape(-1)          # packed row 4u+g <- g*H + u
+    gsc = torch.tensor(GATE_SCALE, device=dev).repeat(H)[:, None]
+    kc_in = (N + 15) // 16 * 2
+    BN = _bn_for(4 * H)
+    wih, bias, whh = [], [], []
+    for sfx in ("", "_reverse"):
+        wi = getattr(rnn, "weight_ih_l0" + sfx).float()[perm] * gsc
+        wh = getattr(rnn, "weight_hh_l0" + sfx).float()[perm] * gsc
+        b = (getattr(rnn, "bias_ih_l0" + sfx) + getattr(rnn, "bias_hh_l0" + sfx)).float()[perm] * gsc[:, 0]
+        wih.append(wi); bias.append(b); whh.append(to_kb8(wh, BN, H // 8))
+    return dict(wih=to_kb8(torch.cat(wih, 0), BN, kc_in), bias=torch.cat(bias).contiguous(), whh=whh, BN=BN, H=H, N=N,
+                kc_in=kc_in, n_tiles=4 * H // BN)
+
+
+class StepsWorkspace:
+    def __init__(self, steps, tiles, H, dev):
+        rows = steps * tiles * 128
+        self.gates = torch.empty(rows, 2 * 4 * H, dtype=torch.float16, device=dev)
+        self.y = [torch.empty(steps * tiles * (H // 8) * 1024, dtype=torch.float16, device=dev) for _ in range(2)]
+        self.c = [torch.empty(tiles * 128, H, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.zero = torch.zeros(tiles * (H // 8) * 1024, dtype=torch.float16, device=dev)
+
+
+def blstm_steps_tc(xhat, p, steps, tiles, ws: StepsWorkspace):
+    """xhat: KB8 operand tiles of the normalised input (steps*tiles m-tiles).  Fills ws.y[0] (forward) / ws.y[1]."""
+    st = L.stream_ptr()
+    H, BN, nt = p["H"], p["BN"], p["n_tiles"]
+    m_all = steps * tiles
+    # all steps, both directions: gates rows = m*128 + r (identity row map), bias added in the epilogue
+    L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bias"].data_ptr(), ws.gates.data_ptr(), None, m_all,
+           2 * nt, p["kc_in"], BN, L.TC_F16_ROWS, 8 * H, 8 * H, 0, 1, m_all, m_all * 128, 1 << 40, 0, 1, 0, st)
+    tile_halves = (H // 8) * 1024
+    for d in (0, 1):
+        ws.c[d].zero_()
+    for s in range(steps):
+        for d in (0, 1):
+            cur = s if d == 0 else steps - 1 - s
+            prev = cur - 1 if d == 0 else cur + 1
+            a_ptr = ws.zero.data_ptr() if s == 0 else ws.y[d].data_ptr() + 2 * prev * tiles * tile_halves
+            L.call("bsrnn_lstm_step_tc", a_ptr, p["whh"][d].data_ptr(),
+                   ws.gates.data_ptr() + 2 * (cur * tiles * 128 * 8 * H + d * 4 * H), ws.c[d].data_ptr(),
+                   ws.y[d].data_ptr() + 2 * cur * tiles * tile_halves, tiles, nt, BN, H, 8 * H, st)
+    return ws.y
+
+
+# ------------------------------------------------------------------------------------------------ dual path (FlowSE)
+def pack_dual_path_steps(mod):
+    """Tensor-core packing of the 2*num_layer (GN, BLSTM, Linear) blocks of a module with norm_/rnn_/fc_{time,freq}
+    ModuleLists, for the step-wise kernels: the Linear(2H -> N) is split into its forward / backward K halves."""
+    layers = []
+    for i in range(mod.num_layer):
+        e = {}
+        for axis in ("time", "freq"):
+            norm, rnn, fc = getattr(mod, f"norm_{axis}")[i], getattr(mod, f"rnn_{axis}")[i], getattr(mod, f"fc_{axis}")[i]
+            p = pack_lstm_steps_tc(rnn)
+            H, N = p["H"], fc.weight.shape[0]
+            bn = next(b for b in (256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16)
+                      if ((N + 15) // 16 * 16) % b == 0)
+            nt = ((N + 15) // 16 * 16) // bn
+            w = fc.weight.float()
+            bias = torch.zeros(nt * bn, device=w.device)
+            bias[:N] = fc.bias.float()
+            p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(),
+                     fcw=[to_kb8(w[:, :H], bn, H // 8), to_kb8(w[:, H:], bn, H // 8)], fcb=bias,
+                     fcb0=torch.zeros_like(bias), fc_bn=bn, fc_nt=nt)
+            e[axis] = p
+        layers.append(e)
+    return layers
+
+
+_WS = {}
+
+
+def dual_path_tc_steps(skip, layers, t_emb=None):
+    """In-place 2*num_layer residual blocks on skip (B,T,K,N) f32 with fp16 tensor-core GEMMs and the step-wise BLSTM.
+    Same call pattern as runtime.dual_path_f32 (t_emb: list of (B,N) per layer, added after the time-axis GroupNorm)."""
+    from .runtime import _layer_norm_tables, region
+    B, T, K, N = skip.shape
+    dev = skip.device
+    st = L.stream_ptr()
+    H = layers[0]["time"]["H"]
+    tiles_t, tiles_f = (B * K + 127) // 128, (B * T + 127) // 128
+    key = (B, T, K, N, H, str(dev))
+    ws = _WS.get(key)
+    if ws is None:
+        _WS.clear()
+        kc_in = layers[0]["time"]["kc_in"]
+        ntile = max(T * tiles_t, K * tiles_f)
+        ws = _WS[key] = dict(xhat=torch.empty(ntile * kc_in * 1024, dtype=torch.float16, device=dev),
+                             time=StepsWorkspace(T, tiles_t, H, dev), freq=StepsWorkspace(K, tiles_f, H, dev))
+    for i, lay in enumerate(layers):
+        for axis in ("time", "freq"):
+            w = lay[axis]
+            extra = t_emb[i] if (t_emb is not None and axis == "time") else None      # bsrnn_flowse.py:293-294
+            if axis == "time":
+                R_, steps, tiles, addr = B * K, T, tiles_t, (K, T * K, 1, K)
+            else:
+                R_, steps, tiles, addr = B * T, K, tiles_f, (1, K, 0, 1)
+            with region("norm"):
+                scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra)
+                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws["xhat"].data_ptr(),
+                       N, 0, N, w["kc_in"], steps * tiles, tiles, R_, *addr, T * K, 1, st)
+            with region(f"lstm_{axis}"):
+                y = blstm_steps_tc(ws["xhat"], w, steps, tiles, ws[axis])
+            with region("fc"):
+                for half, bias in ((0, w["fcb"]), (1, w["fcb0"])):       # skip += y_fwd W_f^T + b, then += y_bwd W_b^T
+                    L.call("bsrnn_gemm_tc", y[half].data_ptr(), w["fcw"][half].data_ptr(), bias.data_ptr(), skip.data_ptr(),
+                           None, steps * tiles, w["fc_nt"], H // 8, w["fc_bn"], L.TC_RESID_F32, N, N, 0, T * K,
+                           tiles, R_, *addr, st)
+    return skip
