@@ -201,13 +201,14 @@ def test_flowse_vs_golden(fs):
     assert rel_l2(enh2.cpu(), enh3.cpu()) < 1e-4
 
 
-@pytest.mark.parametrize("fs", (16000, 48000))
-def test_flowse_tensorcore_steps_vs_golden(fs):
+@pytest.mark.parametrize("fs,graph", [(16000, False), (48000, False), (48000, True)])
+def test_flowse_tensorcore_steps_vs_golden(fs, graph):
     """FlowSE with the dual path on fp16 tensor-core GEMMs + the step-wise tensor-core BLSTM (runtime_tc_steps, any
     H % 16 == 0): vector field and sampled waveform against the verbatim reference's outputs; bar 1e-2 (16-bit mode)."""
     g = golden("flowse_n16_l1.npz")
     m = _flow_model(g)
     m.dnn.precision = "fp16"
+    m.dnn.cuda_graph = graph                    # graph: one captured network evaluation replayed per Euler step
     y, lens = torch.from_numpy(g[f"in/{fs}/wav"]), torch.from_numpy(g[f"in/{fs}/lens"])
     z, t = torch.from_numpy(g[f"in/{fs}/z"]), torch.from_numpy(g[f"in/{fs}/t"])
     Y = m.speech_to_feature(y, fs, lens)
@@ -215,8 +216,11 @@ def test_flowse_tensorcore_steps_vs_golden(fs):
     e_vf = rel_l2(vf.cpu(), g[f"out/{fs}/vf"])
     enh = m.enhance(y, fs, lens, N=3, z=z)
     e_enh = rel_l2(enh.cpu(), g[f"out/{fs}/enhanced"])
-    print(f"fs={fs} FlowSE tensor-core steps: vf rel_l2={e_vf:.3e} enhanced rel_l2={e_enh:.3e}")
-    assert e_vf < 1e-2 and e_enh < 1e-2
+    enh_again = m.enhance(y, fs, lens, N=3, z=z)   # second call: pure replays (graph) / reused workspaces
+    print(f"fs={fs} graph={graph} FlowSE tensor-core steps: vf rel_l2={e_vf:.3e} enhanced rel_l2={e_enh:.3e}")
+    assert e_vf < 1e-2 and e_enh < 1e-2 and rel_l2(enh_again.cpu(), enh.cpu()) < 1e-6
+    if graph:
+        assert len(m.dnn._graphs) == 1
 
 
 def test_lstm_step_tc_vs_torch_h768():

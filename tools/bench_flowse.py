@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=2); ap.add_argument("--seconds", type=float, default=10.0)
 ap.add_argument("--nfe", type=int, default=15); ap.add_argument("--hidden", type=int, default=384)
 ap.add_argument("--layers", type=int, default=6); ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"])
+ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"]); ap.add_argument("--graph", action="store_true")
 a = ap.parse_args()
 _lib.require_device()
 torch.manual_seed(0)
@@ -25,6 +25,7 @@ cfg = Config(model_type="flowse", ema_decay=0.999, sigma_max=0.5, sigma_min=0.05
              spec_factor=0.065, bsrnn_hidden=a.hidden, num_layer=a.layers, learning_rate=1e-4)
 m = FlowSEModel(cfg).cuda().eval(no_ema=True)
 m.dnn.precision = a.precision
+m.dnn.cuda_graph = a.graph
 fs, n = 48000, int(48000 * a.seconds)
 y = R.synth_noisy(a.batch, n, fs, seed=5).cuda()
 lens = torch.full((a.batch,), n, dtype=torch.int32)
@@ -37,6 +38,6 @@ for _ in range(a.reps):
     e0.record(); out = m.enhance(y, fs, lens, N=a.nfe); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ms = min(ts)
-print(json.dumps({"workload": f"BSRNN_flowse N={a.hidden} L={a.layers}, {a.batch}x{a.seconds:g}s@48kHz, NFE={a.nfe}, dual path {a.precision}",
+print(json.dumps({"workload": f"BSRNN_flowse N={a.hidden} L={a.layers}, {a.batch}x{a.seconds:g}s@48kHz, NFE={a.nfe}, dual path {a.precision}{', CUDA graph' if a.graph else ''}",
                   "ms": ms, "audio_s_per_s": a.batch * a.seconds / (ms / 1e3), "finite": bool(torch.isfinite(out).all()),
                   "out_shape": list(out.shape)}))

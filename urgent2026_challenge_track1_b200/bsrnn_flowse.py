@@ -61,6 +61,11 @@ class BSRNN(nn.Module):
         # band split, condition_fc and GradDecoder stay f32.  Default f32 everywhere (BSRNN_FLOWSE_PRECISION overrides).
         self.precision = os.environ.get("BSRNN_FLOWSE_PRECISION", "fp32")
         self._dual_steps = R.PackedCache(self, TS.pack_dual_path_steps)
+        # cuda_graph: replay one network evaluation (tens of thousands of launches in the step-wise mode) from a captured
+        # CUDA graph, one graph per input shape, rebuilt when parameters change.  Default from BSRNN_B200_GRAPH (off).
+        self.cuda_graph = os.environ.get("BSRNN_B200_GRAPH", "0") == "1"
+        self._graphs = {}
+        self._zz = {}
         self._bsx = R.PackedCache(self.band_split_x, R.pack_band_split)
         self._bsy = R.PackedCache(self.band_split_y, R.pack_band_split)
         self._gd = R.PackedCache(self.grad_decoder, R.pack_grad_decoder)
@@ -71,13 +76,35 @@ class BSRNN(nn.Module):
         B, T, F, _ = y_btf.shape
         plan = R.BandPlan.make(self.band_split_x.subbands, F)
         N = self.num_channel
-        zz = torch.empty(B, T, plan.K, 2 * N, dtype=torch.float32, device=y_btf.device)
+        zkey = (B, T, plan.K, 2 * N, str(y_btf.device))
+        zz = self._zz.get(zkey)                 # persistent per shape: a captured graph keeps pointing at it
+        if zz is None:
+            self._zz.clear()
+            zz = self._zz[zkey] = torch.empty(B, T, plan.K, 2 * N, dtype=torch.float32, device=y_btf.device)
         R.band_split_f32(y_btf, plan, self._bsy.get(), N, out=zz, out_col=N, out_width=2 * N)
         return zz, plan
 
     @torch.no_grad()
     def mask_resid(self, x_btf, zz, plan, t):
-        """One network evaluation on the (B,T,F,2) layout -> (mask, resid) with g = mask*x + resid."""
+        """One network evaluation on the (B,T,F,2) layout -> (mask, resid) with g = mask*x + resid.  With cuda_graph the
+        returned tensors are the graph's own outputs: valid until the next call (the Euler update consumes them at once)."""
+        if not self.cuda_graph:
+            return self._mask_resid_eager(x_btf, zz, plan, t)
+        dev = x_btf.device
+        t = t.to(device=dev, dtype=torch.float32)
+        params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = (tuple(x_btf.shape), zz.data_ptr(), self.precision)
+        entry = self._graphs.get(key)
+        if entry is None or entry[1] != params:
+            torch.cuda.synchronize(dev)         # a replay of the graph being replaced may still be running
+            self._graphs.clear()
+            xs, ts = x_btf.clone(), t.clone()
+            g = R.GraphedForward(lambda a, b: self._mask_resid_eager(a, zz, plan, b), [xs, ts], keep=[zz])
+            entry = self._graphs[key] = (g, params)
+        return entry[0].run(x_btf, t)
+
+    @torch.no_grad()
+    def _mask_resid_eager(self, x_btf, zz, plan, t):
         B, T, F, _ = x_btf.shape
         N = self.num_channel
         dev = x_btf.device
