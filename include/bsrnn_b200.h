@@ -169,6 +169,11 @@ int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, do
  *     cstate: [m_tiles*128][H] f32. */
 int bsrnn_lstm_step_tc(const void* A, const void* W, const void* gx, float* cstate, void* out_h, int m_tiles, int n_tiles,
                        int BN, int H, long ld_gx, void* stream);
+/* bsrnn_blstm_step_tc: the forward and the backward direction of one BLSTM time step in ONE launch (row tiles
+ *     [0, m_tiles) use the *_f pointers, [m_tiles, 2*m_tiles) the *_b pointers); arguments as bsrnn_lstm_step_tc. */
+int bsrnn_blstm_step_tc(const void* A_f, const void* W_f, const void* gx_f, float* c_f, void* out_f, const void* A_b,
+                        const void* W_b, const void* gx_b, float* c_b, void* out_b, int m_tiles, int n_tiles, int BN,
+                        int H, long ld_gx, void* stream);
 int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R, int steps,
                               int seq_tiles, int max_clusters, void* stream);
 int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,

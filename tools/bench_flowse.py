@@ -38,6 +38,13 @@ for _ in range(a.reps):
     e0.record(); out = m.enhance(y, fs, lens, N=a.nfe); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ms = min(ts)
+if os.environ.get("BSRNN_FLOWSE_REGIONS", "0") == "1":
+    from urgent2026_challenge_track1_b200 import runtime
+    m.dnn.cuda_graph = False
+    with runtime.Profile() as prof:
+        out = m.enhance(y, fs, lens, N=1)
+        torch.cuda.synchronize()
+        print("regions of ONE network evaluation (ms):", {k: round(v[0], 1) for k, v in prof.totals_ms().items()}, file=sys.stderr)
 print(json.dumps({"workload": f"BSRNN_flowse N={a.hidden} L={a.layers}, {a.batch}x{a.seconds:g}s@48kHz, NFE={a.nfe}, dual path {a.precision}{', CUDA graph' if a.graph else ''}",
                   "ms": ms, "audio_s_per_s": a.batch * a.seconds / (ms / 1e3), "finite": bool(torch.isfinite(out).all()),
                   "out_shape": list(out.shape)}))

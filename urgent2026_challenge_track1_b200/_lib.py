@@ -40,6 +40,8 @@ PROTOTYPES = {
     "bsrnn_gemm_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long,
                       c_int, c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
     "bsrnn_lstm_step_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long, c_void_p],
+    "bsrnn_blstm_step_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_int, c_int, c_int, c_int, c_long, c_void_p],
     "bsrnn_blstm_recurrence_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p],

@@ -63,6 +63,10 @@ struct GemmTcArgs {
   float* cstate;                    // EPI_LSTM_STEP: cell state [m*128 + r][H] f32 (this direction), updated in place
   long ld_gx;
   int H;
+  // EPI_LSTM_STEP, both directions in one launch: row tiles m >= dir_tiles belong to the second direction and use the
+  // *2 pointers with m - dir_tiles (0 = single direction)
+  int dir_tiles;
+  const __half* A2; const __half* W2; const __half* gx2; float* cstate2; void* out2;
   int debug;                        // BSRNN_GEMM_DEBUG (A/B experiments on the input projection): 1 = every tile
                                     // writes the first tile's output block (stores stay in L2), 2 = no stores
   int stages;                       // pipeline depth: 8 when the shared memory allows (short-K GEMMs: one tile is 4 stages,
@@ -173,9 +177,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
     if (NC == 32) {
       const int u0 = gc0 >> 2;
       if (u0 < a.H) {
-        const long grow = (long)m * 128 + r;
-        const uint4* gp = reinterpret_cast<const uint4*>(a.gx + grow * a.ld_gx + gc0);
-        float* cp = a.cstate + grow * a.H + u0;
+        const bool dir2 = a.dir_tiles > 0 && m >= a.dir_tiles;
+        const int md = dir2 ? m - a.dir_tiles : m;
+        const long grow = (long)md * 128 + r;
+        const uint4* gp = reinterpret_cast<const uint4*>((dir2 ? a.gx2 : a.gx) + grow * a.ld_gx + gc0);
+        float* cp = (dir2 ? a.cstate2 : a.cstate) + grow * a.H + u0;
         uint4 g4[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) g4[i] = __ldg(gp + i);
@@ -193,7 +199,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
         }
         *reinterpret_cast<float4*>(cp) = c4[0];
         *reinterpret_cast<float4*>(cp + 4) = c4[1];
-        __half* o = reinterpret_cast<__half*>(a.out) + (((long)m * (a.H >> 3) + (u0 >> 3)) * 128 + r) * 8;
+        __half* o = reinterpret_cast<__half*>(dir2 ? a.out2 : a.out) + (((long)md * (a.H >> 3) + (u0 >> 3)) * 128 + r) * 8;
         *reinterpret_cast<uint4*>(o) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
       }
     }
@@ -336,8 +342,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
       }
       for (; ti.valid(); ti.next()) {
-        const uint8_t* gA = reinterpret_cast<const uint8_t*>(a.A) + (size_t)ti.m * a.kcores * 2048;
-        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)ti.n * a.kcores * BN * 16;
+        const bool dir2 = a.dir_tiles > 0 && ti.m >= a.dir_tiles;
+        const uint8_t* gA = reinterpret_cast<const uint8_t*>(dir2 ? a.A2 : a.A) + (size_t)(dir2 ? ti.m - a.dir_tiles : ti.m) * a.kcores * 2048;
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>(dir2 ? a.W2 : a.W) + (size_t)ti.n * a.kcores * BN * 16;
         if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
           const TileIter t3 = ti.ahead(a.pf_dist);
           if (t3.valid() && (a.b_resident ? ti.n == pf_mod : t3.n == 0))
@@ -640,5 +647,26 @@ extern "C" int bsrnn_lstm_step_tc(const void* A, const void* W, const void* gx, 
   a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = H / 8; a.BN = BN; a.n_valid = 4 * H; a.out_kcores = H / 8;
   a.gx = reinterpret_cast<const __half*>(gx); a.cstate = cstate; a.ld_gx = ld_gx; a.H = H;
   a.rows = RowMap{m_tiles, m_tiles * 128, 1L << 40, 0, 1, 0};
+  return launch_tc<EPI_LSTM_STEP>(a, (cudaStream_t)stream);
+}
+
+// Both directions of one BLSTM time step in ONE launch (the two chains are independent, so their launch / prologue /
+// first-load latencies overlap): the *_f pointers serve row tiles [0, m_tiles), the *_b pointers row tiles
+// [m_tiles, 2*m_tiles).  Arguments as bsrnn_lstm_step_tc.
+extern "C" int bsrnn_blstm_step_tc(const void* A_f, const void* W_f, const void* gx_f, float* c_f, void* out_f,
+                                   const void* A_b, const void* W_b, const void* gx_b, float* c_b, void* out_b, int m_tiles,
+                                   int n_tiles, int BN, int H, long ld_gx, void* stream) {
+  BSRNN_CHECK_ARG(A_f && W_f && gx_f && c_f && out_f && A_b && W_b && gx_b && c_b && out_b, "blstm_step_tc: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 16 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
+                  (long)n_tiles * BN >= 4L * H && ld_gx >= 4L * H && ld_gx % 8 == 0, "blstm_step_tc: bad dims");
+  GemmTcArgs a{};
+  a.A = reinterpret_cast<const __half*>(A_f); a.W = reinterpret_cast<const __half*>(W_f);
+  a.A2 = reinterpret_cast<const __half*>(A_b); a.W2 = reinterpret_cast<const __half*>(W_b);
+  a.bias = nullptr; a.out = out_f; a.out2 = out_b; a.stats = nullptr; a.ldo = 0; a.tokens_per_sample = 1;
+  a.m_tiles = 2 * m_tiles; a.dir_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = H / 8; a.BN = BN; a.n_valid = 4 * H;
+  a.out_kcores = H / 8;
+  a.gx = reinterpret_cast<const __half*>(gx_f); a.gx2 = reinterpret_cast<const __half*>(gx_b);
+  a.cstate = c_f; a.cstate2 = c_b; a.ld_gx = ld_gx; a.H = H;
+  a.rows = RowMap{2 * m_tiles, 2 * m_tiles * 128, 1L << 40, 0, 1, 0};
   return launch_tc<EPI_LSTM_STEP>(a, (cudaStream_t)stream);
 }

@@ -67,14 +67,17 @@ def blstm_steps_tc(xhat, p, steps, tiles, ws: StepsWorkspace):
     tile_halves = (H // 8) * 1024
     for d in (0, 1):
         ws.c[d].zero_()
+    g0 = ws.gates.data_ptr()
     for s in range(steps):
+        ptrs = []
         for d in (0, 1):
             cur = s if d == 0 else steps - 1 - s
             prev = cur - 1 if d == 0 else cur + 1
             a_ptr = ws.zero.data_ptr() if s == 0 else ws.y[d].data_ptr() + 2 * prev * tiles * tile_halves
-            L.call("bsrnn_lstm_step_tc", a_ptr, p["whh"][d].data_ptr(),
-                   ws.gates.data_ptr() + 2 * (cur * tiles * 128 * 8 * H + d * 4 * H), ws.c[d].data_ptr(),
-                   ws.y[d].data_ptr() + 2 * cur * tiles * tile_halves, tiles, nt, BN, H, 8 * H, st)
+            ptrs += [a_ptr, p["whh"][d].data_ptr(), g0 + 2 * (cur * tiles * 128 * 8 * H + d * 4 * H), ws.c[d].data_ptr(),
+                     ws.y[d].data_ptr() + 2 * cur * tiles * tile_halves]
+        # both directions of the step in one launch: their launch / prologue / first-load latencies overlap
+        L.call("bsrnn_blstm_step_tc", *ptrs, tiles, nt, BN, H, 8 * H, st)
     return ws.y
 
 
