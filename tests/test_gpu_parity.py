@@ -176,6 +176,7 @@ def _flow_model(g):
                  spec_abs_exponent=0.667, spec_factor=0.065, bsrnn_hidden=16, num_layer=1, learning_rate=1e-4)
     m = FlowSEModel(cfg)
     m.load_state_dict(golden_sd(g))
+    m.dnn.precision = "fp32"                    # the f32-bar tests below; the tensor-core tests switch it themselves
     return m.cuda().eval(no_ema=True)
 
 

@@ -16,7 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=2); ap.add_argument("--seconds", type=float, default=10.0)
 ap.add_argument("--nfe", type=int, default=15); ap.add_argument("--hidden", type=int, default=384)
 ap.add_argument("--layers", type=int, default=6); ap.add_argument("--reps", type=int, default=2)
-ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16"]); ap.add_argument("--graph", action="store_true")
+ap.add_argument("--precision", default="fp16", choices=["fp32", "fp16"]); ap.add_argument("--graph", action="store_true")
 a = ap.parse_args()
 _lib.require_device()
 torch.manual_seed(0)

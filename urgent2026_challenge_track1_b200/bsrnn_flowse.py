@@ -2,8 +2,9 @@
 bsrnn_flowse.py:171-318) with the same constructor, ``forward(dnn_input, t, fs=None)`` signature, ``current_fs``
 attribute and state_dict keys (band_split_x/y, condition_fc, norm/rnn/fc_{time,freq}, t_cond.{i}.W, grad_decoder.*).
 
-All arithmetic runs in libbsrnn_b200 kernels: f32 mode by default; ``precision = "fp16"`` runs the dual path on fp16
-tensor-core GEMMs with the step-wise tensor-core BLSTM of runtime_tc_steps (any H % 16 == 0, so H = 768 too).  Besides
+All arithmetic runs in libbsrnn_b200 kernels.  ``precision = "fp16"`` (default) runs the dual path on fp16 tensor-core
+GEMMs with the step-wise tensor-core BLSTM of runtime_tc_steps (any H % 16 == 0, so H = 768 too); ``"fp32"`` keeps
+everything on the CUDA-core kernels.  Besides
 the reference API the class exposes ``mask_resid(x, y_embed, t)`` working on the (B,T,F,2) layout so the sampler can
 fuse the Euler update with the network output and hoist the loop-invariant ``band_split_y``.
 """
@@ -57,9 +58,12 @@ class BSRNN(nn.Module):
         self.grad_decoder = GradDecoderParams(input_dim, self.band_split_x.subbands, channels=num_channel, num_spk=1)
         self.current_fs = None
         self._dual = R.PackedCache(self, R.pack_dual_path)
-        # precision "fp16": fp16 tensor-core GEMMs + the step-wise tensor-core BLSTM (runtime_tc_steps) for the dual path;
-        # band split, condition_fc and GradDecoder stay f32.  Default f32 everywhere (BSRNN_FLOWSE_PRECISION overrides).
-        self.precision = os.environ.get("BSRNN_FLOWSE_PRECISION", "fp32")
+        # precision "fp16" (default when H = 2*num_channel is a multiple of 16): fp16 tensor-core GEMMs + the step-wise
+        # tensor-core BLSTM (runtime_tc_steps) for the dual path -- 99 % of the FLOPs; band split, condition_fc and
+        # GradDecoder stay f32.  Against the f32 path at the full width (N=384, L=6): vector field 3.2e-4, enhanced
+        # waveform 8.7e-5 relative L2 (tools/flowse_fp16_vs_f32.py), i.e. inside the f32 bar of 1e-3 as well.
+        # "fp32": CUDA-core kernels everywhere.  BSRNN_FLOWSE_PRECISION overrides the default.
+        self.precision = os.environ.get("BSRNN_FLOWSE_PRECISION", "fp16" if (2 * num_channel) % 16 == 0 else "fp32")
         self._dual_steps = R.PackedCache(self, TS.pack_dual_path_steps)
         # cuda_graph: replay one network evaluation (tens of thousands of launches in the step-wise mode) from a captured
         # CUDA graph, one graph per input shape, rebuilt when parameters change.  Default from BSRNN_B200_GRAPH (off).
