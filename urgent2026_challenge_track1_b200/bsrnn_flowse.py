@@ -59,9 +59,9 @@ class BSRNN(nn.Module):
         self.current_fs = None
         self._dual = R.PackedCache(self, R.pack_dual_path)
         # precision "fp16" (default when H = 2*num_channel is a multiple of 16): fp16 tensor-core GEMMs + the step-wise
-        # tensor-core BLSTM (runtime_tc_steps) for the dual path -- 99 % of the FLOPs; band split, condition_fc and
-        # GradDecoder stay f32.  Against the f32 path at the full width (N=384, L=6): vector field 3.2e-4, enhanced
-        # waveform 8.7e-5 relative L2 (tools/flowse_fp16_vs_f32.py), i.e. inside the f32 bar of 1e-3 as well.
+        # tensor-core BLSTM (runtime_tc_steps) for the dual path and condition_fc -- 99 % of the FLOPs; band split and
+        # GradDecoder stay f32.  Against the f32 path at the full width (N=384, L=6): vector field 4.2e-4, enhanced
+        # waveform 1.3e-4 relative L2 (tools/flowse_fp16_vs_f32.py), i.e. inside the f32 bar of 1e-3 as well.
         # "fp32": CUDA-core kernels everywhere.  BSRNN_FLOWSE_PRECISION overrides the default.
         self.precision = os.environ.get("BSRNN_FLOWSE_PRECISION", "fp16" if (2 * num_channel) % 16 == 0 else "fp32")
         self._dual_steps = R.PackedCache(self, TS.pack_dual_path_steps)
@@ -70,6 +70,8 @@ class BSRNN(nn.Module):
         self.cuda_graph = os.environ.get("BSRNN_B200_GRAPH", "0") == "1"
         self._graphs = {}
         self._zz = {}
+        self._cond_tc = R.PackedCache(self.condition_fc, TS.pack_linear_tc)
+        self._cond_ws = None
         self._bsx = R.PackedCache(self.band_split_x, R.pack_band_split)
         self._bsy = R.PackedCache(self.band_split_y, R.pack_band_split)
         self._gd = R.PackedCache(self.grad_decoder, R.pack_grad_decoder)
@@ -116,12 +118,28 @@ class BSRNN(nn.Module):
         R.band_split_f32(x_btf, plan, self._bsx.get(), N, out=zz, out_col=0, out_width=2 * N)
         skip = torch.empty(B, T, plan.K, N, dtype=torch.float32, device=dev)
         M = B * T * plan.K
-        dl = R.DescList()
-        w, b = self.condition_fc.weight, self.condition_fc.bias               # bsrnn_flowse.py:284-285
-        dl.add(**R._rows_desc(zz.data_ptr(), w.data_ptr(), b.data_ptr(), skip.data_ptr(), M, N, 2 * N,
-                              a_stride=2 * N, c_stride=N))
-        dl.upload(dev)
-        L.call("bsrnn_gemm_f32", dl.ptr(0), 1, M, N, st)
+        if self.precision in ("fp16", "bf16") and (2 * N) % 8 == 0 and N % 4 == 0:
+            # condition_fc Linear(2N -> N) [bsrnn_flowse.py:284-285] on tensor cores: zz -> fp16 KB8 operand tiles (token
+            # order), then the residual-epilogue GEMM into a zeroed skip (1.1 TFLOP per evaluation at config 4: 45 ms on
+            # the f32 CUDA-core GEMM)
+            cp = self._cond_tc.get()
+            m_tiles = (M + 127) // 128
+            ckey = (M, 2 * N, str(dev))
+            if self._cond_ws is None or self._cond_ws[0] != ckey:
+                self._cond_ws = (ckey, torch.empty(m_tiles * (2 * N // 8) * 1024, dtype=torch.float16, device=dev))
+            xz = self._cond_ws[1]
+            L.call("bsrnn_norm_cast_kb8", zz.data_ptr(), None, None, xz.data_ptr(), 2 * N, 0, 2 * N, 2 * N // 8, m_tiles,
+                   m_tiles, M, 1 << 40, 0, 1, 0, M, 1, st)
+            skip.zero_()
+            L.call("bsrnn_gemm_tc", xz.data_ptr(), cp["w"].data_ptr(), cp["b"].data_ptr(), skip.data_ptr(), None, m_tiles,
+                   cp["nt"], 2 * N // 8, cp["bn"], L.TC_RESID_F32, N, N, 0, M, m_tiles, M, 1 << 40, 0, 1, 0, st)
+        else:
+            dl = R.DescList()
+            w, b = self.condition_fc.weight, self.condition_fc.bias               # bsrnn_flowse.py:284-285
+            dl.add(**R._rows_desc(zz.data_ptr(), w.data_ptr(), b.data_ptr(), skip.data_ptr(), M, N, 2 * N,
+                                  a_stride=2 * N, c_stride=N))
+            dl.upload(dev)
+            L.call("bsrnn_gemm_f32", dl.ptr(0), 1, M, N, st)
         t = t.to(device=dev, dtype=torch.float32)
         t_emb = [self.t_cond[i](t) for i in range(self.num_layer)]          # bsrnn_flowse.py:293
         if self.precision in ("fp16", "bf16"):

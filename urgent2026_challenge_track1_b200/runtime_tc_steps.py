@@ -106,6 +106,16 @@ def pack_dual_path_steps(mod):
     return layers
 
 
+def pack_linear_tc(fc):
+    """nn.Linear(K -> N) -> KB8 weight tiles + padded bias for bsrnn_gemm_tc (N tiles of bn columns, bn | ceil16(N))."""
+    N, K = fc.weight.shape
+    n16 = (N + 15) // 16 * 16
+    bn = next(b for b in (256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16) if n16 % b == 0)
+    bias = torch.zeros(n16, device=fc.weight.device)
+    bias[:N] = fc.bias.float()
+    return dict(w=to_kb8(fc.weight.float(), bn, (K + 7) // 8), b=bias, bn=bn, nt=n16 // bn)
+
+
 _WS = {}
 
 
