@@ -8,12 +8,12 @@
  * Conventions
  *   - Stateless and stream-ordered: every pointer is a DEVICE pointer owned by the caller (torch allocates), every
  *     call enqueues on `stream` (a cudaStream_t passed as void*) and returns without synchronising.
- *   - No allocation inside; scratch comes from the caller, sized by the matching *_workspace_bytes() query.
+ *   - No allocation inside; scratch and workspaces come from the caller (sizes follow from the documented layouts).
  *   - Return value: 0 = ok, non-zero = error; bsrnn_last_error() returns a thread-local message.
  *   - "spec" tensors are complex64 stored as interleaved float pairs, layout (B, T, F, 2).
  *   - "token-major" activations are (B, T, K, N) f32: token index ((b*T + t)*K + k).
- *   - precision modes: the *_f32 entry points compute in f32 on CUDA cores (parity bar 1e-3); the *_bf16 ones
- *     use tcgen05 tensor cores with bf16 operands and f32 accumulation in TMEM (parity bar 1e-2).
+ *   - precision modes: the *_f32 entry points compute in f32 on CUDA cores (parity bar 1e-3); the *_tc ones use
+ *     tcgen05 tensor cores with fp16 operands (KB8 tiling) and f32 accumulation in TMEM (parity bar 1e-2).
  */
 #ifndef BSRNN_B200_H_
 #define BSRNN_B200_H_
@@ -210,6 +210,17 @@ int bsrnn_grad_sumsq(const float* grad, long n, double* stats, void* stream);
 int bsrnn_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, long n,
                      const double* stats, float grad_scale, float max_norm, float lr, float beta1, float beta2,
                      float eps, float weight_decay, int step, float ema_decay, void* stream);
+/* bsrnn_adamw_step2: the same tail with the step counters kept ON THE DEVICE, so a step skipped for non-finite
+ *     gradients does not advance Adam's bias correction (reference: optimizer.zero_grad() makes AdamW skip every
+ *     parameter AND its step counter, d_model.py:48-59) while torch_ema's update still runs (flow_model.py:66-84).
+ *     state (double[8]) = {sum g^2, non-finite flag [both written by bsrnn_grad_sumsq], adam steps, ema updates,
+ *     1-beta1^t, 1-beta2^t, effective ema decay, -}; zero it once.  skip_ranges: n_skip (<= 32) half-open element
+ *     ranges [lo, hi) (long pairs, device memory) of parameters that received NO gradient on any rank this step
+ *     (bands beyond K' at low sample rates): torch AdamW skips grad=None parameters entirely -- no weight decay, no
+ *     moment decay.  ema_decay is the nominal decay; the warm-up min(decay, (1+n)/(10+n)) is applied inside. */
+int bsrnn_adamw_step2(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, long n,
+                      double* state, const long* skip_ranges, int n_skip, float grad_scale, float max_norm, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, float ema_decay, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- FlowSE pieces
  * bsrnn_time_embed: GaussianFourierProjection [bsrnn_flowse.py:90-99]: out (B, 2*E) = [sin(2*pi*t*W), cos(...)].

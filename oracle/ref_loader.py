@@ -1,25 +1,49 @@
-"""TEST INFRASTRUCTURE: import the reference's own files *verbatim* from /root/reference on top of the
-third-party shim in oracle/shim (espnet2 subset, pytorch_lightning, torch_ema, matplotlib).
+"""TEST INFRASTRUCTURE: import the reference's own files *verbatim* on top of the third-party shim in oracle/shim
+(espnet2 subset, pytorch_lightning, torch_ema, matplotlib).
 
-Only usable in the build container (``/root/reference`` does not exist on the GPU box); used to pin
-``oracle/restated.py`` and to generate ``tests/golden/*.npz`` (tests/golden/make_golden.py).
+Source of the files: ``/root/reference`` in the build container; on the GPU box (where that path does not exist) the
+git-ignored snapshot ``oracle/_ref/`` written by ``oracle/make_ref.sh`` (it travels with the gpurun snapshot, it is
+never committed).  Used to pin ``oracle/restated.py``, to generate ``tests/golden/*.npz``
+(tests/golden/make_golden.py), as the full-width checker of the GPU parity tests and as bench.py's reference arm.
 """
 import importlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("URGENT_REFERENCE_ROOT", "/root/reference")
-SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(_HERE, "shim")
+SNAPSHOT = os.path.join(_HERE, "_ref")
+
+
+def _pick_root():
+    for cand in (os.environ.get("URGENT_REFERENCE_ROOT"), "/root/reference", SNAPSHOT):
+        if cand and os.path.isfile(os.path.join(cand, "baseline_code", "models", "bsrnn_flowse.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "baseline_code"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "baseline_code", "models", "bsrnn_flowse.py"))
+
+
+def kind():
+    """'reference' when the verbatim files are importable (tree or snapshot), else 'port' (oracle/restated.py only)."""
+    return "reference" if available() else "port"
 
 
 def load():
     """Returns a namespace with the reference classes (BSRNN_SE, FlowBSRNN, FlowSEModel, SEModel, Config, ...)."""
     if not available():
         raise RuntimeError(f"reference tree not found under {REFERENCE_ROOT}")
+    # the product's checkpoint module may have registered an ALIAS package ``baseline_code`` (empty __path__) so that
+    # pickled reference Configs resolve without the reference; the real package must win here
+    pkg = sys.modules.get("baseline_code")
+    if pkg is not None and list(getattr(pkg, "__path__", [])) == []:
+        for name in [n for n in sys.modules if n == "baseline_code" or n.startswith("baseline_code.")]:
+            del sys.modules[name]
     for p in (REFERENCE_ROOT, SHIM):
         if p in sys.path:
             sys.path.remove(p)
@@ -28,6 +52,12 @@ def load():
     if not torch.cuda.is_available():
         # flow_model.py:194 hard-codes Y.cuda(); identity on a CPU-only box.
         torch.Tensor.cuda = lambda self, *a, **k: self
+    if "torchaudio" not in sys.modules:
+        try:                                   # d_model.py / flow_model.py import torchaudio but never use it
+            import torchaudio  # noqa: F401
+        except Exception:                      # a CUDA-mismatched torchaudio build must not take the oracle down
+            import types
+            sys.modules["torchaudio"] = types.ModuleType("torchaudio")
     ns = type("ref", (), {})()
     ns.bsrnn = importlib.import_module("baseline_code.models.bsrnn")
     ns.bsrnn_flowse = importlib.import_module("baseline_code.models.bsrnn_flowse")

@@ -19,8 +19,11 @@ def choose_norm(norm_type, channel_size, shape="BDTF"):
 
 
 def choose_norm1d(norm_type, channel_size):
+    # espnet2/enh/layers/bsrnn.py imports this name as ``from espnet2.enh.layers.tcn import choose_norm as
+    # choose_norm1d``; tcn.choose_norm builds "GN" as nn.GroupNorm(1, C, eps=1e-8), unlike the 4-D choose_norm
+    # above (torch default 1e-5).  Used by BandSplit and the Mask/Grad decoders (reference bsrnn_flowse.py:48,121,128).
     if norm_type == "GN":
-        return nn.GroupNorm(1, channel_size)
+        return nn.GroupNorm(1, channel_size, eps=1e-8)
     if norm_type == "BN":
         return nn.BatchNorm1d(channel_size)
     raise ValueError(f"oracle shim only restates GN/BN, got {norm_type}")

@@ -125,3 +125,109 @@ def test_trainer_steps_reduce_the_loss():
     assert 0 < float((tr.ema - tr.flat.flat).abs().max())
     out, _ = m(x, lens, 16000)                                                  # inference kernels see the updated weights
     assert torch.isfinite(out).all()
+
+
+def test_fused_adamw_v2_device_counters_and_untouched_ranges():
+    """bsrnn_adamw_step2: counters on the device (a non-finite step advances neither Adam's bias correction nor the
+    parameters, while torch_ema's update still runs -- flow_model.py:66-84), untouched ranges behave like grad=None
+    parameters in torch.optim.AdamW (no weight decay, no moment decay)."""
+    from urgent2026_challenge_track1_b200 import _lib as L
+    torch.manual_seed(0)
+    n, lo, hi = 50000, 12000, 20000
+    p0 = torch.randn(n, device="cuda")
+    segs = [p0[:lo].clone().requires_grad_(True), p0[lo:hi].clone().requires_grad_(True), p0[hi:].clone().requires_grad_(True)]
+    opt = torch.optim.AdamW(segs, lr=1e-3, eps=1e-8, weight_decay=1e-2)
+    p, m, v = p0.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ema, ema_ref, n_ema = p.clone(), p0.clone(), 0
+    state = torch.zeros(8, dtype=torch.float64, device="cuda")
+    skip = torch.tensor([lo, hi], dtype=torch.int64, device="cuda")
+    st = L.stream_ptr()
+    for step in range(1, 7):
+        g = torch.randn(n, device="cuda") * (10.0 if step % 2 else 0.001)
+        bad = step == 3
+        if bad:
+            g[7] = float("inf")
+        touched_mid = step >= 5                                                   # the middle segment joins later
+        if not bad:
+            segs[0].grad, segs[2].grad = g[:lo].clone(), g[hi:].clone()
+            segs[1].grad = g[lo:hi].clone() if touched_mid else None
+            torch.nn.utils.clip_grad_norm_([s for s in segs if s.grad is not None], 0.5)
+            opt.step()
+        gk = g.clone()
+        if not touched_mid:
+            gk[lo:hi] = 0                                                         # an unused parameter's flat gradient is zero
+        n_ema += 1
+        d = min(0.9, (1 + n_ema) / (10 + n_ema))
+        ema_ref -= (1 - d) * (ema_ref - torch.cat([s.detach() for s in segs]))
+        L.call("bsrnn_grad_sumsq", gk.data_ptr(), n, state.data_ptr(), st)
+        L.call("bsrnn_adamw_step2", p.data_ptr(), gk.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
+               state.data_ptr(), skip.data_ptr(), 0 if touched_mid else 1, 1.0, 0.5, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 0.9, st)
+        ref = torch.cat([s.detach() for s in segs])
+        if step < 5:
+            assert torch.equal(p[lo:hi], p0[lo:hi]), step                        # never touched: not even weight decay
+            assert rel_l2(p[:lo].cpu(), ref[:lo].cpu()) < 1e-6 and rel_l2(p[hi:].cpu(), ref[hi:].cpu()) < 1e-6, step
+        else:
+            # torch keeps a per-parameter step counter (the late joiner's bias correction restarts at 1); ours is
+            # global, so only the always-touched segments are compared exactly from here on
+            assert rel_l2(p[:lo].cpu(), ref[:lo].cpu()) < 1e-6 and rel_l2(p[hi:].cpu(), ref[hi:].cpu()) < 1e-6, step
+            assert not torch.equal(p[lo:hi], p0[lo:hi])
+        if step < 5:
+            assert rel_l2(ema.cpu(), ema_ref.cpu()) < 1e-6, step
+    assert int(state[2]) == 5 and int(state[3]) == 6                             # the non-finite step is not an Adam step
+
+
+def test_inference_sees_every_parameter_update():
+    """forward -> optimizer step (raw-pointer writes) -> forward must use the NEW weights in every
+    precision mode and through CUDA graphs; compared against a freshly constructed module carrying the same weights."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    from urgent2026_challenge_track1_b200.training import SETrainer
+    for precision, width, tol in (("fp32", 16, 1e-5), ("fp16", 196, 2e-3)):
+        torch.manual_seed(0)
+        m = BSRNN_SE(num_channel=width, num_layer=1, precision=precision).cuda()
+        fs, n = 16000, 8000
+        x, clean, lens = R.synth_noisy(2, n, fs, seed=1), R.synth_noisy(2, n, fs, seed=7), torch.tensor([n, n - 300])
+        for graph in (False, True):
+            m.cuda_graph = graph
+            before = m(x, lens, fs)[0].clone()                                   # packs weights (and captures a graph)
+            tr = SETrainer(m, lr=5e-2) if not hasattr(m, "_tr") else m._tr
+            m._tr = tr
+            tr.step(x.cuda().view(2, 1, -1), clean.cuda().view(2, 1, -1), lens, fs)
+            after = m(x, lens, fs)[0].clone()
+            fresh = BSRNN_SE(num_channel=width, num_layer=1, precision=precision)
+            fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+            want = fresh.cuda()(x, lens, fs)[0]
+            assert rel_l2(after.cpu(), want.cpu()) < tol, (precision, graph, rel_l2(after.cpu(), want.cpu()))
+            assert rel_l2(after.cpu(), before.cpu()) > 10 * tol, (precision, graph)
+
+
+def test_flowse_eval_after_forward_uses_ema_weights():
+    """a forward before eval() must not pin the pre-swap packed weights."""
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    cfg = Config(model_type="flowse", ema_decay=0.5, sigma_max=0.5, sigma_min=0.05, t_eps=0.03, T_rev=1.0,
+                 loss_type="mse", loss_abs_exponent=0.5, n_fft=1536, hop_length=384, spec_transform_type="exponent",
+                 spec_abs_exponent=0.667, spec_factor=0.065, bsrnn_hidden=16, num_layer=1, learning_rate=1e-4)
+    torch.manual_seed(0)
+    fm = FlowSEModel(cfg).cuda()
+    fm.train()
+    fs, n = 16000, 6000
+    y, lens = R.synth_noisy(2, n, fs, seed=3), torch.tensor([n, n - 100])
+    torch.manual_seed(5)
+    z = torch.randn_like(fm.speech_to_feature(y, fs, lens))
+    live = fm.enhance(y, fs, lens, N=2, z=z).clone()                            # packs the live weights
+    with torch.no_grad():
+        for p in fm.parameters():
+            if p.requires_grad:
+                p.mul_(1.05)
+    fm.ema.update(fm.parameters())                                               # shadow now differs from live
+    live2 = fm.enhance(y, fs, lens, N=2, z=z).clone()
+    fm.eval()                                                                    # EMA swapped in (flow_model.py:98-109)
+    ema_out = fm.enhance(y, fs, lens, N=2, z=z).clone()
+    fresh = FlowSEModel(cfg)
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in fm.state_dict().items()})
+    want = fresh.cuda().eval(no_ema=True).enhance(y, fs, lens, N=2, z=z)
+    assert rel_l2(ema_out.cpu(), want.cpu()) < 1e-5
+    assert rel_l2(ema_out.cpu(), live2.cpu()) > 1e-4 and rel_l2(live2.cpu(), live.cpu()) > 1e-4
+    fm.train()
+    back = fm.enhance(y, fs, lens, N=2, z=z)
+    assert rel_l2(back.cpu(), live2.cpu()) < 1e-5

@@ -150,3 +150,131 @@ def test_utterance_sharding_world2_gloo():
     assert sorted(gathered[0] + gathered[1]) == list(range(7))            # every utterance exactly once
     assert not set(gathered[0]) & set(gathered[1])
     assert ms == 11.0                                                      # max over ranks
+
+
+def test_equal_length_batches_and_batch_split():
+    """Default batching never pads (the reference is batch-1, inference.py:48-64): only equal-length utterances share
+    a batch; a pad ratio relaxes that.  shard_batch is the contiguous 64/G split of BASELINE config 2."""
+    from urgent2026_challenge_track1_b200.sharding import shard_utterances, shard_batch
+    lengths = [1000, 900, 1000, 1000, 500, 900, 1000]
+    fss = [16000] * 6 + [8000]
+    got = shard_utterances(lengths, fss, 0, 1, max_batch=2)
+    assert sorted(i for _, idx in got for i in idx) == list(range(7))
+    for fs, idx in got:
+        assert len(idx) <= 2 and len({lengths[i] for i in idx}) == 1 and len({fss[i] for i in idx}) == 1
+    padded = shard_utterances(lengths, fss, 0, 1, max_batch=8, max_pad_ratio=0.15)
+    assert [sorted(idx) for fs, idx in padded if fs == 16000] == [[0, 1, 2, 3, 5], [4]]
+    for world in (1, 2, 3, 8):
+        parts = [shard_batch(64, r, world) for r in range(world)]
+        assert sum(c for _, c in parts) == 64 and parts[0][0] == 0
+        assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_packed_cache_invalidation_paths():
+    """writers torch's version counter does not see -- the fused optimizer kernel and p.data.copy_ --
+    must invalidate packed weights; the EMA swap must bump versions.  (Pure host logic: counts rebuilds.)"""
+    from urgent2026_challenge_track1_b200 import runtime as R
+    from urgent2026_challenge_track1_b200.ema import ExponentialMovingAverage
+    lin = torch.nn.Linear(4, 4)
+    builds = []
+    cache = R.PackedCache(lin, lambda m: builds.append(1) or m.weight.detach().clone())
+    cache.get(); cache.get()
+    assert len(builds) == 1
+    lin.weight.data.mul_(2.0)                            # invisible to _version ...
+    cache.get()
+    assert len(builds) == 1
+    R.invalidate_packed()                                # ... so raw writers declare it
+    assert torch.equal(cache.get(), lin.weight) and len(builds) == 2
+    ema = ExponentialMovingAverage(lin.parameters(), decay=0.5)
+    with torch.no_grad():
+        lin.weight.add_(1.0)
+    ema.update(lin.parameters())
+    cache.get()
+    n = len(builds)
+    v0 = lin.weight._version
+    ema.store(lin.parameters()); ema.copy_to(lin.parameters())
+    assert lin.weight._version > v0 and torch.equal(cache.get(), lin.weight) and len(builds) == n + 1
+    ema.restore(lin.parameters())
+    assert torch.equal(cache.get(), lin.weight) and len(builds) == n + 2
+
+
+def test_untouched_parameter_ranges():
+    from urgent2026_challenge_track1_b200.training import FlatParams
+    m = torch.nn.ModuleList([torch.nn.Linear(3, 2) for _ in range(4)])      # 8 params: (6, 2) x 4 = 32 elements
+    fp = FlatParams(m)
+    assert fp.untouched_ranges() == [[0, 32]]
+    out = m[0](torch.ones(1, 3)).sum() + m[3](torch.ones(1, 3)).sum()
+    out.backward()
+    assert fp.untouched_ranges() == [[8, 24]]                                 # m[1], m[2] merged into one range
+    assert float(fp.grad[:8].abs().sum()) > 0 and float(fp.grad[8:24].abs().sum()) == 0
+    fp.zero_grad()
+    assert fp.untouched_ranges() == [[0, 32]]
+
+
+def _flow_cfg(**kw):
+    from urgent2026_challenge_track1_b200.config import Config
+    base = dict(model_type="flowse", ema_decay=0.999, sigma_max=0.5, sigma_min=0.05, t_eps=0.03, T_rev=1.0,
+                loss_type="mse", loss_abs_exponent=0.5, n_fft=1536, hop_length=384, spec_transform_type="exponent",
+                spec_abs_exponent=0.667, spec_factor=0.065, bsrnn_hidden=16, num_layer=1, learning_rate=1e-4)
+    base.update(kw)
+    return Config(**base)
+
+
+def test_lightning_checkpoint_roundtrip(tmp_path):
+    """Write a Lightning-format .ckpt (state_dict + pickled baseline_code.config.Config + ema) and read it back through
+    the same-flags loaders; SEModel loader refuses a FlowSE file so inference.py's fallback (inference.py:30-33) works."""
+    from urgent2026_challenge_track1_b200.checkpoint import save_checkpoint, load_checkpoint, model_kind
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.d_model import SEModel
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    cfg = Config(se_model="bsrnn", model_configs={"num_channel": 16, "num_layer": 1}, learning_rate=3e-4)
+    m = SEModel(cfg)
+    p = save_checkpoint(str(tmp_path / "se.ckpt"), m, cfg, global_step=123, epoch=4)
+    sd, cfg2, raw = load_checkpoint(p)
+    assert type(raw["hyper_parameters"]["cfg"]).__module__ == "baseline_code.config"     # what the reference unpickles
+    assert raw["global_step"] == 123 and model_kind(sd) == "se" and cfg2.model_configs == cfg.model_configs
+    m2 = SEModel.load_from_checkpoint(p, map_location="cpu")
+    assert all(torch.equal(v, m2.state_dict()[k]) for k, v in m.state_dict().items())
+    fcfg = _flow_cfg()
+    fm = FlowSEModel(fcfg)
+    with torch.no_grad():
+        fm.dnn.condition_fc.bias.add_(1.0)
+    fm.ema.update(fm.parameters())
+    fp = save_checkpoint(str(tmp_path / "flow.ckpt"), fm, fcfg)
+    with pytest.raises(KeyError):
+        SEModel.load_from_checkpoint(fp, map_location="cpu")
+    fm2 = FlowSEModel.load_from_checkpoint(fp, map_location="cpu")
+    assert fm2.ema.num_updates == 1 and not fm2._error_loading_ema
+    assert all(torch.equal(a, b) for a, b in zip(fm.ema.shadow_params, fm2.ema.shadow_params))
+    live = fm2.dnn.condition_fc.bias.detach().clone()
+    fm2.eval()                                                                  # EMA weights swapped in (flow_model.py:98-109)
+    assert not torch.equal(fm2.dnn.condition_fc.bias, live)
+
+
+@pytest.mark.reference
+def test_checkpoints_interchange_with_the_verbatim_reference(tmp_path, ref_ns):
+    """Our .ckpt loads into the reference's own SEModel / FlowSEModel classes (real Config class unpickled) and a
+    checkpoint written from the reference's modules loads into ours."""
+    from urgent2026_challenge_track1_b200.checkpoint import save_checkpoint, load_checkpoint
+    from urgent2026_challenge_track1_b200.config import Config
+    from urgent2026_challenge_track1_b200.d_model import SEModel
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    cfg = Config(se_model="bsrnn", model_configs={"num_channel": 16, "num_layer": 1})
+    m = SEModel(cfg)
+    p = save_checkpoint(str(tmp_path / "se.ckpt"), m, cfg)
+    raw = torch.load(p, map_location="cpu", weights_only=False)
+    rcfg = raw["hyper_parameters"]["cfg"]
+    assert isinstance(rcfg, ref_ns.Config)
+    rm = ref_ns.SEModel(rcfg)
+    rm.load_state_dict(raw["state_dict"], strict=True)
+    # reference -> ours (FlowSE incl. EMA)
+    from oracle import ref_loader
+    rfm = ref_ns.FlowSEModel(ref_loader.flowse_config(ref_ns, bsrnn_hidden=16, num_layer=1))
+    ck = {"state_dict": rfm.state_dict(), "hyper_parameters": {"cfg": rfm.cfg}, "epoch": 0, "global_step": 0}
+    rfm.on_save_checkpoint(ck)
+    torch.save(ck, str(tmp_path / "ref_flow.ckpt"))
+    fm = FlowSEModel.load_from_checkpoint(str(tmp_path / "ref_flow.ckpt"), map_location="cpu")
+    assert all(torch.equal(v, fm.state_dict()[k]) for k, v in rfm.state_dict().items())
+    sd, cfg2, _ = load_checkpoint(str(tmp_path / "ref_flow.ckpt"))
+    assert cfg2.bsrnn_hidden == 16 and cfg2.n_fft == 1536

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "bsrnn_grad_sumsq": [c_void_p, c_long, c_void_p, c_void_p],
     "bsrnn_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_float, c_float, c_float,
                          c_float, c_float, c_float, c_float, c_int, c_float, c_void_p],
+    "bsrnn_adamw_step2": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_int, c_float,
+                          c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p],
     "bsrnn_time_embed": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "bsrnn_conv5x5_glu": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_long, c_void_p],

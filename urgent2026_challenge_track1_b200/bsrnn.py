@@ -82,7 +82,7 @@ class BSRNN_SE(nn.Module):
             lens = lens_host.to(device=dev, dtype=torch.int32, non_blocking=True)
             return self._forward_device(wav, lens, L_out, fs)
         # ---- CUDA-graph path: one captured launch sequence per input signature and parameter version
-        params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        params = R.param_signature(self.parameters())
         key = (tuple(speech_mix.shape), fs, tuple(int(v) for v in lens_host.tolist()), self.precision)
         entry = self._graphs.get(key)
         if entry is None or entry[1] != params:

@@ -98,7 +98,7 @@ class BSRNN(nn.Module):
             return self._mask_resid_eager(x_btf, zz, plan, t)
         dev = x_btf.device
         t = t.to(device=dev, dtype=torch.float32)
-        params = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        params = R.param_signature(self.parameters())
         key = (tuple(x_btf.shape), zz.data_ptr(), self.precision)
         entry = self._graphs.get(key)
         if entry is None or entry[1] != params:

@@ -15,7 +15,7 @@ void count_launches(long n) { g_launches += n; }
 }  // namespace bsrnn
 
 extern "C" const char* bsrnn_last_error(void) { return bsrnn::g_err; }
-extern "C" int bsrnn_abi_version(void) { return 2; }
+extern "C" int bsrnn_abi_version(void) { return 3; }
 extern "C" int bsrnn_device_check(void) {
   int dev = 0;
   cudaDeviceProp p;

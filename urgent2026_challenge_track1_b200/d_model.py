@@ -70,9 +70,10 @@ class SEModel(nn.Module):
     def load_from_checkpoint(cls, ckpt_path, map_location="cuda", precision=None):
         """Reads a Lightning-style .ckpt (``state_dict`` + ``hyper_parameters['cfg']``) or a raw state_dict
         (reference train_se.py:55-60 accepts both for init_from)."""
-        ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
-        sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
-        cfg = ckpt.get("hyper_parameters", {}).get("cfg") if isinstance(ckpt, dict) else None
+        from .checkpoint import load_checkpoint, model_kind
+        sd, cfg, _ = load_checkpoint(ckpt_path)
+        if model_kind(sd) != "se":
+            raise KeyError("not an SEModel checkpoint (no se_model.* keys)")      # inference.py:30-33 falls back on this
         if cfg is None:
             from .config import Config
             n = sd["se_model.bsrnn.bsrnn.fc_time.0.bias"].numel()

@@ -6,6 +6,11 @@ from __future__ import annotations
 import torch
 
 
+def _invalidate():
+    from .runtime import invalidate_packed
+    invalidate_packed()
+
+
 class ExponentialMovingAverage:
     def __init__(self, parameters, decay, use_num_updates=True):
         if decay < 0.0 or decay > 1.0:
@@ -27,7 +32,8 @@ class ExponentialMovingAverage:
     @torch.no_grad()
     def copy_to(self, parameters):
         for s, p in zip(self.shadow_params, parameters):
-            p.data.copy_(s.data)
+            p.copy_(s)                       # (not p.data.copy_: the version counter must see the swap)
+        _invalidate()
 
     def store(self, parameters):
         self.collected_params = [p.clone() for p in parameters]
@@ -37,7 +43,8 @@ class ExponentialMovingAverage:
         if self.collected_params is None:
             raise RuntimeError("This ExponentialMovingAverage has no `store()`ed weights to `restore()`")
         for c, p in zip(self.collected_params, parameters):
-            p.data.copy_(c.data)
+            p.copy_(c)
+        _invalidate()
 
     def to(self, device=None, dtype=None):
         self.shadow_params = [s.to(device=device, dtype=dtype) if s.is_floating_point() else s.to(device=device)

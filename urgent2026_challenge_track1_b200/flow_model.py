@@ -42,6 +42,21 @@ class FlowSEModel(nn.Module):
         self.ode.T_rev = cfg.T_rev
         self.loss_type = cfg.loss_type
 
+    @classmethod
+    def load_from_checkpoint(cls, ckpt_path, map_location="cuda"):
+        """Lightning-style .ckpt -> FlowSEModel: ``hyper_parameters['cfg']`` builds the module, ``state_dict`` fills
+        it, ``on_load_checkpoint`` restores the EMA shadow weights that ``eval()`` swaps in (flow_model.py:87-112)."""
+        from .checkpoint import load_checkpoint, model_kind
+        sd, cfg, ckpt = load_checkpoint(ckpt_path)
+        if model_kind(sd) != "flowse":
+            raise KeyError("not a FlowSEModel checkpoint (no dnn.* keys)")
+        if cfg is None:
+            raise KeyError("FlowSEModel checkpoint without hyper_parameters['cfg']")
+        model = cls(cfg)
+        model.load_state_dict(sd)
+        model.on_load_checkpoint(ckpt)
+        return model.to(map_location)
+
     # ---- checkpoint hooks (Lightning names kept so a trainer can call them) ---------------------------------
     def on_load_checkpoint(self, checkpoint):
         ema = checkpoint.get("ema", None)
@@ -56,6 +71,7 @@ class FlowSEModel(nn.Module):
 
     def train(self, mode=True, no_ema=False):
         res = super().train(mode)
+        R.invalidate_packed()                      # the EMA swap below rewrites every parameter in place
         if not self._error_loading_ema:
             if mode is False and not no_ema:
                 self.ema.store(self.parameters())

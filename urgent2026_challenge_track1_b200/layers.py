@@ -9,6 +9,14 @@ import torch.nn as nn
 
 from .runtime import subbands_for
 
+# GroupNorm eps per construction site (espnet==202412): the 1-D norms of BandSplit and the decoders come from
+# ``espnet2.enh.layers.tcn.choose_norm`` (imported as choose_norm1d; "GN" = nn.GroupNorm(1, C, eps=1e-8),
+# reference bsrnn_flowse.py:48,121,128); norm_time / norm_freq come from ``espnet2.enh.layers.bsrnn.choose_norm``
+# ("GN" = nn.GroupNorm(1, C), torch default 1e-5, reference bsrnn_flowse.py:229,239).  The runtime reads
+# ``module.eps`` from these containers, so a different value only needs changing here.
+EPS_NORM1D = 1e-8
+EPS_NORM = 1e-5
+
 
 class BandSplitParams(nn.Module):
     """norm.{k} = GroupNorm(1, 2 s_k), fc.{k} = Conv1d(2 s_k, N, 1)   [reference bsrnn_flowse.py:16-50]."""
@@ -21,7 +29,7 @@ class BandSplitParams(nn.Module):
         self.norm = nn.ModuleList()
         self.fc = nn.ModuleList()
         for s in self.subbands:
-            self.norm.append(nn.GroupNorm(1, 2 * s))
+            self.norm.append(nn.GroupNorm(1, 2 * s, eps=EPS_NORM1D))
             self.fc.append(nn.Conv1d(2 * s, channels, 1))
 
 
@@ -37,7 +45,7 @@ class MaskDecoderParams(nn.Module):
         self.mlp_residual = nn.ModuleList()
         for s in subbands:
             for lst in (self.mlp_mask, self.mlp_residual):
-                lst.append(nn.Sequential(nn.GroupNorm(1, channels), nn.Conv1d(channels, 4 * channels, 1), nn.Tanh(),
+                lst.append(nn.Sequential(nn.GroupNorm(1, channels, eps=EPS_NORM1D), nn.Conv1d(channels, 4 * channels, 1), nn.Tanh(),
                                          nn.Conv1d(4 * channels, int(s * 4 * num_spk), 1), nn.GLU(dim=1)))
 
 
@@ -55,8 +63,8 @@ class GradDecoderParams(nn.Module):
         self.conv_after_mask = nn.Sequential(nn.Conv2d(sub_channel, 4, 5, 1, 2), nn.GLU(dim=1))
         self.conv_after_residual = nn.Sequential(nn.Conv2d(sub_channel, 4, 5, 1, 2), nn.GLU(dim=1))
         for s in subbands:
-            self.mlp_mask.append(nn.Sequential(nn.GroupNorm(1, channels), nn.Conv1d(channels, s * sub_channel, 1), nn.Tanh()))
-            self.mlp_residual.append(nn.Sequential(nn.GroupNorm(1, channels), nn.Conv1d(channels, s * sub_channel, 1), nn.Tanh()))
+            self.mlp_mask.append(nn.Sequential(nn.GroupNorm(1, channels, eps=EPS_NORM1D), nn.Conv1d(channels, s * sub_channel, 1), nn.Tanh()))
+            self.mlp_residual.append(nn.Sequential(nn.GroupNorm(1, channels, eps=EPS_NORM1D), nn.Conv1d(channels, s * sub_channel, 1), nn.Tanh()))
 
 
 def add_dual_path(mod, num_channel, num_layer, with_t_cond=False, t_cond_cls=None):
@@ -70,9 +78,9 @@ def add_dual_path(mod, num_channel, num_layer, with_t_cond=False, t_cond_cls=Non
     for _ in range(num_layer):
         if with_t_cond:
             mod.t_cond.append(t_cond_cls(num_channel // 2, scale=1))
-        mod.norm_time.append(nn.GroupNorm(1, num_channel))
+        mod.norm_time.append(nn.GroupNorm(1, num_channel, eps=EPS_NORM))
         mod.rnn_time.append(nn.LSTM(num_channel, hdim, batch_first=True, bidirectional=True))
         mod.fc_time.append(nn.Linear(2 * hdim, num_channel))
-        mod.norm_freq.append(nn.GroupNorm(1, num_channel))
+        mod.norm_freq.append(nn.GroupNorm(1, num_channel, eps=EPS_NORM))
         mod.rnn_freq.append(nn.LSTM(num_channel, hdim, batch_first=True, bidirectional=True))
         mod.fc_freq.append(nn.Linear(4 * num_channel, num_channel))

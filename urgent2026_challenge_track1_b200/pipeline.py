@@ -4,8 +4,9 @@ batch-1 and synchronous).
 ``StreamedEnhancer`` pushes successive HOST batches through ``BSRNN_SE.forward``: the H2D copy of batch i+1 and the
 D2H copy of batch i-1 run on their own CUDA streams while batch i computes, so a step costs max(compute, copies)
 instead of their sum (at BASELINE config 2 a batch is 123 MB each way).  Inputs should be pinned; outputs land in
-pinned buffers owned by the enhancer (two per shape, reused round-robin: consume a result before asking for the one
-after the next)."""
+pinned buffers owned by the enhancer (one flat buffer per slot, grown to the largest batch seen and viewed per batch,
+reused round-robin: consume a result before asking for the one after the next).  Memory is therefore bounded by
+`depth` x the largest batch, however many different (B, L) shapes a run produces."""
 from __future__ import annotations
 
 import torch
@@ -23,28 +24,38 @@ class StreamedEnhancer:
         self.depth = int(depth)
         self.h2d = torch.cuda.Stream(self.dev)
         self.d2h = torch.cuda.Stream(self.dev)
-        self._in = {}          # (slot, shape) -> device staging buffer
-        self._out = {}         # (slot, shape) -> pinned host buffer
+        self._in = [None] * self.depth         # slot -> flat device staging buffer (grown on demand)
+        self._out = [None] * self.depth        # slot -> flat pinned host buffer (grown on demand)
         self._free = [None] * self.depth      # event: compute that read staging slot s has finished
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    @staticmethod
+    def _numel(shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        return n
+
     def _stage(self, slot, shape):
-        key = (slot, tuple(shape))
-        buf = self._in.get(key)
-        if buf is None:
-            buf = self._in[key] = torch.empty(tuple(shape), dtype=torch.float32, device=self.dev)
+        n = self._numel(shape)
+        buf = self._in[slot]
+        if buf is None or buf.numel() < n:
+            if buf is not None and self._free[slot] is not None:
+                self._free[slot].synchronize()     # the forward still reading the old buffer must finish before it goes
+            buf = self._in[slot] = torch.empty(n, dtype=torch.float32, device=self.dev)
             # the caching allocator may hand out a block that work still queued on the compute stream writes (a
             # tensor freed a moment ago): the copy stream must not touch it before that work has drained
             self.h2d.wait_stream(torch.cuda.current_stream(self.dev))
-        return buf
+        return buf[:n].view(tuple(shape))
 
     def _host_out(self, slot, shape):
-        key = (slot, tuple(shape))
-        buf = self._out.get(key)
-        if buf is None:
-            buf = self._out[key] = torch.empty(tuple(shape), dtype=torch.float32).pin_memory()
-        return buf
+        n = self._numel(shape)
+        buf = self._out[slot]
+        if buf is None or buf.numel() < n:
+            self.d2h.synchronize()                 # a copy into the old pinned buffer may still be in flight
+            buf = self._out[slot] = torch.empty(n, dtype=torch.float32).pin_memory()
+        return buf[:n].view(tuple(shape))
 
     def _submit(self, i, wav_host, lens, fs):
         """Enqueue H2D (copy stream), forward (current stream) and D2H (copy-back stream) of batch i."""

@@ -216,8 +216,24 @@ def istft(spec, mask, resid, L_out, n_fft, hop, want_spec=True, transform=0, exp
 
 
 # ------------------------------------------------------------------------------------------------ weight packing
+# Parameters are mutated in place by writers torch's version counter does not see: the fused optimizer kernel writes
+# the flat parameter buffer through raw pointers (training.SETrainer.apply_gradients) and ``p.data.copy_`` (what
+# torch_ema's copy_to / restore do, flow_model.py:98-109) bypasses ``_version``.  Every such writer calls
+# ``invalidate_packed()``; the generation is part of every packed-weight and CUDA-graph cache key.
+_GENERATION = [0]
+
+
+def invalidate_packed():
+    """Declare that parameter VALUES may have changed without a version bump: packed copies and graphs are rebuilt."""
+    _GENERATION[0] += 1
+
+
+def param_signature(params):
+    return (_GENERATION[0],) + tuple((p.data_ptr(), p._version) for p in params)
+
+
 def _param_key(params):
-    return tuple((p.data_ptr(), p._version) for p in params)
+    return param_signature(params)
 
 
 class PackedCache:
@@ -251,10 +267,18 @@ def pack_dual_path(mod):
                              rnn.bias_ih_l0_reverse + rnn.bias_hh_l0_reverse], 0).float().contiguous()
             whh = torch.stack([rnn.weight_hh_l0, rnn.weight_hh_l0_reverse], 0).float().contiguous()     # (2,4H,H)
             entry[axis] = dict(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(),
-                               wih=wih, bih=bih, whh=whh, fcw=fc.weight.float().contiguous(),
+                               eps=float(norm.eps), wih=wih, bih=bih, whh=whh, fcw=fc.weight.float().contiguous(),
                                fcb=fc.bias.float().contiguous())
         layers.append(entry)
     return layers
+
+
+def _uniform_eps(norms):
+    """GroupNorm eps of a family of per-band norms (one value per family: they are built by one constructor)."""
+    eps = {float(n.eps) for n in norms}
+    if len(eps) != 1:
+        raise ValueError(f"per-band GroupNorm eps values differ: {sorted(eps)}")
+    return eps.pop()
 
 
 def pack_band_split(bs):
@@ -269,7 +293,7 @@ def pack_band_split(bs):
         beta[k, : 2 * s] = bs.norm[k].bias
     w = [bs.fc[k].weight[:, :, 0].float().contiguous() for k in range(K)]
     b = [bs.fc[k].bias.float().contiguous() for k in range(K)]
-    return dict(gamma=gamma, beta=beta, w=w, b=b, cmax=cmax)
+    return dict(gamma=gamma, beta=beta, w=w, b=b, cmax=cmax, eps=_uniform_eps(bs.norm))
 
 
 def pack_mask_decoder(md):
@@ -281,7 +305,8 @@ def pack_mask_decoder(md):
             gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
             beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
             w1=[m[1].weight[:, :, 0].float().contiguous() for m in mlps], b1=[m[1].bias.float().contiguous() for m in mlps],
-            w2=[m[3].weight[:, :, 0].float().contiguous() for m in mlps], b2=[m[3].bias.float().contiguous() for m in mlps])
+            w2=[m[3].weight[:, :, 0].float().contiguous() for m in mlps], b2=[m[3].bias.float().contiguous() for m in mlps],
+            eps=_uniform_eps([m[0] for m in mlps]))
     return out
 
 
@@ -300,7 +325,8 @@ def pack_grad_decoder(gd):
         c = getattr(gd, conv)[0]
         out[name] = dict(gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
                          beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
-                         w1=w1, b1=b1, cw=c.weight.float().contiguous(), cb=c.bias.float().contiguous())
+                         w1=w1, b1=b1, cw=c.weight.float().contiguous(), cb=c.bias.float().contiguous(),
+                         eps=_uniform_eps([m[0] for m in mlps]))
     return out
 
 
@@ -373,7 +399,7 @@ def band_split_f32(spec, plan: BandPlan, bs_pack, N, out=None, out_col=0, out_wi
     scale = torch.empty(B * K, cmax, dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
     L.call("bsrnn_gn_finalize", stats.data_ptr(), bs_pack["gamma"].data_ptr(), bs_pack["beta"].data_ptr(), None,
-           scale.data_ptr(), shift.data_ptr(), B * K, cmax, counts.data_ptr(), 1e-5, K, st)
+           scale.data_ptr(), shift.data_ptr(), B * K, cmax, counts.data_ptr(), bs_pack["eps"], K, st)
     width = out_width or N
     if out is None:
         out = torch.empty(B, T, K, width, dtype=torch.float32, device=dev)
@@ -390,7 +416,7 @@ def band_split_f32(spec, plan: BandPlan, bs_pack, N, out=None, out_col=0, out_wi
     return out
 
 
-def _layer_norm_tables(skip, gamma, beta, extra=None):
+def _layer_norm_tables(skip, gamma, beta, extra=None, eps=1e-5):
     """GroupNorm(1,N) over (N,T,K) per sample -> (scale, shift) (B,N)."""
     B, T, K, N = skip.shape
     dev = skip.device
@@ -401,7 +427,7 @@ def _layer_norm_tables(skip, gamma, beta, extra=None):
     shift = torch.empty_like(scale)
     counts = _f64([float(T) * K * N], dev)
     L.call("bsrnn_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), L.ptr(extra), scale.data_ptr(),
-           shift.data_ptr(), B, N, counts.data_ptr(), 1e-5, 1, st)
+           shift.data_ptr(), B, N, counts.data_ptr(), eps, 1, st)
     return scale, shift
 
 
@@ -419,7 +445,7 @@ def dual_path_f32(skip, layers, t_emb=None):
         for axis in ("time", "freq"):
             w = lay[axis]
             extra = t_emb[i] if (t_emb is not None and axis == "time") else None      # bsrnn_flowse.py:293-294
-            scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra)
+            scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra, w["eps"])
             dl = DescList()
             dl.add(**_rows_desc(skip.data_ptr(), w["wih"].data_ptr(), w["bih"].data_ptr(), gates.data_ptr(),
                                 M, 8 * H, N, a_stride=N, c_stride=8 * H, scale=scale.data_ptr(), shift=shift.data_ptr(),
@@ -457,7 +483,7 @@ def _decoder_norm_tables(skip, packs):
         shift = torch.empty_like(scale)
         gamma, beta = p["gamma"][:K].contiguous(), p["beta"][:K].contiguous()
         L.call("bsrnn_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), None, scale.data_ptr(),
-               shift.data_ptr(), B * K, N, counts.data_ptr(), 1e-5, K, st)
+               shift.data_ptr(), B * K, N, counts.data_ptr(), p["eps"], K, st)
         out[name] = (scale, shift, gamma, beta)
     return out
 

@@ -103,7 +103,8 @@ def pack_dual_path_tc(mod):
         for axis in ("time", "freq"):
             norm, rnn, fc = getattr(mod, f"norm_{axis}")[i], getattr(mod, f"rnn_{axis}")[i], getattr(mod, f"fc_{axis}")[i]
             p = pack_lstm_tc(rnn)
-            p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(), fc=pack_fc_tc(fc, p["H"]))
+            p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(), eps=float(norm.eps),
+                     fc=pack_fc_tc(fc, p["H"]))
             e[axis] = p
         layers.append(e)
     return layers
@@ -164,7 +165,7 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                 R, steps, tiles, addr = B * T, K, ws.tiles_freq, (1, K, 0, 1)
             with region("norm"):
                 L.call("bsrnn_gn_finalize", ws.stats.data_ptr(), w["gamma"].data_ptr(), w["beta"].data_ptr(), L.ptr(extra),
-                       ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), 1e-5, 1, st)
+                       ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), w["eps"], 1, st)
                 # operand tiles in the axis' (step, sequence tile) order: the GEMM output tiles are then the
                 # recurrence kernel's gates_x tiles
                 L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(),
@@ -216,7 +217,8 @@ def pack_mask_decoder_tc(md):
             bn2.append(BN)
         out[name] = dict(gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
                          beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
-                         w1=w1, b1=b1, w2=w2, b2=b2, bn2=bn2, kc1=kc1, kc2=kc2, nt1=nt1, N=N)
+                         w1=w1, b1=b1, w2=w2, b2=b2, bn2=bn2, kc1=kc1, kc2=kc2, nt1=nt1, N=N,
+                         eps=float(mlps[0][0].eps))
     return out
 
 

@@ -98,7 +98,7 @@ def pack_dual_path_steps(mod):
             w = fc.weight.float()
             bias = torch.zeros(nt * bn, device=w.device)
             bias[:N] = fc.bias.float()
-            p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(),
+            p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(), eps=float(norm.eps),
                      fcw=[to_kb8(w[:, :H], bn, H // 8), to_kb8(w[:, H:], bn, H // 8)], fcb=bias,
                      fcb0=torch.zeros_like(bias), fc_bn=bn, fc_nt=nt)
             e[axis] = p
@@ -145,7 +145,7 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
             else:
                 R_, steps, tiles, addr = B * T, K, tiles_f, (1, K, 0, 1)
             with region("norm"):
-                scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra)
+                scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra, w["eps"])
                 L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws["xhat"].data_ptr(),
                        N, 0, N, w["kc_in"], steps * tiles, tiles, R_, *addr, T * K, 1, st)
             with region(f"lstm_{axis}"):

@@ -124,14 +124,14 @@ def bsrnn_se_train_forward(model, wav, lens, fs):
         if w < s:
             xk = F.pad(xk, (0, 0, 0, s - w))
         xk = xk.reshape(B, T, 2 * s)
-        xk = _gn(xk, (1, 2), core.band_split.norm[k].weight, core.band_split.norm[k].bias)
+        xk = _gn(xk, (1, 2), core.band_split.norm[k].weight, core.band_split.norm[k].bias, core.band_split.norm[k].eps)
         zs.append(F.linear(xk, core.band_split.fc[k].weight[:, :, 0], core.band_split.fc[k].bias))
     skip = torch.stack(zs, dim=2)                                               # (B,T,K',N)
 
     for i in range(core.num_layer):
         for axis, norm, rnn, fc in (("time", core.norm_time[i], core.rnn_time[i], core.fc_time[i]),
                                     ("freq", core.norm_freq[i], core.rnn_freq[i], core.fc_freq[i])):
-            out = _gn(skip, (1, 2, 3), norm.weight, norm.bias)
+            out = _gn(skip, (1, 2, 3), norm.weight, norm.bias, norm.eps)
             out = blstm(out, rnn, axis)
             skip = skip + F.linear(out, fc.weight, fc.bias)
 
@@ -141,7 +141,7 @@ def bsrnn_se_train_forward(model, wav, lens, fs):
         parts = []
         for k in range(plan.K):
             m = mlps[k]
-            xk = _gn(skip[:, :, k, :], (1, 2), m[0].weight, m[0].bias)
+            xk = _gn(skip[:, :, k, :], (1, 2), m[0].weight, m[0].bias, m[0].eps)
             hk = torch.tanh(F.linear(xk, m[1].weight[:, :, 0], m[1].bias))
             ok = F.glu(F.linear(hk, m[3].weight[:, :, 0], m[3].bias), dim=-1)   # (B,T,2s)
             parts.append(ok.reshape(B, T, plan.subbands[k], 2))
@@ -169,17 +169,37 @@ class FlatParams:
         self.flat = torch.zeros(self.numel + pad, dtype=torch.float32, device=dev)
         self.grad = torch.zeros_like(self.flat)
         self.offsets = []
+        self.touched = [False] * len(self.params)      # did autograd deliver a gradient for parameter i this step?
         off = 0
-        for p in self.params:
+        for i, p in enumerate(self.params):
             n = p.numel()
             self.flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)
             p.grad = self.grad[off:off + n].view_as(p)
             self.offsets.append(off)
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self._touch(i))
             off += n
+
+    def _touch(self, i):
+        self.touched[i] = True
+
+    def untouched_ranges(self, touched=None):
+        """Merged [lo, hi) element ranges of the parameters that got no gradient (bands beyond K' at low sample
+        rates): torch AdamW skips grad=None parameters altogether, and so does bsrnn_adamw_step2."""
+        touched = self.touched if touched is None else touched
+        out = []
+        for p, off, t in zip(self.params, self.offsets, touched):
+            if t:
+                continue
+            if out and out[-1][1] == off:
+                out[-1][1] = off + p.numel()
+            else:
+                out.append([off, off + p.numel()])
+        return out
 
     def zero_grad(self):
         self.grad.zero_()
+        self.touched = [False] * len(self.params)
         for p, off in zip(self.params, self.offsets):           # autograd may have replaced .grad: re-attach the views
             n = p.numel()
             view = self.grad[off:off + n].view_as(p)
@@ -210,8 +230,10 @@ class SETrainer:
         self.exp_avg_sq = torch.zeros_like(self.flat.flat)
         self.ema = self.flat.flat.clone() if ema_decay else None
         self.ema_decay, self.ema_updates = ema_decay, 0
-        self.stats = torch.zeros(2, dtype=torch.float64, device=self.flat.flat.device)
-        self.step_count = 0
+        # {sum g^2, non-finite flag, adam steps, ema updates, 1-b1^t, 1-b2^t, ema decay, -}: the counters live on the
+        # device so a step skipped for non-finite gradients does not advance them (bsrnn_adamw_step2)
+        self.stats = torch.zeros(8, dtype=torch.float64, device=self.flat.flat.device)
+        self._skip_cache = {}
         self.group = process_group
         self.forward_fn = forward_fn or bsrnn_se_train_forward
 
@@ -252,24 +274,47 @@ class SETrainer:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.group)
         return world
 
+    def _touched_any_rank(self, world):
+        """Which parameters received a gradient on ANY rank (after the allreduce those hold real gradients everywhere,
+        like the zeros-contributing unused parameters of ddp_find_unused_parameters_true)."""
+        touched = list(self.flat.touched)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor(touched, dtype=torch.int32, device=self.flat.grad.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            touched = [bool(v) for v in t.tolist()]
+        return touched
+
+    def _skip_ranges(self, world):
+        ranges = self.flat.untouched_ranges(self._touched_any_rank(world))
+        if len(ranges) > 32:                       # cannot happen for BSRNN (4 contiguous band suffixes); stay correct
+            ranges = []
+        key = tuple(map(tuple, ranges))
+        dev = self._skip_cache.get(key)
+        if dev is None:
+            flat = [v for r in ranges for v in r] or [0, 0]
+            dev = self._skip_cache[key] = torch.tensor(flat, dtype=torch.int64, device=self.flat.grad.device)
+        return dev, len(ranges)
+
+    @property
+    def step_count(self):
+        """Optimizer steps actually taken (device counter; non-finite steps are not counted)."""
+        return int(self.stats[2])
+
     def apply_gradients(self):
         """allreduce (sum) of the flat gradient buffer, then the fused clip + AdamW (+EMA) tail."""
         world = self.allreduce_gradients()
-        self.step_count += 1
-        ema_d = 0.0
-        if self.ema is not None:                                   # torch_ema: d = min(decay, (1+n)/(10+n))
-            self.ema_updates += 1
-            ema_d = min(self.ema_decay, (1 + self.ema_updates) / (10 + self.ema_updates))
         g = self.flat.grad
-        if g.is_cuda:
-            st = L.stream_ptr()
-            L.call("bsrnn_grad_sumsq", g.data_ptr(), g.numel(), self.stats.data_ptr(), st)
-            L.call("bsrnn_adamw_step", self.flat.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
-                   self.exp_avg_sq.data_ptr(), L.ptr(self.ema), g.numel(), self.stats.data_ptr(), 1.0 / world,
-                   float(self.clip or 0.0), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                   self.step_count, ema_d, st)
-        else:
+        if not g.is_cuda:
             raise L.NativeLibraryError("SETrainer.apply_gradients needs CUDA parameters (no CPU fallback)")
+        skip, n_skip = self._skip_ranges(world)
+        st = L.stream_ptr()
+        L.call("bsrnn_grad_sumsq", g.data_ptr(), g.numel(), self.stats.data_ptr(), st)
+        L.call("bsrnn_adamw_step2", self.flat.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(),
+               self.exp_avg_sq.data_ptr(), L.ptr(self.ema), g.numel(), self.stats.data_ptr(), skip.data_ptr(), n_skip,
+               1.0 / world, float(self.clip or 0.0), self.lr, self.betas[0], self.betas[1], self.eps,
+               self.weight_decay, float(self.ema_decay or 0.0), st)
+        R.invalidate_packed()          # the kernel wrote the parameters through raw pointers: packed copies are stale
 
     def grad_norm(self):
         """Global L2 norm of the (averaged) gradients of the last step — the reference logs it as `Grad_norm`."""
