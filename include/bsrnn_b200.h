@@ -182,6 +182,17 @@ int bsrnn_blstm_tc_max_clusters(void);
 /* Co-resident 16-CTA clusters of the CTA-pair schedule (BSRNN_LSTM_VER=7: cta_group::2 MMAs, half of the W_hh slice
  * per CTA); <= 0 when the device cannot host one. */
 int bsrnn_blstm_tc_max_pair_clusters(void);
+/* bsrnn_blstm_recurrence_tc_flag: the same recurrence with FLAG GROUPS instead of thread-block clusters: the 8 CTAs
+ *     of a work unit announce "h_t is in L2" through gpu-scope release/acquire counters in sync_ws, so they need not
+ *     share a GPC: floor(148/8) = 18 groups (144 SMs) are co-resident instead of 15 clusters (120 SMs).  sync_ws:
+ *     bsrnn_blstm_tc_sync_bytes() bytes of caller-owned device memory (zeroed inside, stream-ordered).  max_groups
+ *     <= 0: all co-resident groups; slots <= 0: the fewest interleaved tiles per group that cover every unit in one
+ *     wave.  The launch must be the only resident kernel of its size class: its CTAs spin on each other. */
+int bsrnn_blstm_recurrence_tc_flag(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
+                                   int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+int bsrnn_blstm_tc_flag_max_groups(void);
+int bsrnn_blstm_tc_sync_bytes(void);
+
 /* Debug / A-B timing: selects the recurrence schedule (4, 5, 6: 8-CTA clusters; 7: CTA pairs); any other value
  * returns to the BSRNN_LSTM_VER environment default. */
 void bsrnn_debug_set_lstm_schedule(int ver);

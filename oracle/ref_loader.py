@@ -74,6 +74,22 @@ def load():
     return ns
 
 
+class on_cpu:
+    """Context manager: run the reference on the CPU of a box that HAS a GPU.  flow_model.py:194 hard-codes
+    ``Y.cuda()`` inside ``enhance``; while the context is active ``torch.Tensor.cuda`` is the identity, so the CPU-resident
+    reference model keeps its tensors where its weights are.  (Never active while product code runs.)"""
+
+    def __enter__(self):
+        import torch
+        self._saved = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda t, *a, **k: t
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.Tensor.cuda = self._saved
+
+
 def flowse_config(ns, **over):
     """Config carrying conf/models/BSRNN_flowse.yaml:31-53 values."""
     cfg = ns.Config(model_type="flowse", ema_decay=0.999, theta=1.5, sigma_max=0.5, sigma_min=0.05, t_eps=0.03,

@@ -77,9 +77,18 @@ def test_bsrnn_se_band_limited_input_eps_sensitivity(se_pair):
             alt, _ = R.bsrnn_se_forward(sd, x, lens, fs, num_layer=6)
     finally:
         R.EPS_NORM1D = old
-    print(f"band-limited 4 kHz @48k: fp16 {rel_l2(out16, ref_wav):.3e} fp32 {rel_l2(out32, ref_wav):.3e}; "
-          f"eps 1e-5 vs 1e-8 at the choose_norm1d sites: {rel_l2(alt, ref_wav):.3e}")
-    assert rel_l2(out32, ref_wav) < 1e-3 and rel_l2(out16, ref_wav) < 1e-2
+    # The empty bands hold only the STFT's own f32 rounding noise (~1e-7 of the peak), which eps = 1e-8 amplifies by up
+    # to 1e4: the REFERENCE's f32 result is itself only defined to that noise there.  Its floor is measured by running
+    # the same arithmetic in f64; our f32 mode must sit at that floor, not at the 1e-3 bar of well-conditioned inputs.
+    sd64 = {k: v.double() for k, v in sd.items()}
+    with torch.no_grad():
+        ref64, _ = R.bsrnn_se_forward(sd64, x.double(), lens, fs, num_layer=6)
+    floor = rel_l2(ref_wav.double(), ref64)
+    e32, e16 = rel_l2(out32.double(), ref64), rel_l2(out16.double(), ref64)
+    print(f"band-limited 4 kHz @48k vs f64 oracle: reference-f32 {floor:.3e}  ours fp32 {e32:.3e}  ours fp16 {e16:.3e}; "
+          f"ours vs reference-f32: fp32 {rel_l2(out32, ref_wav):.3e} fp16 {rel_l2(out16, ref_wav):.3e}; "
+          f"eps 1e-5 instead of 1e-8 at the choose_norm1d sites moves the output by {rel_l2(alt, ref_wav):.3e}")
+    assert e32 < 3 * floor + 1e-4 and e16 < 1e-2 and rel_l2(out16, ref_wav) < 1e-2
 
 
 @pytest.fixture(scope="module")
@@ -107,7 +116,8 @@ def test_flowse_fullwidth_vs_verbatim_reference(flow_pair, fs, precision, bar):
     y = R.synth_noisy(2, n, fs, seed=fs + 1)
     lens = torch.tensor([n, n - 301])
     t = torch.tensor([0.7, 0.31])
-    with torch.no_grad():
+    from oracle import ref_loader
+    with torch.no_grad(), ref_loader.on_cpu():
         Y = rm.speech_to_feature(y, fs, lens)
         torch.manual_seed(11)
         z = torch.randn_like(Y)
@@ -120,3 +130,30 @@ def test_flowse_fullwidth_vs_verbatim_reference(flow_pair, fs, precision, bar):
     e_vf, e_enh = rel_l2(vf.cpu(), vf_ref), rel_l2(enh.cpu(), enh_ref)
     print(f"FlowSE N=384 fs={fs} {precision}: vf rel_l2={e_vf:.3e} enhanced rel_l2={e_enh:.3e}")
     assert e_vf < bar and e_enh < bar
+
+
+@pytest.mark.parametrize("fs", (16000, 48000))
+def test_acceptance_metrics_within_002_of_reference(se_pair, fs):
+    """north_star: ESTOI / SDR (evaluation_metrics/calculate_intrusive_se_metrics.py:37-48,90-109, restated in
+    oracle/metrics.py) of OUR enhanced output within 0.02 of the same metrics of the REFERENCE's output, against the
+    clean signal, on the speech-like synthetic set.  (PESQ: the ITU C code is not available here -- unpinned.)"""
+    import numpy as np
+    from oracle import metrics as M
+    from urgent2026_challenge_track1_b200.synth import synth_pair
+    rm, mine = se_pair
+    n = fs * 3
+    clean, noisy = synth_pair(2, n, fs, seed=fs + 9)
+    rng = np.random.RandomState(fs)
+    breath = torch.from_numpy(rng.randn(2, n).astype(np.float32)) * clean.std() * 10 ** (-25 / 20)
+    clean, noisy = clean + breath, noisy + breath
+    lens = torch.tensor([n, n])
+    with torch.no_grad():
+        ref_wav, _ = rm(noisy, lens, fs)
+    for prec in ("fp16", "fp32"):
+        out = mine[prec](noisy, lens, fs)[0].cpu()
+        for b in range(2):
+            c, r, o = clean[b].numpy(), ref_wav[b].numpy(), out[b].numpy()
+            d_estoi = abs(M.estoi(c, o, fs) - M.estoi(c, r, fs))
+            d_sdr = abs(M.sdr(c, o) - M.sdr(c, r))
+            print(f"fs={fs} {prec} utt {b}: ESTOI ref {M.estoi(c, r, fs):.4f} |d|={d_estoi:.2e}  SDR ref {M.sdr(c, r):.3f} dB |d|={d_sdr:.2e}")
+            assert d_estoi < 0.02 and d_sdr < 0.02

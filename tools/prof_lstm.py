@@ -13,6 +13,7 @@ ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, d
 ap.add_argument("--slots", type=int, default=0); ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--trace-cid", type=int, default=0); ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..9 (0 = BSRNN_LSTM_VER / default)")
+ap.add_argument("--flag", action="store_true", help="flag-group schedule (bsrnn_blstm_recurrence_tc_flag)")
 ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 B, T, K, axis = a.B, a.T, a.K, a.axis
@@ -54,14 +55,21 @@ else:
 y = torch.zeros(steps * tiles * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
 
 
+sync = torch.zeros(L.lib().bsrnn_blstm_tc_sync_bytes() // 4, dtype=torch.int32, device="cuda")
+
+
 def run():
+    if a.flag:
+        L.call("bsrnn_blstm_recurrence_tc_flag", gates.data_ptr(), p["whh"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R,
+               steps, tiles, a.maxcl, a.slots, sync.data_ptr(), st)
+        return
     L.call("bsrnn_blstm_recurrence_tc_ex", gates.data_ptr(), p["whh"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
            tiles, a.maxcl, a.slots, st)
 
 
 if a.ver:
     L.lib().bsrnn_debug_set_lstm_schedule(a.ver)
-tag = f"v{a.ver or os.environ.get('BSRNN_LSTM_VER', '8')} slots={a.slots} maxcl={a.maxcl}"
+tag = f"{'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
 if (a.ver or int(os.environ.get('BSRNN_LSTM_VER', '8'))) == 7:
     print(f"[{tag}] co-resident 16-CTA clusters: {L.lib().bsrnn_blstm_tc_max_pair_clusters()}  (8-CTA: {L.lib().bsrnn_blstm_tc_max_clusters()})", flush=True)
 for _ in range(a.reps):

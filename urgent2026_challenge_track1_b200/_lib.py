@@ -45,6 +45,10 @@ PROTOTYPES = {
     "bsrnn_blstm_recurrence_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_blstm_recurrence_tc_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p],
+    "bsrnn_blstm_recurrence_tc_flag": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_void_p],
+    "bsrnn_blstm_tc_flag_max_groups": [],
+    "bsrnn_blstm_tc_sync_bytes": [],
     "bsrnn_blstm_tc_max_clusters": [],
     "bsrnn_blstm_tc_max_pair_clusters": [],
     "bsrnn_debug_set_lstm_schedule": [c_int],

@@ -39,6 +39,7 @@ class _Separator(nn.Module):
 
 class BSRNN_SE(nn.Module):
     N_FFT, HOP, DEFAULT_FS = 960, 480, 48000          # reference bsrnn.py:14-25
+    MAX_GRAPHS = 16                                   # captured (shape, fs, lengths) signatures kept alive
 
     def __init__(self, num_channel=192, num_layer=6, precision=None, cuda_graph=None):
         super().__init__()
@@ -90,8 +91,8 @@ class BSRNN_SE(nn.Module):
             # batches): destroying or replacing its graph would hand its private memory pool to the next capture, so
             # drain the device before touching the cache (a capture is a slow path anyway).
             torch.cuda.synchronize(dev)
-            if len(self._graphs) >= 4:
-                self._graphs.clear()                       # graphs pin their workspaces: keep only a few alive
+            while len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))   # graphs pin their workspaces: oldest signature goes first
             x_static = torch.empty(tuple(speech_mix.shape), dtype=torch.float32, device=dev)
             x_static.copy_(speech_mix)
             lens = lens_host.to(device=dev, dtype=torch.int32)

@@ -81,7 +81,24 @@ struct LstmTcArgs {
   int gpd;                   // groups per direction (each group = up to `slots` consecutive sequence tiles)
   long long* probe;          // optional (debug): per-role wait/busy cycle totals of cluster probe_cid / CTA 0
   int probe_cid;
+  unsigned* sync;            // flag-group schedule only: [0] ticket counter, [32 + 32*(3*group + slot)] h_ready counters
 };
+
+// ---- flag groups (lstm_tc_flag_kernel): the 8 CTAs that share a work unit need not be a hardware cluster.  The only
+// cluster feature the recurrence uses is the remote mbarrier arrive that announces "h_t of slot k is in L2"; a
+// gpu-scope release/acquire counter in global memory does the same job between ANY 8 co-resident CTAs.  That lifts
+// the 15-cluster co-residency limit of 8-CTA clusters (GPC granularity: 120 of 148 SMs) to 18 groups = 144 SMs, and
+// the time axis of BASELINE config 2 (34 units) fits with 2 interleaved tiles per group instead of 3.
+__device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int L_SYNC_WORDS = 32 + 32 * 3 * 32;     // ticket line + (up to 32 groups) x 3 slots, one 128-byte line each
+__device__ __forceinline__ unsigned* flag_of(const LstmTcArgs& a, int cid, int k) { return a.sync + 32 + 32 * (3 * cid + k); }
 
 struct Group {
   int d, j0, nact;
@@ -572,9 +589,10 @@ __device__ __forceinline__ void epilogue5_role(const LstmTcArgs& a, uint32_t tme
   (void)q;
 }
 
-template <int VER>   // 4: slot-specialised epilogue; 5: all-warps epilogue; 6: 5 + multicast h loads + pipelined gate loads;
-                     // 8: 5 + register-refilled gates, FHADD, software-pipelined TMEM loads (epi8_item)
-__global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
+// VER 4: slot-specialised epilogue; 5: all-warps epilogue; 6: 5 + multicast h loads + pipelined gate loads;
+//     8: 5 + register-refilled gates, FHADD, software-pipelined TMEM loads (epi8_item)
+template <int VER, bool GF>   // GF: flag groups instead of clusters (see above)
+__device__ __forceinline__ void lstm_tc_body(const LstmTcArgs& a) {
   constexpr bool V5 = VER >= 5;
   constexpr bool MC = VER == 6 || VER == 9;          // 9: v8 epilogue + multicast h loads
   extern __shared__ __align__(128) uint8_t smem[];
@@ -591,8 +609,21 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t q = cluster_ctarank();
-  const int cid = cluster_id_x(), ncl = num_clusters_x();
+  uint32_t q;
+  int cid, ncl;
+  if (GF) {
+    // rank within the launch by arrival order: group = ticket / 8, unit slice = ticket % 8 (any placement works)
+    if (threadIdx.x == 0) tmem_slot[1] = atomicAdd(a.sync, 1u);
+    __syncthreads();
+    const uint32_t ticket = tmem_slot[1];
+    q = ticket % LCL;
+    cid = (int)(ticket / LCL);
+    ncl = (int)(gridDim.x / LCL);
+  } else {
+    q = cluster_ctarank();
+    cid = cluster_id_x();
+    ncl = num_clusters_x();
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FSTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, MC ? LCL : 1); }
@@ -606,7 +637,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   if (warp == 2) tmem_alloc(tmem_slot, 2 * LACC);
   tc_fence_before();
   __syncthreads();
-  cluster_sync();                       // every CTA's barriers are initialised before any remote arrive
+  if (!GF) cluster_sync();              // every CTA's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -623,6 +654,7 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     {
       uint32_t stage = 0, phase = 0, hphase = 0, wfphase = 0;
+      uint32_t npub0 = 0u, npub1 = 0u, npub2 = 0u;   // GF: h tiles of slot k published so far by each CTA of the group
       int cur_dir = -1;
       long long w_h = 0, w_e = 0, w_o = 0;
       P_DECL(true);
@@ -649,7 +681,18 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
             const uint8_t* src = reinterpret_cast<const uint8_t*>(a.zero_tile);
             if (s > 0) {
               P_MARK(w_o);
-              mbar_wait_cluster(h_ready + k, (hphase >> k) & 1);
+              if (GF) {
+                // all 8 CTAs of the group have released their slice of h_{t-1} (gpu-scope acquire on the counter)
+                uint32_t& np = k == 0 ? npub0 : (k == 1 ? npub1 : npub2);
+                const uint32_t want = LCL * (++np);
+                const unsigned* fl = flag_of(a, cid, k);
+                uint32_t spins = 0;
+                while ((int32_t)(ld_acquire_gpu(fl) - want) < 0) {
+                  if (++spins > (1u << 22)) { __trap(); }
+                }
+              } else {
+                mbar_wait_cluster(h_ready + k, (hphase >> k) & 1);
+              }
               P_MARK(w_h);
               hphase ^= 1u << k;
               src = reinterpret_cast<const uint8_t*>(a.y + (((size_t)p_prev * a.seq_tiles + (G.j0 + k)) * 2 + G.d) * y_tile);
@@ -744,7 +787,12 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
           // completes once the 4 epilogue warps of slot k have stored their h_t slices
           if (V5) asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
           else asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(128 + 32) : "memory");
-          if (lane < LCL) {
+          if (GF) {
+            if (lane == 0) {
+              fence_proxy_async_global();
+              red_release_gpu_add(flag_of(a, cid, k), 1u);     // release: the CTA's h stores (ordered by the bar.sync) first
+            }
+          } else if (lane < LCL) {
             fence_proxy_async_global();
             fence_acq_rel_cluster();
             mbar_arrive_cluster_relaxed(h_ready + k, lane);
@@ -774,12 +822,20 @@ __global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync();                       // no CTA exits while peers may still arrive on its barriers
+  if (!GF) cluster_sync();              // no CTA exits while peers may still arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * LACC);
   }
 }
+
+template <int VER>
+__global__ void __cluster_dims__(LCL, 1, 1) __launch_bounds__(LTHREADS, 1) lstm_tc_kernel(const LstmTcArgs a) {
+  lstm_tc_body<VER, false>(a);
+}
+// flag-group launch: ordinary grid (no cluster), groups of 8 CTAs by arrival ticket; all CTAs must be co-resident
+// (grid <= SMs x 1 CTA/SM, checked by the host) because the groups spin on each other's counters.
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_tc_flag_kernel(const LstmTcArgs a) { lstm_tc_body<8, true>(a); }
 
 // ================================================================================================ v7: CTA pairs
 // Same decomposition as v5, but the cluster has 16 CTAs = 8 CTA PAIRS and every MMA is a cta_group::2 instruction
@@ -1152,7 +1208,7 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
   if (slots > seq_tiles) slots = seq_tiles;
   LstmTcArgs a{reinterpret_cast<const __half*>(gates_x), reinterpret_cast<const __half*>(w_pack),
                reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y), R, steps, seq_tiles,
-               (seq_tiles + slots - 1) / slots, g_lstm_probe, g_lstm_probe_cid};
+               (seq_tiles + slots - 1) / slots, g_lstm_probe, g_lstm_probe_cid, nullptr};
   static int max_active = -1;
   if (max_active < 0) {
     const int n = max_active_clusters();
@@ -1201,6 +1257,54 @@ extern "C" int bsrnn_blstm_recurrence_tc_ex(const void* gates_x, const void* w_p
   BSRNN_LAUNCH_OK();
   return 0;
 }
+
+// Flag-group schedule (lstm_tc_flag_kernel): up to floor(SMs / 8) = 18 groups of 8 CTAs on a B200, each group owning
+// `slots` interleaved sequence tiles.  sync_ws: BSRNN_LSTM_SYNC_BYTES of device memory owned by the caller (zeroed
+// here, stream-ordered, before every launch).  slots <= 0: as few interleaved tiles as still cover all units with the
+// co-resident groups (2 for the time axis of BASELINE config 2: 34 units on 18 groups; 3 when units abound).
+static int flag_max_groups() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int dev = 0, sms = 0, occ = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(lstm_tc_flag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lstm_tc_flag_kernel, LTHREADS, F_SMEM) != cudaSuccess) return -1;
+  cached = (sms * occ) / LCL;
+  if (cached > 32) cached = 32;                       // L_SYNC_WORDS holds 32 groups
+  return cached;
+}
+
+extern "C" int bsrnn_blstm_recurrence_tc_flag(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
+                                              int steps, int seq_tiles, int max_groups, int slots, void* sync_ws,
+                                              void* stream) {
+  BSRNN_CHECK_ARG(gates_x && w_pack && zero_tile && y && sync_ws, "blstm_recurrence_tc_flag: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_recurrence_tc_flag: bad dims");
+  int cap = flag_max_groups();
+  if (cap <= 0) {
+    cudaGetLastError();
+    set_error("blstm_recurrence_tc_flag: kernel does not fit (512 threads, %zu B shared memory)", F_SMEM);
+    return 2;
+  }
+  if (max_groups > 0 && cap > max_groups) cap = max_groups;
+  if (slots <= 0) {
+    slots = (2 * seq_tiles + cap - 1) / cap;
+    if (slots < 1) slots = 1;
+  }
+  if (slots > LNS) slots = LNS;
+  if (slots > seq_tiles) slots = seq_tiles;
+  LstmTcArgs a{reinterpret_cast<const __half*>(gates_x), reinterpret_cast<const __half*>(w_pack),
+               reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y), R, steps, seq_tiles,
+               (seq_tiles + slots - 1) / slots, g_lstm_probe, g_lstm_probe_cid, reinterpret_cast<unsigned*>(sync_ws)};
+  int ncl = 2 * a.gpd;
+  if (ncl > cap) ncl = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  BSRNN_CUDA_OK(cudaMemsetAsync(sync_ws, 0, (size_t)L_SYNC_WORDS * sizeof(unsigned), st));
+  lstm_tc_flag_kernel<<<ncl * LCL, LTHREADS, F_SMEM, st>>>(a);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+extern "C" int bsrnn_blstm_tc_flag_max_groups(void) { return flag_max_groups(); }
+extern "C" int bsrnn_blstm_tc_sync_bytes(void) { return (int)(L_SYNC_WORDS * sizeof(unsigned)); }
 
 extern "C" int bsrnn_blstm_recurrence_tc(const void* gates_x, const void* w_pack, const void* zero_tile, void* y, int R,
                                          int steps, int seq_tiles, int max_clusters, void* stream) {

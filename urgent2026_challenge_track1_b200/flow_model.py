@@ -83,9 +83,17 @@ class FlowSEModel(nn.Module):
     def eval(self, no_ema=False):
         return self.train(False, no_ema=no_ema)
 
-    def to(self, *args, **kwargs):
-        self.ema.to(*args, **kwargs)
-        return super().to(*args, **kwargs)
+    def _apply(self, fn, *args, **kwargs):
+        """The EMA shadow (and any stored copy) follows the module through .to() / .cuda() / .float() -- the reference
+        overrides only ``to`` (flow_model.py:114-117: Lightning moves modules with .to); nn.Module routes all of them
+        through ``_apply``."""
+        res = super()._apply(fn, *args, **kwargs)
+        ema = self.__dict__.get("ema")
+        if ema is not None:
+            ema.shadow_params = [fn(s) for s in ema.shadow_params]
+            if ema.collected_params is not None:
+                ema.collected_params = [fn(c) for c in ema.collected_params]
+        return res
 
     # ---- features ---------------------------------------------------------------------------------------------
     def _dims(self, fs):

@@ -18,6 +18,14 @@ for _kv in os.environ.get("BSRNN_LSTM_SLOTS", "").split(","):
     if "=" in _kv:
         _ax, _sv = _kv.split("=")
         _LSTM_SLOTS[_ax] = int(_sv)
+# recurrence schedule: "flag" = groups of 8 CTAs synchronised through global-memory counters (18 groups = 144 SMs),
+# "cluster" = 8-CTA thread-block clusters (15 co-resident = 120 SMs).  BSRNN_LSTM_SCHED overrides.
+LSTM_SCHED = os.environ.get("BSRNN_LSTM_SCHED", "flag")
+_FLAG_SLOTS = {"time": 0, "freq": 0}    # 0 = automatic (fewest interleaved tiles that cover all units in one wave)
+for _kv in os.environ.get("BSRNN_LSTM_FLAG_SLOTS", "").split(","):
+    if "=" in _kv:
+        _ax, _sv = _kv.split("=")
+        _FLAG_SLOTS[_ax] = int(_sv)
 CL, LU, LBN, LKC = 8, 49, 208, 50       # cluster size, units per CTA, gate columns per CTA, k-cores of h (K = 400)
 LGC = LBN // 8                           # gates_x cores per CTA
 GATE_SCALE = (0.5, 0.5, 1.0, 0.5)       # i, f, o rows pre-halved: sigmoid(x) = 0.5*tanh(x/2) + 0.5 in the kernel
@@ -129,17 +137,24 @@ class TcWorkspace:
         self.scale = torch.empty(B, N, dtype=torch.float32, device=dev)
         self.shift = torch.empty(B, N, dtype=torch.float32, device=dev)
         self.counts = _f64([float(T) * K * N], dev)
+        self.sync = torch.zeros(L.lib().bsrnn_blstm_tc_sync_bytes() // 4, dtype=torch.int32, device=dev)
+        self.nbytes = sum(t.numel() * t.element_size() for t in (self.xhat, self.gates, self.y))
 
 
-_WS = {}
+_WS = {}                                 # insertion-ordered: least recently used first
+WS_BUDGET_BYTES = int(os.environ.get("BSRNN_WS_BUDGET_GB", "64")) << 30
 
 
 def workspace(B, T, K, N, dev):
+    """Per-shape workspaces, least-recently-used eviction under a byte budget (config 2 needs ~25 GB for one shape; a
+    mixed-sample-rate sweep alternates between many small ones and must not re-zero y on every batch)."""
     key = (B, T, K, N, str(dev))
-    ws = _WS.get(key)
+    ws = _WS.pop(key, None)
     if ws is None:
-        _WS.clear()                     # one live shape at a time keeps the footprint bounded
-        ws = _WS[key] = TcWorkspace(B, T, K, N, dev)
+        ws = TcWorkspace(B, T, K, N, dev)
+        while _WS and sum(w.nbytes for w in _WS.values()) + ws.nbytes > WS_BUDGET_BYTES:
+            _WS.pop(next(iter(_WS)))
+    _WS[key] = ws
     return ws
 
 
@@ -176,8 +191,13 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                        steps * tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_KB8, 0, 2 * CL * LBN, 2 * CL * LGC, T * K,
                        tiles, R, *addr, st)
             with region(f"lstm_{axis}"):
-                L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.zero_tile.data_ptr(),
-                       ws.y.data_ptr(), R, steps, tiles, max_clusters, _LSTM_SLOTS[axis], st)
+                if LSTM_SCHED == "flag":
+                    L.call("bsrnn_blstm_recurrence_tc_flag", ws.gates.data_ptr(), w["whh"].data_ptr(),
+                           ws.zero_tile.data_ptr(), ws.y.data_ptr(), R, steps, tiles, max_clusters, _FLAG_SLOTS[axis],
+                           ws.sync.data_ptr(), st)
+                else:
+                    L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.zero_tile.data_ptr(),
+                           ws.y.data_ptr(), R, steps, tiles, max_clusters, _LSTM_SLOTS[axis], st)
             with region("fc"):
                 ws.stats.zero_()
                 fc = w["fc"]
