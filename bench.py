@@ -615,8 +615,7 @@ def run_config5(ctx, args):
     rank, world, dev = ctx.rank, ctx.world, ctx.dev
     torch.manual_seed(0)
     m = BSRNN_SE(NUM_CHANNEL, NUM_LAYER, precision="fp32").to(dev)
-    tr = SETrainer(m, lr=1e-3, precision=args.train_precision) if "precision" in SETrainer.__init__.__code__.co_varnames \
-        else SETrainer(m, lr=1e-3)
+    tr = SETrainer(m, lr=1e-3, precision=args.train_precision)
     B, ns = args.train_batch, args.train_samples
     clean_h, noisy_h = synth_pair(B, ns, FS, seed=1 + rank)
     clean_h, noisy_h = clean_h.view(B, 1, ns).pin_memory(), noisy_h.view(B, 1, ns).pin_memory()
@@ -716,7 +715,7 @@ def main():
     ap.add_argument("--nfe", type=int, default=15)
     ap.add_argument("--train-batch", type=int, default=4)
     ap.add_argument("--train-samples", type=int, default=96000)
-    ap.add_argument("--train-precision", default="fp32")
+    ap.add_argument("--train-precision", default="fp16", help="config 5: fp16 = BLSTM blocks fwd+bwd on tensor cores; fp32")
     ap.add_argument("--fp32-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")

@@ -233,6 +233,52 @@ int bsrnn_adamw_step2(float* param, const float* grad, float* exp_avg, float* ex
                       double* state, const long* skip_ranges, int n_skip, float grad_scale, float max_norm, float lr,
                       float beta1, float beta2, float eps, float weight_decay, float ema_decay, void* stream);
 
+/* ---------------------------------------------------------------------------------------------- training (tensor cores)
+ * The BLSTM blocks of the training step on tcgen05 (fp16 operands, f32 accumulation, f32 master weights), replacing
+ * autograd through nn.LSTM / nn.Linear [reference d_model.py:61-95, bsrnn_flowse.py:296-307]:
+ * bsrnn_blstm_step_train_tc: one forward time step of both directions that also saves what BPTT needs (activated gates
+ *     over the input projection, c_t per step).
+ * bsrnn_blstm_bwd_step_tc: one BPTT step of both directions: recurrent GEMM dG_{t+1} W_hh + gate derivatives -> dG_t
+ *     (KB8 tiles: next step's operand and the operand of the dx / dW GEMMs).
+ * bsrnn_gemm_tc_scaled: out += scale * A W^T (f32, row-mapped): dx = dG W_ih, dW = dG^T X (tokens as K), with the fp16
+ *     loss scale (a device scalar, so choosing it costs no host sync) removed in f32.
+ * bsrnn_kb8_transpose: KB8 operand -> KB8 operand of its transpose (tokens become the K axis for the dW GEMMs). */
+int bsrnn_blstm_step_train_tc(const void* A_f, const void* W_f, void* gx_f, const float* cprev_f, float* cout_f, void* out_f,
+                              const void* A_b, const void* W_b, void* gx_b, const float* cprev_b, float* cout_b,
+                              void* out_b, int m_tiles, int n_tiles, int BN, int H, long ld_gx, void* stream);
+int bsrnn_blstm_bwd_step_tc(const void* A_f, const void* W_f, const void* sg_f, const void* dy_f, const float* ccur_f,
+                            const float* cprev_f, float* dc_f, void* out_f, const void* A_b, const void* W_b,
+                            const void* sg_b, const void* dy_b, const float* ccur_b, const float* cprev_b, float* dc_b,
+                            void* out_b, int m_tiles, int n_tiles, int BN, int H, long ld_sg, long ld_dy, int valid_rows,
+                            void* stream);
+/* whole-sequence drivers (the host loop over the time steps of both directions, in C) */
+int bsrnn_blstm_train_fwd_tc(const void* zero_tile, void* y_f, void* y_b, const void* W_f, const void* W_b, void* gates,
+                             float* c_f, float* c_b, int steps, int tiles, int n_tiles, int BN, int H, void* stream);
+int bsrnn_blstm_train_bwd_tc(const void* zero_tile, void* dG_f, void* dG_b, const void* WT_f, const void* WT_b,
+                             const void* gates, const void* dy, const float* c_f, const float* c_b, float* dc_f, float* dc_b,
+                             int steps, int tiles, int n_tiles, int BN, int H, int valid_rows, void* stream);
+int bsrnn_gemm_tc_scaled(const void* A, const void* W, const float* bias, void* out, int m_tiles, int n_tiles, int kcores,
+                         int BN, long ldo, int n_valid, float out_scale, const float* out_scale_ptr, int ksplit,
+                         int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride,
+                         long step_stride, void* stream);   /* scale = *out_scale_ptr (device) if non-null; ksplit > 1:
+                         K split over CTAs with atomic adds (weight gradients: few output tiles, K = tokens) */
+int bsrnn_kb8_transpose(const void* src, void* dst, int src_m0, int m_count, int kc_src, int BN, int n_tiles,
+                        long dst_kcores, long dst_kc0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- training loss
+ * The core of espnet2 MultiResL1SpecLoss as configured at d_model.py:24 (window_sz [256,512,768,1024], hop w/2,
+ * rectangular window, center=True reflect padding, onesided, reduction "sum"), VALUE AND GRADIENT in one pass
+ * [replaces d_model.py:74 forward + the autograd backward of the four torch.stft/abs pairs]:
+ *   loss[b] += weight * sum |e - t|                                  (bsrnn_l1_time_fwd_bwd, the time-domain term)
+ *   loss[b] += weight * sum_{frames,bins} | |STFT_w(e)| - |STFT_w(t)| |   (bsrnn_mrl1_spec_fwd_bwd, one window size w)
+ * and grad (B, L) accumulates d loss[b] / d e[b, :].  est, tgt (B, L) f32 are the already scaled / variance-normalised
+ * signals; loss (B) double and grad (B, L) f32 are zeroed by the caller; twiddle from bsrnn_fft_twiddle(window).
+ * Call the time-domain term first (plain stores into grad), then the spectral terms (atomic adds). */
+int bsrnn_l1_time_fwd_bwd(const float* est, const float* tgt, double* loss, float* grad, int B, int L, float weight,
+                          void* stream);
+int bsrnn_mrl1_spec_fwd_bwd(const float* est, const float* tgt, double* loss, float* grad, const float* twiddle, int B,
+                            int L, int window, float weight, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- FlowSE pieces
  * bsrnn_time_embed: GaussianFourierProjection [bsrnn_flowse.py:90-99]: out (B, 2*E) = [sin(2*pi*t*W), cos(...)].
  * bsrnn_conv5x5_glu: GradDecoder.conv_after_* = Conv2d(16->4, 5x5, pad 2) + GLU(dim=1) [bsrnn_flowse.py:114-117,

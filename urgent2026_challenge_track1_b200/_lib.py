@@ -61,6 +61,15 @@ PROTOTYPES = {
                          c_float, c_float, c_float, c_float, c_int, c_float, c_void_p],
     "bsrnn_adamw_step2": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_int, c_float,
                           c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_void_p],
+    "bsrnn_blstm_step_train_tc": [c_void_p] * 12 + [c_int, c_int, c_int, c_int, c_long, c_void_p],
+    "bsrnn_blstm_bwd_step_tc": [c_void_p] * 16 + [c_int, c_int, c_int, c_int, c_long, c_long, c_int, c_void_p],
+    "bsrnn_blstm_train_fwd_tc": [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "bsrnn_blstm_train_bwd_tc": [c_void_p] * 11 + [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "bsrnn_gemm_tc_scaled": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long, c_int, c_float,
+                             c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
+    "bsrnn_kb8_transpose": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long, c_long, c_void_p],
+    "bsrnn_l1_time_fwd_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
+    "bsrnn_mrl1_spec_fwd_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],
     "bsrnn_time_embed": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "bsrnn_conv5x5_glu": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_euler_step": [c_void_p, c_void_p, c_void_p, c_float, c_long, c_void_p],
@@ -114,10 +123,16 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed (rc={rc}): {lib().bsrnn_last_error().decode()}")
 
 
+_DEVICE_OK = set()
+
+
 def require_device():
     if not torch.cuda.is_available():
         raise NativeLibraryError("no CUDA device: the B200 path has no CPU fallback")
-    check(lib().bsrnn_device_check(), "bsrnn_device_check")
+    dev = torch.cuda.current_device()
+    if dev not in _DEVICE_OK:                          # once per device and process
+        check(lib().bsrnn_device_check(), "bsrnn_device_check")
+        _DEVICE_OK.add(dev)
 
 
 def ptr(t):

@@ -72,9 +72,24 @@ struct GemmTcArgs {
   int stages;                       // pipeline depth: 8 when the shared memory allows (short-K GEMMs: one tile is 4 stages,
                                     // and a ring of one tile exposes the HBM latency of every A tile), else 4
   RowMap rows;
+  float out_scale;                  // EPI_RESID_F32: the accumulator is multiplied by this before it is added (0 = 1)
+  const float* out_scale_ptr;       // ... or by *out_scale_ptr (device scalar: no host sync to learn the loss scale)
+  // split-K (EPI_RESID_F32 with atomic adds; weight-gradient GEMMs: few output tiles, K = tokens): the launch iterates
+  // over m_tiles = m_log * ksplit tiles; tile m' = split * m_log + m covers k-cores [split*kps, split*kps + kps)
+  int ksplit, kps, m_log;
+  // training (EPI_LSTM_STEP with save_gates, EPI_LSTM_BWD)
+  int save_gates;                   // EPI_LSTM_STEP: write the ACTIVATED gates i,f,g,o back over gx (fp16, same columns) and
+                                    // c_t to cstate_out (c_{t-1} is read from cstate; null = zeros): what BPTT needs
+  float* cstate_out; float* cstate_out2;
+  const __half* dy; const __half* dy2;     // EPI_LSTM_BWD: dL/dh_t rows [m*128 + r][ld_dy] (this step, this direction)
+  long ld_dy;
+  const float* c_cur; const float* c_cur2;    // c_t rows [m*128 + r][H]
+  const float* c_prev; const float* c_prev2;  // c_{t-1} rows (null at the first step of the sequence = zeros)
+  int valid_rows;                   // rows >= valid_rows (padding of the last sequence tile) get zero gradients
 };
 
-enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4, EPI_LSTM_STEP = 5 };
+enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4, EPI_LSTM_STEP = 5,
+       EPI_LSTM_BWD = 6 };
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -86,6 +101,56 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(fast_tanh(0
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// EPI_LSTM_BWD: the operands of one 8-unit sub-block of a row (saved gates, dy, c_t, c_{t-1}, dc carry)
+struct BwdSub {
+  uint4 g[4];
+  uint4 dy;
+  float4 cc[2], cq[2], dc[2];
+};
+__device__ __forceinline__ void bwd_load(BwdSub& R, const __half* sgp, const __half* dyp, const float* ccp, const float* cpp,
+                                         const float* dcp, int b8) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) R.g[i] = __ldg(reinterpret_cast<const uint4*>(sgp + 32 * b8) + i);
+  R.dy = __ldg(reinterpret_cast<const uint4*>(dyp + 8 * b8));
+  R.cc[0] = __ldg(reinterpret_cast<const float4*>(ccp + 8 * b8));
+  R.cc[1] = __ldg(reinterpret_cast<const float4*>(ccp + 8 * b8 + 4));
+  R.cq[0] = R.cq[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cpp) {
+    R.cq[0] = __ldg(reinterpret_cast<const float4*>(cpp + 8 * b8));
+    R.cq[1] = __ldg(reinterpret_cast<const float4*>(cpp + 8 * b8 + 4));
+  }
+  R.dc[0] = *reinterpret_cast<const float4*>(dcp + 8 * b8);
+  R.dc[1] = *reinterpret_cast<const float4*>(dcp + 8 * b8 + 4);
+}
+__device__ __forceinline__ void bwd_unit(float dh_rec, float dy, float i_, float f_, float g_, float o_, float ct, float cprev,
+                                         float& dc_carry, uint32_t& w0, uint32_t& w1) {
+  const float dh = dy + dh_rec;
+  const float tc = fast_tanh(ct);
+  const float d_o = dh * tc;
+  const float dc = dc_carry + dh * o_ * (1.f - tc * tc);
+  const float d_i = dc * g_, d_g = dc * i_, d_f = dc * cprev;
+  dc_carry = dc * f_;
+  w0 = pack_h2(d_i * i_ * (1.f - i_), d_f * f_ * (1.f - f_));
+  w1 = pack_h2(d_g * (1.f - g_ * g_), d_o * o_ * (1.f - o_));
+}
+__device__ __forceinline__ void bwd_compute(BwdSub& R, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                            float a7, uint32_t (&dgw)[16]) {
+  const __half2* gh = reinterpret_cast<const __half2*>(R.g);
+  const __half2* dyh = reinterpret_cast<const __half2*>(&R.dy);
+  const float acc[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+  const float ct[8] = {R.cc[0].x, R.cc[0].y, R.cc[0].z, R.cc[0].w, R.cc[1].x, R.cc[1].y, R.cc[1].z, R.cc[1].w};
+  const float cp[8] = {R.cq[0].x, R.cq[0].y, R.cq[0].z, R.cq[0].w, R.cq[1].x, R.cq[1].y, R.cq[1].z, R.cq[1].w};
+  float dcs[8] = {R.dc[0].x, R.dc[0].y, R.dc[0].z, R.dc[0].w, R.dc[1].x, R.dc[1].y, R.dc[1].z, R.dc[1].w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 g_if = __half22float2(gh[2 * j]), g_go = __half22float2(gh[2 * j + 1]);
+    const float2 d2 = __half22float2(dyh[j >> 1]);
+    bwd_unit(acc[j], (j & 1) ? d2.y : d2.x, g_if.x, g_if.y, g_go.x, g_go.y, ct[j], cp[j], dcs[j], dgw[2 * j], dgw[2 * j + 1]);
+  }
+  R.dc[0] = make_float4(dcs[0], dcs[1], dcs[2], dcs[3]);
+  R.dc[1] = make_float4(dcs[4], dcs[5], dcs[6], dcs[7]);
 }
 
 // Epilogue for NC (16 or 32) accumulator columns [c0, c0+NC) of row r of tile (m, n).
@@ -103,6 +168,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
   } else {               // bias folded into the weights (constant-one operand column): nothing to add
 #pragma unroll
     for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(acc[i]);
+  }
+  if (EPI == EPI_RESID_F32 && (a.out_scale != 0.f || a.out_scale_ptr)) {
+    const float sc = a.out_scale_ptr ? __ldg(a.out_scale_ptr) : a.out_scale;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] *= sc;
   }
 
   if (EPI == EPI_F16_ROWS) {
@@ -135,7 +205,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
       const long tok = __shfl_sync(0xffffffffu, token, rr);
       optr[i] = (((okmask >> rr) & 1u) && col_ok) ? reinterpret_cast<float*>(a.out) + tok * a.ldo + gc0 + c4 : nullptr;
       old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (optr[i]) old[i] = *reinterpret_cast<const float4*>(optr[i]);
+      if (optr[i] && a.ksplit <= 1) old[i] = *reinterpret_cast<const float4*>(optr[i]);
+    }
+    if (a.ksplit > 1) {                  // split-K: several CTAs add into the same rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (optr[i]) {
+          const float4 nv = *reinterpret_cast<const float4*>(scr + (4 * i + sub) * TC_SCR_LD + c4);
+          atomicAdd(optr[i], nv.x); atomicAdd(optr[i] + 1, nv.y); atomicAdd(optr[i] + 2, nv.z); atomicAdd(optr[i] + 3, nv.w);
+        }
+      }
+      __syncwarp();
+      return;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -181,14 +262,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
         const int md = dir2 ? m - a.dir_tiles : m;
         const long grow = (long)md * 128 + r;
         const uint4* gp = reinterpret_cast<const uint4*>((dir2 ? a.gx2 : a.gx) + grow * a.ld_gx + gc0);
-        float* cp = (dir2 ? a.cstate2 : a.cstate) + grow * a.H + u0;
+        const float* cin = dir2 ? a.cstate2 : a.cstate;                     // c_{t-1} (null: zeros, training's first step)
+        float* cout = dir2 ? a.cstate_out2 : a.cstate_out;                  // c_t (null: in place)
+        const float* cp = cin ? cin + grow * a.H + u0 : nullptr;
+        float* cpo = cout ? cout + grow * a.H + u0 : const_cast<float*>(cp);
         uint4 g4[4];
+        if (a.save_gates) {                // (the buffer is rewritten below: no read-only path)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g4[i] = __ldg(gp + i);
-        float4 c4[2] = {*reinterpret_cast<const float4*>(cp), *reinterpret_cast<const float4*>(cp + 4)};
+          for (int i = 0; i < 4; ++i) g4[i] = gp[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g4[i] = __ldg(gp + i);
+        }
+        float4 c4[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        if (cp) { c4[0] = *reinterpret_cast<const float4*>(cp); c4[1] = *reinterpret_cast<const float4*>(cp + 4); }
         float* c = reinterpret_cast<float*>(c4);
         const __half2* gh = reinterpret_cast<const __half2*>(g4);
         float h[8];
+        uint32_t sv[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 g01 = __half22float2(gh[2 * j]), g23 = __half22float2(gh[2 * j + 1]);
@@ -196,11 +287,65 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
           const float gg = fast_tanh(v[4 * j + 2] + g23.x), og = fmaf(fast_tanh(v[4 * j + 3] + g23.y), 0.5f, 0.5f);
           c[j] = fmaf(fg, c[j], ig * gg);
           h[j] = og * fast_tanh(c[j]);
+          sv[2 * j] = pack_h2(ig, fg);
+          sv[2 * j + 1] = pack_h2(gg, og);
         }
-        *reinterpret_cast<float4*>(cp) = c4[0];
-        *reinterpret_cast<float4*>(cp + 4) = c4[1];
-        __half* o = reinterpret_cast<__half*>(dir2 ? a.out2 : a.out) + (((long)md * (a.H >> 3) + (u0 >> 3)) * 128 + r) * 8;
+        if (a.save_gates) {
+          uint4* gw = const_cast<uint4*>(gp);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gw[i] = make_uint4(sv[4 * i], sv[4 * i + 1], sv[4 * i + 2], sv[4 * i + 3]);
+        }
+        *reinterpret_cast<float4*>(cpo) = c4[0];
+        *reinterpret_cast<float4*>(cpo + 4) = c4[1];
+        __half* o = reinterpret_cast<__half*>(dir2 ? a.out2 : a.out) + (((long)md * a.out_kcores + (u0 >> 3)) * 128 + r) * 8;
         *reinterpret_cast<uint4*>(o) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+      }
+    }
+  } else if (EPI == EPI_LSTM_BWD) {
+    // One step of back-propagation through time (training): the GEMM is dG_{t+1} * W_hh (K = 4H gate columns in the
+    // interleaved order 4u + gate, TRUE weights; N = H hidden units), so accumulator column u holds the recurrent part
+    // of dL/dh_t[u].  With the activations saved by the forward (i,f,g,o fp16 in gx's place, c_t f32):
+    //   dh = dy + acc;  do = dh*tanh(c_t);  dc = dc_carry + dh*o*(1 - tanh(c_t)^2);  di = dc*g;  dg = dc*i;  df = dc*c_{t-1};
+    //   dc_carry' = dc*f;   dG = [di*i(1-i), df*f(1-f), dg*(1-g^2), do*o(1-o)]   (w.r.t. the true pre-activations)
+    // dG is stored as the KB8 tile that is the next (earlier) step's A operand and the operand of the dx / dW GEMMs.
+    // [reference: autograd through nn.LSTM, bsrnn_flowse.py:296-297,303-304; d_model.py:74 loss.backward()]
+    if (NC == 32) {
+      const int u0 = gc0;
+      if (u0 < a.H) {
+        const bool dir2 = a.dir_tiles > 0 && m >= a.dir_tiles;
+        const int md = dir2 ? m - a.dir_tiles : m;
+        const long grow = (long)md * 128 + r;
+        const bool live = grow < a.valid_rows;
+        const __half* sgp = (dir2 ? a.gx2 : a.gx) + grow * a.ld_gx + 4 * u0;
+        const __half* dyp = (dir2 ? a.dy2 : a.dy) + grow * a.ld_dy + u0;
+        const float* ccp = (dir2 ? a.c_cur2 : a.c_cur) + grow * a.H + u0;
+        const float* cpv = dir2 ? a.c_prev2 : a.c_prev;
+        const float* cpp = cpv ? cpv + grow * a.H + u0 : nullptr;
+        float* dcp = (dir2 ? a.cstate2 : a.cstate) + grow * a.H + u0;
+        __half* o = reinterpret_cast<__half*>(dir2 ? a.out2 : a.out) + (((long)md * a.out_kcores + (u0 >> 1)) * 128 + r) * 8;
+        // four 8-unit sub-blocks, one after the other: a double-buffered variant (loads of sub-block b+1 under the math
+        // of b) needs ~90 more registers and spilled 4.4 KB at the 168-register cap of this 320-thread kernel; the host
+        // instead picks narrow N tiles (BN = 64) for small batches so that a warp owns one chunk and many CTAs share the
+        // step (training_tc.pack_block)
+        BwdSub ra;
+#pragma unroll
+        for (int b8 = 0; b8 < 4; ++b8) {
+          if (u0 + 8 * b8 >= a.H) break;
+          uint32_t dgw[16];
+          if (live) {
+            bwd_load(ra, sgp, dyp, ccp, cpp, dcp, b8);
+            bwd_compute(ra, v[8 * b8], v[8 * b8 + 1], v[8 * b8 + 2], v[8 * b8 + 3], v[8 * b8 + 4], v[8 * b8 + 5], v[8 * b8 + 6],
+                        v[8 * b8 + 7], dgw);
+            *reinterpret_cast<float4*>(dcp + 8 * b8) = ra.dc[0];
+            *reinterpret_cast<float4*>(dcp + 8 * b8 + 4) = ra.dc[1];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dgw[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(o + (size_t)(4 * b8 + i) * 1024) = make_uint4(dgw[4 * i], dgw[4 * i + 1], dgw[4 * i + 2], dgw[4 * i + 3]);
+        }
       }
     }
   } else if (EPI == EPI_TANH_KB8) {
@@ -343,8 +488,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       }
       for (; ti.valid(); ti.next()) {
         const bool dir2 = a.dir_tiles > 0 && ti.m >= a.dir_tiles;
-        const uint8_t* gA = reinterpret_cast<const uint8_t*>(dir2 ? a.A2 : a.A) + (size_t)(dir2 ? ti.m - a.dir_tiles : ti.m) * a.kcores * 2048;
-        const uint8_t* gB = reinterpret_cast<const uint8_t*>(dir2 ? a.W2 : a.W) + (size_t)ti.n * a.kcores * BN * 16;
+        const int split = a.ksplit > 1 ? ti.m / a.m_log : 0;
+        const int mrow = dir2 ? ti.m - a.dir_tiles : (a.ksplit > 1 ? ti.m - split * a.m_log : ti.m);
+        const int kbase = split * a.kps;
+        const int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - kbase) : a.kcores;
+        const int nstage_t = (kcnt + TC_KS - 1) / TC_KS;
+        const uint8_t* gA = reinterpret_cast<const uint8_t*>(dir2 ? a.A2 : a.A) + ((size_t)mrow * a.kcores + kbase) * 2048;
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>(dir2 ? a.W2 : a.W) + ((size_t)ti.n * a.kcores + kbase) * BN * 16;
         if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
           const TileIter t3 = ti.ahead(a.pf_dist);
           if (t3.valid() && (a.b_resident ? ti.n == pf_mod : t3.n == 0))
@@ -352,9 +502,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           pf_mod += pf_dmod;
           if (pf_mod >= a.n_tiles) pf_mod -= a.n_tiles;
         }
-        for (int ks = 0; ks < nstage_k; ++ks) {
+        for (int ks = 0; ks < nstage_t; ++ks) {
           const int kc0 = ks * TC_KS;
-          const int nk = min(TC_KS, a.kcores - kc0);
+          const int nk = min(TC_KS, kcnt - kc0);
           mbar_wait(empty + stage, phase ^ 1);
           mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
           bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
@@ -381,8 +531,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           mbar_wait(acc_empty + buf, acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
-          for (int ks = 0; ks < nstage_k; ++ks) {
-            const int nk = min(TC_KS, a.kcores - ks * TC_KS);
+          const int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - (ti.m / a.m_log) * a.kps) : a.kcores;
+          const int nstage_t = (kcnt + TC_KS - 1) / TC_KS;
+          for (int ks = 0; ks < nstage_t; ++ks) {
+            const int nk = min(TC_KS, kcnt - ks * TC_KS);
             mbar_wait(full + stage, phase);
             tc_fence_after();
             const uint64_t da = da0 + (uint64_t)(stage * (a_stage_bytes >> 4));
@@ -463,7 +615,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
     float* scr = reinterpret_cast<float*>(smem_scr) + (warp - 2) * 32 * TC_SCR_LD;
     TileIter ti(a);
     for (int it = 0; ti.valid(); ti.next(), ++it) {
-      const int m = ti.m, n = ti.n;
+      const int m = a.ksplit > 1 ? ti.m % a.m_log : ti.m, n = ti.n;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       long token = 0;
@@ -471,7 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       float s_sum = 0.f, s_sq = 0.f;
       if (EPI == EPI_RESID_F32) {                      // next tile's residual rows -> L2 while this tile is processed
         const TileIter t2 = ti.ahead(1);
-        const int m2 = t2.m, n2 = t2.n;
+        const int m2 = a.ksplit > 1 ? t2.m % a.m_log : t2.m, n2 = t2.n;
         long tok2 = 0;
         if (t2.valid() && a.rows.map(m2, r, &tok2)) {
           const char* p = reinterpret_cast<const char*>(reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + n2 * a.BN);
@@ -556,12 +708,15 @@ static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch, int
 
 template <int EPI>
 static int launch_tc(GemmTcArgs a, cudaStream_t st) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;                     // one process per GPU: the SM count is queried once
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
   // weight-resident schedule when several N tiles exist, the tile fits beside the A ring, and there is enough M work
   a.b_resident = (a.n_tiles > 1 && a.n_tiles <= sms && (size_t)a.kcores * a.BN * 16 <= 120 * 1024 &&
-                  a.m_tiles >= 2 * (sms / a.n_tiles)) ? 1 : 0;
+                  a.m_tiles >= 2 * (sms / a.n_tiles) && a.ksplit <= 1) ? 1 : 0;
   a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8) <= 227 * 1024 ? 8 : 4;
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
   if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
@@ -581,7 +736,11 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
   if (pfd >= 0) a.pf_dist = pfd;
   const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages);
-  BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set = 0;             // per instantiation: the attribute only ever needs to grow (step-wise launches
+  if (smem > smem_set) {                  // call this thousands of times per training step)
+    BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;
   if (a.b_resident) grid = (sms / a.n_tiles) * a.n_tiles;
@@ -631,20 +790,21 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
 }
 
 // One time step of an LSTM direction on tensor cores, any H % 8 == 0 (csrc/gemm_tc.cu, EPI_LSTM_STEP):
-//   A      [m_tiles][H/8][128][8] fp16  h_{t-1} tiles (a zero tile set for the first step)
-//   W      [n_tiles][H/8][BN][8]  fp16  W_hh with rows reordered to 4u + gate and i/f/o rows pre-halved; BN % 32 == 0
+//   A      [m_tiles][kc][128][8] fp16  h_{t-1} tiles (a zero tile set for the first step); kc = 2*ceil(H/16): K is padded
+//                                       to a multiple of 16 and the pad k-core of the tiles must stay zero
+//   W      [n_tiles][kc][BN][8]  fp16  W_hh with rows reordered to 4u + gate and i/f/o rows pre-halved; BN % 32 == 0
 //   gx     rows [m*128 + r][ld_gx] fp16: input projection (+ bias) of THIS step and direction, same column order
 //   cstate [m_tiles*128][H] f32, updated in place;   out_h: h_t tiles, same layout as A
 extern "C" int bsrnn_lstm_step_tc(const void* A, const void* W, const void* gx, float* cstate, void* out_h, int m_tiles,
                                   int n_tiles, int BN, int H, long ld_gx, void* stream) {
   BSRNN_CHECK_ARG(A && W && gx && cstate && out_h, "lstm_step_tc: null pointer");
-  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 16 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 8 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
                   (long)n_tiles * BN >= 4L * H && ld_gx >= 4L * H && ld_gx % 8 == 0, "lstm_step_tc: bad dims");
   GemmTcArgs a{};
   a.A = reinterpret_cast<const __half*>(A);
   a.W = reinterpret_cast<const __half*>(W);
   a.bias = nullptr; a.out = out_h; a.stats = nullptr; a.ldo = 0; a.tokens_per_sample = 1;
-  a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = H / 8; a.BN = BN; a.n_valid = 4 * H; a.out_kcores = H / 8;
+  a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = (H + 15) / 16 * 2; a.BN = BN; a.n_valid = 4 * H; a.out_kcores = (H + 15) / 16 * 2;
   a.gx = reinterpret_cast<const __half*>(gx); a.cstate = cstate; a.ld_gx = ld_gx; a.H = H;
   a.rows = RowMap{m_tiles, m_tiles * 128, 1L << 40, 0, 1, 0};
   return launch_tc<EPI_LSTM_STEP>(a, (cudaStream_t)stream);
@@ -657,16 +817,161 @@ extern "C" int bsrnn_blstm_step_tc(const void* A_f, const void* W_f, const void*
                                    const void* A_b, const void* W_b, const void* gx_b, float* c_b, void* out_b, int m_tiles,
                                    int n_tiles, int BN, int H, long ld_gx, void* stream) {
   BSRNN_CHECK_ARG(A_f && W_f && gx_f && c_f && out_f && A_b && W_b && gx_b && c_b && out_b, "blstm_step_tc: null pointer");
-  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 16 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 8 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
                   (long)n_tiles * BN >= 4L * H && ld_gx >= 4L * H && ld_gx % 8 == 0, "blstm_step_tc: bad dims");
   GemmTcArgs a{};
   a.A = reinterpret_cast<const __half*>(A_f); a.W = reinterpret_cast<const __half*>(W_f);
   a.A2 = reinterpret_cast<const __half*>(A_b); a.W2 = reinterpret_cast<const __half*>(W_b);
   a.bias = nullptr; a.out = out_f; a.out2 = out_b; a.stats = nullptr; a.ldo = 0; a.tokens_per_sample = 1;
-  a.m_tiles = 2 * m_tiles; a.dir_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = H / 8; a.BN = BN; a.n_valid = 4 * H;
-  a.out_kcores = H / 8;
+  a.m_tiles = 2 * m_tiles; a.dir_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = (H + 15) / 16 * 2; a.BN = BN; a.n_valid = 4 * H;
+  a.out_kcores = (H + 15) / 16 * 2;
   a.gx = reinterpret_cast<const __half*>(gx_f); a.gx2 = reinterpret_cast<const __half*>(gx_b);
   a.cstate = c_f; a.cstate2 = c_b; a.ld_gx = ld_gx; a.H = H;
   a.rows = RowMap{2 * m_tiles, 2 * m_tiles * 128, 1L << 40, 0, 1, 0};
   return launch_tc<EPI_LSTM_STEP>(a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------- training entry points
+// bsrnn_gemm_tc with an output scale (EPI_RESID_F32: out += scale * A W^T): the fp16 gradient operands of the training
+// backward carry a power-of-two loss scale that is removed here, in f32.
+extern "C" int bsrnn_gemm_tc_scaled(const void* A, const void* W, const float* bias, void* out, int m_tiles, int n_tiles,
+                                    int kcores, int BN, long ldo, int n_valid, float out_scale, const float* out_scale_ptr,
+                                    int ksplit, int tiles_per_step, int R, long seq_inner, long seq_outer,
+                                    long seq_inner_stride, long step_stride, void* stream) {
+  BSRNN_CHECK_ARG(A && W && out, "gemm_tc_scaled: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && kcores > 0 && kcores % 2 == 0, "gemm_tc_scaled: bad tile counts (kcores=%d)", kcores);
+  BSRNN_CHECK_ARG(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc_scaled: BN=%d must be a multiple of 16 in [16,256]", BN);
+  BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && n_valid % 4 == 0 && ldo % 4 == 0, "gemm_tc_scaled: bad row map / strides");
+  GemmTcArgs a{};
+  a.A = reinterpret_cast<const __half*>(A);
+  a.W = reinterpret_cast<const __half*>(W);
+  a.bias = bias; a.out = out; a.stats = nullptr; a.ldo = ldo; a.tokens_per_sample = 1;
+  a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = kcores; a.BN = BN; a.n_valid = n_valid; a.out_kcores = 0;
+  a.out_scale = out_scale; a.out_scale_ptr = out_scale_ptr;
+  a.ksplit = 1; a.kps = kcores; a.m_log = m_tiles;
+  if (ksplit > 1) {                                   // K split over CTAs, partial sums meet through atomic adds
+    BSRNN_CHECK_ARG(bias == nullptr, "gemm_tc_scaled: split-K has no bias epilogue");
+    const int kps = ((kcores + ksplit - 1) / ksplit + TC_KS - 1) / TC_KS * TC_KS;
+    a.kps = kps;
+    a.ksplit = (kcores + kps - 1) / kps;
+    a.m_tiles = m_tiles * a.ksplit;
+  }
+  a.rows = RowMap{tiles_per_step, R, seq_inner, seq_outer, seq_inner_stride, step_stride};
+  return launch_tc<EPI_RESID_F32>(a, (cudaStream_t)stream);
+}
+
+// Both directions of one BLSTM time step, TRAINING forward: as bsrnn_blstm_step_tc, but c_{t-1} is read from cprev_*
+// (null = zeros: first step of the sequence), c_t is written to cout_*, and the activated gates (i, f, g, o; fp16) replace
+// the input projection in gx_* -- the quantities bsrnn_blstm_bwd_step_tc consumes.
+extern "C" int bsrnn_blstm_step_train_tc(const void* A_f, const void* W_f, void* gx_f, const float* cprev_f, float* cout_f,
+                                         void* out_f, const void* A_b, const void* W_b, void* gx_b, const float* cprev_b,
+                                         float* cout_b, void* out_b, int m_tiles, int n_tiles, int BN, int H, long ld_gx,
+                                         void* stream) {
+  BSRNN_CHECK_ARG(A_f && W_f && gx_f && cout_f && out_f && A_b && W_b && gx_b && cout_b && out_b, "blstm_step_train_tc: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 8 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
+                  (long)n_tiles * BN >= 4L * H && ld_gx >= 4L * H && ld_gx % 8 == 0, "blstm_step_train_tc: bad dims");
+  GemmTcArgs a{};
+  a.A = reinterpret_cast<const __half*>(A_f); a.W = reinterpret_cast<const __half*>(W_f);
+  a.A2 = reinterpret_cast<const __half*>(A_b); a.W2 = reinterpret_cast<const __half*>(W_b);
+  a.bias = nullptr; a.out = out_f; a.out2 = out_b; a.stats = nullptr; a.ldo = 0; a.tokens_per_sample = 1;
+  a.m_tiles = 2 * m_tiles; a.dir_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = (H + 15) / 16 * 2; a.BN = BN; a.n_valid = 4 * H;
+  a.out_kcores = (H + 15) / 16 * 2;
+  a.gx = reinterpret_cast<const __half*>(gx_f); a.gx2 = reinterpret_cast<const __half*>(gx_b);
+  a.cstate = const_cast<float*>(cprev_f); a.cstate2 = const_cast<float*>(cprev_b);
+  a.cstate_out = cout_f; a.cstate_out2 = cout_b; a.save_gates = 1;
+  a.ld_gx = ld_gx; a.H = H;
+  a.rows = RowMap{2 * m_tiles, 2 * m_tiles * 128, 1L << 40, 0, 1, 0};
+  return launch_tc<EPI_LSTM_STEP>(a, (cudaStream_t)stream);
+}
+
+// Both directions of one BPTT step (EPI_LSTM_BWD above).  Per direction:
+//   A     [m_tiles][4H/8][128][8] fp16  dG of the step processed just before (a zero tile set for the first one)
+//   W     [n_tiles][4H/8][BN][8]  fp16  W_hh^T: row = hidden unit u, K = gate column 4u' + gate (true weights); BN % 32 == 0
+//   sg    rows [m*128 + r][ld_sg] fp16  activated gates of THIS step (written by bsrnn_blstm_step_train_tc)
+//   dy    rows [m*128 + r][ld_dy] fp16  dL/dh_t from the layers above (loss-scaled)
+//   ccur / cprev  rows [m*128 + r][H] f32  c_t / c_{t-1} (cprev null = zeros)
+//   dc    [m_tiles*128][H] f32 carry, updated in place (zero before the first step)
+//   out   dG tiles of THIS step, layout as A.     Rows >= valid_rows get zero gradients.
+extern "C" int bsrnn_blstm_bwd_step_tc(const void* A_f, const void* W_f, const void* sg_f, const void* dy_f, const float* ccur_f,
+                                       const float* cprev_f, float* dc_f, void* out_f, const void* A_b, const void* W_b,
+                                       const void* sg_b, const void* dy_b, const float* ccur_b, const float* cprev_b, float* dc_b,
+                                       void* out_b, int m_tiles, int n_tiles, int BN, int H, long ld_sg, long ld_dy,
+                                       int valid_rows, void* stream) {
+  BSRNN_CHECK_ARG(A_f && W_f && sg_f && dy_f && ccur_f && dc_f && out_f && A_b && W_b && sg_b && dy_b && ccur_b && dc_b && out_b,
+                  "blstm_bwd_step_tc: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && H > 0 && H % 8 == 0 && (4 * H / 8) % 2 == 0 && BN % 32 == 0 && BN >= 32 && BN <= 256 &&
+                  (long)n_tiles * BN >= H && ld_sg >= 4L * H && ld_sg % 8 == 0 && ld_dy >= H && ld_dy % 8 == 0 && valid_rows > 0,
+                  "blstm_bwd_step_tc: bad dims");
+  GemmTcArgs a{};
+  a.A = reinterpret_cast<const __half*>(A_f); a.W = reinterpret_cast<const __half*>(W_f);
+  a.A2 = reinterpret_cast<const __half*>(A_b); a.W2 = reinterpret_cast<const __half*>(W_b);
+  a.bias = nullptr; a.out = out_f; a.out2 = out_b; a.stats = nullptr; a.ldo = 0; a.tokens_per_sample = 1;
+  a.m_tiles = 2 * m_tiles; a.dir_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = 4 * H / 8; a.BN = BN; a.n_valid = H;
+  a.out_kcores = 4 * H / 8;
+  a.gx = reinterpret_cast<const __half*>(sg_f); a.gx2 = reinterpret_cast<const __half*>(sg_b); a.ld_gx = ld_sg;
+  a.dy = reinterpret_cast<const __half*>(dy_f); a.dy2 = reinterpret_cast<const __half*>(dy_b); a.ld_dy = ld_dy;
+  a.c_cur = ccur_f; a.c_cur2 = ccur_b; a.c_prev = cprev_f; a.c_prev2 = cprev_b;
+  a.cstate = dc_f; a.cstate2 = dc_b; a.H = H; a.valid_rows = valid_rows;
+  a.rows = RowMap{2 * m_tiles, 2 * m_tiles * 128, 1L << 40, 0, 1, 0};
+  return launch_tc<EPI_LSTM_BWD>(a, (cudaStream_t)stream);
+}
+
+// Whole-sequence drivers of the two step kernels above: the host loop over time steps lives here (a launch every few
+// microseconds) instead of in the Python caller (tens of microseconds per ctypes call x thousands of steps).
+//   y_*   [steps*tiles][kc][128][8] fp16 h tiles (kc = 2*ceil(H/16); zero-initialised by the caller: the pad core stays 0)
+//   gates rows [(step*tiles*128 + r)][8H] fp16: input projection on entry, ACTIVATED gates on return (direction-major)
+//   c_*   [steps][tiles*128][H] f32
+// Direction f walks positions 0..steps-1, direction b walks steps-1..0; position p of either lives at step index p.
+extern "C" int bsrnn_blstm_train_fwd_tc(const void* zero_tile, void* y_f, void* y_b, const void* W_f, const void* W_b,
+                                        void* gates, float* c_f, float* c_b, int steps, int tiles, int n_tiles, int BN, int H,
+                                        void* stream) {
+  BSRNN_CHECK_ARG(zero_tile && y_f && y_b && W_f && W_b && gates && c_f && c_b && steps > 0 && tiles > 0,
+                  "blstm_train_fwd_tc: bad arguments");
+  const size_t kc = (size_t)((H + 15) / 16 * 2);
+  const size_t y_step = (size_t)tiles * kc * 1024;            // halves
+  const size_t g_step = (size_t)tiles * 128 * 8 * H;          // halves
+  const size_t c_step = (size_t)tiles * 128 * H;              // floats
+  __half* yf = reinterpret_cast<__half*>(y_f);
+  __half* yb = reinterpret_cast<__half*>(y_b);
+  __half* g = reinterpret_cast<__half*>(gates);
+  for (int s = 0; s < steps; ++s) {
+    const int pf = s, pb = steps - 1 - s;
+    const int rc = bsrnn_blstm_step_train_tc(
+        s == 0 ? zero_tile : (const void*)(yf + (size_t)(pf - 1) * y_step), W_f, g + (size_t)pf * g_step,
+        s == 0 ? nullptr : c_f + (size_t)(pf - 1) * c_step, c_f + (size_t)pf * c_step, yf + (size_t)pf * y_step,
+        s == 0 ? zero_tile : (const void*)(yb + (size_t)(pb + 1) * y_step), W_b, g + (size_t)pb * g_step + 4 * (size_t)H,
+        s == 0 ? nullptr : c_b + (size_t)(pb + 1) * c_step, c_b + (size_t)pb * c_step, yb + (size_t)pb * y_step, tiles, n_tiles,
+        BN, H, 8L * H, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+//   dG_*  [steps*tiles][4H/8][128][8] fp16 (output);  dy rows [(step*tiles*128 + r)][2H] fp16;  dc_* [tiles*128][H] f32 zeroed
+extern "C" int bsrnn_blstm_train_bwd_tc(const void* zero_tile, void* dG_f, void* dG_b, const void* WT_f, const void* WT_b,
+                                        const void* gates, const void* dy, const float* c_f, const float* c_b, float* dc_f,
+                                        float* dc_b, int steps, int tiles, int n_tiles, int BN, int H, int valid_rows,
+                                        void* stream) {
+  BSRNN_CHECK_ARG(zero_tile && dG_f && dG_b && WT_f && WT_b && gates && dy && c_f && c_b && dc_f && dc_b && steps > 0 && tiles > 0,
+                  "blstm_train_bwd_tc: bad arguments");
+  const size_t dg_step = (size_t)tiles * (4 * H / 8) * 1024;  // halves
+  const size_t g_step = (size_t)tiles * 128 * 8 * H;
+  const size_t dy_step = (size_t)tiles * 128 * 2 * H;
+  const size_t c_step = (size_t)tiles * 128 * H;
+  __half* df = reinterpret_cast<__half*>(dG_f);
+  __half* db = reinterpret_cast<__half*>(dG_b);
+  const __half* g = reinterpret_cast<const __half*>(gates);
+  const __half* dyh = reinterpret_cast<const __half*>(dy);
+  for (int sb = 0; sb < steps; ++sb) {
+    const int pf = steps - 1 - sb, pb = sb;                   // reverse of the forward order of each direction
+    const int rc = bsrnn_blstm_bwd_step_tc(
+        sb == 0 ? zero_tile : (const void*)(df + (size_t)(pf + 1) * dg_step), WT_f, g + (size_t)pf * g_step,
+        dyh + (size_t)pf * dy_step, c_f + (size_t)pf * c_step, pf > 0 ? c_f + (size_t)(pf - 1) * c_step : nullptr, dc_f,
+        df + (size_t)pf * dg_step,
+        sb == 0 ? zero_tile : (const void*)(db + (size_t)(pb - 1) * dg_step), WT_b, g + (size_t)pb * g_step + 4 * (size_t)H,
+        dyh + (size_t)pb * dy_step + H, c_b + (size_t)pb * c_step, pb < steps - 1 ? c_b + (size_t)(pb + 1) * c_step : nullptr, dc_b,
+        db + (size_t)pb * dg_step, tiles, n_tiles, BN, H, 8L * H, 2L * H, valid_rows, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }

@@ -223,3 +223,51 @@ extern "C" int bsrnn_norm_cast_kb8(const float* x, const float* scale, const flo
   return bsrnn_norm_cast_kb8_ones(x, scale, shift, out, ldx, col0, C, kcores, m_tiles, tiles_per_step, R, seq_inner,
                                   seq_outer, seq_inner_stride, step_stride, tokens_per_sample, g_inner, -1, stream);
 }
+
+// ---------------------------------------------------------------------------------------------- KB8 transpose (training)
+// The weight-gradient GEMMs contract over TOKENS (dW = dG^T X), so both operands are needed with tokens as the K axis.
+// src: KB8 [..][kc_src][128][8] = matrix X[row = m*128 + r][col = kc*8 + e].  dst: KB8 of X^T,
+// [n_tiles][dst_kcores][BN][8]: dst row (n*BN + c) = src column, dst k index = dst_kc0*8 + (m - src_m0)*128 + r.
+// Source columns >= kc_src*8 read as zero.  grid (m_count, n_tiles); the caller zeroes whatever dst k-cores no source
+// tile covers (the one-step shift of h_{t-1} leaves a block of zeros).
+namespace bsrnn {
+__global__ void __launch_bounds__(256) kb8_transpose_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int kc_src,
+                                                            int BN, long dst_kcores, long dst_kc0, int src_m0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* tile = reinterpret_cast<__half*>(smem_raw);            // [128][BN + 8]
+  const int ld = BN + 8;
+  const int m = blockIdx.x, n = blockIdx.y;
+  const int ncores = BN >> 3;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src) + ((size_t)(src_m0 + m) * kc_src) * 128;
+  for (int idx = threadIdx.x; idx < ncores * 128; idx += blockDim.x) {
+    const int kc = idx >> 7, r = idx & 127;
+    const int gkc = n * ncores + kc;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (gkc < kc_src) v = __ldg(s4 + (size_t)gkc * 128 + r);
+    *reinterpret_cast<uint4*>(tile + (size_t)r * ld + kc * 8) = v;
+  }
+  __syncthreads();
+  uint4* d4 = reinterpret_cast<uint4*>(dst) + ((size_t)n * dst_kcores + dst_kc0 + (size_t)m * 16) * BN;
+  for (int idx = threadIdx.x; idx < 16 * BN; idx += blockDim.x) {
+    const int kk = idx / BN, c = idx - kk * BN;
+    __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = tile[(size_t)(kk * 8 + e) * ld + c];
+    d4[(size_t)kk * BN + c] = *reinterpret_cast<const uint4*>(h);
+  }
+}
+}  // namespace bsrnn
+
+extern "C" int bsrnn_kb8_transpose(const void* src, void* dst, int src_m0, int m_count, int kc_src, int BN, int n_tiles,
+                                   long dst_kcores, long dst_kc0, void* stream) {
+  BSRNN_CHECK_ARG(src && dst && m_count > 0 && kc_src > 0 && BN >= 16 && BN <= 256 && BN % 8 == 0 && n_tiles > 0 &&
+                  dst_kc0 >= 0 && dst_kc0 + (long)m_count * 16 <= dst_kcores, "kb8_transpose: bad arguments");
+  const size_t smem = (size_t)128 * (BN + 8) * 2;
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(bsrnn::kb8_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(m_count, n_tiles);
+  bsrnn::kb8_transpose_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(src),
+                                                                          reinterpret_cast<__half*>(dst), kc_src, BN,
+                                                                          dst_kcores, dst_kc0, src_m0);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}

@@ -122,6 +122,31 @@ class FlowSEModel(nn.Module):
                          exponent=float(self.spec_abs_exponent), factor=float(self.spec_factor))
         return wav
 
+    # ---- training (reference flow_model.py:149-187, :211-231) -------------------------------------------------
+    def forward_step(self, batch, t=None, z=None):
+        """(clean (B,1,T), noisy (B,1,T), fs, lengths) -> flow-matching loss (differentiable; training.py)."""
+        from .training import flowse_forward_step
+        clean, noisy, fs, lengths = batch
+        assert clean.shape[1] == 1                                               # flow_model.py:153
+        return flowse_forward_step(self, noisy, clean, lengths, int(fs), t=t, z=z)[0]
+
+    def configure_optimizers(self, process_group=None):
+        """AdamW(lr, eps=adam_epsilon, weight_decay) [flow_model.py:238-249] + EMA [:84] as one FlowSETrainer."""
+        from .training import FlowSETrainer
+        cfg = self.cfg
+        self.trainer_ = FlowSETrainer(self, weight_decay=getattr(cfg, "weight_decay", 1e-6),
+                                      eps=getattr(cfg, "adam_epsilon", 1e-8),
+                                      gradient_clip=getattr(cfg, "gradient_clip", 0.5), process_group=process_group)
+        return self.trainer_
+
+    def training_step(self, batch, batch_idx=0):
+        clean, noisy, fs, lengths = batch
+        if not hasattr(self, "trainer_"):
+            self.configure_optimizers()
+        loss, _ = self.trainer_.step(noisy, clean, lengths, fs)
+        self.logged = {"train_loss": float(loss)}
+        return loss
+
     # ---- network ----------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, t, y):

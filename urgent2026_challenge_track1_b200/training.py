@@ -101,7 +101,89 @@ def _gn(x, dims, weight, bias, eps=1e-5):
     return (x - mean) * torch.rsqrt(var + eps) * weight + bias
 
 
-def bsrnn_se_train_forward(model, wav, lens, fs):
+def band_split_diff(bs, spec, plan):
+    """BandSplit [bsrnn_flowse.py:65-86 / espnet2 BandSplit] on a (B,T,F,2) spectrum -> (B,T,K',N), differentiable."""
+    B, T = spec.shape[0], spec.shape[1]
+    zs = []
+    for k in range(plan.K):
+        s, b0, w = plan.subbands[k], plan.bin0[k], plan.width[k]
+        xk = spec[:, :, b0:b0 + w, :]
+        if w < s:
+            xk = F.pad(xk, (0, 0, 0, s - w))
+        xk = xk.reshape(B, T, 2 * s)
+        xk = _gn(xk, (1, 2), bs.norm[k].weight, bs.norm[k].bias, bs.norm[k].eps)
+        zs.append(F.linear(xk, bs.fc[k].weight[:, :, 0], bs.fc[k].bias))
+    return torch.stack(zs, dim=2)
+
+
+def block_f32(x, rnn, fc, axis):
+    """(BLSTM -> Linear) block, f32: CUDA-core recurrence kernels + library GEMMs (parity ~1e-6)."""
+    return F.linear(blstm(x, rnn, axis), fc.weight, fc.bias)
+
+
+def block_tc(x, rnn, fc, axis):
+    """(BLSTM -> Linear) block on tensor cores, forward and backward (training_tc.BLSTMBlockTC)."""
+    from .training_tc import blstm_block_tc
+    return blstm_block_tc(x, rnn, fc, axis)
+
+
+BLOCKS = {"fp32": block_f32, "fp16": block_tc, "bf16": block_tc}
+
+
+def dual_path_diff(core, skip, t_emb=None, blstm_fn=None):
+    """The 2*num_layer (GN -> [+ t-embedding] -> BLSTM -> Linear -> residual) blocks [bsrnn_flowse.py:288-307] on a
+    token-major (B,T,K,N) tensor.  t_emb: list of (B,N) per layer, added after the time-axis GroupNorm (:293-294).
+    blstm_fn(x, rnn, fc, axis) -> Linear(BLSTM(x)): block_f32 (default) or block_tc."""
+    blstm_fn = blstm_fn or block_f32
+    for i in range(core.num_layer):
+        for axis, norm, rnn, fc in (("time", core.norm_time[i], core.rnn_time[i], core.fc_time[i]),
+                                    ("freq", core.norm_freq[i], core.rnn_freq[i], core.fc_freq[i])):
+            out = _gn(skip, (1, 2, 3), norm.weight, norm.bias, norm.eps)
+            if t_emb is not None and axis == "time":
+                out = out + t_emb[i][:, None, None, :]
+            skip = skip + blstm_fn(out, rnn, fc, axis)
+    return skip
+
+
+def mask_decoder_diff(md, skip, plan, F_bins):
+    """espnet2 MaskDecoder: per band GN -> Conv1d(N,4N) -> tanh -> Conv1d(4N,4s) -> GLU -> (mask, resid) complex (B,T,F)."""
+    B, T = skip.shape[0], skip.shape[1]
+    outs = []
+    for mlps in (md.mlp_mask, md.mlp_residual):
+        parts = []
+        for k in range(plan.K):
+            m = mlps[k]
+            xk = _gn(skip[:, :, k, :], (1, 2), m[0].weight, m[0].bias, m[0].eps)
+            hk = torch.tanh(F.linear(xk, m[1].weight[:, :, 0], m[1].bias))
+            ok = F.glu(F.linear(hk, m[3].weight[:, :, 0], m[3].bias), dim=-1)   # (B,T,2s)
+            parts.append(ok.reshape(B, T, plan.subbands[k], 2))
+        outs.append(torch.cat(parts, dim=2)[:, :, :F_bins, :])
+    return torch.view_as_complex(outs[0].contiguous()), torch.view_as_complex(outs[1].contiguous())
+
+
+def grad_decoder_diff(gd, skip, plan, F_bins):
+    """GradDecoder [bsrnn_flowse.py:136-168]: per band GN -> Conv1d(N,16 s) -> tanh -> (B,16,s,T); cat over bins;
+    Conv2d(16->4, 5x5, pad 2) + GLU(dim=1) -> (mask, resid) complex (B,T,F)."""
+    B, T = skip.shape[0], skip.shape[1]
+    sc = gd.sub_channel
+    outs = []
+    for mlps, conv in ((gd.mlp_mask, gd.conv_after_mask), (gd.mlp_residual, gd.conv_after_residual)):
+        parts = []
+        for k in range(plan.K):
+            m = mlps[k]
+            xk = _gn(skip[:, :, k, :], (1, 2), m[0].weight, m[0].bias, m[0].eps)
+            ok = torch.tanh(F.linear(xk, m[1].weight[:, :, 0], m[1].bias))       # (B,T,16 s), channel c = sc*s + f
+            parts.append(ok.reshape(B, T, sc, plan.subbands[k]).permute(0, 2, 3, 1))   # (B,16,s,T)
+        g = torch.cat(parts, dim=2)                                              # (B,16,F',T)
+        g = F.glu(F.conv2d(g, conv[0].weight, conv[0].bias, padding=2), dim=1)   # (B,2,F',T)
+        g = g.permute(0, 3, 2, 1)                                                # (B,T,F',2)
+        if g.shape[2] < F_bins:
+            g = F.pad(g, (0, 0, 0, F_bins - g.shape[2]))
+        outs.append(torch.view_as_complex(g[:, :, :F_bins, :].contiguous()))
+    return outs[0], outs[1]
+
+
+def bsrnn_se_train_forward(model, wav, lens, fs, blstm_fn=None):
     """Differentiable BSRNN_SE.forward on CUDA tensors: wav (B,L) f32, lens (B,) int -> (enhanced (B, max len),
     enhanced spectrum (B,T,F) complex64).  Same arithmetic as the inference kernels / the reference
     (bsrnn.py:36-41; espnet2 BSRNN.forward), zeros of padded frames and truncated bands
@@ -114,46 +196,34 @@ def bsrnn_se_train_forward(model, wav, lens, fs):
     lens_dev = lens.to(device=wav.device, dtype=torch.int32)
     with torch.no_grad():
         spec = R.stft(wav.contiguous().float(), lens_dev, n_fft, hop)           # (B,T,F,2), frames >= olens are zeros
-    B, T = spec.shape[0], spec.shape[1]
-
-    # BandSplit [bsrnn_flowse.py:65-86 / espnet2 BandSplit]
-    zs = []
-    for k in range(plan.K):
-        s, b0, w = plan.subbands[k], plan.bin0[k], plan.width[k]
-        xk = spec[:, :, b0:b0 + w, :]
-        if w < s:
-            xk = F.pad(xk, (0, 0, 0, s - w))
-        xk = xk.reshape(B, T, 2 * s)
-        xk = _gn(xk, (1, 2), core.band_split.norm[k].weight, core.band_split.norm[k].bias, core.band_split.norm[k].eps)
-        zs.append(F.linear(xk, core.band_split.fc[k].weight[:, :, 0], core.band_split.fc[k].bias))
-    skip = torch.stack(zs, dim=2)                                               # (B,T,K',N)
-
-    for i in range(core.num_layer):
-        for axis, norm, rnn, fc in (("time", core.norm_time[i], core.rnn_time[i], core.fc_time[i]),
-                                    ("freq", core.norm_freq[i], core.rnn_freq[i], core.fc_freq[i])):
-            out = _gn(skip, (1, 2, 3), norm.weight, norm.bias, norm.eps)
-            out = blstm(out, rnn, axis)
-            skip = skip + F.linear(out, fc.weight, fc.bias)
-
-    # MaskDecoder (espnet2): per band GN -> Conv1d(N,4N) -> tanh -> Conv1d(4N,4s) -> GLU
-    outs = []
-    for mlps in (core.mask_decoder.mlp_mask, core.mask_decoder.mlp_residual):
-        parts = []
-        for k in range(plan.K):
-            m = mlps[k]
-            xk = _gn(skip[:, :, k, :], (1, 2), m[0].weight, m[0].bias, m[0].eps)
-            hk = torch.tanh(F.linear(xk, m[1].weight[:, :, 0], m[1].bias))
-            ok = F.glu(F.linear(hk, m[3].weight[:, :, 0], m[3].bias), dim=-1)   # (B,T,2s)
-            parts.append(ok.reshape(B, T, plan.subbands[k], 2))
-        outs.append(torch.cat(parts, dim=2)[:, :, :F_bins, :])
-    m_c, r_c = torch.view_as_complex(outs[0].contiguous()), torch.view_as_complex(outs[1].contiguous())
+    skip = band_split_diff(core.band_split, spec, plan)                          # (B,T,K',N)
+    skip = dual_path_diff(core, skip, blstm_fn=blstm_fn)
+    m_c, r_c = mask_decoder_diff(core.mask_decoder, skip, plan, F_bins)
     est = m_c * torch.view_as_complex(spec) + r_c                               # (B,T,F)
-
     window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32, device=wav.device)
     L_out = int(lens.max())
     wav_out = torch.istft(est.transpose(1, 2), n_fft, hop, n_fft, window, center=True, normalized=False, onesided=True,
                           length=L_out)
     return wav_out, est
+
+
+def flow_bsrnn_train_forward(dnn, x_btf, y_btf, t, blstm_fn=None):
+    """Differentiable flow BSRNN.forward [bsrnn_flowse.py:255-318] on the kernel layout: x_t, y (B,T,F,2) f32, t (B,) ->
+    g = m*x_t + r as complex (B,T,F).  (FlowSEModel.forward negates it: flow_model.py:203-209.)"""
+    import math
+    F_bins = x_btf.shape[2]
+    plan = R.BandPlan.make(dnn.band_split_x.subbands, F_bins)
+    xx = band_split_diff(dnn.band_split_x, x_btf, plan)
+    yy = band_split_diff(dnn.band_split_y, y_btf, plan)
+    skip = F.linear(torch.cat([xx, yy], dim=-1), dnn.condition_fc.weight, dnn.condition_fc.bias)    # :284-285
+    t = t.to(device=x_btf.device, dtype=torch.float32)
+    t_emb = []
+    for i in range(dnn.num_layer):                                               # GaussianFourierProjection :90-99
+        proj = t[:, None] * dnn.t_cond[i].W[None, :] * 2 * math.pi
+        t_emb.append(torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1))
+    skip = dual_path_diff(dnn, skip, t_emb=t_emb, blstm_fn=blstm_fn)
+    m_c, r_c = grad_decoder_diff(dnn.grad_decoder, skip, plan, F_bins)
+    return m_c * torch.view_as_complex(x_btf.contiguous()) + r_c
 
 
 # ------------------------------------------------------------------------------------------------ flat parameters + step
@@ -222,8 +292,15 @@ class SETrainer:
     allreduce(avg) -> clip-by-norm -> AdamW(lr, eps=adam_epsilon, weight_decay) -> optional EMA; StepLR via set_lr()."""
 
     def __init__(self, se_model, lr=1e-3, weight_decay=1e-6, eps=1e-8, betas=(0.9, 0.999), gradient_clip=0.5,
-                 ema_decay=None, process_group=None, forward_fn=None):
+                 ema_decay=None, process_group=None, forward_fn=None, loss_fn=None, precision="fp32"):
+        # precision: "fp32" = f32 recurrence kernels + library GEMMs; "fp16" (alias "bf16") = the BLSTM blocks forward and
+        # backward on tcgen05 with fp16 operands, f32 accumulation and f32 master weights (training_tc.py)
+        if precision not in BLOCKS:
+            raise NotImplementedError(f"precision {precision!r}")
+        self.precision = precision
+        self.block_fn = BLOCKS[precision]
         self.model = se_model
+        self.loss_fn = loss_fn             # (model, noisy, clean, lengths, fs) -> (loss, logged scalar): other criteria
         self.flat = FlatParams(se_model)
         self.lr, self.weight_decay, self.eps, self.betas, self.clip = lr, weight_decay, eps, betas, gradient_clip
         self.exp_avg = torch.zeros_like(self.flat.flat)
@@ -246,12 +323,14 @@ class SETrainer:
 
     def loss(self, noisy, clean, lengths, fs):
         """SEModel.forward_step [d_model.py:61-89]: returns (loss scalar, SI-SNR in dB averaged over the batch)."""
+        if self.loss_fn is not None:
+            return self.loss_fn(self.model, noisy, clean, lengths, fs, blstm_fn=self.block_fn)
         Bn = clean.shape[0]
         clean, noisy = clean.reshape(Bn, -1).float(), noisy.reshape(Bn, -1).float()
-        est = self.forward_fn(self.model, noisy, lengths, fs)[0]
+        est = self.forward_fn(self.model, noisy, lengths, fs, blstm_fn=self.block_fn)[0]
         loss = multires_l1_spec_loss(clean, est).mean()
-        if torch.isnan(loss):
-            loss = est.mean() * 0
+        # d_model.py:75-77 (NaN loss -> est.mean() * 0), selected on the device: `if torch.isnan(loss)` is a host sync
+        loss = torch.where(torch.isnan(loss), est.mean() * 0, loss)
         with torch.no_grad():
             sisnr = -si_snr_loss(clean, est).mean()
         return loss, sisnr
@@ -319,3 +398,55 @@ class SETrainer:
     def grad_norm(self):
         """Global L2 norm of the (averaged) gradients of the last step — the reference logs it as `Grad_norm`."""
         return math.sqrt(float(self.stats[0])) / self.world_size()
+
+
+# ------------------------------------------------------------------------------------------------ FlowSE
+def flowse_forward_step(model, noisy, clean, lengths, fs, t=None, z=None, blstm_fn=None):
+    """FlowSEModel.forward_step [flow_model.py:149-187]: STFT (+ exponent compression) of clean and noisy, t ~
+    min((1-U)(T_rev - t_eps) + t_eps, T_rev), x_t = (1-t) x0 + t y + sigma_t z, target condVF = (sigma_max - sigma_min) z
+    + (y - x0) [odes.py:74-98], loss = mean_b 0.5 * sum |v - condVF|^2 with v = -dnn([x_t, y], t) [:122-132, :203-209].
+    ``t`` (B,) and ``z`` complex (B,T,F) may be passed in for parity tests (the reference draws them with torch.rand /
+    randn_like).  Returns (loss, loss detached) in SETrainer's (loss, logged scalar) convention."""
+    B = clean.shape[0]
+    clean = torch.nan_to_num(clean.reshape(B, -1).float(), nan=0.0)
+    noisy = torch.nan_to_num(noisy.reshape(B, -1).float(), nan=0.0)
+    with torch.no_grad():
+        x0 = torch.view_as_complex(model._encode(clean, fs, lengths))              # (B,T,F) compressed spectra
+        y = torch.view_as_complex(model._encode(noisy, fs, lengths))
+        dev = x0.device
+        if t is None:
+            rdm = (1 - torch.rand(B, device=dev)) * (model.T_rev - model.t_eps) + model.t_eps
+            t = torch.clamp(rdm, max=model.T_rev)
+        t = t.to(dev).float()
+        if z is None:
+            z = torch.randn_like(x0)
+        z = z.to(dev)
+        ode = model.ode
+        std = ((1 - t) * ode.sigma_min + t * ode.sigma_max)[:, None, None]
+        xt = (1 - t)[:, None, None] * x0 + t[:, None, None] * y + std * z
+        cond_vf = (ode.sigma_max - ode.sigma_min) * z + (y - x0)
+    g = flow_bsrnn_train_forward(model.dnn, torch.view_as_real(xt).contiguous(), torch.view_as_real(y).contiguous(), t,
+                                 blstm_fn=blstm_fn)
+    err = (-g) - cond_vf
+    loss = (0.5 * (err.real ** 2 + err.imag ** 2).reshape(B, -1).sum(-1)).mean()
+    return loss, loss.detach()
+
+
+class FlowSETrainer(SETrainer):
+    """FlowSEModel's optimisation step [flow_model.py:66-84,149-187,238-249]: flow-matching loss, AdamW, and the
+    torch_ema update fused into the optimizer kernel; ``sync_ema()`` writes the flat EMA back into ``model.ema`` (what
+    ``eval()`` swaps in and ``on_save_checkpoint`` stores)."""
+
+    def __init__(self, flow_model, **kw):
+        kw.setdefault("lr", flow_model.lr)
+        kw.setdefault("ema_decay", flow_model.ema_decay)
+        super().__init__(flow_model, loss_fn=flowse_forward_step, **kw)
+
+    def sync_ema(self):
+        n_upd = int(self.stats[3])
+        shadow = self.model.ema.shadow_params
+        by_id = {id(p): i for i, p in enumerate(self.model.parameters())}
+        with torch.no_grad():
+            for p, off in zip(self.flat.params, self.flat.offsets):
+                shadow[by_id[id(p)]].copy_(self.ema[off:off + p.numel()].view_as(p))
+        self.model.ema.num_updates = n_upd
