@@ -265,6 +265,12 @@ int bsrnn_gemm_tc_scaled(const void* A, const void* W, const float* bias, void* 
 int bsrnn_kb8_transpose(const void* src, void* dst, int src_m0, int m_count, int kc_src, int BN, int n_tiles,
                         long dst_kcores, long dst_kc0, void* stream);
 
+/* bsrnn_istft_bwd: backward of bsrnn_istft_fwd (no mask, no transform) for the training step [replaces autograd through
+ *   torch.istft, reference d_model.py:71-74]: d_wav (B, L_out) -> d_spec (B, T, F, 2) = c_k / N * DFT(w * d_wav / envelope)
+ *   per frame, zero outside [0, L_out), imaginary parts of DC / Nyquist zero. */
+int bsrnn_istft_bwd(const float* d_wav, float* d_spec, const float* twiddle, int B, int T, int L_out, int n_fft, int hop,
+                    void* stream);
+
 /* ---------------------------------------------------------------------------------------------- training loss
  * The core of espnet2 MultiResL1SpecLoss as configured at d_model.py:24 (window_sz [256,512,768,1024], hop w/2,
  * rectangular window, center=True reflect padding, onesided, reduction "sum"), VALUE AND GRADIENT in one pass

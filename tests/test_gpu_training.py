@@ -395,3 +395,43 @@ def test_train_step_tensorcore_gradients_match_oracle():
           f"{(total_num / total_den) ** 0.5:.2e}, worst tensor {worst:.2e}")
     assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 5e-3
     assert (total_num / total_den) ** 0.5 < 1e-2 and worst < 5e-2
+
+
+def test_graphed_train_step_matches_eager():
+    """SETrainer(cuda_graph=True): forward + loss + backward replayed from a captured CUDA graph give the same parameter
+    trajectory as host launches (same data, same steps), for the tensor-core precision."""
+    from urgent2026_challenge_track1_b200.training import SETrainer
+    outs = []
+    for graph in (False, True):
+        m, x, clean, lens = _tiny(fs=16000, n=8000, B=2, width=32, layers=1)
+        m.cuda()
+        tr = SETrainer(m, lr=1e-3, precision="fp16", cuda_graph=graph)
+        noisy, cl = x.cuda().view(2, 1, -1), clean.cuda().view(2, 1, -1)
+        losses = [float(tr.step(noisy * (1 + 0.1 * i), cl, lens, 16000)[0]) for i in range(4)]
+        outs.append((losses, tr.flat.flat.clone(), tr.step_count))
+    (l0, p0, n0), (l1, p1, n1) = outs
+    print("eager", l0, "graph", l1)
+    assert n0 == n1 == 4
+    assert all(abs(a - b) / abs(a) < 1e-3 for a, b in zip(l0, l1))
+    assert rel_l2(p1.cpu(), p0.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("fs", (16000, 22050, 48000))
+def test_istft_backward_is_the_adjoint_of_torch_istft(fs):
+    """bsrnn_istft_bwd against autograd through torch.istft (what the reference's training step differentiates)."""
+    from urgent2026_challenge_track1_b200.training import ISTFTFunction
+    n_fft, hop = R.stft_dims(fs, 960, 480)
+    g = torch.Generator().manual_seed(fs)
+    B, T = 2, 23
+    L_out = (T - 1) * hop - 37
+    spec = torch.randn(B, T, n_fft // 2 + 1, 2, generator=g, dtype=torch.float64)
+    wgt = torch.randn(B, L_out, generator=g, dtype=torch.float64)
+    sr = spec.clone().requires_grad_(True)
+    win = torch.hann_window(n_fft, dtype=torch.float64)
+    ref = torch.istft(torch.view_as_complex(sr).transpose(1, 2), n_fft, hop, n_fft, win, center=True, length=L_out)
+    (ref * wgt).sum().backward()
+    sg = spec.float().cuda().requires_grad_(True)
+    out = ISTFTFunction.apply(sg, L_out, n_fft, hop)
+    (out * wgt.float().cuda()).sum().backward()
+    assert rel_l2(out.detach().cpu().double(), ref.detach()) < 5e-6
+    assert rel_l2(sg.grad.cpu().double(), sr.grad) < 5e-6

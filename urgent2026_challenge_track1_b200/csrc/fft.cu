@@ -26,7 +26,12 @@ __global__ void twiddle_kernel(float2* tw, int n) {
 
 constexpr int kStftThreads = 256;
 
-// grid (ceil(T/FPB), B)
+// grid (ceil(T/FPB), B).  ADJ = false: the STFT encoder.  ADJ = true: the ADJOINT of istft_kernel (training backward of
+// the iSTFT decoder, replaces autograd through torch.istft at d_model.py:71-74): `wav` is dL/d(enhanced waveform) of L
+// samples; frame t is w[n] * g[t*hop + n - N/2] / env (zero outside [0, L): trimmed samples carry no gradient; env = the
+// window-square envelope the forward divides by), and bin k of its DFT is scaled by c_k / N (c_0 = c_{N/2} = 1, else 2;
+// the imaginary parts of DC / Nyquist are ignored by the forward, so their gradient is 0).
+template <bool ADJ>
 __global__ void __launch_bounds__(kStftThreads)
 stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, float2* __restrict__ spec,
             const float2* __restrict__ twiddle, FftPlan plan, int L, int T, int hop, int fpb, int transform,
@@ -41,7 +46,7 @@ stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, flo
   const int t0 = blockIdx.x * fpb;
   const int nfr = min(fpb, T - t0);
   const int len_b = lens ? lens[b] : L;
-  const int olen = (len_b + 2 * (N / 2) - N) / hop + 1;
+  const int olen = ADJ ? T : (len_b + 2 * (N / 2) - N) / hop + 1;
   // live frames of this CTA form a prefix [t0, t0+nlive)
   const int nlive = max(0, min(nfr, olen - t0));
 
@@ -52,9 +57,27 @@ stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, flo
     const int f = idx / N;
     const int n = idx - f * N;
     int i = (t0 + f) * hop - N / 2 + n;
+    const float w = 0.5f - 0.5f * tw[n].x;          // periodic Hann: cos(2*pi*n/N) = Re tw[n]
+    if (ADJ) {
+      float v = 0.f;
+      if (i >= 0 && i < L) {
+        const long ip = (long)i + N / 2;            // position in the padded (un-trimmed) overlap-add buffer
+        long a = ip - N + 1;
+        a = a <= 0 ? 0 : (a + hop - 1) / hop;
+        long z = ip / hop;
+        if (z > T - 1) z = T - 1;
+        float env = 0.f;
+        for (long t = a; t <= z; ++t) {
+          const float we = 0.5f - 0.5f * tw[ip - t * hop].x;
+          env += we * we;
+        }
+        v = env > 1e-11f ? row[i] * w / env : 0.f;
+      }
+      buf0[idx] = make_float2(v, 0.0f);
+      continue;
+    }
     if (i < 0) i = -i;
     if (i >= L) i = 2 * (L - 1) - i;
-    const float w = 0.5f - 0.5f * tw[n].x;          // periodic Hann: cos(2*pi*n/N) = Re tw[n]
     buf0[idx] = make_float2(row[i] * w, 0.0f);
   }
   __syncthreads();
@@ -66,6 +89,12 @@ stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, flo
     float2 v = make_float2(0.f, 0.f);
     if (f < nlive) {
       v = res[(size_t)f * N + k];
+      if (ADJ) {
+        const bool edge = k == 0 || (N % 2 == 0 && k == N / 2);
+        const float c = (edge ? 1.0f : 2.0f) / (float)N;
+        v.x *= c;
+        v.y = edge ? 0.f : v.y * c;
+      }
       if (transform == 1) {
         const float mag = sqrtf(v.x * v.x + v.y * v.y);
         const float sc = mag > 0.f ? __powf(mag, exponent - 1.0f) * factor : 0.f;
@@ -197,9 +226,9 @@ extern "C" int bsrnn_stft_fwd(const float* wav, const int32_t* lens, float* spec
   const int T = 1 + L / hop;
   const int fpb = pick_fpb(n_fft, 0, 8);
   const size_t smem = (size_t)n_fft * 8 * (1 + 2 * fpb);
-  BSRNN_CUDA_OK(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(stft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(T, fpb), B);
-  stft_kernel<<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(
+  stft_kernel<false><<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(
       wav, lens, reinterpret_cast<float2*>(spec), reinterpret_cast<const float2*>(twiddle), plan, L, T, hop, fpb,
       transform, exponent, factor);
   BSRNN_LAUNCH_OK();
@@ -227,6 +256,24 @@ extern "C" int bsrnn_istft_fwd(const float* spec, const float* mask, const float
       reinterpret_cast<const float2*>(resid), reinterpret_cast<float2*>(spec_out), wav_out,
       reinterpret_cast<const float2*>(twiddle), plan, T, L_out, hop, fpb, G, transform,
       transform == 1 ? 1.0f / exponent : 1.0f, transform == 1 ? 1.0f / factor : 1.0f);
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+
+// Backward of bsrnn_istft_fwd without mask / transform (training): d_wav (B, L_out) -> d_spec (B, T, F, 2).
+extern "C" int bsrnn_istft_bwd(const float* d_wav, float* d_spec, const float* twiddle, int B, int T, int L_out, int n_fft,
+                               int hop, void* stream) {
+  BSRNN_CHECK_ARG(d_wav && d_spec && twiddle, "istft_bwd: null pointer");
+  BSRNN_CHECK_ARG(B > 0 && T > 0 && L_out > 0 && n_fft >= 4 && hop > 0, "istft_bwd: bad dims");
+  FftPlan plan;
+  BSRNN_CHECK_ARG(make_plan(n_fft, &plan), "istft_bwd: cannot factorise n_fft=%d", n_fft);
+  const int fpb = pick_fpb(n_fft, 0, 8);
+  const size_t smem = (size_t)n_fft * 8 * (1 + 2 * fpb);
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(stft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(T, fpb), B);
+  stft_kernel<true><<<grid, kStftThreads, smem, (cudaStream_t)stream>>>(
+      d_wav, nullptr, reinterpret_cast<float2*>(d_spec), reinterpret_cast<const float2*>(twiddle), plan, L_out, T, hop, fpb,
+      0, 1.0f, 1.0f);
   BSRNN_LAUNCH_OK();
   return 0;
 }

@@ -103,7 +103,7 @@ class FlowSEModel(nn.Module):
         """(B,L) -> compressed spectrum in the kernel layout (B,T,F,2)."""
         dev = self.dnn.condition_fc.weight.device
         wav = speech.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        lens = torch.as_tensor(speech_length).to(device=dev, dtype=torch.int32)
+        lens = R.device_lengths(speech_length, dev)
         n_fft, hop = self._dims(fs)
         tr = 1 if self.spec_transform_type == "exponent" else 0
         return R.stft(wav, lens, n_fft, hop, tr, float(self.spec_abs_exponent), float(self.spec_factor))

@@ -351,6 +351,25 @@ def _f64(vals, device):
     return _const_table(vals, torch.float64, device)
 
 
+_LENS_CACHE = {}
+
+
+def device_lengths(lens, device):
+    """(B,) utterance lengths as an int32 tensor on `device`, cached by value: a host->device copy from pageable memory is
+    a stream synchronisation and is not allowed while a CUDA graph is being captured (the training-step graph re-uses the
+    copy made during its warm-up)."""
+    if torch.is_tensor(lens) and lens.is_cuda:
+        return lens.to(dtype=torch.int32)
+    vals = tuple(int(v) for v in torch.as_tensor(lens).reshape(-1).tolist())
+    key = (vals, str(device))
+    t = _LENS_CACHE.get(key)
+    if t is None:
+        if len(_LENS_CACHE) >= 256:
+            _LENS_CACHE.clear()
+        t = _LENS_CACHE[key] = torch.tensor(vals, dtype=torch.int32, device=device)
+    return t
+
+
 class GraphedForward:
     """CUDA-graph replay of a fixed-shape forward (launch-bound glue between ~600 kernels disappears).
 

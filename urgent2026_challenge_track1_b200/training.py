@@ -183,6 +183,28 @@ def grad_decoder_diff(gd, skip, plan, F_bins):
     return outs[0], outs[1]
 
 
+class ISTFTFunction(torch.autograd.Function):
+    """STFTDecoder / torch.istft (window, overlap-add, envelope division, trim) as our kernels in both directions:
+    forward bsrnn_istft_fwd, backward its exact adjoint bsrnn_istft_bwd.  (torch.istft is also not CUDA-graph capturable:
+    it reads the window envelope back to the host.)"""
+
+    @staticmethod
+    def forward(ctx, spec_ri, L_out, n_fft, hop):
+        ctx.dims = (L_out, n_fft, hop, spec_ri.shape[1])
+        wav, _ = R.istft(spec_ri.contiguous().float(), None, None, L_out, n_fft, hop, want_spec=False)
+        return wav
+
+    @staticmethod
+    def backward(ctx, d_wav):
+        L_out, n_fft, hop, T = ctx.dims
+        d_wav = d_wav.contiguous().float()
+        B = d_wav.shape[0]
+        d_spec = torch.empty(B, T, n_fft // 2 + 1, 2, dtype=torch.float32, device=d_wav.device)
+        L.call("bsrnn_istft_bwd", d_wav.data_ptr(), d_spec.data_ptr(), R.twiddle(n_fft, d_wav.device).data_ptr(), B, T, L_out,
+               n_fft, hop, L.stream_ptr())
+        return d_spec, None, None, None
+
+
 def bsrnn_se_train_forward(model, wav, lens, fs, blstm_fn=None):
     """Differentiable BSRNN_SE.forward on CUDA tensors: wav (B,L) f32, lens (B,) int -> (enhanced (B, max len),
     enhanced spectrum (B,T,F) complex64).  Same arithmetic as the inference kernels / the reference
@@ -193,17 +215,15 @@ def bsrnn_se_train_forward(model, wav, lens, fs, blstm_fn=None):
     n_fft, hop = R.stft_dims(fs, model.N_FFT, model.HOP, model.DEFAULT_FS)
     F_bins = n_fft // 2 + 1
     plan = R.BandPlan.make(core.band_split.subbands, F_bins)
-    lens_dev = lens.to(device=wav.device, dtype=torch.int32)
+    lens_dev = R.device_lengths(lens, wav.device)
     with torch.no_grad():
         spec = R.stft(wav.contiguous().float(), lens_dev, n_fft, hop)           # (B,T,F,2), frames >= olens are zeros
     skip = band_split_diff(core.band_split, spec, plan)                          # (B,T,K',N)
     skip = dual_path_diff(core, skip, blstm_fn=blstm_fn)
     m_c, r_c = mask_decoder_diff(core.mask_decoder, skip, plan, F_bins)
     est = m_c * torch.view_as_complex(spec) + r_c                               # (B,T,F)
-    window = torch.hann_window(n_fft, periodic=True, dtype=torch.float32, device=wav.device)
-    L_out = int(lens.max())
-    wav_out = torch.istft(est.transpose(1, 2), n_fft, hop, n_fft, window, center=True, normalized=False, onesided=True,
-                          length=L_out)
+    L_out = int(torch.as_tensor(lens).max()) if not (torch.is_tensor(lens) and lens.is_cuda) else int(lens.max())
+    wav_out = ISTFTFunction.apply(torch.view_as_real(est), L_out, n_fft, hop)
     return wav_out, est
 
 
@@ -292,13 +312,15 @@ class SETrainer:
     allreduce(avg) -> clip-by-norm -> AdamW(lr, eps=adam_epsilon, weight_decay) -> optional EMA; StepLR via set_lr()."""
 
     def __init__(self, se_model, lr=1e-3, weight_decay=1e-6, eps=1e-8, betas=(0.9, 0.999), gradient_clip=0.5,
-                 ema_decay=None, process_group=None, forward_fn=None, loss_fn=None, precision="fp32"):
+                 ema_decay=None, process_group=None, forward_fn=None, loss_fn=None, precision="fp32", cuda_graph=False):
         # precision: "fp32" = f32 recurrence kernels + library GEMMs; "fp16" (alias "bf16") = the BLSTM blocks forward and
         # backward on tcgen05 with fp16 operands, f32 accumulation and f32 master weights (training_tc.py)
         if precision not in BLOCKS:
             raise NotImplementedError(f"precision {precision!r}")
         self.precision = precision
         self.block_fn = BLOCKS[precision]
+        self.cuda_graph = bool(cuda_graph)
+        self._graphs = {}
         self.model = se_model
         self.loss_fn = loss_fn             # (model, noisy, clean, lengths, fs) -> (loss, logged scalar): other criteria
         self.flat = FlatParams(se_model)
@@ -336,12 +358,54 @@ class SETrainer:
         return loss, sisnr
 
     def step(self, noisy, clean, lengths, fs):
+        if self.cuda_graph:
+            return self._step_graphed(noisy, clean, lengths, fs)
         self.flat.zero_grad()
         loss, sisnr = self.loss(noisy, clean, lengths, fs)
         loss.backward()
         self.flat.gather_grads()
         self.apply_gradients()
         return loss.detach(), sisnr
+
+    # ---- CUDA-graph replay of forward + loss + backward (the step is launch-bound: ~8 700 kernels, profiles/r02 call05) ----
+    def _step_graphed(self, noisy, clean, lengths, fs):
+        """One captured graph per batch signature (shapes, fs, lengths): zero_grad + forward + loss + backward + gather are
+        replayed; the allreduce and the fused optimizer tail stay eager (two kernels and one collective).  Random draws
+        inside the loss (FlowSE's t and z) use the graph-safe CUDA generator, so every replay draws afresh."""
+        lens_key = tuple(int(v) for v in torch.as_tensor(lengths).tolist())
+        key = (tuple(noisy.shape), tuple(clean.shape), int(fs), lens_key)
+        entry = self._graphs.get(key)
+        if entry is None:
+            dev = self.flat.flat.device
+            n_s, c_s = torch.empty_like(noisy, device=dev), torch.empty_like(clean, device=dev)
+            n_s.copy_(noisy); c_s.copy_(clean)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                     # warm-up on a side stream (allocator, caches, lazy inits)
+                for _ in range(2):
+                    self.flat.zero_grad()
+                    l0, _ = self.loss(n_s, c_s, lengths, fs)
+                    l0.backward()
+                    self.flat.gather_grads()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            touched = list(self.flat.touched)                  # hooks do not run at replay: the set is part of the signature
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.flat.zero_grad()
+                loss, logged = self.loss(n_s, c_s, lengths, fs)
+                loss.backward()
+                self.flat.gather_grads()
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[key] = (g, n_s, c_s, loss, logged, touched)
+        g, n_s, c_s, loss, logged, touched = entry
+        n_s.copy_(noisy, non_blocking=True)
+        c_s.copy_(clean, non_blocking=True)
+        g.replay()
+        self.flat.touched = list(touched)
+        self.apply_gradients()
+        return loss.detach().clone(), logged.detach().clone()
 
     def allreduce_gradients(self):
         """ONE collective over the flat gradient buffer (sum; the 1/world factor is folded into the optimizer kernel).
