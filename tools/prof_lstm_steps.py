@@ -8,7 +8,11 @@ from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L
 ap = argparse.ArgumentParser()
 ap.add_argument("--R", type=int, default=96); ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--N", type=int, default=384); ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--bn", type=int, default=0, help="N-tile width of the step GEMM (0 = default choice)")
+ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay of the whole sequence (no host launch cost)")
 a = ap.parse_args()
+if a.bn:
+    S._bn_for = lambda cols, kcores=None: a.bn
 torch.manual_seed(0)
 N, H, R, steps = a.N, 2 * a.N, a.R, a.steps
 rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
@@ -29,11 +33,17 @@ L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, 
        1 << 40, 0, steps, 1, R * steps, 1, st)                      # token = seq*steps + step
 run = lambda: S.blstm_steps_tc(xhat, p, steps, tiles, ws)
 run(); torch.cuda.synchronize()
+if a.graph:
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    run = g.replay
+    run(); torch.cuda.synchronize()
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"[steps-tc N={N} H={H}] R={R} steps={steps}: {ms:.3f} ms, {1e3 * ms / steps:.1f} us per step (both directions), "
+    print(f"[steps-tc N={N} H={H} BN={p['BN']}{' graph' if a.graph else ''}] R={R} steps={steps}: {ms:.3f} ms, {1e3 * ms / steps:.1f} us per step (both directions), "
           f"{2 * 2.0 * R * steps * H * 4 * H / ms / 1e9:.1f} TFLOP/s recurrent", flush=True)
 if a.check:
     outs = []

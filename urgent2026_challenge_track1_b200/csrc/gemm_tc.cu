@@ -77,6 +77,11 @@ struct GemmTcArgs {
   // split-K (EPI_RESID_F32 with atomic adds; weight-gradient GEMMs: few output tiles, K = tokens): the launch iterates
   // over m_tiles = m_log * ksplit tiles; tile m' = split * m_log + m covers k-cores [split*kps, split*kps + kps)
   int ksplit, kps, m_log;
+  // A-tile multicast (weight-resident schedule): the launch runs in clusters of `mc` CTAs that own consecutive N tiles of
+  // the same M-tile walk; each fetches 1/mc of every A stage and multicasts it into all mc shared memories, so the L2->SM
+  // traffic of the operand every N tile re-reads drops by mc (the input projection re-read xhat 16 times: 14.5 GB of L2
+  // reads per launch next to 13.9 GB of writes -- the kernel sat on the L2, not on HBM)
+  int mc;
   // training (EPI_LSTM_STEP with save_gates, EPI_LSTM_BWD)
   int save_gates;                   // EPI_LSTM_STEP: write the ACTIVATED gates i,f,g,o back over gx (fp16, same columns) and
                                     // c_t to cstate_out (c_{t-1} is read from cstate; null = zeros): what BPTT needs
@@ -377,12 +382,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
 // The schedule above as an iterator without a division per tile: the control warps have ~1 350 cycles of MMA per tile at
 // K = 208 and every dependent integer division costs them ~150 (profiles/r01/call32: the MMA warp spent more time
 // between tiles than issuing).
+// Weight-resident mode with two directions in one launch (dir_tiles > 0: M tiles [0, dir_tiles) use W, the rest W2): a CTA
+// owns the VIRTUAL N tile (direction, n) -- blockIdx % (2 n_tiles) -- and walks only its direction's M tiles.
 struct TileIter {
   int m, n;
-  int dm, dn, n_tiles, m_tiles;
+  int dm, dn, n_tiles, m_tiles;     // m_tiles = end of this CTA's M range
   bool resident;
   __device__ __forceinline__ TileIter(const GemmTcArgs& a) {
     n_tiles = a.n_tiles; m_tiles = a.m_tiles; resident = a.b_resident != 0;
+    if (resident && a.dir_tiles > 0) {
+      const int nt2 = 2 * n_tiles;
+      const int vn = (int)blockIdx.x % nt2;
+      const int dir = vn / n_tiles;
+      n = vn - dir * n_tiles;
+      dm = (int)gridDim.x / nt2;
+      m = dir * a.dir_tiles + (int)blockIdx.x / nt2;
+      m_tiles = dir == 0 ? a.dir_tiles : a.m_tiles;
+      dn = 0;
+      return;
+    }
     n = (int)blockIdx.x % n_tiles;
     m = (int)blockIdx.x / n_tiles;
     dm = (int)gridDim.x / n_tiles;
@@ -452,7 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, a.mc > 1 ? a.mc : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, BNC ? TC_EPI_WARPS / 2 : TC_EPI_WARPS); }
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -460,10 +478,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   if (warp == 2) tmem_alloc(tmem_slot, 2 * TC_ACC_COLS);
   tc_fence_before();
   __syncthreads();
+  if (a.mc > 1) cluster_sync();          // every CTA's barriers exist before a peer multicasts into it
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const int nstage_k = (a.kcores + TC_KS - 1) / TC_KS;
+  const uint32_t crank = a.mc > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << (a.mc > 1 ? a.mc : 1)) - 1u);
 
   // Control warps: the whole role runs inside ONE `if (elect_one())` region.  The compiler then knows a single
   // thread executes it and emits back-to-back UTCHMMA / UBLKCP / UTCBAR with descriptors in uniform registers.  Under
@@ -481,7 +500,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         pf_mod = t3.m % a.n_tiles; pf_dmod = ti.dm % a.n_tiles;
       }
       if (a.b_resident && ti.valid()) {
-        const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.W) + (size_t)ti.n * a.kcores * BN * 16;
+        const uint8_t* gB = reinterpret_cast<const uint8_t*>((a.dir_tiles > 0 && ti.m >= a.dir_tiles) ? a.W2 : a.W) +
+                            (size_t)ti.n * a.kcores * BN * 16;
         const uint32_t bytes = (uint32_t)a.kcores * BN * 16;
         mbar_expect_tx(b_full, bytes);
         for (uint32_t off = 0; off < bytes; off += 32768) bulk_g2s(sB + off, gB + off, min(32768u, bytes - off), b_full);
@@ -507,6 +527,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           const int nk = min(TC_KS, kcnt - kc0);
           mbar_wait(empty + stage, phase ^ 1);
           mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
+          if (a.mc > 1) {                  // my 1/mc of the stage, into the same ring slot of every CTA of the cluster
+            const uint32_t slice = (uint32_t)nk * 2048 / (uint32_t)a.mc;
+            bulk_g2s_multicast(sA + stage * a_stage_bytes + crank * slice, gA + (size_t)kc0 * 2048 + crank * slice, slice,
+                               full + stage, cmask);
+          } else
           bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
           if (!a.b_resident)
             bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
@@ -540,7 +565,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
             const uint64_t da = da0 + (uint64_t)(stage * (a_stage_bytes >> 4));
             const uint64_t db = db0 + (uint64_t)(a.b_resident ? (uint32_t)ks * (TC_KS / 2) * b_step : stage * (b_stage_bytes >> 4));
             for (int j = 0; j < nk / 2; ++j) mma_f16_ss(d_tmem, da + (uint64_t)(j * a_step), db + (uint64_t)(j * b_step), idesc, (ks | j) != 0);
-            mma_commit(empty + stage);
+            if (a.mc > 1) mma_commit_multicast(empty + stage, cmask);     // the slot is free once ALL mc CTAs have read it
+            else mma_commit(empty + stage);
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
           mma_commit(acc_full + buf);
@@ -695,6 +721,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   }
   tc_fence_before();
   __syncthreads();
+  if (a.mc > 1) cluster_sync();          // no CTA exits while peers may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * TC_ACC_COLS);
@@ -716,7 +743,27 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   }
   // weight-resident schedule when several N tiles exist, the tile fits beside the A ring, and there is enough M work
   a.b_resident = (a.n_tiles > 1 && a.n_tiles <= sms && (size_t)a.kcores * a.BN * 16 <= 120 * 1024 &&
-                  a.m_tiles >= 2 * (sms / a.n_tiles) && a.ksplit <= 1) ? 1 : 0;
+                  a.m_tiles >= 2 * (sms / a.n_tiles) && a.ksplit <= 1 && a.dir_tiles == 0) ? 1 : 0;
+  int step_mc = 1;
+  if (EPI == EPI_LSTM_STEP && a.n_tiles > 1) {
+    // LSTM step (any H): keep the W_hh tile resident whenever it fits beside a 4-stage A ring (H = 768: BN = 96 -> 147 KB)
+    // and multicast the h tiles across clusters of N-tile CTAs: un-multicast, every step re-streams its W tile AND its A
+    // tile per output tile (4.4 GB of L2->SM traffic per band-axis step of FlowSE config 4: 830 us, profiles/r02 call12)
+    // MEASURED (profiles/r02 call13, FlowSE config-4 shapes): BN = 96 resident + multicast 52 us / 1 130 us per step (time /
+    // band axis) against 33.6 / 830 us for BN = 256 streaming, identical for multicast 1 / 2 / 4 -- the step GEMM is paced
+    // by the per-K-stage producer/MMA handshake (~400 cycles per 64-wide stage), not by L2->SM bandwidth.  Default OFF.
+    static int res_env = -1, mc_env = -1;               // BSRNN_STEP_RESIDENT=0|1 (default 0), BSRNN_STEP_MC=1|2|4 (default 4)
+    if (res_env < 0) { const char* e = getenv("BSRNN_STEP_RESIDENT"); res_env = (e && e[0] == '1') ? 1 : 0; }
+    if (mc_env < 0) { const char* e = getenv("BSRNN_STEP_MC"); mc_env = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 4; }
+    const int ndir = a.dir_tiles > 0 ? 2 : 1;
+    const int nt_all = a.n_tiles * ndir;
+    const int per_dir = a.dir_tiles > 0 ? a.dir_tiles : a.m_tiles;
+    if (res_env && nt_all <= sms && tc_smem_bytes(a.BN, a.kcores, true, false, 4) <= 227 * 1024 && per_dir >= 2 * (sms / nt_all) &&
+        (a.dir_tiles == 0 || a.m_tiles == 2 * a.dir_tiles)) {
+      a.b_resident = 1;
+      if (mc_env > 1 && a.n_tiles % mc_env == 0) step_mc = mc_env;
+    }
+  }
   a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8) <= 227 * 1024 ? 8 : 4;
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
   if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
@@ -743,14 +790,74 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   }
   const int total = a.m_tiles * a.n_tiles;
   int grid = total < sms ? total : sms;
-  if (a.b_resident) grid = (sms / a.n_tiles) * a.n_tiles;
+  if (a.b_resident) {
+    const int nt_all = a.n_tiles * (a.dir_tiles > 0 ? 2 : 1);
+    grid = (sms / nt_all) * nt_all;
+    if (a.dir_tiles > 0) a.pf_dist = 0;             // the A-tile L2 prefetcher is not direction-aware
+  }
   if (EPI == EPI_F16_KB8 && a.BN == 208 && a.kcores == 26 && a.bias == nullptr && a.b_resident &&
       a.out_kcores >= a.n_tiles * 26) {
     // specialised input-projection kernel: 5 ring stages + two 28 KB staging blocks for the bulk stores
     a.stages = 5;
     const size_t smem_ip = tc_smem_bytes(a.BN, a.kcores, true, false, a.stages) + 2 * 14 * 2048;
     BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F16_KB8, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ip));
+    static int mc_env = -1;               // BSRNN_GEMM_MC=1|2|4: A-tile multicast cluster size (default 1 = off: measured 42.1 / 43.3 / 45.6 ms per step for 1 / 2 / 4, profiles/r02 call11 -- the L2->SM re-reads are not what bounds this GEMM)
+    if (mc_env < 0) { const char* e = getenv("BSRNN_GEMM_MC"); mc_env = (e && (e[0] == '1' || e[0] == '2' || e[0] == '4')) ? e[0] - '0' : 1; }
+    int mc = mc_env;
+    if (mc > 1 && (a.n_tiles % mc != 0 || a.m_tiles < 2 * (sms / a.n_tiles))) mc = 1;
+    if (mc > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_ip; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      static int max_cl[5] = {0, 0, 0, 0, 0};           // co-resident clusters of this size (whole N-tile groups only)
+      if (max_cl[mc] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<EPI_F16_KB8, 208>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+        max_cl[mc] = n;
+      }
+      if (max_cl[mc] > 0) {
+        const int groups = (max_cl[mc] * mc) / a.n_tiles;          // the persistent CTAs must all be resident at once
+        if (groups >= 1) {
+          if (groups * a.n_tiles < grid) grid = groups * a.n_tiles;
+          cfg.gridDim = dim3(grid);
+          a.mc = mc;
+          BSRNN_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI_F16_KB8, 208>, a));
+          BSRNN_LAUNCH_OK();
+          return 0;
+        }
+      }
+    }
+    a.mc = 1;
     gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, TC_THREADS, smem_ip, st>>>(a);
+  } else if (step_mc > 1) {
+    // cluster launch: mc consecutive CTAs = mc consecutive N tiles of the same (direction, M walk)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = step_mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    static int max_cl = 0;
+    static size_t max_cl_smem = 0;
+    if (max_cl == 0 || smem > max_cl_smem) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<EPI>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+      max_cl = n; max_cl_smem = smem;
+    }
+    const int nt_all = a.n_tiles * (a.dir_tiles > 0 ? 2 : 1);
+    const int groups = max_cl > 0 ? (max_cl * step_mc) / nt_all : 0;     // persistent CTAs: all must be resident at once
+    if (groups >= 1) {
+      if (groups * nt_all < grid) grid = groups * nt_all;
+      cfg.gridDim = dim3(grid);
+      a.mc = step_mc;
+      BSRNN_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI>, a));
+    } else {
+      a.mc = 1;
+      gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
+    }
   } else {
     gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
   }

@@ -20,8 +20,21 @@ from . import _lib as L
 from .runtime_tc import GATE_SCALE, to_kb8
 
 
-def _bn_for(cols):
-    for bn in (256, 224, 192, 160, 128, 96, 64, 32):
+def _bn_for(cols, kcores=None):
+    """N-tile width of the step GEMM (widest that divides the gate columns).  BSRNN_STEP_RESIDENT=1 instead picks the widest
+    tile whose W_hh slice stays RESIDENT in shared memory beside a 4-stage A ring (H = 768 -> BN = 96, 147 KB) with the h
+    tiles multicast across clusters of N-tile CTAs -- measured slower (52 vs 34 us per step, profiles/r02 call13): the
+    narrow tiles pay the per-K-stage pipeline handshake 2.7x more often; kept as an A/B switch."""
+    import os
+    forced = int(os.environ.get("BSRNN_STEP_BN", "0"))
+    if forced:
+        return forced
+    widths = (256, 224, 192, 160, 128, 96, 64, 32)
+    if kcores is not None and os.environ.get("BSRNN_STEP_RESIDENT", "0") == "1":      # A/B switch, off: see launch_tc
+        for bn in widths:
+            if cols % bn == 0 and bn >= 64 and kcores * bn * 16 + 65536 + 1024 <= 225 * 1024:
+                return bn
+    for bn in widths:
         if cols % bn == 0:
             return bn
     return 256
@@ -36,7 +49,7 @@ def pack_lstm_steps_tc(rnn):
     perm = (torch.arange(4, device=dev)[None, :] * H + u[:, None]).reshape(-1)          # packed row 4u+g <- g*H + u
     gsc = torch.tensor(GATE_SCALE, device=dev).repeat(H)[:, None]
     kc_in = (N + 15) // 16 * 2
-    BN = _bn_for(4 * H)
+    BN = _bn_for(4 * H, H // 8)
     wih, bias, whh = [], [], []
     for sfx in ("", "_reverse"):
         wi = getattr(rnn, "weight_ih_l0" + sfx).float()[perm] * gsc
