@@ -265,6 +265,21 @@ int bsrnn_gemm_tc_scaled(const void* A, const void* W, const float* bias, void* 
 int bsrnn_kb8_transpose(const void* src, void* dst, int src_m0, int m_count, int kc_src, int BN, int n_tiles,
                         long dst_kcores, long dst_kc0, void* stream);
 
+/* bsrnn_stft_stats_fwd: bsrnn_stft_fwd that also accumulates, per (utterance, band), the sum and the sum of squares of the
+ *   spectrum it writes (band_stats (B, n_bands, 2) double, zeroed inside; band_bin0 [n_bands + 1] first bins): the
+ *   reduction half of BandSplit's GroupNorm(1, 2 s_k) [bsrnn_flowse.py:72-73] without a second pass over the spectrum.
+ * bsrnn_band_split_fwd: BandSplit.forward [bsrnn_flowse.py:65-86] for all bands: normalise on load (scale / shift from
+ *   bsrnn_gn_finalize, zero padding of a truncated band BEFORE the norm), Conv1d(2 s_k -> N, 1) with the band's transposed
+ *   weight resident in shared memory, rows of the token-major (B, T, K', out_width) output written whole.  wT: all bands'
+ *   weights transposed and concatenated ((sum_k 2 s_k) x N); c_off [K+1] channel offsets (device + host copy). */
+int bsrnn_stft_stats_fwd(const float* wav, const int32_t* lens, float* spec, const float* twiddle, int B, int L, int n_fft,
+                         int hop, int transform, float exponent, float factor, double* band_stats,
+                         const int32_t* band_bin0, int n_bands, void* stream);
+int bsrnn_band_split_fwd(const float* spec, const float* scale, const float* shift, const float* wT, const float* bias,
+                         float* out, const int32_t* c_off, const int32_t* bin0, const int32_t* width2,
+                         const int32_t* c_off_host, int K, long rows, int T, int F2, int N, int cmax, long ldo,
+                         int out_width, int out_col, void* stream);
+
 /* bsrnn_istft_bwd: backward of bsrnn_istft_fwd (no mask, no transform) for the training step [replaces autograd through
  *   torch.istft, reference d_model.py:71-74]: d_wav (B, L_out) -> d_spec (B, T, F, 2) = c_k / N * DFT(w * d_wav / envelope)
  *   per frame, zero outside [0, L_out), imaginary parts of DC / Nyquist zero. */

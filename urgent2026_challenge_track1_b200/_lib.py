@@ -68,6 +68,9 @@ PROTOTYPES = {
     "bsrnn_gemm_tc_scaled": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long, c_int, c_float,
                              c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
     "bsrnn_kb8_transpose": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long, c_long, c_void_p],
+    "bsrnn_stft_stats_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                             c_void_p, c_void_p, c_int, c_void_p],
+    "bsrnn_band_split_fwd": [c_void_p] * 10 + [c_int, c_long, c_int, c_int, c_int, c_int, c_long, c_int, c_int, c_void_p],
     "bsrnn_istft_bwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "bsrnn_l1_time_fwd_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p],
     "bsrnn_mrl1_spec_fwd_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p],

@@ -107,9 +107,9 @@ class BSRNN_SE(nn.Module):
         core = self.bsrnn.bsrnn
         plan = R.BandPlan.make(core.band_split.subbands, n_fft // 2 + 1)
 
-        spec = R.stft(wav, lens, n_fft, hop)
+        spec, bstats = R.stft(wav, lens, n_fft, hop, plan=plan)        # band statistics fused into the STFT epilogue
         if self.precision == "fp32":
-            skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel)
+            skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel, stats=bstats)
             R.dual_path_f32(skip, self._dual.get())
             mask, resid = R.mask_decoder_f32(skip, plan, self._md.get())
         elif self.precision == "fp16":
@@ -117,7 +117,7 @@ class BSRNN_SE(nn.Module):
                 raise NotImplementedError(
                     f"the tensor-core BLSTM kernel is specialised for num_channel=196 (H=392); got {self.num_channel}. "
                     "Use precision='fp32' for other widths.")
-            skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel)
+            skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel, stats=bstats)
             TC.dual_path_tc(skip, self._dual_tc.get())
             mask, resid = TC.mask_decoder_tc(skip, plan, self._md_tc.get())
         else:

@@ -1,0 +1,125 @@
+// bandsplit.cu — BandSplit as ONE kernel family: per band k, GroupNorm(1, 2 s_k) applied on load + Conv1d(2 s_k -> N, 1)
+// [reference bsrnn_flowse.py:65-86; espnet2 BandSplit], writing the token-major residual stream (B, T, K', N).
+//
+// The op is write-bound (config 2: reads the 246 MB spectrum once, writes 1.71 GB; 24 GFLOP): a CTA owns 128 tokens of one
+// band, keeps the band's transposed weight (2 s_k x N, <= 94 KB) and the normalised inputs (128 x 2 s_k) in shared memory
+// and each warp writes whole 784-byte output rows.  It replaces the generic 64x64x16 SIMT grouped GEMM (gemm_f32.cu), which
+// spent 2.83 ms on it (10 % of the copy bandwidth, profiles/r01 call47 / r02 call08).
+#include "common.cuh"
+
+namespace bsrnn {
+
+constexpr int kBsRows = 128;
+constexpr int kBsThreads = 256;
+
+struct BandSplitArgs {
+  const float* spec;        // (rows, 2F) interleaved re/im
+  const float* scale;       // (B * K, cmax): GroupNorm scale per (sample, band, channel)
+  const float* shift;
+  const float* wT;          // concatenated transposed weights: band k at row c_off[k], (2 s_k rows) x N
+  const float* bias;        // (K, N)
+  float* out;
+  const int* c_off;         // [K + 1] channel offsets into wT
+  const int* bin0;          // [K] first bin of each band
+  const int* width2;        // [K] 2 * real bins of the band (the rest of its 2 s_k channels are zero padding)
+  long rows;                // B * T
+  int T, F2, N, K, cmax, k_lo;
+  long ldo;                 // output row stride (floats) = K * out_width
+  int out_width, out_col;
+};
+
+__global__ void __launch_bounds__(kBsThreads, 2) band_split_kernel(const BandSplitArgs a) {
+  extern __shared__ __align__(16) float bs_smem[];
+  const int k = a.k_lo + blockIdx.y;
+  const int C = a.c_off[k + 1] - a.c_off[k];          // 2 s_k
+  const int Cp = (C + 3) & ~3;                        // padded to float4
+  const int N = a.N;
+  float* Ws = bs_smem;                                // [Cp][N]
+  float* xs = bs_smem + (size_t)Cp * N;               // [128][Cp]
+  const long r0 = (long)blockIdx.x * kBsRows;
+  const float* wsrc = a.wT + (size_t)a.c_off[k] * N;
+  for (int i = threadIdx.x; i < Cp * N; i += kBsThreads) Ws[i] = i < C * N ? wsrc[i] : 0.f;
+  const int cvalid = a.width2[k];
+  const int col0 = 2 * a.bin0[k];
+  for (int i = threadIdx.x; i < kBsRows * Cp; i += kBsThreads) {
+    const int r = i / Cp, c = i - r * Cp;
+    const long row = r0 + r;
+    float v = 0.f;
+    if (row < a.rows && c < C) {
+      const long b = row / a.T;
+      const float x = c < cvalid ? a.spec[row * a.F2 + col0 + c] : 0.f;       // truncated band: zero-padded BEFORE the norm
+      const size_t g = ((size_t)b * a.K + k) * a.cmax + c;
+      v = fmaf(x, a.scale[g], a.shift[g]);
+    }
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngrp = N >> 2;                            // float4 column groups (N % 4 == 0)
+  const float* bias = a.bias + (size_t)k * N;
+  for (int pass = 0; pass * 32 < ngrp; ++pass) {
+    const int grp = pass * 32 + lane;
+    const bool act = grp < ngrp;
+    float4 acc[16];
+    const float4 b4 = act ? *reinterpret_cast<const float4*>(bias + 4 * grp) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = b4;
+    if (act) {
+      for (int c = 0; c < Cp; c += 4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + (size_t)(c + 0) * N + 4 * grp);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + (size_t)(c + 1) * N + 4 * grp);
+        const float4 w2 = *reinterpret_cast<const float4*>(Ws + (size_t)(c + 2) * N + 4 * grp);
+        const float4 w3 = *reinterpret_cast<const float4*>(Ws + (size_t)(c + 3) * N + 4 * grp);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(xs + (size_t)(16 * warp + r) * Cp + c);     // broadcast
+          acc[r].x = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[r].x))));
+          acc[r].y = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[r].y))));
+          acc[r].z = fmaf(x.x, w0.z, fmaf(x.y, w1.z, fmaf(x.z, w2.z, fmaf(x.w, w3.z, acc[r].z))));
+          acc[r].w = fmaf(x.x, w0.w, fmaf(x.y, w1.w, fmaf(x.z, w2.w, fmaf(x.w, w3.w, acc[r].w))));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const long row = r0 + 16 * warp + r;
+        if (row < a.rows)
+          *reinterpret_cast<float4*>(a.out + row * a.ldo + (size_t)k * a.out_width + a.out_col + 4 * grp) = acc[r];
+      }
+    }
+  }
+}
+
+}  // namespace bsrnn
+using namespace bsrnn;
+
+// Launches bands [0, K) in two shared-memory classes (narrow bands: many CTAs per SM; wide bands: up to 157 KB).
+extern "C" int bsrnn_band_split_fwd(const float* spec, const float* scale, const float* shift, const float* wT,
+                                    const float* bias, float* out, const int32_t* c_off, const int32_t* bin0,
+                                    const int32_t* width2, const int32_t* c_off_host, int K, long rows, int T, int F2, int N,
+                                    int cmax, long ldo, int out_width, int out_col, void* stream) {
+  BSRNN_CHECK_ARG(spec && scale && shift && wT && bias && out && c_off && bin0 && width2 && c_off_host, "band_split_fwd: null pointer");
+  BSRNN_CHECK_ARG(K > 0 && rows > 0 && T > 0 && N > 0 && N % 4 == 0 && out_col % 4 == 0 && out_width % 4 == 0 && ldo % 4 == 0,
+                  "band_split_fwd: bad dims (N, out_col, out_width and ldo must be multiples of 4)");
+  BandSplitArgs a{spec, scale, shift, wT, bias, out, c_off, bin0, width2, rows, T, F2, N, K, cmax, 0, ldo, out_width, out_col};
+  auto smem_of = [&](int C) { const int Cp = (C + 3) & ~3; return (size_t)Cp * N * 4 + (size_t)kBsRows * Cp * 4; };
+  // consecutive runs of bands whose shared-memory need is within 2x of the run's maximum share one launch
+  int k = 0;
+  while (k < K) {
+    size_t need = smem_of(c_off_host[k + 1] - c_off_host[k]);
+    int e = k + 1;
+    while (e < K) {
+      const size_t s = smem_of(c_off_host[e + 1] - c_off_host[e]);
+      if (s > 2 * need || 2 * s < need) break;
+      if (s > need) need = s;
+      ++e;
+    }
+    BSRNN_CHECK_ARG(need <= 227 * 1024, "band_split_fwd: band of %d channels does not fit in shared memory", c_off_host[k + 1] - c_off_host[k]);
+    BSRNN_CUDA_OK(cudaFuncSetAttribute(band_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    a.k_lo = k;
+    dim3 grid((unsigned)((rows + kBsRows - 1) / kBsRows), e - k);
+    band_split_kernel<<<grid, kBsThreads, need, (cudaStream_t)stream>>>(a);
+    BSRNN_LAUNCH_OK();
+    k = e;
+  }
+  return 0;
+}

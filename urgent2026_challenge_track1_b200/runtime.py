@@ -13,6 +13,11 @@ import torch
 
 from . import _lib as L
 
+import os
+
+# BSRNN_BAND_SPLIT=gemm: the generic grouped f32 GEMM (gemm_f32.cu) instead of the dedicated band-split kernel (A/B)
+BAND_SPLIT_KERNEL = os.environ.get("BSRNN_BAND_SPLIT", "kernel") != "gemm"
+
 SUBBANDS = {
     481: (5,) + (4,) * 19 + (10,) * 6 + (40,) * 7 + (60,),          # reference bsrnn_flowse.py:29
     769: (5,) + (4,) * 26 + (10,) * 10 + (50,) * 10 + (60,),        # reference bsrnn_flowse.py:36
@@ -194,14 +199,22 @@ def twiddle(n_fft, device):
     return tw
 
 
-def stft(wav, lens, n_fft, hop, transform=0, exponent=1.0, factor=1.0):
-    """wav (B,L) f32 cuda, lens (B,) int32 cuda or None -> spec (B,T,F,2) f32."""
+def stft(wav, lens, n_fft, hop, transform=0, exponent=1.0, factor=1.0, plan=None):
+    """wav (B,L) f32 cuda, lens (B,) int32 cuda or None -> spec (B,T,F,2) f32.  With a BandPlan: -> (spec, stats) where
+    stats (B, K', 2) double = per-band sum / sum of squares of the spectrum (BandSplit's GroupNorm reduction, fused into the
+    STFT kernel's epilogue)."""
     B, Ls = wav.shape
     T, F = 1 + Ls // hop, n_fft // 2 + 1
     spec = torch.empty(B, T, F, 2, dtype=torch.float32, device=wav.device)
-    L.call("bsrnn_stft_fwd", wav.data_ptr(), L.ptr(lens), spec.data_ptr(), twiddle(n_fft, wav.device).data_ptr(),
-           B, Ls, n_fft, hop, transform, exponent, factor, L.stream_ptr())
-    return spec
+    if plan is None:
+        L.call("bsrnn_stft_fwd", wav.data_ptr(), L.ptr(lens), spec.data_ptr(), twiddle(n_fft, wav.device).data_ptr(),
+               B, Ls, n_fft, hop, transform, exponent, factor, L.stream_ptr())
+        return spec
+    stats = torch.empty(B, plan.K, 2, dtype=torch.float64, device=wav.device)
+    edges = _i32(list(plan.bin0) + [plan.bin0[-1] + plan.width[-1]], wav.device)
+    L.call("bsrnn_stft_stats_fwd", wav.data_ptr(), L.ptr(lens), spec.data_ptr(), twiddle(n_fft, wav.device).data_ptr(),
+           B, Ls, n_fft, hop, transform, exponent, factor, stats.data_ptr(), edges.data_ptr(), plan.K, L.stream_ptr())
+    return spec, stats
 
 
 def istft(spec, mask, resid, L_out, n_fft, hop, want_spec=True, transform=0, exponent=1.0, factor=1.0):
@@ -293,7 +306,13 @@ def pack_band_split(bs):
         beta[k, : 2 * s] = bs.norm[k].bias
     w = [bs.fc[k].weight[:, :, 0].float().contiguous() for k in range(K)]
     b = [bs.fc[k].bias.float().contiguous() for k in range(K)]
-    return dict(gamma=gamma, beta=beta, w=w, b=b, cmax=cmax, eps=_uniform_eps(bs.norm))
+    # bsrnn_band_split_fwd operands: every band's weight transposed (2 s_k, N) and concatenated, bias table, channel offsets
+    wT = torch.cat([wk.t().contiguous() for wk in w], 0).contiguous()
+    c_off = [0]
+    for s in bs.subbands:
+        c_off.append(c_off[-1] + 2 * s)
+    return dict(gamma=gamma, beta=beta, w=w, b=b, cmax=cmax, eps=_uniform_eps(bs.norm), wT=wT, bias=torch.stack(b).contiguous(),
+                c_off=torch.tensor(c_off, dtype=torch.int32, device=dev), c_off_host=np.array(c_off, dtype=np.int32))
 
 
 def pack_mask_decoder(md):
@@ -403,17 +422,19 @@ class GraphedForward:
         return self.outputs
 
 
-def band_split_f32(spec, plan: BandPlan, bs_pack, N, out=None, out_col=0, out_width=None):
-    """spec (B,T,F,2) -> z (B,T,K',N) (or into columns [out_col, out_col+N) of a wider `out`)."""
+def band_split_f32(spec, plan: BandPlan, bs_pack, N, out=None, out_col=0, out_width=None, stats=None):
+    """spec (B,T,F,2) -> z (B,T,K',N) (or into columns [out_col, out_col+N) of a wider `out`).  stats: per-band sums from the
+    STFT kernel (`stft(..., plan=plan)`); computed here by bsrnn_band_stats otherwise."""
     B, T, F, _ = spec.shape
     dev = spec.device
     K = plan.K
     cmax = bs_pack["cmax"]
     st = L.stream_ptr()
-    stats = torch.empty(B, K, 2, dtype=torch.float64, device=dev)
-    off = _i32([2 * b0 for b0 in plan.bin0], dev)
     wid = _i32([2 * w for w in plan.width], dev)
-    L.call("bsrnn_band_stats", spec.data_ptr(), stats.data_ptr(), B, T, 2 * F, off.data_ptr(), wid.data_ptr(), K, st)
+    if stats is None:
+        stats = torch.empty(B, K, 2, dtype=torch.float64, device=dev)
+        off = _i32([2 * b0 for b0 in plan.bin0], dev)
+        L.call("bsrnn_band_stats", spec.data_ptr(), stats.data_ptr(), B, T, 2 * F, off.data_ptr(), wid.data_ptr(), K, st)
     counts = _f64([2.0 * plan.subbands[k] * T for k in range(K)], dev)      # padded bins count (bsrnn_flowse.py:68-73)
     scale = torch.empty(B * K, cmax, dtype=torch.float32, device=dev)
     shift = torch.empty_like(scale)
@@ -422,6 +443,14 @@ def band_split_f32(spec, plan: BandPlan, bs_pack, N, out=None, out_col=0, out_wi
     width = out_width or N
     if out is None:
         out = torch.empty(B, T, K, width, dtype=torch.float32, device=dev)
+    cw = 2 * max(plan.subbands[:K])                                          # widest band: weight + input tile in shared memory
+    fits = ((cw + 3) // 4 * 4) * (N + 128) * 4 <= 227 * 1024
+    if N % 4 == 0 and width % 4 == 0 and out_col % 4 == 0 and BAND_SPLIT_KERNEL and fits:
+        bin0 = _i32(list(plan.bin0), dev)
+        L.call("bsrnn_band_split_fwd", spec.data_ptr(), scale.data_ptr(), shift.data_ptr(), bs_pack["wT"].data_ptr(),
+               bs_pack["bias"].data_ptr(), out.data_ptr(), bs_pack["c_off"].data_ptr(), bin0.data_ptr(), wid.data_ptr(),
+               bs_pack["c_off_host"].ctypes.data, K, B * T, T, 2 * F, N, cmax, K * width, width, out_col, st)
+        return out
     dl = DescList()
     for k in range(K):
         s = plan.subbands[k]
