@@ -192,6 +192,18 @@ int bsrnn_blstm_recurrence_tc_flag(const void* gates_x, const void* w_pack, cons
                                    int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
 int bsrnn_blstm_tc_flag_max_groups(void);
 int bsrnn_blstm_tc_sync_bytes(void);
+/* bsrnn_blstm_fused_tc: the whole nn.LSTM(N=196, H=392, bidirectional) layer [reference bsrnn_flowse.py:226-238,
+ *     called at :296-297 / :303-304] in ONE persistent kernel: gates_t = [x_t | h_{t-1}] [W_ih | W_hh]^T per step, so
+ *     the input-projection GEMM and its gates_x tensor (13.9 GB per call at BASELINE config 2) disappear.  CTA pairs
+ *     (tcgen05 cta_group::2, M = 256) hold half of a 208 x 608 weight slice each; groups of 8 pairs synchronise through
+ *     gpu-scope counters in sync_ws (bsrnn_blstm_fused_sync_bytes() bytes, zeroed inside, stream-ordered).
+ *     xhat: fp16 [steps*seq_tiles][26][128][8] as written by bsrnn_norm_cast_kb8_ones (column 196 = 1 carries the
+ *     bias); w_fused: fp16 [2 dirs][8 pairs][2 halves][76 k-cores][104][8]; zero_tile / y as bsrnn_blstm_recurrence_tc.
+ *     max_groups <= 0: all co-resident groups; slots <= 0: automatic (1..3 interleaved tile pairs per group). */
+int bsrnn_blstm_fused_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y, int R, int steps,
+                         int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+int bsrnn_blstm_fused_max_groups(void);
+int bsrnn_blstm_fused_sync_bytes(void);
 
 /* Debug / A-B timing: selects the recurrence schedule (4, 5, 6: 8-CTA clusters; 7: CTA pairs); any other value
  * returns to the BSRNN_LSTM_VER environment default. */

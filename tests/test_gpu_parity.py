@@ -224,6 +224,67 @@ def test_flowse_tensorcore_steps_vs_golden(fs, graph):
         assert len(m.dnn._graphs) == 1
 
 
+@pytest.mark.parametrize("axis,B,T,slots", [("time", 12, 40, 1), ("time", 10, 24, 2), ("freq", 3, 300, 3), ("freq", 5, 77, 0),
+                                             ("time", 40, 30, 0), ("time", 2, 50, 0)])
+def test_blstm_fused_vs_torch(axis, B, T, slots):
+    """bsrnn_blstm_fused_tc (input projection inside the persistent recurrence, CTA pairs + flag groups) against
+    torch.nn.LSTM on the CPU; even / odd tile counts (the odd CTA of the last pair idles), 1..3 interleaved tile pairs,
+    single-tile inputs."""
+    from urgent2026_challenge_track1_b200 import runtime_tc as tc, _lib as L
+    torch.manual_seed(0)
+    N, H, K = 196, 392, 34
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, K, N) * 0.7
+    with torch.no_grad():
+        if axis == "time":
+            ref = rnn(x.permute(0, 2, 1, 3).reshape(B * K, T, N))[0].reshape(B, K, T, 2 * H).permute(0, 2, 1, 3)
+            R_, steps, addr = B * K, T, (K, T * K, 1, K)
+        else:
+            ref = rnn(x.reshape(B * T, K, N))[0].reshape(B, T, K, 2 * H)
+            R_, steps, addr = B * T, K, (1, K, 0, 1)
+    p = tc.pack_lstm_tc(rnn.cuda())
+    st = L.stream_ptr()
+    M, tiles = B * T * K, (R_ + 127) // 128
+    ntile = steps * tiles
+    xhat = torch.empty(ntile * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
+    xg = x.cuda().reshape(M, N).contiguous()
+    L.call("bsrnn_norm_cast_kb8_ones", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], ntile, tiles, R_,
+           *addr, M, 1, p["one_col"], st)
+    y = torch.zeros(ntile * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
+    zero_tile = torch.zeros(50 * 1024, dtype=torch.float16, device="cuda")
+    sync = torch.zeros(L.lib().bsrnn_blstm_fused_sync_bytes() // 4, dtype=torch.int32, device="cuda")
+    for _ in range(2):                                  # the second launch reuses y and the counters
+        L.call("bsrnn_blstm_fused_tc", xhat.data_ptr(), p["wfused"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R_, steps,
+               tiles, 0, slots, sync.data_ptr(), st)
+    yv = y.view(steps, tiles, 2, 50, 128, 8).permute(0, 1, 4, 2, 3, 5).reshape(steps, tiles * 128, 2, 400)[:, :R_, :, :H]
+    yv = yv.reshape(steps, R_, 2 * H).float().cpu()
+    mine = yv.reshape(T, B, K, 2 * H).permute(1, 0, 2, 3) if axis == "time" else yv.reshape(K, B, T, 2 * H).permute(1, 2, 0, 3)
+    assert y.view(steps, tiles, 2, 50, 128, 8)[:, :, :, 49].abs().max().item() == 0      # K padding of y stays zero
+    e = rel_l2(mine, ref)
+    print(f"fused blstm {axis} B={B} T={T} slots={slots}: rel_l2={e:.3e}")
+    assert e < 3e-3
+
+
+def test_bsrnn_se_fused_and_unfused_schedules_agree(monkeypatch):
+    """The default schedule (fused layer kernel on both axes) and the separate input-projection GEMM + flag-group
+    recurrence compute the same network: outputs agree to the fp16 noise floor of the gates_x rounding."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE, runtime_tc as tc
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=196, num_layer=2, precision="fp16").cuda()
+    fs, n = 16000, 16000
+    x = R.synth_noisy(3, n, fs, seed=1)
+    lens = torch.tensor([n, n - 555, n - 1999])
+    assert tc.FUSED_AXES == ("time", "freq")
+    a = m(x, lens, fs)[0].clone()
+    monkeypatch.setattr(tc, "FUSED_AXES", ())
+    b = m(x, lens, fs)[0].clone()
+    monkeypatch.setattr(tc, "FUSED_AXES", ("freq",))
+    c = m(x, lens, fs)[0].clone()
+    e_ab, e_ac = rel_l2(a.cpu(), b.cpu()), rel_l2(a.cpu(), c.cpu())
+    print(f"fused vs unfused: {e_ab:.3e}, fused vs freq-only fused: {e_ac:.3e}")
+    assert 0 < e_ab < 2e-3 and 0 < e_ac < 2e-3
+
+
 def test_lstm_step_tc_vs_torch_h768():
     """bsrnn_lstm_step_tc at the FlowSE width (N = 384, H = 768), ragged last tile: against torch.nn.LSTM on the CPU."""
     from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+LOG=gpurun_out/r02c19_fused.log
+: > $LOG
+run() { timeout 300 python tools/prof_lstm.py "$@" >> $LOG 2>&1 || echo "FAILED rc=$? : $*" >> $LOG; }
+run --fused --B 12 --T 40 --K 34 --axis time --slots 1
+run --fused --B 64 --T 1001 --K 34 --axis freq --slots 3
+run --fused --B 64 --T 1001 --K 34 --axis freq --slots 3 --maxcl 4
+run --fused --B 64 --T 1001 --K 34 --axis freq --slots 3 --maxcl 2
+grep -v Warning $LOG | tail -30

@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+LOG=gpurun_out/r02c20_fused_probe.log
+: > $LOG
+run() { timeout 300 python tools/prof_lstm.py "$@" >> $LOG 2>&1 || echo "FAILED rc=$? : $*" >> $LOG; }
+run --fused --trace --reps 2 --B 12 --T 40 --K 34 --axis time --slots 1
+run --fused --trace --reps 2 --B 64 --T 1001 --K 34 --axis freq --slots 3
+run --fused --trace --reps 2 --B 64 --T 1001 --K 34 --axis time --slots 3
+grep -v Warning $LOG | tail -40

@@ -14,6 +14,7 @@ ap.add_argument("--slots", type=int, default=0); ap.add_argument("--variant", ty
 ap.add_argument("--trace-cid", type=int, default=0); ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..9 (0 = BSRNN_LSTM_VER / default)")
 ap.add_argument("--flag", action="store_true", help="flag-group schedule (bsrnn_blstm_recurrence_tc_flag)")
+ap.add_argument("--fused", action="store_true", help="fused layer (bsrnn_blstm_fused_tc): x * W_ih inside the recurrence")
 ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 B, T, K, axis = a.B, a.T, a.K, a.axis
@@ -38,15 +39,16 @@ rnn = rnn.cuda()
 p = tc.pack_lstm_tc(rnn)
 st = L.stream_ptr()
 ntile = steps * tiles
-gates = torch.empty(ntile * 416 * 1024, dtype=torch.float16, device="cuda")
+gates = torch.empty((1 if a.fused else ntile) * 416 * 1024, dtype=torch.float16, device="cuda")
 zero_tile = torch.zeros(50 * 1024, dtype=torch.float16, device="cuda")
-if a.check:
-    xg = x.cuda().reshape(M, N).contiguous()
-    xhat = torch.empty(ntile * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
-    L.call("bsrnn_norm_cast_kb8", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], ntile, tiles, R,
-           *addr, M, 1, st)
-    L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bih"].data_ptr(), gates.data_ptr(), None, ntile, 16,
-           p["kc_in"], 208, L.TC_F16_KB8, 0, 3328, 416, M, tiles, R, *addr, st)
+xhat = torch.empty(ntile * p["kc_in"] * 1024, dtype=torch.float16, device="cuda")
+if a.check or a.fused:
+    xg = (x.cuda() if a.check else torch.randn(B, T, K, N, device="cuda") * 0.7).reshape(M, N).contiguous()
+    L.call("bsrnn_norm_cast_kb8_ones", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], ntile, tiles, R,
+           *addr, M, 1, p["one_col"], st)
+    if not a.fused:
+        L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), None, gates.data_ptr(), None, ntile, 16,
+               p["kc_in"], 208, L.TC_F16_KB8, 0, 3328, 416, M, tiles, R, *addr, st)
 else:
     chunk = 1 << 26
     for i in range(0, gates.numel(), chunk):
@@ -55,10 +57,15 @@ else:
 y = torch.zeros(steps * tiles * 2 * 50 * 1024, dtype=torch.float16, device="cuda")
 
 
-sync = torch.zeros(L.lib().bsrnn_blstm_tc_sync_bytes() // 4, dtype=torch.int32, device="cuda")
+sync = torch.zeros(max(L.lib().bsrnn_blstm_tc_sync_bytes(), L.lib().bsrnn_blstm_fused_sync_bytes()) // 4, dtype=torch.int32,
+                   device="cuda")
 
 
 def run():
+    if a.fused:
+        L.call("bsrnn_blstm_fused_tc", xhat.data_ptr(), p["wfused"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
+               tiles, a.maxcl, a.slots, sync.data_ptr(), st)
+        return
     if a.flag:
         L.call("bsrnn_blstm_recurrence_tc_flag", gates.data_ptr(), p["whh"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R,
                steps, tiles, a.maxcl, a.slots, sync.data_ptr(), st)
@@ -69,9 +76,11 @@ def run():
 
 if a.ver:
     L.lib().bsrnn_debug_set_lstm_schedule(a.ver)
-tag = f"{'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
+tag = f"{'FUSED' if a.fused else 'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
 if (a.ver or int(os.environ.get('BSRNN_LSTM_VER', '8'))) == 7:
     print(f"[{tag}] co-resident 16-CTA clusters: {L.lib().bsrnn_blstm_tc_max_pair_clusters()}  (8-CTA: {L.lib().bsrnn_blstm_tc_max_clusters()})", flush=True)
+if a.fused:
+    print(f"[{tag}] co-resident fused groups (8 CTA pairs each): {L.lib().bsrnn_blstm_fused_max_groups()}", flush=True)
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record()
@@ -88,7 +97,21 @@ if a.check:
     pad = y.view(steps, tiles, 2, 50, 128, 8)[:, :, :, 49].abs().max().item()
     print(f"[{tag}] CHECK {axis} B={B} T={T} K={K}: rel_l2={err:.3e} pad_core_max={pad}  {'OK' if err < 3e-3 and pad == 0 else 'FAIL'}", flush=True)
 
-if a.trace:
+if a.trace and a.fused:
+    import ctypes
+    tr = torch.zeros(32, dtype=torch.int64, device="cuda")
+    L.lib().bsrnn_debug_set_fused_probe.argtypes = [ctypes.c_void_p]
+    L.lib().bsrnn_debug_set_fused_probe(tr.data_ptr())
+    run(); torch.cuda.synchronize()
+    L.lib().bsrnn_debug_set_fused_probe(None)
+    acc = tr.cpu().tolist()
+    print(f"[{tag}] pair 0 whole-launch cycles (needs a -DBSRNN_FUSED_PROBE build):")
+    for e in (0, 1):
+        o = 16 * e
+        print(f"  CTA {e} producer : wait flag {acc[o]:>12d}  wait ring-empty {acc[o+1]:>12d}  other {acc[o+2]:>12d}   total {acc[o]+acc[o+1]+acc[o+2]}")
+        print(f"  CTA {e} epilogue (third 0, quadrant 0): wait acc_full {acc[o+12]:>11d}  busy {acc[o+13]:>12d}  acc_empty arrive {acc[o+14]:>10d}")
+    print(f"  leader mma : wait acc_empty {acc[4]:>10d}  wait full {acc[5]:>12d}  wait pfull {acc[6]:>12d}  other {acc[7]:>12d}")
+elif a.trace:
     import ctypes
     tr = torch.zeros(32, dtype=torch.int64, device="cuda")
     L.lib().bsrnn_debug_set_lstm_probe.argtypes = [ctypes.c_void_p, ctypes.c_int]

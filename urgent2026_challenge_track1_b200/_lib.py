@@ -47,6 +47,9 @@ PROTOTYPES = {
                                      c_void_p],
     "bsrnn_blstm_recurrence_tc_flag": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_void_p],
+    "bsrnn_blstm_fused_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "bsrnn_blstm_fused_max_groups": [],
+    "bsrnn_blstm_fused_sync_bytes": [],
     "bsrnn_blstm_tc_flag_max_groups": [],
     "bsrnn_blstm_tc_sync_bytes": [],
     "bsrnn_blstm_tc_max_clusters": [],

@@ -1,0 +1,546 @@
+// lstm_fused.cu — BLSTM layer for H = 392 with the INPUT PROJECTION FUSED into the persistent recurrence:
+//     gates_t = [x_t | h_{t-1}] * [W_ih | W_hh]^T          (one K = 208 + 400 contraction per step)
+// so the 13.9 GB gates_x tensor that lstm_tc.cu reads (and the input-projection GEMM writes) per BLSTM call is never
+// materialised.  Replaces nn.LSTM(N, 2N, bidirectional) [reference bsrnn_flowse.py:226-238, called at :296-297 (time
+// axis) and :303-304 (band axis)] including its x * W_ih^T + b half.
+//
+// Why CTA pairs.  With 8 CTAs per sequence tile a CTA would have to keep a 208 x 608 fp16 slice (253 KB) resident —
+// more than the 227 KB of shared memory.  A CTA PAIR (2-CTA cluster, tcgen05 cta_group::2, M = 256) shares one slice:
+// each CTA keeps HALF of the pair's gate columns (104 x 608 fp16 = 126 KB) and supplies its own 128 sequence rows; the
+// MMA delivers all 208 gate columns of those rows into the CTA's own TMEM.  Per CTA and item the L2 -> SM traffic is
+// the 100 KB h tile plus the 53 KB x tile, the same as the h tile plus the 50 KB gates_x slice before.
+//
+// Decomposition.  Work unit = (direction, PAIR of 128-sequence tiles).  A GROUP = 8 pairs (16 CTAs, any placement:
+// pairs rank themselves by an arrival ticket) owns up to 3 interleaved units of one direction; pair q owns hidden
+// units [49q, 49q+49).  The even CTA of each pair serves tile 2j, the odd CTA tile 2j+1; the 8 CTAs of one parity
+// exchange h_t of "their" tile through y in L2 and a gpu-scope release/acquire counter in global memory (the flag
+// protocol of lstm_tc_flag_kernel), so the only cluster traffic is inside a pair:
+//   warp 0  producer : per item 3 ring stages of x_t (26 k-cores, no dependency: they stream ahead) and, once the
+//                      parity's counter shows h_{t-1} complete, 5 stages of h (50 k-cores); 5-stage ring of 20 KB.
+//   warp 1  leader   : MMA issuer — 13 + 25 tcgen05.mma.cta_group::2 (M=256, N=208, K=16) per item, commits multicast
+//                      to both CTAs' `empty` / `acc_full` barriers;
+//           odd CTA  : relays its `full` completions to the leader's `pfull` barriers (remote arrive).
+//   warp 2  publisher: named barrier with the epilogue warps, then one red.release on the parity's counter.
+//   warps 4..15      : epilogue, all 12 warps on every item (thread = sequence row x third of the units): tcgen05.ld
+//                      in 16-column chunks software-pipelined against the MUFU work, c in registers, h_t -> y.
+// The bias rides in the weights (operand column N is the constant 1 written by norm_cast_kb8_ones), the i/f/o rows are
+// pre-halved (sigmoid(x) = 0.5*tanh(x/2)+0.5), step 0 skips the h half (h_{-1} = 0).
+//
+// x (fp16)   : [step][seq_tile][26 k-cores][128 rows][8]   — what bsrnn_norm_cast_kb8_ones writes
+// y (fp16)   : [step][seq_tile][dir][50 k-cores][128 rows][8]   (same as lstm_tc.cu)
+// w pack     : [dir][q][parity e][76 k-cores: 26 of W_ih (+bias column) then 50 of W_hh][104 gate rows][8]
+#include "lstm_tc_common.cuh"
+#include <stdlib.h>
+
+namespace bsrnn {
+
+constexpr int XKC = 26;                                    // k-cores of the x operand (K = 208)
+constexpr int UKC = XKC + LKC;                             // 76 k-cores of [x | h]
+constexpr int UBH = LBN / 2;                               // 104 B rows (gate columns) per CTA
+constexpr int USTAGES = 5;
+constexpr int UPG = 8;                                     // pairs per group
+constexpr uint32_t U_W_BYTES = UKC * UBH * 16;             // 126464
+constexpr uint32_t U_STAGE = LKS * 128 * 16;               // 20480: 10 k-cores of a 128-row operand tile
+constexpr uint32_t U_XLAST = (XKC - 2 * LKS) * 128 * 16;   // 12288: third x stage holds 6 k-cores
+constexpr int U_NBARS = 3 * USTAGES + LNS + 2 + 3;
+constexpr size_t U_SMEM = U_W_BYTES + USTAGES * U_STAGE + U_NBARS * 8 + 16;
+static_assert(U_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+static_assert(U_W_BYTES % 4 == 0 && (U_W_BYTES / 4) % 16 == 0, "W half is fetched as 4 bulk copies");
+constexpr int U_MAX_GROUPS = 16;
+constexpr int U_SYNC_WORDS = 32 + 32 * (U_MAX_GROUPS * LNS * 2);
+
+struct FusedArgs {
+  const __half* x;
+  const __half* w;
+  const __half* zero_tile;   // 50*128*8 zeros (stands in for the h tile of a missing odd tile)
+  __half* y;
+  int R, steps, seq_tiles;
+  int gpd;                   // work groups per direction (each = up to `slots` consecutive tile PAIRS)
+  unsigned* sync;            // [0] ticket counter, [32 + 32*((3*group + slot)*2 + parity)] h_ready counters
+  long long* probe;          // debug (-DBSRNN_FUSED_PROBE): per-role wait / busy cycle totals of pair 0, [16*e + i]
+};
+
+#ifdef BSRNN_FUSED_PROBE
+#define FP_DECL(cond) const bool prb_ = a.probe && ticket == 0 && (cond); long long pt_ = prb_ ? clock64() : 0
+#define FP_MARK(v)                     \
+  do {                                 \
+    if (prb_) {                        \
+      const long long n_ = clock64();  \
+      (v) += n_ - pt_;                 \
+      pt_ = n_;                        \
+    }                                  \
+  } while (0)
+#else
+#define FP_DECL(cond) constexpr bool prb_ = false
+#define FP_MARK(v) do { (void)(v); } while (0)
+#endif
+
+struct PGroup {
+  int d, j0, nact;           // direction, first tile pair, tile pairs
+};
+__device__ __forceinline__ PGroup pgroup_of(const FusedArgs& a, int g) {
+  const int ptiles = (a.seq_tiles + 1) >> 1;
+  PGroup r;
+  r.d = g / a.gpd;
+  const int gi = g - r.d * a.gpd;
+  r.j0 = (int)(((long)gi * ptiles) / a.gpd);
+  r.nact = (int)(((long)(gi + 1) * ptiles) / a.gpd) - r.j0;
+  return r;
+}
+__device__ __forceinline__ unsigned* uflag_of(const FusedArgs& a, int cid, int k, int e) {
+  return a.sync + 32 + 32 * ((3 * cid + k) * 2 + e);
+}
+
+// 4 hidden units from 16 accumulator columns (i, f, g, o interleaved)
+template <int CH>
+__device__ __forceinline__ void epif_chunk(const uint32_t (&acc)[16], float (&c)[17], float (&h)[16]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    gate_update(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
+                __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u]);
+}
+// One item for one thread (row r, third T of the pair's 49 units).  Unit j of third T is h column 49Q + 16T + j ->
+// k-core 6Q + 2T + (Q+j)/8, slot (Q+j)%8 of the y tile (store pattern depends on Q only).
+template <int Q>
+__device__ __forceinline__ void epif_item(uint32_t t_col, bool last_third, uint32_t t_col48, __half* ycore, float (&c)[17],
+                                          bool st) {
+  constexpr size_t CORE = 128 * 8;
+  float h[16];
+  uint32_t accA[16], accB[16];
+  tmem_ld_x16(t_col, accA);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 16, accB);
+  tmem_ld_pin16(accA);
+  epif_chunk<0>(accA, c, h);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 32, accA);
+  tmem_ld_pin16(accB);
+  epif_chunk<1>(accB, c, h);
+  if (st) {
+    if (Q == 0) store_full<0>(ycore, h);
+    else store_partial<Q, 8, 0>(ycore, h);              // core A: slots Q..7 <- j = 0..7-Q
+  }
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 48, accB);
+  tmem_ld_pin16(accA);
+  epif_chunk<2>(accA, c, h);
+  uint32_t a4[4] = {0u, 0u, 0u, 0u};
+  tmem_ld_wait();
+  if (last_third) tmem_ld_x4(t_col48, a4);
+  tmem_ld_pin16(accB);
+  epif_chunk<3>(accB, c, h);
+  if (st) {
+    store_full<8 - Q>(ycore + CORE, h);                 // core B: j = 8-Q .. 15-Q
+    if (Q > 0) store_partial<0, Q, 16 - Q>(ycore + 2 * CORE, h);   // core C: slots 0..Q-1 <- j = 16-Q .. 15
+  }
+  if (last_third) {                                     // local unit 48 -> slot Q of core C
+    tmem_ld_wait();
+    asm volatile("" : "+r"(a4[0]), "+r"(a4[1]), "+r"(a4[2]), "+r"(a4[3]));
+    float h48;
+    gate_update(__uint_as_float(a4[0]), __uint_as_float(a4[1]), __uint_as_float(a4[2]), __uint_as_float(a4[3]), c[16], h48);
+    if (st) ycore[2 * CORE + Q] = __float2half_rn(h48);
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
+                                               int ncl, int e, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free, uint32_t ticket) {
+  const int r = quad * 32 + lane;
+  long long w_acc = 0, w_busy = 0, w_arr = 0;
+  FP_DECL(T == 0 && quad == 0 && lane == 0);
+  const bool last_third = T == 2;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + 64 * T;
+  const uint32_t t_lane48 = tmem_base + ((uint32_t)(quad * 32) << 16) + 192;
+  const int ngroups = 2 * a.gpd;
+  const size_t y_tile = (size_t)LKC * 128 * 8;                 // halves per (step, tile, dir) of y
+  uint32_t it0 = 0, nfull = 0;
+  float c0[17], c1[17], c2[17];
+  for (int g = cid; g < ngroups; g += ncl) {
+    const PGroup G = pgroup_of(a, g);
+#pragma unroll
+    for (int i = 0; i < 17; ++i) c0[i] = c1[i] = c2[i] = 0.f;
+    for (int s = 0; s < a.steps; ++s) {
+      const int p = G.d == 0 ? s : a.steps - 1 - s;
+#pragma unroll
+      for (int k = 0; k < LNS; ++k) {
+        if (k < G.nact) {
+          const int j = 2 * (G.j0 + k) + e;
+          const bool valid = j < a.seq_tiles;                  // odd tile count: the last odd CTA computes and drops
+          const size_t tile = (size_t)p * a.seq_tiles + (valid ? j : 0);
+          __half* ycore = a.y + (tile * 2 + G.d) * y_tile + (size_t)(6 * Q + 2 * T) * (128 * 8) + (size_t)r * 8;
+          const uint32_t it = it0 + (uint32_t)(s * G.nact + k);
+          const uint32_t buf = it & 1;
+          FP_MARK(w_busy);
+          mbar_wait(acc_full + k, (nfull >> k) & 1);
+          nfull ^= 1u << k;
+          tc_fence_after();
+          FP_MARK(w_acc);
+          if (k == 0) epif_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, ycore, c0, valid);
+          else if (k == 1) epif_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, ycore, c1, valid);
+          else epif_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, ycore, c2, valid);
+          tc_fence_before();
+          __syncwarp();
+          FP_MARK(w_busy);
+          // the pair's MMA issuer counts both CTAs' warps.  Relaxed remote arrive: the accumulator reads were completed
+          // by tcgen05.wait::ld; a release at cluster scope would make every warp drain its h stores first (~1 000 cycles)
+          if (lane == 0) {
+            if (e == 0) mbar_arrive(acc_empty + buf);
+            else mbar_arrive_cluster_relaxed(acc_empty + buf, 0);
+          }
+          FP_MARK(w_arr);
+          // h_t slice of this warp is stored: tell the publisher (non-blocking)
+          if (s + 1 < a.steps) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+        }
+      }
+    }
+    const int gn = g + ncl;                          // next work group of this hardware group switches direction?
+    if (gn < ngroups && gn / a.gpd != G.d) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(w_free);            // this warp consumed the last accumulator: W may go
+    }
+    it0 += (uint32_t)(a.steps * G.nact);
+  }
+  FP_MARK(w_busy);
+  if (prb_) { a.probe[16 * e + 12] = w_acc; a.probe[16 * e + 13] = w_busy; a.probe[16 * e + 14] = w_arr; }
+}
+
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + U_W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + USTAGES * U_STAGE);
+  uint64_t* full = bars;                       // [USTAGES] this CTA's ring stage landed
+  uint64_t* empty = full + USTAGES;            // [USTAGES] MMAs that read the stage retired (multicast commit)
+  uint64_t* pfull = empty + USTAGES;           // [USTAGES] leader only: the odd CTA's stage landed (relayed)
+  uint64_t* acc_full = pfull + USTAGES;        // [LNS]
+  uint64_t* acc_empty = acc_full + LNS;        // [2]   leader only: 24 epilogue warps of the pair
+  uint64_t* w_full = acc_empty + 2;
+  uint64_t* w_free = w_full + 1;
+  uint64_t* pw_full = w_free + 1;              // leader only: the odd CTA's W half landed (relayed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pw_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = (int)cluster_ctarank();        // tile parity served by this CTA; CTA 0 of the pair is the leader
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < USTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(pfull + i, 1); }
+    for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, 24);
+    mbar_init(w_full, 1);
+    mbar_init(w_free, 12);
+    mbar_init(pw_full, 1);
+    fence_barrier_init();
+    if (e == 0) tmem_slot[1] = atomicAdd(a.sync, 1u);   // the pair's rank within the launch by arrival order
+  }
+  if (warp == 2) tmem_alloc2(tmem_slot, 2 * LACC);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                       // both CTAs run and their barriers are initialised
+  if (e == 1 && threadIdx.x == 0) {     // the odd CTA reads the pair's ticket from the leader's shared memory
+    uint32_t remote, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(tmem_slot + 1)), "r"(0));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+    tmem_slot[1] = v;
+  }
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot[0];
+  const uint32_t ticket = tmem_slot[1];
+  const uint32_t q = ticket % UPG;
+  const int cid = (int)(ticket / UPG);
+  const int ncl = (int)(gridDim.x / (2 * UPG));
+
+  const int ngroups = 2 * a.gpd;
+  const size_t y_tile = (size_t)LKC * 128 * 8;         // halves per (step, tile, dir)
+  const size_t x_tile = (size_t)XKC * 128 * 8;         // halves per (step, tile) of x
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: W half + this CTA's x / h tiles
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    uint32_t stage = 0, phase = 0, wfphase = 0;
+    uint32_t npub0 = 0u, npub1 = 0u, npub2 = 0u;       // h tiles of slot k published so far by each CTA of this parity
+    int cur_dir = -1;
+    long long w_h = 0, w_e = 0, w_o = 0;
+    FP_DECL(lane == 0);
+    for (int g = cid; g < ngroups; g += ncl) {
+      const PGroup G = pgroup_of(a, g);
+      if (G.d != cur_dir) {
+        if (cur_dir >= 0) {
+          mbar_wait(w_free, wfphase);
+          wfphase ^= 1;
+        }
+        if (elect_one()) {
+          mbar_expect_tx(w_full, U_W_BYTES);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w) + (((size_t)G.d * UPG + q) * 2 + e) * U_W_BYTES;
+          for (uint32_t off = 0; off < U_W_BYTES; off += U_W_BYTES / 4) bulk_g2s(sW + off, src + off, U_W_BYTES / 4, w_full);
+        }
+        __syncwarp();
+        cur_dir = G.d;
+      }
+      for (int s = 0; s < a.steps; ++s) {
+        const int p = G.d == 0 ? s : a.steps - 1 - s;
+        const int p_prev = G.d == 0 ? s - 1 : a.steps - s;        // position whose h feeds this step
+        for (int k = 0; k < G.nact; ++k) {
+          const int j = 2 * (G.j0 + k) + e;
+          const bool valid = j < a.seq_tiles;
+          const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.x + ((size_t)p * a.seq_tiles + (valid ? j : 0)) * x_tile);
+#pragma unroll
+          for (int xs = 0; xs < 3; ++xs) {
+            const uint32_t bytes = xs == 2 ? U_XLAST : U_STAGE;
+            FP_MARK(w_o);
+            mbar_wait(empty + stage, phase ^ 1);
+            FP_MARK(w_e);
+            if (elect_one()) {
+              mbar_expect_tx(full + stage, bytes);
+              bulk_g2s(sA + stage * U_STAGE, xsrc + (size_t)xs * U_STAGE, bytes, full + stage);
+            }
+            __syncwarp();
+            if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+          }
+          if (s > 0) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(a.zero_tile);
+            if (valid) {
+              // all 8 CTAs of this parity have released their slice of h_{t-1} (gpu-scope acquire on the counter)
+              uint32_t& np = k == 0 ? npub0 : (k == 1 ? npub1 : npub2);
+              const uint32_t want = UPG * (++np);
+              const unsigned* fl = uflag_of(a, cid, k, e);
+              uint32_t spins = 0;
+              FP_MARK(w_o);
+              while ((int32_t)(ld_acquire_gpu(fl) - want) < 0) {
+                if (++spins > (1u << 22)) { __trap(); }
+              }
+              FP_MARK(w_h);
+              src = reinterpret_cast<const uint8_t*>(a.y + (((size_t)p_prev * a.seq_tiles + j) * 2 + G.d) * y_tile);
+            }
+#pragma unroll 1
+            for (int ks = 0; ks < LNST; ++ks) {
+              FP_MARK(w_o);
+              mbar_wait(empty + stage, phase ^ 1);
+              FP_MARK(w_e);
+              if (elect_one()) {
+                if (ks == 0) fence_proxy_async_global();      // peers' generic-proxy h stores -> this thread's async-proxy reads
+                mbar_expect_tx(full + stage, U_STAGE);
+                bulk_g2s(sA + stage * U_STAGE, src + (size_t)ks * U_STAGE, U_STAGE, full + stage);
+              }
+              __syncwarp();
+              if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    FP_MARK(w_o);
+    if (prb_) { a.probe[16 * e + 0] = w_h; a.probe[16 * e + 1] = w_e; a.probe[16 * e + 2] = w_o; }
+  } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (e == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA of the pair)
+      const uint32_t idesc = idesc_f16_f32(256, LBN);
+      uint32_t stage = 0, phase = 0, it = 0, wphase = 0;
+      int cur_dir = -1;
+      // descriptors advance by adding to the 14-bit (address >> 4) field: shared memory is < 256 KB, no carry out
+      const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
+      const uint64_t db0 = smem_desc_kb8(smem_u32(sW), UBH * 16, 128);
+      long long w_a = 0, w_f = 0, w_p = 0, w_o = 0;
+      FP_DECL(lane == 0);
+      for (int g = cid; g < ngroups; g += ncl) {
+        const PGroup G = pgroup_of(a, g);
+        if (G.d != cur_dir) {
+          mbar_wait(w_full, wphase);
+          mbar_wait(pw_full, wphase);
+          wphase ^= 1;
+          cur_dir = G.d;
+        }
+        for (int s = 0; s < a.steps; ++s) {
+          for (int k = 0; k < G.nact; ++k, ++it) {
+            const uint32_t buf = it & 1;
+            FP_MARK(w_o);
+            mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+            FP_MARK(w_a);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * LACC;
+#pragma unroll
+            for (int xs = 0; xs < 3; ++xs) {                   // x_t * W_ih^T: k-cores 0..25
+              FP_MARK(w_o);
+              mbar_wait(full + stage, phase);
+              FP_MARK(w_f);
+              mbar_wait(pfull + stage, phase);
+              FP_MARK(w_p);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t da = da0 + (uint64_t)(stage * (U_STAGE >> 4));
+                const uint64_t db = db0 + (uint64_t)(xs * LKS * ((UBH * 16) >> 4));
+#pragma unroll
+                for (int jk = 0; jk < (xs == 2 ? (XKC - 2 * LKS) / 2 : LKS / 2); ++jk)
+                  mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * UBH * 16) >> 4)),
+                                  idesc, (xs | jk) != 0);
+                mma_commit2_multicast(empty + stage, (uint16_t)3);
+                if (s == 0 && xs == 2) mma_commit2_multicast(acc_full + k, (uint16_t)3);
+              }
+              __syncwarp();
+              if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+            }
+            if (s > 0) {
+#pragma unroll
+              for (int ks = 0; ks < LNST; ++ks) {              // h_{t-1} * W_hh^T: k-cores 26..75
+                FP_MARK(w_o);
+                mbar_wait(full + stage, phase);
+                FP_MARK(w_f);
+                mbar_wait(pfull + stage, phase);
+                FP_MARK(w_p);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t da = da0 + (uint64_t)(stage * (U_STAGE >> 4));
+                  const uint64_t db = db0 + (uint64_t)((XKC + ks * LKS) * ((UBH * 16) >> 4));
+#pragma unroll
+                  for (int jk = 0; jk < LKS / 2; ++jk)
+                    mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * UBH * 16) >> 4)),
+                                    idesc, 1u);
+                  mma_commit2_multicast(empty + stage, (uint16_t)3);
+                  if (ks == LNST - 1) mma_commit2_multicast(acc_full + k, (uint16_t)3);
+                }
+                __syncwarp();
+                if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+        }
+      }
+      FP_MARK(w_o);
+      if (prb_) { a.probe[4] = w_a; a.probe[5] = w_f; a.probe[6] = w_p; a.probe[7] = w_o; }
+    } else {
+      // ---------------------------------------------------------------- relay (odd CTA): my stages -> leader's pfull
+      uint32_t stage = 0, phase = 0, wphase = 0;
+      int cur_dir = -1;
+      for (int g = cid; g < ngroups; g += ncl) {
+        const PGroup G = pgroup_of(a, g);
+        if (G.d != cur_dir) {
+          mbar_wait(w_full, wphase);
+          wphase ^= 1;
+          if (lane == 0) mbar_arrive_cluster_relaxed(pw_full, 0);
+          __syncwarp();
+          cur_dir = G.d;
+        }
+        const int nfills = G.nact * (3 + (a.steps - 1) * (3 + LNST));
+        for (int i = 0; i < nfills; ++i) {
+          mbar_wait(full + stage, phase);
+          if (lane == 0) mbar_arrive_cluster_relaxed(pfull + stage, 0);   // no fence: a release.cluster per stage paces the ring
+          __syncwarp();
+          if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ publisher
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    for (int g = cid; g < ngroups; g += ncl) {
+      const PGroup G = pgroup_of(a, g);
+      for (int s = 0; s + 1 < a.steps; ++s) {
+        for (int k = 0; k < G.nact; ++k) {
+          // completes once the 12 epilogue warps have stored their h_t slices of slot k
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+          if (lane == 0 && 2 * (G.j0 + k) + e < a.seq_tiles) {
+            fence_proxy_async_global();
+            red_release_gpu_add(uflag_of(a, cid, k, e), 1u);   // release: the CTA's h stores (ordered by the bar.sync) first
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // idle 4th warp of warpgroup 0
+  } else {
+    // ------------------------------------------------------------------ epilogue: 12 warps, every item
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int T = (warp - 4) >> 2, quad = warp & 3;
+#define BSRNN_EPIF_CASE(QQ) \
+  case QQ: epiloguef_role<QQ>(a, tmem_base, T, quad, lane, cid, ncl, e, acc_full, acc_empty, w_free, ticket); break;
+    switch (q) {
+      BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3)
+      BSRNN_EPIF_CASE(4) BSRNN_EPIF_CASE(5) BSRNN_EPIF_CASE(6) BSRNN_EPIF_CASE(7)
+    }
+#undef BSRNN_EPIF_CASE
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                       // neither CTA exits (or frees TMEM) while its peer may still arrive / read
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * LACC);
+  }
+}
+
+static cudaError_t launch_fused(const FusedArgs& a, int ncl, cudaStream_t st, int* occupancy) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e1 = cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U_SMEM);
+    if (e1 != cudaSuccess) return e1;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((occupancy ? 64 : ncl) * 2 * UPG);
+  cfg.blockDim = dim3(LTHREADS);
+  cfg.dynamicSmemBytes = U_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (occupancy) return cudaOccupancyMaxActiveClusters(occupancy, lstm_fused_kernel, &cfg);
+  return cudaLaunchKernelEx(&cfg, lstm_fused_kernel, a);
+}
+// co-resident groups of 8 CTA pairs (all CTAs of a launch must be resident: the groups spin on each other's counters)
+static int fused_max_groups() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int n = 0;
+  FusedArgs dummy{};
+  if (launch_fused(dummy, 0, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  cached = n / UPG;
+  if (cached > U_MAX_GROUPS) cached = U_MAX_GROUPS;
+  return cached;
+}
+
+}  // namespace bsrnn
+using namespace bsrnn;
+
+static long long* g_fused_probe = nullptr;
+extern "C" void bsrnn_debug_set_fused_probe(void* p) { g_fused_probe = reinterpret_cast<long long*>(p); }
+
+// Fused BLSTM layer (see the header of this file).  sync_ws: bsrnn_blstm_fused_sync_bytes() of device memory owned by
+// the caller (zeroed here, stream-ordered, before every launch).  slots <= 0: as few interleaved tile pairs per group as
+// still cover all units of a direction with half of the co-resident groups.
+extern "C" int bsrnn_blstm_fused_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y, int R, int steps,
+                                    int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y && sync_ws, "blstm_fused_tc: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused_tc: bad dims");
+  int cap = fused_max_groups();
+  if (cap <= 0) {
+    cudaGetLastError();
+    set_error("blstm_fused_tc: kernel does not fit (2-CTA clusters, 512 threads, %zu B shared memory)", U_SMEM);
+    return 2;
+  }
+  if (max_groups > 0 && cap > max_groups) cap = max_groups;
+  const int ptiles = (seq_tiles + 1) / 2;
+  if (slots <= 0) {
+    // a hardware group serves one direction at a time: with both directions running side by side each has cap/2 groups
+    const int per_dir = cap >= 2 ? cap / 2 : 1;
+    slots = (ptiles + per_dir - 1) / per_dir;
+    if (slots < 1) slots = 1;
+  }
+  if (slots > LNS) slots = LNS;
+  if (slots > ptiles) slots = ptiles;
+  FusedArgs a{reinterpret_cast<const __half*>(xhat), reinterpret_cast<const __half*>(w_fused),
+              reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y), R, steps, seq_tiles,
+              (ptiles + slots - 1) / slots, reinterpret_cast<unsigned*>(sync_ws), g_fused_probe};
+  int ncl = 2 * a.gpd;
+  if (ncl > cap) ncl = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  BSRNN_CUDA_OK(cudaMemsetAsync(sync_ws, 0, (size_t)U_SYNC_WORDS * sizeof(unsigned), st));
+  cudaError_t le = launch_fused(a, ncl, st, nullptr);
+  if (le != cudaSuccess) { set_error("blstm_fused_tc: %s", cudaGetErrorString(le)); return 3; }
+  BSRNN_LAUNCH_OK();
+  return 0;
+}
+extern "C" int bsrnn_blstm_fused_max_groups(void) { return fused_max_groups(); }
+extern "C" int bsrnn_blstm_fused_sync_bytes(void) { return (int)(U_SYNC_WORDS * sizeof(unsigned)); }

@@ -26,6 +26,14 @@ for _kv in os.environ.get("BSRNN_LSTM_FLAG_SLOTS", "").split(","):
     if "=" in _kv:
         _ax, _sv = _kv.split("=")
         _FLAG_SLOTS[_ax] = int(_sv)
+# axes whose BLSTM runs as ONE fused kernel (input projection inside the recurrence, csrc/lstm_fused.cu):
+# BSRNN_LSTM_FUSED="time,freq" (default) | "freq" | "none" (separate input-projection GEMM + bsrnn_blstm_recurrence_tc*)
+FUSED_AXES = tuple(a for a in os.environ.get("BSRNN_LSTM_FUSED", "time,freq").split(",") if a in ("time", "freq"))
+_FUSED_SLOTS = {"time": 0, "freq": 0}
+for _kv in os.environ.get("BSRNN_LSTM_FUSED_SLOTS", "").split(","):
+    if "=" in _kv:
+        _ax, _sv = _kv.split("=")
+        _FUSED_SLOTS[_ax] = int(_sv)
 CL, LU, LBN, LKC = 8, 49, 208, 50       # cluster size, units per CTA, gate columns per CTA, k-cores of h (K = 400)
 LGC = LBN // 8                           # gates_x cores per CTA
 GATE_SCALE = (0.5, 0.5, 1.0, 0.5)       # i, f, o rows pre-halved: sigmoid(x) = 0.5*tanh(x/2) + 0.5 in the kernel
@@ -88,8 +96,13 @@ def pack_lstm_tc(rnn):
             bih_rows.append(brow)
             whh.append(to_kb8(wh[sel] * valid, LBN, LKC)[0])
     wih = to_kb8(torch.cat(wih_rows, 0), LBN, kc_in)                # 16 tiles of 208 rows
-    return dict(wih=wih, bih=torch.cat(bih_rows).contiguous(), whh=torch.stack(whh).view(2, CL, LKC, LBN, 8).contiguous(),
-                kc_in=kc_in, H=H, N=N, one_col=one_col)
+    whh = torch.stack(whh).view(2, CL, LKC, LBN, 8).contiguous()
+    out = dict(wih=wih, bih=torch.cat(bih_rows).contiguous(), whh=whh, kc_in=kc_in, H=H, N=N, one_col=one_col)
+    if one_col >= 0:
+        # bsrnn_blstm_fused_tc: [dir][pair q][half e][kc_in k-cores of W_ih (+ bias column) | 50 of W_hh][104 rows][8]
+        wf = torch.cat([wih.view(2, CL, kc_in, LBN, 8), whh], 2)
+        out["wfused"] = wf.view(2, CL, kc_in + LKC, 2, LBN // 2, 8).permute(0, 1, 3, 2, 4, 5).contiguous()
+    return out
 
 
 def pack_fc_tc(fc, H):
@@ -137,7 +150,8 @@ class TcWorkspace:
         self.scale = torch.empty(B, N, dtype=torch.float32, device=dev)
         self.shift = torch.empty(B, N, dtype=torch.float32, device=dev)
         self.counts = _f64([float(T) * K * N], dev)
-        self.sync = torch.zeros(L.lib().bsrnn_blstm_tc_sync_bytes() // 4, dtype=torch.int32, device=dev)
+        self.sync = torch.zeros(max(L.lib().bsrnn_blstm_tc_sync_bytes(), L.lib().bsrnn_blstm_fused_sync_bytes()) // 4,
+                                dtype=torch.int32, device=dev)
         self.nbytes = sum(t.numel() * t.element_size() for t in (self.xhat, self.gates, self.y))
 
 
@@ -185,19 +199,25 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                 # recurrence kernel's gates_x tiles
                 L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(),
                        ws.xhat.data_ptr(), N, 0, N, w["kc_in"], steps * tiles, tiles, R, *addr, T * K, 1, w["one_col"], st)
-            with region("inproj"):
-                L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(),
-                       None if w["one_col"] >= 0 else w["bih"].data_ptr(), ws.gates.data_ptr(), None,
-                       steps * tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_KB8, 0, 2 * CL * LBN, 2 * CL * LGC, T * K,
-                       tiles, R, *addr, st)
-            with region(f"lstm_{axis}"):
-                if LSTM_SCHED == "flag":
-                    L.call("bsrnn_blstm_recurrence_tc_flag", ws.gates.data_ptr(), w["whh"].data_ptr(),
-                           ws.zero_tile.data_ptr(), ws.y.data_ptr(), R, steps, tiles, max_clusters, _FLAG_SLOTS[axis],
-                           ws.sync.data_ptr(), st)
-                else:
-                    L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(), ws.zero_tile.data_ptr(),
-                           ws.y.data_ptr(), R, steps, tiles, max_clusters, _LSTM_SLOTS[axis], st)
+            if axis in FUSED_AXES and "wfused" in w:
+                # input projection inside the recurrence: gates_t = [x_t | h_{t-1}] [W_ih | W_hh]^T, no gates_x tensor
+                with region(f"lstm_{axis}"):
+                    L.call("bsrnn_blstm_fused_tc", ws.xhat.data_ptr(), w["wfused"].data_ptr(), ws.zero_tile.data_ptr(),
+                           ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis], ws.sync.data_ptr(), st)
+            else:
+                with region("inproj"):
+                    L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(),
+                           None if w["one_col"] >= 0 else w["bih"].data_ptr(), ws.gates.data_ptr(), None,
+                           steps * tiles, 2 * CL, w["kc_in"], LBN, L.TC_F16_KB8, 0, 2 * CL * LBN, 2 * CL * LGC, T * K,
+                           tiles, R, *addr, st)
+                with region(f"lstm_{axis}"):
+                    if LSTM_SCHED == "flag":
+                        L.call("bsrnn_blstm_recurrence_tc_flag", ws.gates.data_ptr(), w["whh"].data_ptr(),
+                               ws.zero_tile.data_ptr(), ws.y.data_ptr(), R, steps, tiles, max_clusters, _FLAG_SLOTS[axis],
+                               ws.sync.data_ptr(), st)
+                    else:
+                        L.call("bsrnn_blstm_recurrence_tc_ex", ws.gates.data_ptr(), w["whh"].data_ptr(),
+                               ws.zero_tile.data_ptr(), ws.y.data_ptr(), R, steps, tiles, max_clusters, _LSTM_SLOTS[axis], st)
             with region("fc"):
                 ws.stats.zero_()
                 fc = w["fc"]
