@@ -272,23 +272,50 @@ def mask_decoder_tc(skip, plan, md_pack):
     tabs = _decoder_norm_tables(skip, md_pack)
     tiles = (B * T + 127) // 128
     outs = {}
-    p0 = md_pack["mlp_mask"]
-    xhat = torch.empty(K * tiles * p0["kc1"] * 1024, dtype=torch.float16, device=dev)
-    hidden = torch.empty(tiles * p0["kc2"] * 1024, dtype=torch.float16, device=dev)
-    for name in ("mlp_mask", "mlp_residual"):
+    # The mask and the residual MLP families are independent chains of 2 x K small GEMMs: they run on two streams (two
+    # parallel branches of a captured graph), so one chain's launch gaps and tile tails are filled by the other's.
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    fork = torch.cuda.Event()
+    capturing = torch.cuda.is_current_stream_capturing()
+    bufs = {}
+    for name in ("mlp_residual", "mlp_mask"):            # every buffer belongs to the main stream's allocator pool
         p = md_pack[name]
-        scale, shift = tabs[name][0], tabs[name][1]
-        o = torch.empty(B, T, F, 2, dtype=torch.float32, device=dev)
-        with region("maskdec"):
-            # rows of tile (k, j) are the (b,t) tokens of band k: same row map as the band-axis BLSTM
-            L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
-                   p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, st)
-            for k in range(K):
-                L.call("bsrnn_gemm_tc", xhat.data_ptr() + 2 * k * tiles * p["kc1"] * 1024, p["w1"][k].data_ptr(),
-                       p["b1"][k].data_ptr(), hidden.data_ptr(), None, tiles, p["nt1"], p["kc1"], LBN, L.TC_TANH_KB8,
-                       0, 4 * N, p["kc2"], B * T, tiles, B * T, BIG, 0, 1, 0, st)
-                L.call("bsrnn_gemm_tc", hidden.data_ptr(), p["w2"][k].data_ptr(), p["b2"][k].data_ptr(),
-                       o.data_ptr() + 8 * plan.bin0[k], None, tiles, 1, p["kc2"], p["bn2"][k], L.TC_GLU_F32, 2 * F,
-                       2 * plan.width[k], 0, B * T, tiles, B * T, BIG, 0, 1, 0, st)
-        outs[name] = o
+        bufs[name] = (torch.empty(K * tiles * p["kc1"] * 1024, dtype=torch.float16, device=dev),
+                      torch.empty(tiles * p["kc2"] * 1024, dtype=torch.float16, device=dev),
+                      torch.empty(B, T, F, 2, dtype=torch.float32, device=dev))
+    with region("maskdec"):
+        fork.record(main)
+        side.wait_event(fork)
+        for name, stream in (("mlp_residual", side), ("mlp_mask", main)):
+            p = md_pack[name]
+            scale, shift = tabs[name][0], tabs[name][1]
+            xhat, hidden, o = bufs[name]
+            with torch.cuda.stream(stream):
+                st = L.stream_ptr()
+                # rows of tile (k, j) are the (b,t) tokens of band k: same row map as the band-axis BLSTM
+                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
+                       p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, st)
+                for k in range(K):
+                    L.call("bsrnn_gemm_tc", xhat.data_ptr() + 2 * k * tiles * p["kc1"] * 1024, p["w1"][k].data_ptr(),
+                           p["b1"][k].data_ptr(), hidden.data_ptr(), None, tiles, p["nt1"], p["kc1"], LBN, L.TC_TANH_KB8,
+                           0, 4 * N, p["kc2"], B * T, tiles, B * T, BIG, 0, 1, 0, st)
+                    L.call("bsrnn_gemm_tc", hidden.data_ptr(), p["w2"][k].data_ptr(), p["b2"][k].data_ptr(),
+                           o.data_ptr() + 8 * plan.bin0[k], None, tiles, 1, p["kc2"], p["bn2"][k], L.TC_GLU_F32, 2 * F,
+                           2 * plan.width[k], 0, B * T, tiles, B * T, BIG, 0, 1, 0, st)
+            if stream is side and not capturing:
+                for t in (xhat, hidden, o, skip, scale, shift):
+                    t.record_stream(side)
+            outs[name] = o
+        main.wait_stream(side)
     return outs["mlp_mask"], outs["mlp_residual"]
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = str(dev)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
