@@ -204,6 +204,15 @@ int bsrnn_blstm_fused_tc(const void* xhat, const void* w_fused, const void* zero
                          int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
 int bsrnn_blstm_fused_max_groups(void);
 int bsrnn_blstm_fused_sync_bytes(void);
+/* bsrnn_blstm_fused768_tc: the same fused layer kernel for nn.LSTM(N=384, H=768, bidirectional) of BSRNN_flowse
+ *     [reference bsrnn_flowse.py:226-238 at the conf/models/BSRNN_flowse.yaml width]: groups of 24 CTA pairs (32 hidden
+ *     units = 128 gate columns per pair), replacing the input-projection GEMM + one bsrnn_blstm_step_tc launch per time
+ *     step.  xhat: fp16 [steps*seq_tiles][50][128][8] (bsrnn_norm_cast_kb8_ones with kcores = 50, column 384 = 1);
+ *     w_fused: fp16 [2][24][2][146][64][8]; zero_tile: 96*128*8 zeros; y_f / y_b: fp16 [steps*seq_tiles][96][128][8]
+ *     per direction (the layout bsrnn_blstm_step_tc writes).  sync_ws as bsrnn_blstm_fused_tc. */
+int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b, int R,
+                            int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+int bsrnn_blstm_fused768_max_groups(void);
 
 /* Debug / A-B timing: selects the recurrence schedule (4, 5, 6: 8-CTA clusters; 7: CTA pairs); any other value
  * returns to the BSRNN_LSTM_VER environment default. */

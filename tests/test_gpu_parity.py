@@ -310,6 +310,37 @@ def test_lstm_step_tc_vs_torch_h768():
     assert rel_l2(torch.cat(outs, 2), ref) < 3e-3
 
 
+@pytest.mark.parametrize("Rr,steps,slots", [(150, 9, 0), (700, 5, 2), (130, 33, 1), (1000, 4, 3)])
+def test_blstm_fused768_vs_torch(Rr, steps, slots):
+    """bsrnn_blstm_fused768_tc (FlowSE width N = 384 / H = 768: input projection inside the persistent recurrence, groups
+    of 24 CTA pairs) against torch.nn.LSTM on the CPU; ragged last tile, odd / even tile counts, 1..3 interleaved pairs."""
+    from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L
+    torch.manual_seed(0)
+    N, H = 384, 768
+    rnn = torch.nn.LSTM(N, H, batch_first=True, bidirectional=True)
+    x = torch.randn(Rr, steps, N) * 0.7
+    with torch.no_grad():
+        ref = rnn(x)[0]
+    p = S.pack_lstm_fused768(rnn.cuda())
+    tiles = (Rr + 127) // 128
+    ws = S.StepsWorkspace(steps, tiles, H, "cuda")
+    xhat = torch.empty(steps * tiles * p["kc_fused"] * 1024, dtype=torch.float16, device="cuda")
+    xg = x.cuda().contiguous()
+    st = L.stream_ptr()
+    L.call("bsrnn_norm_cast_kb8_ones", xg.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_fused"],
+           steps * tiles, tiles, Rr, 1 << 40, 0, steps, 1, Rr * steps, 1, p["one_col"], st)
+    for _ in range(2):
+        L.call("bsrnn_blstm_fused768_tc", xhat.data_ptr(), p["wfused"].data_ptr(), ws.zero.data_ptr(), ws.y[0].data_ptr(),
+               ws.y[1].data_ptr(), Rr, steps, tiles, 0, slots, ws.sync.data_ptr(), st)
+    outs = []
+    for d in (0, 1):
+        yd = ws.y[d].view(steps, tiles, H // 8, 128, 8).permute(0, 1, 3, 2, 4).reshape(steps, tiles * 128, H)[:, :Rr]
+        outs.append(yd.permute(1, 0, 2).float().cpu())
+    e = rel_l2(torch.cat(outs, 2), ref)
+    print(f"fused768 R={Rr} steps={steps} slots={slots}: rel_l2={e:.3e}")
+    assert e < 3e-3
+
+
 def test_flowse_solver_registry_errors():
     from urgent2026_challenge_track1_b200.sampling import ODEsolverRegistry
     assert set(ODEsolverRegistry.get_all_names()) >= {"euler", "midpoint", "heun"}

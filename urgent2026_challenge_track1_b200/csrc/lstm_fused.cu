@@ -1,59 +1,85 @@
-// lstm_fused.cu — BLSTM layer for H = 392 with the INPUT PROJECTION FUSED into the persistent recurrence:
-//     gates_t = [x_t | h_{t-1}] * [W_ih | W_hh]^T          (one K = 208 + 400 contraction per step)
-// so the 13.9 GB gates_x tensor that lstm_tc.cu reads (and the input-projection GEMM writes) per BLSTM call is never
-// materialised.  Replaces nn.LSTM(N, 2N, bidirectional) [reference bsrnn_flowse.py:226-238, called at :296-297 (time
-// axis) and :303-304 (band axis)] including its x * W_ih^T + b half.
+// lstm_fused.cu — BLSTM layer with the INPUT PROJECTION FUSED into the persistent recurrence:
+//     gates_t = [x_t | h_{t-1}] * [W_ih | W_hh]^T          (one contraction over K = N_in + H per step)
+// so the gates_x tensor that the step-wise / lstm_tc.cu kernels read (13.9 GB per BLSTM call at BASELINE config 2, written
+// by a separate input-projection GEMM) is never materialised.  Replaces nn.LSTM(N, 2N, bidirectional) [reference
+// bsrnn_flowse.py:226-238, called at :296-297 (time axis) and :303-304 (band axis)] including its x * W_ih^T + b half,
+// for the two widths the reference configures: N = 196 / H = 392 (BSRNN_baseline) and N = 384 / H = 768 (BSRNN_flowse).
 //
-// Why CTA pairs.  With 8 CTAs per sequence tile a CTA would have to keep a 208 x 608 fp16 slice (253 KB) resident —
-// more than the 227 KB of shared memory.  A CTA PAIR (2-CTA cluster, tcgen05 cta_group::2, M = 256) shares one slice:
-// each CTA keeps HALF of the pair's gate columns (104 x 608 fp16 = 126 KB) and supplies its own 128 sequence rows; the
-// MMA delivers all 208 gate columns of those rows into the CTA's own TMEM.  Per CTA and item the L2 -> SM traffic is
-// the 100 KB h tile plus the 53 KB x tile, the same as the h tile plus the 50 KB gates_x slice before.
+// Why CTA pairs.  At H = 392 with 8 CTAs per sequence tile a CTA would have to keep a 208 x 608 fp16 slice (253 KB)
+// resident — more than the 227 KB of shared memory.  A CTA PAIR (2-CTA cluster, tcgen05 cta_group::2, M = 256) shares one
+// slice: each CTA keeps HALF of the pair's gate columns and supplies its own 128 sequence rows; the MMA delivers all gate
+// columns of those rows into the CTA's own TMEM.  Per CTA and item the L2 -> SM traffic is the h tile plus the x tile, the
+// same as the h tile plus the gates_x slice before.
 //
-// Decomposition.  Work unit = (direction, PAIR of 128-sequence tiles).  A GROUP = 8 pairs (16 CTAs, any placement:
-// pairs rank themselves by an arrival ticket) owns up to 3 interleaved units of one direction; pair q owns hidden
-// units [49q, 49q+49).  The even CTA of each pair serves tile 2j, the odd CTA tile 2j+1; the 8 CTAs of one parity
+// Decomposition.  Work unit = (direction, PAIR of 128-sequence tiles).  A GROUP = PPG pairs (any placement: pairs rank
+// themselves by an arrival ticket) owns up to 3 interleaved units of one direction; pair q owns hidden units
+// [UPP*q, UPP*q + UPP).  The even CTA of each pair serves tile 2j, the odd CTA tile 2j+1; the PPG CTAs of one parity
 // exchange h_t of "their" tile through y in L2 and a gpu-scope release/acquire counter in global memory (the flag
 // protocol of lstm_tc_flag_kernel), so the only cluster traffic is inside a pair:
-//   warp 0  producer : per item 3 ring stages of x_t (26 k-cores, no dependency: they stream ahead) and, once the
-//                      parity's counter shows h_{t-1} complete, 5 stages of h (50 k-cores); 5-stage ring of 20 KB.
-//   warp 1  leader   : MMA issuer — 13 + 25 tcgen05.mma.cta_group::2 (M=256, N=208, K=16) per item, commits multicast
-//                      to both CTAs' `empty` / `acc_full` barriers;
-//           odd CTA  : relays its `full` completions to the leader's `pfull` barriers (remote arrive).
-//   warp 2  publisher: named barrier with the epilogue warps, then one red.release on the parity's counter.
-//   warps 4..15      : epilogue, all 12 warps on every item (thread = sequence row x third of the units): tcgen05.ld
-//                      in 16-column chunks software-pipelined against the MUFU work, c in registers, h_t -> y.
+//   warp 0  producer : per item the ring stages of x_t (no dependency: they stream ahead) and, once the parity's
+//                      counter shows h_{t-1} complete, the stages of h;
+//   warp 1  leader   : MMA issuer — tcgen05.mma.cta_group::2 (M=256, N=BN, K=16), commits multicast to both CTAs'
+//                      `empty` / `acc_full` barriers;
+//           odd CTA  : relays its `full` completions to the leader's `pfull` barriers (RELAXED remote arrive: a
+//                      release.cluster arrive costs ~1 000 cycles per stage and paced the whole ring, profiles/r02 call20/21);
+//   warp 2  publisher: named barrier with the epilogue warps, then one red.release on the parity's counter;
+//   warps 4..        : epilogue, all warps on every item (thread = sequence row x share of the units): tcgen05.ld in
+//                      16-column chunks software-pipelined against the MUFU work, c in registers, h_t -> y.
 // The bias rides in the weights (operand column N is the constant 1 written by norm_cast_kb8_ones), the i/f/o rows are
 // pre-halved (sigmoid(x) = 0.5*tanh(x/2)+0.5), step 0 skips the h half (h_{-1} = 0).
 //
-// x (fp16)   : [step][seq_tile][26 k-cores][128 rows][8]   — what bsrnn_norm_cast_kb8_ones writes
-// y (fp16)   : [step][seq_tile][dir][50 k-cores][128 rows][8]   (same as lstm_tc.cu)
-// w pack     : [dir][q][parity e][76 k-cores: 26 of W_ih (+bias column) then 50 of W_hh][104 gate rows][8]
+//                     H = 392 (Geo392)                          H = 768 (Geo768)
+//   pairs per group   8 x 49 units (N = 208 incl. 12 pad)       24 x 32 units (N = 128)
+//   K                 26 + 50 k-cores (208 + 400)               50 + 96 k-cores (400 + 768)
+//   W half per CTA    76 x 104 x 16 B = 126 KB                  146 x 64 x 16 B = 150 KB
+//   ring              5 stages x 10 k-cores (20 KB)             3 stages x 12 k-cores (24 KB)
+//   epilogue          12 warps: row x third (16/16/17 units)    16 warps: row x quarter (8 units = one 16-byte k-core row)
+//   TMEM              2 accumulators x 256 columns              4 accumulators x 128 columns
+//   co-resident       9 groups of 16 CTAs (144 SMs)             3 groups of 48 CTAs (144 SMs)
+//
+// x (fp16)   : [step][seq_tile][XKC k-cores][128 rows][8]   — what bsrnn_norm_cast_kb8_ones writes
+// y (fp16)   : per direction [step][seq_tile][HKC k-cores][128 rows][8]; H = 392 interleaves the directions in one buffer
+//              ([step][seq_tile][dir][50]...: the Linear GEMM's 128 x 800 operand tile), H = 768 keeps two buffers
+// w pack     : [dir][pair q][parity e][XKC k-cores of W_ih (+bias column) then HKC of W_hh][BN/2 gate rows][8]
 #include "lstm_tc_common.cuh"
 #include <stdlib.h>
 
 namespace bsrnn {
 
-constexpr int XKC = 26;                                    // k-cores of the x operand (K = 208)
-constexpr int UKC = XKC + LKC;                             // 76 k-cores of [x | h]
-constexpr int UBH = LBN / 2;                               // 104 B rows (gate columns) per CTA
-constexpr int USTAGES = 5;
-constexpr int UPG = 8;                                     // pairs per group
-constexpr uint32_t U_W_BYTES = UKC * UBH * 16;             // 126464
-constexpr uint32_t U_STAGE = LKS * 128 * 16;               // 20480: 10 k-cores of a 128-row operand tile
-constexpr uint32_t U_XLAST = (XKC - 2 * LKS) * 128 * 16;   // 12288: third x stage holds 6 k-cores
-constexpr int U_NBARS = 3 * USTAGES + LNS + 2 + 3;
-constexpr size_t U_SMEM = U_W_BYTES + USTAGES * U_STAGE + U_NBARS * 8 + 16;
-static_assert(U_SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
-static_assert(U_W_BYTES % 4 == 0 && (U_W_BYTES / 4) % 16 == 0, "W half is fetched as 4 bulk copies");
+struct Geo392 {
+  static constexpr int UPP = 49, BN = 208, PPG = 8, XKC = 26, HKC = 50, KS = 10, STAGES = 5;
+  static constexpr int EPI_WARPS = 12, ACC = 256, NBUF = 2, EPI_REGS = 152, NC = 17;
+};
+struct Geo768 {
+  static constexpr int UPP = 32, BN = 128, PPG = 24, XKC = 50, HKC = 96, KS = 12, STAGES = 3;
+  static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 8;
+};
+template <class G>
+struct Der {
+  static constexpr int BH = G::BN / 2;                                  // B rows (gate columns) per CTA
+  static constexpr int UKC = G::XKC + G::HKC;
+  static constexpr uint32_t W_BYTES = UKC * BH * 16;
+  static constexpr uint32_t STAGE = G::KS * 128 * 16;
+  static constexpr int XST = (G::XKC + G::KS - 1) / G::KS;              // ring stages of the x tile (last one partial)
+  static constexpr int XLAST = G::XKC - (XST - 1) * G::KS;
+  static constexpr int HST = G::HKC / G::KS;
+  static constexpr int THREADS = (4 + G::EPI_WARPS) * 32;
+  static constexpr int NBARS = 3 * G::STAGES + LNS + G::NBUF + 3;
+  static constexpr size_t SMEM = W_BYTES + G::STAGES * STAGE + NBARS * 8 + 16;
+  static_assert(G::HKC % G::KS == 0 && XLAST % 2 == 0 && G::KS % 2 == 0, "stages hold whole K = 16 MMAs");
+  static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static_assert(W_BYTES % 64 == 0, "W half is fetched as 4 bulk copies");
+  static_assert(G::NBUF * G::ACC <= 512 && (G::NBUF & (G::NBUF - 1)) == 0, "TMEM accumulators");
+};
 constexpr int U_MAX_GROUPS = 16;
 constexpr int U_SYNC_WORDS = 32 + 32 * (U_MAX_GROUPS * LNS * 2);
 
 struct FusedArgs {
   const __half* x;
   const __half* w;
-  const __half* zero_tile;   // 50*128*8 zeros (stands in for the h tile of a missing odd tile)
-  __half* y;
+  const __half* zero_tile;   // HKC*128*8 zeros (stands in for the h tile of a missing odd tile)
+  __half *y0, *y1;           // per direction: block of (step p, tile j) at y_d + (p*seq_tiles + j) * y_stride
+  long y_stride;             // halves
   int R, steps, seq_tiles;
   int gpd;                   // work groups per direction (each = up to `slots` consecutive tile PAIRS)
   unsigned* sync;            // [0] ticket counter, [32 + 32*((3*group + slot)*2 + parity)] h_ready counters
@@ -92,18 +118,18 @@ __device__ __forceinline__ unsigned* uflag_of(const FusedArgs& a, int cid, int k
 }
 
 // 4 hidden units from 16 accumulator columns (i, f, g, o interleaved)
-template <int CH>
-__device__ __forceinline__ void epif_chunk(const uint32_t (&acc)[16], float (&c)[17], float (&h)[16]) {
+template <int CH, int NC, int NH>
+__device__ __forceinline__ void epif_chunk(const uint32_t (&acc)[16], float (&c)[NC], float (&h)[NH]) {
 #pragma unroll
   for (int u = 0; u < 4; ++u)
     gate_update(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
                 __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u]);
 }
-// One item for one thread (row r, third T of the pair's 49 units).  Unit j of third T is h column 49Q + 16T + j ->
-// k-core 6Q + 2T + (Q+j)/8, slot (Q+j)%8 of the y tile (store pattern depends on Q only).
+// H = 392: one item for one thread (row r, third T of the pair's 49 units).  Unit j of third T is h column
+// 49Q + 16T + j -> k-core 6Q + 2T + (Q+j)/8, slot (Q+j)%8 of the y tile (store pattern depends on Q only).
 template <int Q>
-__device__ __forceinline__ void epif_item(uint32_t t_col, bool last_third, uint32_t t_col48, __half* ycore, float (&c)[17],
-                                          bool st) {
+__device__ __forceinline__ void epif_item392(uint32_t t_col, bool last_third, uint32_t t_col48, __half* ycore, float (&c)[17],
+                                             bool st) {
   constexpr size_t CORE = 128 * 8;
   float h[16];
   uint32_t accA[16], accB[16];
@@ -141,43 +167,68 @@ __device__ __forceinline__ void epif_item(uint32_t t_col, bool last_third, uint3
     if (st) ycore[2 * CORE + Q] = __float2half_rn(h48);
   }
 }
+// H = 768: thread = (row r, quarter T of the pair's 32 units): 8 units = 32 accumulator columns = one 16-byte row of
+// k-core 4q + T of the y tile.
+__device__ __forceinline__ void epif_item768(uint32_t t_col, __half* ycore, float (&c)[8], bool st) {
+  float h[8];
+  uint32_t accA[16], accB[16];
+  tmem_ld_x16(t_col, accA);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 16, accB);
+  tmem_ld_pin16(accA);
+  epif_chunk<0>(accA, c, h);
+  tmem_ld_wait();
+  tmem_ld_pin16(accB);
+  epif_chunk<1>(accB, c, h);
+  if (st)
+    *reinterpret_cast<uint4*>(ycore) = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+}
 
-template <int Q>
+template <class G, int Q>
 __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
-                                               int ncl, int e, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free, uint32_t ticket) {
+                                               int ncl, int e, int q, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free,
+                                               uint32_t ticket) {
+  constexpr bool G392 = G::UPP == 49;
   const int r = quad * 32 + lane;
   long long w_acc = 0, w_busy = 0, w_arr = 0;
   FP_DECL(T == 0 && quad == 0 && lane == 0);
   const bool last_third = T == 2;
-  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + 64 * T;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (G392 ? 64 : 32) * T;
   const uint32_t t_lane48 = tmem_base + ((uint32_t)(quad * 32) << 16) + 192;
   const int ngroups = 2 * a.gpd;
-  const size_t y_tile = (size_t)LKC * 128 * 8;                 // halves per (step, tile, dir) of y
+  // this thread's first k-core row inside a y tile
+  const size_t y_off = (size_t)(G392 ? 6 * Q + 2 * T : 4 * q + T) * (128 * 8) + (size_t)r * 8;
   uint32_t it0 = 0, nfull = 0;
-  float c0[17], c1[17], c2[17];
+  float c0[G::NC], c1[G::NC], c2[G::NC];
   for (int g = cid; g < ngroups; g += ncl) {
-    const PGroup G = pgroup_of(a, g);
+    const PGroup GR = pgroup_of(a, g);
 #pragma unroll
-    for (int i = 0; i < 17; ++i) c0[i] = c1[i] = c2[i] = 0.f;
+    for (int i = 0; i < G::NC; ++i) c0[i] = c1[i] = c2[i] = 0.f;
     for (int s = 0; s < a.steps; ++s) {
-      const int p = G.d == 0 ? s : a.steps - 1 - s;
+      const int p = GR.d == 0 ? s : a.steps - 1 - s;
 #pragma unroll
       for (int k = 0; k < LNS; ++k) {
-        if (k < G.nact) {
-          const int j = 2 * (G.j0 + k) + e;
+        if (k < GR.nact) {
+          const int j = 2 * (GR.j0 + k) + e;
           const bool valid = j < a.seq_tiles;                  // odd tile count: the last odd CTA computes and drops
           const size_t tile = (size_t)p * a.seq_tiles + (valid ? j : 0);
-          __half* ycore = a.y + (tile * 2 + G.d) * y_tile + (size_t)(6 * Q + 2 * T) * (128 * 8) + (size_t)r * 8;
-          const uint32_t it = it0 + (uint32_t)(s * G.nact + k);
-          const uint32_t buf = it & 1;
+          __half* ycore = (GR.d == 0 ? a.y0 : a.y1) + tile * a.y_stride + y_off;
+          const uint32_t it = it0 + (uint32_t)(s * GR.nact + k);
+          const uint32_t buf = it & (G::NBUF - 1);
           FP_MARK(w_busy);
           mbar_wait(acc_full + k, (nfull >> k) & 1);
           nfull ^= 1u << k;
           tc_fence_after();
           FP_MARK(w_acc);
-          if (k == 0) epif_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, ycore, c0, valid);
-          else if (k == 1) epif_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, ycore, c1, valid);
-          else epif_item<Q>(t_lane + buf * LACC, last_third, t_lane48 + buf * LACC, ycore, c2, valid);
+          if constexpr (G392) {
+            if (k == 0) epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c0, valid);
+            else if (k == 1) epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c1, valid);
+            else epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c2, valid);
+          } else {
+            if (k == 0) epif_item768(t_lane + buf * G::ACC, ycore, c0, valid);
+            else if (k == 1) epif_item768(t_lane + buf * G::ACC, ycore, c1, valid);
+            else epif_item768(t_lane + buf * G::ACC, ycore, c2, valid);
+          }
           tc_fence_before();
           __syncwarp();
           FP_MARK(w_busy);
@@ -189,32 +240,34 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
           }
           FP_MARK(w_arr);
           // h_t slice of this warp is stored: tell the publisher (non-blocking)
-          if (s + 1 < a.steps) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
+          if (s + 1 < a.steps) asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(G::EPI_WARPS * 32 + 32) : "memory");
         }
       }
     }
     const int gn = g + ncl;                          // next work group of this hardware group switches direction?
-    if (gn < ngroups && gn / a.gpd != G.d) {
+    if (gn < ngroups && gn / a.gpd != GR.d) {
       __syncwarp();
       if (lane == 0) mbar_arrive(w_free);            // this warp consumed the last accumulator: W may go
     }
-    it0 += (uint32_t)(a.steps * G.nact);
+    it0 += (uint32_t)(a.steps * GR.nact);
   }
   FP_MARK(w_busy);
   if (prb_) { a.probe[16 * e + 12] = w_acc; a.probe[16 * e + 13] = w_busy; a.probe[16 * e + 14] = w_arr; }
 }
 
-__global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs a) {
+template <class G>
+__global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const FusedArgs a) {
+  using D = Der<G>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
-  uint8_t* sA = smem + U_W_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + USTAGES * U_STAGE);
-  uint64_t* full = bars;                       // [USTAGES] this CTA's ring stage landed
-  uint64_t* empty = full + USTAGES;            // [USTAGES] MMAs that read the stage retired (multicast commit)
-  uint64_t* pfull = empty + USTAGES;           // [USTAGES] leader only: the odd CTA's stage landed (relayed)
-  uint64_t* acc_full = pfull + USTAGES;        // [LNS]
-  uint64_t* acc_empty = acc_full + LNS;        // [2]   leader only: 24 epilogue warps of the pair
-  uint64_t* w_full = acc_empty + 2;
+  uint8_t* sA = smem + D::W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + G::STAGES * D::STAGE);
+  uint64_t* full = bars;                       // [STAGES] this CTA's ring stage landed
+  uint64_t* empty = full + G::STAGES;          // [STAGES] MMAs that read the stage retired (multicast commit)
+  uint64_t* pfull = empty + G::STAGES;         // [STAGES] leader only: the odd CTA's stage landed (relayed)
+  uint64_t* acc_full = pfull + G::STAGES;      // [LNS]
+  uint64_t* acc_empty = acc_full + LNS;        // [NBUF] leader only: the epilogue warps of both CTAs
+  uint64_t* w_full = acc_empty + G::NBUF;
   uint64_t* w_free = w_full + 1;
   uint64_t* pw_full = w_free + 1;              // leader only: the odd CTA's W half landed (relayed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pw_full + 1);
@@ -223,16 +276,16 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
   const int e = (int)cluster_ctarank();        // tile parity served by this CTA; CTA 0 of the pair is the leader
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < USTAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(pfull + i, 1); }
+    for (int i = 0; i < G::STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(pfull + i, 1); }
     for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(acc_empty + i, 24);
+    for (int i = 0; i < G::NBUF; ++i) mbar_init(acc_empty + i, 2 * G::EPI_WARPS);
     mbar_init(w_full, 1);
-    mbar_init(w_free, 12);
+    mbar_init(w_free, G::EPI_WARPS);
     mbar_init(pw_full, 1);
     fence_barrier_init();
     if (e == 0) tmem_slot[1] = atomicAdd(a.sync, 1u);   // the pair's rank within the launch by arrival order
   }
-  if (warp == 2) tmem_alloc2(tmem_slot, 2 * LACC);
+  if (warp == 2) tmem_alloc2(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   cluster_sync();                       // both CTAs run and their barriers are initialised
@@ -246,13 +299,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot[0];
   const uint32_t ticket = tmem_slot[1];
-  const uint32_t q = ticket % UPG;
-  const int cid = (int)(ticket / UPG);
-  const int ncl = (int)(gridDim.x / (2 * UPG));
+  const uint32_t q = ticket % G::PPG;
+  const int cid = (int)(ticket / G::PPG);
+  const int ncl = (int)(gridDim.x / (2 * G::PPG));
 
   const int ngroups = 2 * a.gpd;
-  const size_t y_tile = (size_t)LKC * 128 * 8;         // halves per (step, tile, dir)
-  const size_t x_tile = (size_t)XKC * 128 * 8;         // halves per (step, tile) of x
+  const size_t x_tile = (size_t)G::XKC * 128 * 8;      // halves per (step, tile) of x
 
   if (warp == 0) {
     // ------------------------------------------------------------------ producer: W half + this CTA's x / h tiles
@@ -263,46 +315,46 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
     long long w_h = 0, w_e = 0, w_o = 0;
     FP_DECL(lane == 0);
     for (int g = cid; g < ngroups; g += ncl) {
-      const PGroup G = pgroup_of(a, g);
-      if (G.d != cur_dir) {
+      const PGroup GR = pgroup_of(a, g);
+      if (GR.d != cur_dir) {
         if (cur_dir >= 0) {
           mbar_wait(w_free, wfphase);
           wfphase ^= 1;
         }
         if (elect_one()) {
-          mbar_expect_tx(w_full, U_W_BYTES);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w) + (((size_t)G.d * UPG + q) * 2 + e) * U_W_BYTES;
-          for (uint32_t off = 0; off < U_W_BYTES; off += U_W_BYTES / 4) bulk_g2s(sW + off, src + off, U_W_BYTES / 4, w_full);
+          mbar_expect_tx(w_full, D::W_BYTES);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w) + (((size_t)GR.d * G::PPG + q) * 2 + e) * D::W_BYTES;
+          for (uint32_t off = 0; off < D::W_BYTES; off += D::W_BYTES / 4) bulk_g2s(sW + off, src + off, D::W_BYTES / 4, w_full);
         }
         __syncwarp();
-        cur_dir = G.d;
+        cur_dir = GR.d;
       }
       for (int s = 0; s < a.steps; ++s) {
-        const int p = G.d == 0 ? s : a.steps - 1 - s;
-        const int p_prev = G.d == 0 ? s - 1 : a.steps - s;        // position whose h feeds this step
-        for (int k = 0; k < G.nact; ++k) {
-          const int j = 2 * (G.j0 + k) + e;
+        const int p = GR.d == 0 ? s : a.steps - 1 - s;
+        const int p_prev = GR.d == 0 ? s - 1 : a.steps - s;        // position whose h feeds this step
+        for (int k = 0; k < GR.nact; ++k) {
+          const int j = 2 * (GR.j0 + k) + e;
           const bool valid = j < a.seq_tiles;
           const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.x + ((size_t)p * a.seq_tiles + (valid ? j : 0)) * x_tile);
 #pragma unroll
-          for (int xs = 0; xs < 3; ++xs) {
-            const uint32_t bytes = xs == 2 ? U_XLAST : U_STAGE;
+          for (int xs = 0; xs < D::XST; ++xs) {
+            const uint32_t bytes = (xs == D::XST - 1 ? D::XLAST : G::KS) * 2048;
             FP_MARK(w_o);
             mbar_wait(empty + stage, phase ^ 1);
             FP_MARK(w_e);
             if (elect_one()) {
               mbar_expect_tx(full + stage, bytes);
-              bulk_g2s(sA + stage * U_STAGE, xsrc + (size_t)xs * U_STAGE, bytes, full + stage);
+              bulk_g2s(sA + stage * D::STAGE, xsrc + (size_t)xs * D::STAGE, bytes, full + stage);
             }
             __syncwarp();
-            if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+            if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
           }
           if (s > 0) {
             const uint8_t* src = reinterpret_cast<const uint8_t*>(a.zero_tile);
             if (valid) {
-              // all 8 CTAs of this parity have released their slice of h_{t-1} (gpu-scope acquire on the counter)
+              // all PPG CTAs of this parity have released their slice of h_{t-1} (gpu-scope acquire on the counter)
               uint32_t& np = k == 0 ? npub0 : (k == 1 ? npub1 : npub2);
-              const uint32_t want = UPG * (++np);
+              const uint32_t want = G::PPG * (++np);
               const unsigned* fl = uflag_of(a, cid, k, e);
               uint32_t spins = 0;
               FP_MARK(w_o);
@@ -310,20 +362,20 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
                 if (++spins > (1u << 22)) { __trap(); }
               }
               FP_MARK(w_h);
-              src = reinterpret_cast<const uint8_t*>(a.y + (((size_t)p_prev * a.seq_tiles + j) * 2 + G.d) * y_tile);
+              src = reinterpret_cast<const uint8_t*>((GR.d == 0 ? a.y0 : a.y1) + ((size_t)p_prev * a.seq_tiles + j) * a.y_stride);
             }
 #pragma unroll 1
-            for (int ks = 0; ks < LNST; ++ks) {
+            for (int ks = 0; ks < D::HST; ++ks) {
               FP_MARK(w_o);
               mbar_wait(empty + stage, phase ^ 1);
               FP_MARK(w_e);
               if (elect_one()) {
                 if (ks == 0) fence_proxy_async_global();      // peers' generic-proxy h stores -> this thread's async-proxy reads
-                mbar_expect_tx(full + stage, U_STAGE);
-                bulk_g2s(sA + stage * U_STAGE, src + (size_t)ks * U_STAGE, U_STAGE, full + stage);
+                mbar_expect_tx(full + stage, D::STAGE);
+                bulk_g2s(sA + stage * D::STAGE, src + (size_t)ks * D::STAGE, D::STAGE, full + stage);
               }
               __syncwarp();
-              if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+              if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -335,32 +387,32 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (e == 0) {
       // ---------------------------------------------------------------- MMA issuer (leader CTA of the pair)
-      const uint32_t idesc = idesc_f16_f32(256, LBN);
+      const uint32_t idesc = idesc_f16_f32(256, G::BN);
       uint32_t stage = 0, phase = 0, it = 0, wphase = 0;
       int cur_dir = -1;
       // descriptors advance by adding to the 14-bit (address >> 4) field: shared memory is < 256 KB, no carry out
       const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
-      const uint64_t db0 = smem_desc_kb8(smem_u32(sW), UBH * 16, 128);
+      const uint64_t db0 = smem_desc_kb8(smem_u32(sW), D::BH * 16, 128);
       long long w_a = 0, w_f = 0, w_p = 0, w_o = 0;
       FP_DECL(lane == 0);
       for (int g = cid; g < ngroups; g += ncl) {
-        const PGroup G = pgroup_of(a, g);
-        if (G.d != cur_dir) {
+        const PGroup GR = pgroup_of(a, g);
+        if (GR.d != cur_dir) {
           mbar_wait(w_full, wphase);
           mbar_wait(pw_full, wphase);
           wphase ^= 1;
-          cur_dir = G.d;
+          cur_dir = GR.d;
         }
         for (int s = 0; s < a.steps; ++s) {
-          for (int k = 0; k < G.nact; ++k, ++it) {
-            const uint32_t buf = it & 1;
+          for (int k = 0; k < GR.nact; ++k, ++it) {
+            const uint32_t buf = it & (G::NBUF - 1);
             FP_MARK(w_o);
-            mbar_wait(acc_empty + buf, ((it >> 1) & 1) ^ 1);
+            mbar_wait(acc_empty + buf, ((it / G::NBUF) & 1) ^ 1);
             FP_MARK(w_a);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + buf * LACC;
+            const uint32_t d_tmem = tmem_base + buf * G::ACC;
 #pragma unroll
-            for (int xs = 0; xs < 3; ++xs) {                   // x_t * W_ih^T: k-cores 0..25
+            for (int xs = 0; xs < D::XST; ++xs) {              // x_t * W_ih^T: k-cores [0, XKC)
               FP_MARK(w_o);
               mbar_wait(full + stage, phase);
               FP_MARK(w_f);
@@ -368,21 +420,21 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
               FP_MARK(w_p);
               tc_fence_after();
               if (elect_one()) {
-                const uint64_t da = da0 + (uint64_t)(stage * (U_STAGE >> 4));
-                const uint64_t db = db0 + (uint64_t)(xs * LKS * ((UBH * 16) >> 4));
+                const uint64_t da = da0 + (uint64_t)(stage * (D::STAGE >> 4));
+                const uint64_t db = db0 + (uint64_t)(xs * G::KS * ((D::BH * 16) >> 4));
 #pragma unroll
-                for (int jk = 0; jk < (xs == 2 ? (XKC - 2 * LKS) / 2 : LKS / 2); ++jk)
-                  mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * UBH * 16) >> 4)),
+                for (int jk = 0; jk < (xs == D::XST - 1 ? D::XLAST : G::KS) / 2; ++jk)
+                  mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * D::BH * 16) >> 4)),
                                   idesc, (xs | jk) != 0);
                 mma_commit2_multicast(empty + stage, (uint16_t)3);
-                if (s == 0 && xs == 2) mma_commit2_multicast(acc_full + k, (uint16_t)3);
+                if (s == 0 && xs == D::XST - 1) mma_commit2_multicast(acc_full + k, (uint16_t)3);
               }
               __syncwarp();
-              if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+              if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
             }
             if (s > 0) {
 #pragma unroll
-              for (int ks = 0; ks < LNST; ++ks) {              // h_{t-1} * W_hh^T: k-cores 26..75
+              for (int ks = 0; ks < D::HST; ++ks) {            // h_{t-1} * W_hh^T: k-cores [XKC, XKC + HKC)
                 FP_MARK(w_o);
                 mbar_wait(full + stage, phase);
                 FP_MARK(w_f);
@@ -390,17 +442,17 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
                 FP_MARK(w_p);
                 tc_fence_after();
                 if (elect_one()) {
-                  const uint64_t da = da0 + (uint64_t)(stage * (U_STAGE >> 4));
-                  const uint64_t db = db0 + (uint64_t)((XKC + ks * LKS) * ((UBH * 16) >> 4));
+                  const uint64_t da = da0 + (uint64_t)(stage * (D::STAGE >> 4));
+                  const uint64_t db = db0 + (uint64_t)((G::XKC + ks * G::KS) * ((D::BH * 16) >> 4));
 #pragma unroll
-                  for (int jk = 0; jk < LKS / 2; ++jk)
-                    mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * UBH * 16) >> 4)),
+                  for (int jk = 0; jk < G::KS / 2; ++jk)
+                    mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * D::BH * 16) >> 4)),
                                     idesc, 1u);
                   mma_commit2_multicast(empty + stage, (uint16_t)3);
-                  if (ks == LNST - 1) mma_commit2_multicast(acc_full + k, (uint16_t)3);
+                  if (ks == D::HST - 1) mma_commit2_multicast(acc_full + k, (uint16_t)3);
                 }
                 __syncwarp();
-                if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+                if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
               }
             }
           }
@@ -413,20 +465,20 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
       uint32_t stage = 0, phase = 0, wphase = 0;
       int cur_dir = -1;
       for (int g = cid; g < ngroups; g += ncl) {
-        const PGroup G = pgroup_of(a, g);
-        if (G.d != cur_dir) {
+        const PGroup GR = pgroup_of(a, g);
+        if (GR.d != cur_dir) {
           mbar_wait(w_full, wphase);
           wphase ^= 1;
           if (lane == 0) mbar_arrive_cluster_relaxed(pw_full, 0);
           __syncwarp();
-          cur_dir = G.d;
+          cur_dir = GR.d;
         }
-        const int nfills = G.nact * (3 + (a.steps - 1) * (3 + LNST));
+        const int nfills = GR.nact * (D::XST + (a.steps - 1) * (D::XST + D::HST));
         for (int i = 0; i < nfills; ++i) {
           mbar_wait(full + stage, phase);
           if (lane == 0) mbar_arrive_cluster_relaxed(pfull + stage, 0);   // no fence: a release.cluster per stage paces the ring
           __syncwarp();
-          if (++stage == USTAGES) { stage = 0; phase ^= 1; }
+          if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -434,12 +486,12 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
     // ------------------------------------------------------------------ publisher
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     for (int g = cid; g < ngroups; g += ncl) {
-      const PGroup G = pgroup_of(a, g);
+      const PGroup GR = pgroup_of(a, g);
       for (int s = 0; s + 1 < a.steps; ++s) {
-        for (int k = 0; k < G.nact; ++k) {
-          // completes once the 12 epilogue warps have stored their h_t slices of slot k
-          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(384 + 32) : "memory");
-          if (lane == 0 && 2 * (G.j0 + k) + e < a.seq_tiles) {
+        for (int k = 0; k < GR.nact; ++k) {
+          // completes once all epilogue warps have stored their h_t slices of slot k
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(G::EPI_WARPS * 32 + 32) : "memory");
+          if (lane == 0 && 2 * (GR.j0 + k) + e < a.seq_tiles) {
             fence_proxy_async_global();
             red_release_gpu_add(uflag_of(a, cid, k, e), 1u);   // release: the CTA's h stores (ordered by the bar.sync) first
           }
@@ -450,97 +502,131 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fused_kernel(const FusedArgs
   } else if (warp == 3) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // idle 4th warp of warpgroup 0
   } else {
-    // ------------------------------------------------------------------ epilogue: 12 warps, every item
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // ------------------------------------------------------------------ epilogue: every warp on every item
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::EPI_REGS));
     const int T = (warp - 4) >> 2, quad = warp & 3;
+    if constexpr (G::UPP == 49) {
 #define BSRNN_EPIF_CASE(QQ) \
-  case QQ: epiloguef_role<QQ>(a, tmem_base, T, quad, lane, cid, ncl, e, acc_full, acc_empty, w_free, ticket); break;
-    switch (q) {
-      BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3)
-      BSRNN_EPIF_CASE(4) BSRNN_EPIF_CASE(5) BSRNN_EPIF_CASE(6) BSRNN_EPIF_CASE(7)
-    }
+  case QQ: epiloguef_role<G, QQ>(a, tmem_base, T, quad, lane, cid, ncl, e, QQ, acc_full, acc_empty, w_free, ticket); break;
+      switch (q) {
+        BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3)
+        BSRNN_EPIF_CASE(4) BSRNN_EPIF_CASE(5) BSRNN_EPIF_CASE(6) BSRNN_EPIF_CASE(7)
+      }
 #undef BSRNN_EPIF_CASE
+    } else {
+      epiloguef_role<G, 0>(a, tmem_base, T, quad, lane, cid, ncl, e, (int)q, acc_full, acc_empty, w_free, ticket);
+    }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync();                       // neither CTA exits (or frees TMEM) while its peer may still arrive / read
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc2(tmem_base, 2 * LACC);
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
+template <class G>
 static cudaError_t launch_fused(const FusedArgs& a, int ncl, cudaStream_t st, int* occupancy) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(lstm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U_SMEM);
+    cudaError_t e1 = cudaFuncSetAttribute(lstm_fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Der<G>::SMEM);
     if (e1 != cudaSuccess) return e1;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((occupancy ? 64 : ncl) * 2 * UPG);
-  cfg.blockDim = dim3(LTHREADS);
-  cfg.dynamicSmemBytes = U_SMEM;
+  cfg.gridDim = dim3((occupancy ? 64 : ncl) * 2 * G::PPG);
+  cfg.blockDim = dim3(Der<G>::THREADS);
+  cfg.dynamicSmemBytes = Der<G>::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (occupancy) return cudaOccupancyMaxActiveClusters(occupancy, lstm_fused_kernel, &cfg);
-  return cudaLaunchKernelEx(&cfg, lstm_fused_kernel, a);
+  if (occupancy) return cudaOccupancyMaxActiveClusters(occupancy, lstm_fused_kernel<G>, &cfg);
+  return cudaLaunchKernelEx(&cfg, lstm_fused_kernel<G>, a);
 }
-// co-resident groups of 8 CTA pairs (all CTAs of a launch must be resident: the groups spin on each other's counters)
+// co-resident groups of PPG CTA pairs (all CTAs of a launch must be resident: the groups spin on each other's counters)
+template <class G>
 static int fused_max_groups() {
   static int cached = -1;
   if (cached >= 0) return cached;
   int n = 0;
   FusedArgs dummy{};
-  if (launch_fused(dummy, 0, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return -1; }
-  cached = n / UPG;
+  if (launch_fused<G>(dummy, 0, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return -1; }
+  cached = n / G::PPG;
   if (cached > U_MAX_GROUPS) cached = U_MAX_GROUPS;
   return cached;
+}
+
+static long long* g_fused_probe = nullptr;
+
+// slots <= 0: the number of interleaved tile pairs per group (1..3) that minimises passes x step time, with a step
+// costing max(dependency chain ~ 2.3 items, slots items).
+static int auto_slots(int ptiles, int cap) {
+  int best = 1;
+  double best_t = 1e30;
+  for (int s = 1; s <= LNS && s <= ptiles; ++s) {
+    const int gpd = (ptiles + s - 1) / s;
+    const int passes = (2 * gpd + cap - 1) / cap;
+    const double t = passes * (s > 2.3 ? (double)s : 2.3);
+    if (t < best_t - 1e-9) { best_t = t; best = s; }
+  }
+  return best;
+}
+
+template <class G>
+static int run_fused(const char* what, const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b,
+                     long y_stride, int R, int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  int cap = fused_max_groups<G>();
+  if (cap <= 0) {
+    cudaGetLastError();
+    set_error("%s: kernel does not fit (2-CTA clusters, %d threads, %zu B shared memory)", what, Der<G>::THREADS, Der<G>::SMEM);
+    return 2;
+  }
+  if (max_groups > 0 && cap > max_groups) cap = max_groups;
+  const int ptiles = (seq_tiles + 1) / 2;
+  if (slots <= 0) slots = auto_slots(ptiles, cap);
+  if (slots > LNS) slots = LNS;
+  if (slots > ptiles) slots = ptiles;
+  FusedArgs a{reinterpret_cast<const __half*>(xhat), reinterpret_cast<const __half*>(w_fused),
+              reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y_f), reinterpret_cast<__half*>(y_b),
+              y_stride, R, steps, seq_tiles, (ptiles + slots - 1) / slots, reinterpret_cast<unsigned*>(sync_ws), g_fused_probe};
+  int ncl = 2 * a.gpd;
+  if (ncl > cap) ncl = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  BSRNN_CUDA_OK(cudaMemsetAsync(sync_ws, 0, (size_t)U_SYNC_WORDS * sizeof(unsigned), st));
+  cudaError_t le = launch_fused<G>(a, ncl, st, nullptr);
+  if (le != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(le)); return 3; }
+  BSRNN_LAUNCH_OK();
+  return 0;
 }
 
 }  // namespace bsrnn
 using namespace bsrnn;
 
-static long long* g_fused_probe = nullptr;
 extern "C" void bsrnn_debug_set_fused_probe(void* p) { g_fused_probe = reinterpret_cast<long long*>(p); }
 
-// Fused BLSTM layer (see the header of this file).  sync_ws: bsrnn_blstm_fused_sync_bytes() of device memory owned by
-// the caller (zeroed here, stream-ordered, before every launch).  slots <= 0: as few interleaved tile pairs per group as
-// still cover all units of a direction with half of the co-resident groups.
+// Fused BLSTM layer, H = 392 (see the header of this file).  sync_ws: bsrnn_blstm_fused_sync_bytes() of device memory
+// owned by the caller (zeroed here, stream-ordered, before every launch).  y: [step][seq_tile][dir][50][128][8].
 extern "C" int bsrnn_blstm_fused_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y, int R, int steps,
                                     int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
   BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y && sync_ws, "blstm_fused_tc: null pointer");
   BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused_tc: bad dims");
-  int cap = fused_max_groups();
-  if (cap <= 0) {
-    cudaGetLastError();
-    set_error("blstm_fused_tc: kernel does not fit (2-CTA clusters, 512 threads, %zu B shared memory)", U_SMEM);
-    return 2;
-  }
-  if (max_groups > 0 && cap > max_groups) cap = max_groups;
-  const int ptiles = (seq_tiles + 1) / 2;
-  if (slots <= 0) {
-    // a hardware group serves one direction at a time: with both directions running side by side each has cap/2 groups
-    const int per_dir = cap >= 2 ? cap / 2 : 1;
-    slots = (ptiles + per_dir - 1) / per_dir;
-    if (slots < 1) slots = 1;
-  }
-  if (slots > LNS) slots = LNS;
-  if (slots > ptiles) slots = ptiles;
-  FusedArgs a{reinterpret_cast<const __half*>(xhat), reinterpret_cast<const __half*>(w_fused),
-              reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y), R, steps, seq_tiles,
-              (ptiles + slots - 1) / slots, reinterpret_cast<unsigned*>(sync_ws), g_fused_probe};
-  int ncl = 2 * a.gpd;
-  if (ncl > cap) ncl = cap;
-  cudaStream_t st = (cudaStream_t)stream;
-  BSRNN_CUDA_OK(cudaMemsetAsync(sync_ws, 0, (size_t)U_SYNC_WORDS * sizeof(unsigned), st));
-  cudaError_t le = launch_fused(a, ncl, st, nullptr);
-  if (le != cudaSuccess) { set_error("blstm_fused_tc: %s", cudaGetErrorString(le)); return 3; }
-  BSRNN_LAUNCH_OK();
-  return 0;
+  const long y_tile = (long)Geo392::HKC * 128 * 8;
+  return run_fused<Geo392>("blstm_fused_tc", xhat, w_fused, zero_tile, y, reinterpret_cast<__half*>(y) + y_tile, 2 * y_tile, R,
+                           steps, seq_tiles, max_groups, slots, sync_ws, stream);
 }
-extern "C" int bsrnn_blstm_fused_max_groups(void) { return fused_max_groups(); }
+extern "C" int bsrnn_blstm_fused_max_groups(void) { return fused_max_groups<Geo392>(); }
 extern "C" int bsrnn_blstm_fused_sync_bytes(void) { return (int)(U_SYNC_WORDS * sizeof(unsigned)); }
+
+// Fused BLSTM layer, H = 768 / N = 384 (BSRNN_flowse): xhat [steps*seq_tiles][50][128][8] (column 384 = 1), w_fused
+// [2][24][2][146][64][8], zero_tile 96*128*8 zeros, y_f / y_b: [steps*seq_tiles][96][128][8] per direction.
+extern "C" int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b, int R,
+                                       int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y_f && y_b && sync_ws, "blstm_fused768_tc: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused768_tc: bad dims");
+  return run_fused<Geo768>("blstm_fused768_tc", xhat, w_fused, zero_tile, y_f, y_b, (long)Geo768::HKC * 128 * 8, R, steps,
+                           seq_tiles, max_groups, slots, sync_ws, stream);
+}
+extern "C" int bsrnn_blstm_fused768_max_groups(void) { return fused_max_groups<Geo768>(); }

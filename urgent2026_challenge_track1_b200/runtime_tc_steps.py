@@ -56,8 +56,49 @@ def pack_lstm_steps_tc(rnn):
         wh = getattr(rnn, "weight_hh_l0" + sfx).float()[perm] * gsc
         b = (getattr(rnn, "bias_ih_l0" + sfx) + getattr(rnn, "bias_hh_l0" + sfx)).float()[perm] * gsc[:, 0]
         wih.append(wi); bias.append(b); whh.append(to_kb8(wh, BN, H // 8))
-    return dict(wih=to_kb8(torch.cat(wih, 0), BN, kc_in), bias=torch.cat(bias).contiguous(), whh=whh, BN=BN, H=H, N=N,
-                kc_in=kc_in, n_tiles=4 * H // BN)
+    out = dict(wih=to_kb8(torch.cat(wih, 0), BN, kc_in), bias=torch.cat(bias).contiguous(), whh=whh, BN=BN, H=H, N=N,
+               kc_in=kc_in, n_tiles=4 * H // BN)
+    if H == 768 and N == 384:
+        out.update(pack_lstm_fused768(rnn))
+    return out
+
+
+FUSED768 = dict(PPG=24, UPP=32, XKC=50, HKC=96)          # csrc/lstm_fused.cu Geo768
+# BSRNN_FLOWSE_FUSED=0 returns to the input-projection GEMM + one bsrnn_blstm_step_tc launch per time step
+import os as _os
+FLOWSE_FUSED = _os.environ.get("BSRNN_FLOWSE_FUSED", "1") == "1"
+_FUSED_SLOTS = {"time": 0, "freq": 0}
+for _kv in _os.environ.get("BSRNN_FLOWSE_FUSED_SLOTS", "").split(","):
+    if "=" in _kv:
+        _ax, _sv = _kv.split("=")
+        _FUSED_SLOTS[_ax] = int(_sv)
+
+
+def pack_lstm_fused768(rnn):
+    """nn.LSTM(384, 768, bidirectional) -> wfused [2][24 pairs][2 halves][50 + 96 k-cores][64 gate rows][8] fp16 for
+    bsrnn_blstm_fused768_tc: pair q owns hidden units [32q, 32q+32), packed gate row c = 4*u_local + gate (i, f, g, o; the
+    i/f/o rows pre-halved); operand column 384 carries b_ih + b_hh (norm_cast_kb8_ones writes the constant 1 there)."""
+    g = FUSED768
+    H, N = rnn.weight_hh_l0.shape[1], rnn.weight_ih_l0.shape[1]
+    dev = rnn.weight_hh_l0.device
+    ul = torch.arange(g["UPP"], device=dev)
+    gsc = torch.tensor(GATE_SCALE, device=dev).repeat(g["UPP"])[:, None]            # packed row c = 4*u + gate
+    packs = []
+    for sfx in ("", "_reverse"):
+        wi = getattr(rnn, "weight_ih_l0" + sfx).float()
+        wh = getattr(rnn, "weight_hh_l0" + sfx).float()
+        b = (getattr(rnn, "bias_ih_l0" + sfx) + getattr(rnn, "bias_hh_l0" + sfx)).float()
+        for q in range(g["PPG"]):
+            rows = (torch.arange(4, device=dev)[None, :] * H + (g["UPP"] * q + ul)[:, None]).reshape(-1)     # 128 rows
+            w = torch.zeros(rows.numel(), (g["XKC"] + g["HKC"]) * 8, device=dev)
+            w[:, :N] = wi[rows]
+            w[:, N] = b[rows]
+            w[:, g["XKC"] * 8: g["XKC"] * 8 + H] = wh[rows]
+            w = w * gsc
+            # [rows 128][K] -> [half e][k-core][64 rows][8]
+            packs.append(w.view(2, rows.numel() // 2, g["XKC"] + g["HKC"], 8).permute(0, 2, 1, 3))
+    wf = torch.stack(packs).view(2, g["PPG"], 2, g["XKC"] + g["HKC"], 64, 8).contiguous().to(torch.float16)
+    return dict(wfused=wf, kc_fused=g["XKC"], one_col=N)
 
 
 class StepsWorkspace:
@@ -67,6 +108,7 @@ class StepsWorkspace:
         self.y = [torch.empty(steps * tiles * (H // 8) * 1024, dtype=torch.float16, device=dev) for _ in range(2)]
         self.c = [torch.empty(tiles * 128, H, dtype=torch.float32, device=dev) for _ in range(2)]
         self.zero = torch.zeros(tiles * (H // 8) * 1024, dtype=torch.float16, device=dev)
+        self.sync = torch.zeros(L.lib().bsrnn_blstm_fused_sync_bytes() // 4, dtype=torch.int32, device=dev)
 
 
 def blstm_steps_tc(xhat, p, steps, tiles, ws: StepsWorkspace):
@@ -145,7 +187,7 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
     ws = _WS.get(key)
     if ws is None:
         _WS.clear()
-        kc_in = layers[0]["time"]["kc_in"]
+        kc_in = max(layers[0]["time"]["kc_in"], layers[0]["time"].get("kc_fused", 0))
         ntile = max(T * tiles_t, K * tiles_f)
         ws = _WS[key] = dict(xhat=torch.empty(ntile * kc_in * 1024, dtype=torch.float16, device=dev),
                              time=StepsWorkspace(T, tiles_t, H, dev), freq=StepsWorkspace(K, tiles_f, H, dev))
@@ -157,12 +199,26 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
                 R_, steps, tiles, addr = B * K, T, tiles_t, (K, T * K, 1, K)
             else:
                 R_, steps, tiles, addr = B * T, K, tiles_f, (1, K, 0, 1)
+            fused = FLOWSE_FUSED and "wfused" in w
             with region("norm"):
                 scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra, w["eps"])
-                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws["xhat"].data_ptr(),
-                       N, 0, N, w["kc_in"], steps * tiles, tiles, R_, *addr, T * K, 1, st)
+                if fused:                    # 50 k-cores: column 384 = 1 carries the bias through the fused contraction
+                    L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                           ws["xhat"].data_ptr(), N, 0, N, w["kc_fused"], steps * tiles, tiles, R_, *addr, T * K, 1,
+                           w["one_col"], st)
+                else:
+                    L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws["xhat"].data_ptr(),
+                           N, 0, N, w["kc_in"], steps * tiles, tiles, R_, *addr, T * K, 1, st)
             with region(f"lstm_{axis}"):
-                y = blstm_steps_tc(ws["xhat"], w, steps, tiles, ws[axis])
+                if fused:
+                    # one persistent kernel per BLSTM layer: input projection + all time steps, both directions
+                    sw = ws[axis]
+                    L.call("bsrnn_blstm_fused768_tc", ws["xhat"].data_ptr(), w["wfused"].data_ptr(), sw.zero.data_ptr(),
+                           sw.y[0].data_ptr(), sw.y[1].data_ptr(), R_, steps, tiles, 0, _FUSED_SLOTS[axis],
+                           sw.sync.data_ptr(), st)
+                    y = sw.y
+                else:
+                    y = blstm_steps_tc(ws["xhat"], w, steps, tiles, ws[axis])
             with region("fc"):
                 for half, bias in ((0, w["fcb"]), (1, w["fcb0"])):       # skip += y_fwd W_f^T + b, then += y_bwd W_b^T
                     L.call("bsrnn_gemm_tc", y[half].data_ptr(), w["fcw"][half].data_ptr(), bias.data_ptr(), skip.data_ptr(),
