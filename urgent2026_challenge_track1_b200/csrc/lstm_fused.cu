@@ -44,15 +44,25 @@
 #include "lstm_tc_common.cuh"
 #include <stdlib.h>
 
+#ifndef BSRNN_FUSED768_CLS
+#define BSRNN_FUSED768_CLS 2
+#endif
+
 namespace bsrnn {
 
 struct Geo392 {
   static constexpr int UPP = 49, BN = 208, PPG = 8, XKC = 26, HKC = 50, KS = 10, STAGES = 5;
   static constexpr int EPI_WARPS = 12, ACC = 256, NBUF = 2, EPI_REGS = 152, NC = 17;
+  static constexpr int CLS = 2;             // cluster = one CTA pair
 };
 struct Geo768 {
   static constexpr int UPP = 32, BN = 128, PPG = 24, XKC = 50, HKC = 96, KS = 12, STAGES = 3;
   static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 8;
+  // -DBSRNN_FUSED768_CLS=4: clusters of 2 CTA pairs, the two CTAs of a parity fetch half of each ring stage and
+  // multicast it to both.  Measured (profiles/r02 call28): no gain per item (8 000 vs 7 670 cycles: the 72 KB ring's
+  // round-trip latency paces the loads, not L2 throughput) and only 24 co-resident 4-CTA clusters = 2 groups instead
+  // of 3, so the default stays one pair per cluster.
+  static constexpr int CLS = BSRNN_FUSED768_CLS;
 };
 template <class G>
 struct Der {
@@ -64,12 +74,14 @@ struct Der {
   static constexpr int XLAST = G::XKC - (XST - 1) * G::KS;
   static constexpr int HST = G::HKC / G::KS;
   static constexpr int THREADS = (4 + G::EPI_WARPS) * 32;
+  static constexpr int NP = G::CLS / 2;                                 // pairs per cluster
   static constexpr int NBARS = 3 * G::STAGES + LNS + G::NBUF + 3;
   static constexpr size_t SMEM = W_BYTES + G::STAGES * STAGE + NBARS * 8 + 16;
   static_assert(G::HKC % G::KS == 0 && XLAST % 2 == 0 && G::KS % 2 == 0, "stages hold whole K = 16 MMAs");
   static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static_assert(W_BYTES % 64 == 0, "W half is fetched as 4 bulk copies");
   static_assert(G::NBUF * G::ACC <= 512 && (G::NBUF & (G::NBUF - 1)) == 0, "TMEM accumulators");
+  static_assert(G::PPG % NP == 0 && (G::KS * 2048 / NP) % 16 == 0 && (XLAST * 2048 / NP) % 16 == 0, "multicast shares");
 };
 constexpr int U_MAX_GROUPS = 16;
 constexpr int U_SYNC_WORDS = 32 + 32 * (U_MAX_GROUPS * LNS * 2);
@@ -186,8 +198,8 @@ __device__ __forceinline__ void epif_item768(uint32_t t_col, __half* ycore, floa
 
 template <class G, int Q>
 __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
-                                               int ncl, int e, int q, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* w_free,
-                                               uint32_t ticket) {
+                                               int ncl, int e, int q, uint32_t leader, uint64_t* acc_full, uint64_t* acc_empty,
+                                               uint64_t* w_free, uint32_t ticket) {
   constexpr bool G392 = G::UPP == 49;
   const int r = quad * 32 + lane;
   long long w_acc = 0, w_busy = 0, w_arr = 0;
@@ -236,7 +248,7 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
           // by tcgen05.wait::ld; a release at cluster scope would make every warp drain its h stores first (~1 000 cycles)
           if (lane == 0) {
             if (e == 0) mbar_arrive(acc_empty + buf);
-            else mbar_arrive_cluster_relaxed(acc_empty + buf, 0);
+            else mbar_arrive_cluster_relaxed(acc_empty + buf, leader);
           }
           FP_MARK(w_arr);
           // h_t slice of this warp is stored: tell the publisher (non-blocking)
@@ -273,23 +285,26 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pw_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = (int)cluster_ctarank();        // tile parity served by this CTA; CTA 0 of the pair is the leader
+  const uint32_t crank = cluster_ctarank();
+  const int e = (int)(crank & 1u);             // tile parity served by this CTA; the even CTA of a pair is its leader
+  const uint32_t pc = crank >> 1;              // pair within the cluster
+  const uint32_t leader = crank & ~1u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < G::STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(pfull + i, 1); }
+    for (int i = 0; i < G::STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, D::NP); mbar_init(pfull + i, 1); }
     for (int i = 0; i < LNS; ++i) mbar_init(acc_full + i, 1);
     for (int i = 0; i < G::NBUF; ++i) mbar_init(acc_empty + i, 2 * G::EPI_WARPS);
     mbar_init(w_full, 1);
     mbar_init(w_free, G::EPI_WARPS);
     mbar_init(pw_full, 1);
     fence_barrier_init();
-    if (e == 0) tmem_slot[1] = atomicAdd(a.sync, 1u);   // the pair's rank within the launch by arrival order
+    if (crank == 0) tmem_slot[1] = atomicAdd(a.sync, 1u);   // the cluster's rank within the launch by arrival order
   }
   if (warp == 2) tmem_alloc2(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   cluster_sync();                       // both CTAs run and their barriers are initialised
-  if (e == 1 && threadIdx.x == 0) {     // the odd CTA reads the pair's ticket from the leader's shared memory
+  if (crank != 0 && threadIdx.x == 0) { // the other CTAs read the cluster's ticket from CTA 0's shared memory
     uint32_t remote, v;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(tmem_slot + 1)), "r"(0));
     asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
@@ -298,7 +313,7 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot[0];
-  const uint32_t ticket = tmem_slot[1];
+  const uint32_t ticket = tmem_slot[1] * D::NP + pc;     // this pair's rank within the launch
   const uint32_t q = ticket % G::PPG;
   const int cid = (int)(ticket / G::PPG);
   const int ncl = (int)(gridDim.x / (2 * G::PPG));
@@ -312,6 +327,9 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
     uint32_t stage = 0, phase = 0, wfphase = 0;
     uint32_t npub0 = 0u, npub1 = 0u, npub2 = 0u;       // h tiles of slot k published so far by each CTA of this parity
     int cur_dir = -1;
+    uint16_t mc_mask = 0;                              // the CTAs of my parity in this cluster
+    for (int i = 0; i < D::NP; ++i) mc_mask |= (uint16_t)(1u << (2 * i + e));
+    (void)mc_mask;
     long long w_h = 0, w_e = 0, w_o = 0;
     FP_DECL(lane == 0);
     for (int g = cid; g < ngroups; g += ncl) {
@@ -336,6 +354,10 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
           const int j = 2 * (GR.j0 + k) + e;
           const bool valid = j < a.seq_tiles;
           const uint8_t* xsrc = reinterpret_cast<const uint8_t*>(a.x + ((size_t)p * a.seq_tiles + (valid ? j : 0)) * x_tile);
+          // x comes from DRAM (the operand of a whole BLSTM call is far larger than L2): one pair per group and parity
+          // pulls the slot's tile of the NEXT step into L2, so the ring's copies are L2 hits
+          if (q == 0 && s + 1 < a.steps && elect_one())
+            bulk_prefetch_l2(xsrc + (GR.d == 0 ? 1 : -1) * (long)a.seq_tiles * (long)(x_tile * 2), (uint32_t)(x_tile * 2));
 #pragma unroll
           for (int xs = 0; xs < D::XST; ++xs) {
             const uint32_t bytes = (xs == D::XST - 1 ? D::XLAST : G::KS) * 2048;
@@ -344,7 +366,12 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
             FP_MARK(w_e);
             if (elect_one()) {
               mbar_expect_tx(full + stage, bytes);
-              bulk_g2s(sA + stage * D::STAGE, xsrc + (size_t)xs * D::STAGE, bytes, full + stage);
+              if constexpr (D::NP == 1) {
+                bulk_g2s(sA + stage * D::STAGE, xsrc + (size_t)xs * D::STAGE, bytes, full + stage);
+              } else {             // my share of the stage -> the same ring slot of every CTA of my parity in the cluster
+                const uint32_t sh = bytes / D::NP;
+                bulk_g2s_multicast(sA + stage * D::STAGE + pc * sh, xsrc + (size_t)xs * D::STAGE + pc * sh, sh, full + stage, mc_mask);
+              }
             }
             __syncwarp();
             if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
@@ -372,7 +399,12 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
               if (elect_one()) {
                 if (ks == 0) fence_proxy_async_global();      // peers' generic-proxy h stores -> this thread's async-proxy reads
                 mbar_expect_tx(full + stage, D::STAGE);
-                bulk_g2s(sA + stage * D::STAGE, src + (size_t)ks * D::STAGE, D::STAGE, full + stage);
+                if constexpr (D::NP == 1) {
+                  bulk_g2s(sA + stage * D::STAGE, src + (size_t)ks * D::STAGE, D::STAGE, full + stage);
+                } else {
+                  constexpr uint32_t sh = D::STAGE / D::NP;
+                  bulk_g2s_multicast(sA + stage * D::STAGE + pc * sh, src + (size_t)ks * D::STAGE + pc * sh, sh, full + stage, mc_mask);
+                }
               }
               __syncwarp();
               if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
@@ -393,6 +425,7 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
       // descriptors advance by adding to the 14-bit (address >> 4) field: shared memory is < 256 KB, no carry out
       const uint64_t da0 = smem_desc_kb8(smem_u32(sA), 2048, 128);
       const uint64_t db0 = smem_desc_kb8(smem_u32(sW), D::BH * 16, 128);
+      const uint16_t all_mask = (uint16_t)((1u << G::CLS) - 1), pair_mask = (uint16_t)(3u << (2 * pc));
       long long w_a = 0, w_f = 0, w_p = 0, w_o = 0;
       FP_DECL(lane == 0);
       for (int g = cid; g < ngroups; g += ncl) {
@@ -426,8 +459,8 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
                 for (int jk = 0; jk < (xs == D::XST - 1 ? D::XLAST : G::KS) / 2; ++jk)
                   mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * D::BH * 16) >> 4)),
                                   idesc, (xs | jk) != 0);
-                mma_commit2_multicast(empty + stage, (uint16_t)3);
-                if (s == 0 && xs == D::XST - 1) mma_commit2_multicast(acc_full + k, (uint16_t)3);
+                mma_commit2_multicast(empty + stage, all_mask);
+                if (s == 0 && xs == D::XST - 1) mma_commit2_multicast(acc_full + k, pair_mask);
               }
               __syncwarp();
               if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
@@ -448,8 +481,8 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
                   for (int jk = 0; jk < G::KS / 2; ++jk)
                     mma_f16_ss_2cta(d_tmem, da + (uint64_t)(jk * ((2 * 2048) >> 4)), db + (uint64_t)(jk * ((2 * D::BH * 16) >> 4)),
                                     idesc, 1u);
-                  mma_commit2_multicast(empty + stage, (uint16_t)3);
-                  if (ks == D::HST - 1) mma_commit2_multicast(acc_full + k, (uint16_t)3);
+                  mma_commit2_multicast(empty + stage, all_mask);
+                  if (ks == D::HST - 1) mma_commit2_multicast(acc_full + k, pair_mask);
                 }
                 __syncwarp();
                 if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
@@ -469,14 +502,14 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
         if (GR.d != cur_dir) {
           mbar_wait(w_full, wphase);
           wphase ^= 1;
-          if (lane == 0) mbar_arrive_cluster_relaxed(pw_full, 0);
+          if (lane == 0) mbar_arrive_cluster_relaxed(pw_full, leader);
           __syncwarp();
           cur_dir = GR.d;
         }
         const int nfills = GR.nact * (D::XST + (a.steps - 1) * (D::XST + D::HST));
         for (int i = 0; i < nfills; ++i) {
           mbar_wait(full + stage, phase);
-          if (lane == 0) mbar_arrive_cluster_relaxed(pfull + stage, 0);   // no fence: a release.cluster per stage paces the ring
+          if (lane == 0) mbar_arrive_cluster_relaxed(pfull + stage, leader);   // no fence: a release.cluster per stage paces the ring
           __syncwarp();
           if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -507,14 +540,14 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
     const int T = (warp - 4) >> 2, quad = warp & 3;
     if constexpr (G::UPP == 49) {
 #define BSRNN_EPIF_CASE(QQ) \
-  case QQ: epiloguef_role<G, QQ>(a, tmem_base, T, quad, lane, cid, ncl, e, QQ, acc_full, acc_empty, w_free, ticket); break;
+  case QQ: epiloguef_role<G, QQ>(a, tmem_base, T, quad, lane, cid, ncl, e, QQ, leader, acc_full, acc_empty, w_free, ticket); break;
       switch (q) {
         BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3)
         BSRNN_EPIF_CASE(4) BSRNN_EPIF_CASE(5) BSRNN_EPIF_CASE(6) BSRNN_EPIF_CASE(7)
       }
 #undef BSRNN_EPIF_CASE
     } else {
-      epiloguef_role<G, 0>(a, tmem_base, T, quad, lane, cid, ncl, e, (int)q, acc_full, acc_empty, w_free, ticket);
+      epiloguef_role<G, 0>(a, tmem_base, T, quad, lane, cid, ncl, e, (int)q, leader, acc_full, acc_empty, w_free, ticket);
     }
   }
   tc_fence_before();
@@ -541,7 +574,7 @@ static cudaError_t launch_fused(const FusedArgs& a, int ncl, cudaStream_t st, in
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = G::CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   if (occupancy) return cudaOccupancyMaxActiveClusters(occupancy, lstm_fused_kernel<G>, &cfg);
   return cudaLaunchKernelEx(&cfg, lstm_fused_kernel<G>, a);
@@ -554,7 +587,7 @@ static int fused_max_groups() {
   int n = 0;
   FusedArgs dummy{};
   if (launch_fused<G>(dummy, 0, nullptr, &n) != cudaSuccess) { cudaGetLastError(); return -1; }
-  cached = n / G::PPG;
+  cached = (n * Der<G>::NP) / G::PPG;
   if (cached > U_MAX_GROUPS) cached = U_MAX_GROUPS;
   return cached;
 }
