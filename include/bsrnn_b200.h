@@ -208,10 +208,13 @@ int bsrnn_blstm_fused_sync_bytes(void);
  *     [reference bsrnn_flowse.py:226-238 at the conf/models/BSRNN_flowse.yaml width]: groups of 24 CTA pairs (32 hidden
  *     units = 128 gate columns per pair), replacing the input-projection GEMM + one bsrnn_blstm_step_tc launch per time
  *     step.  xhat: fp16 [steps*seq_tiles][50][128][8] (bsrnn_norm_cast_kb8_ones with kcores = 50, column 384 = 1);
- *     w_fused: fp16 [2][24][2][146][64][8]; zero_tile: 96*128*8 zeros; y_f / y_b: fp16 [steps*seq_tiles][96][128][8]
- *     per direction (the layout bsrnn_blstm_step_tc writes).  sync_ws as bsrnn_blstm_fused_tc. */
-int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b, int R,
-                            int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+ *     w_fused: fp16 [2][24][2][146][64][8]; zero_tile: 96*128*8 zeros; the (step, tile) block [96][128][8] of
+ *     direction d lives at y_d + (step*seq_tiles + tile) * y_stride halves: two buffers as bsrnn_blstm_step_tc writes
+ *     them (y_stride = 96*1024) or one interleaved [..][dir][96][128][8] buffer (y_b = y_f + 96*1024, y_stride =
+ *     2*96*1024), which is the K = 1536 operand of ONE Linear(2H -> N) GEMM.  sync_ws as bsrnn_blstm_fused_tc. */
+int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b,
+                            long y_stride, int R, int steps, int seq_tiles, int max_groups, int slots, void* sync_ws,
+                            void* stream);
 int bsrnn_blstm_fused768_max_groups(void);
 
 /* Debug / A-B timing: selects the recurrence schedule (4, 5, 6: 8-CTA clusters; 7: CTA pairs); any other value

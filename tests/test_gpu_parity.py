@@ -331,7 +331,7 @@ def test_blstm_fused768_vs_torch(Rr, steps, slots):
            steps * tiles, tiles, Rr, 1 << 40, 0, steps, 1, Rr * steps, 1, p["one_col"], st)
     for _ in range(2):
         L.call("bsrnn_blstm_fused768_tc", xhat.data_ptr(), p["wfused"].data_ptr(), ws.zero.data_ptr(), ws.y[0].data_ptr(),
-               ws.y[1].data_ptr(), Rr, steps, tiles, 0, slots, ws.sync.data_ptr(), st)
+               ws.y[1].data_ptr(), (H // 8) * 1024, Rr, steps, tiles, 0, slots, ws.sync.data_ptr(), st)
     outs = []
     for d in (0, 1):
         yd = ws.y[d].view(steps, tiles, H // 8, 128, 8).permute(0, 1, 3, 2, 4).reshape(steps, tiles * 128, H)[:, :Rr]

@@ -32,7 +32,7 @@ st = L.stream_ptr()
 
 def run():
     L.call("bsrnn_blstm_fused768_tc", xhat.data_ptr(), p["wfused"].data_ptr(), zero.data_ptr(), y[0].data_ptr(), y[1].data_ptr(),
-           a.R, a.steps, tiles, a.maxgroups, a.slots, ws.sync.data_ptr(), st)
+           (H // 8) * 1024, a.R, a.steps, tiles, a.maxgroups, a.slots, ws.sync.data_ptr(), st)
 
 
 tag = f"FUSED768 slots={a.slots} maxgroups={a.maxgroups}"

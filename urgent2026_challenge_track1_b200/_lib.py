@@ -48,8 +48,8 @@ PROTOTYPES = {
     "bsrnn_blstm_recurrence_tc_flag": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_void_p],
     "bsrnn_blstm_fused_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    "bsrnn_blstm_fused768_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                c_void_p],
+    "bsrnn_blstm_fused768_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p, c_void_p],
     "bsrnn_blstm_fused768_max_groups": [],
     "bsrnn_blstm_fused_max_groups": [],
     "bsrnn_blstm_fused_sync_bytes": [],

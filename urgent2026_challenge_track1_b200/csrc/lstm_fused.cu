@@ -654,12 +654,16 @@ extern "C" int bsrnn_blstm_fused_max_groups(void) { return fused_max_groups<Geo3
 extern "C" int bsrnn_blstm_fused_sync_bytes(void) { return (int)(U_SYNC_WORDS * sizeof(unsigned)); }
 
 // Fused BLSTM layer, H = 768 / N = 384 (BSRNN_flowse): xhat [steps*seq_tiles][50][128][8] (column 384 = 1), w_fused
-// [2][24][2][146][64][8], zero_tile 96*128*8 zeros, y_f / y_b: [steps*seq_tiles][96][128][8] per direction.
-extern "C" int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b, int R,
-                                       int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+// [2][24][2][146][64][8], zero_tile 96*128*8 zeros.  The (step, tile) block of direction d is y_d + (step*seq_tiles +
+// tile) * y_stride halves, [96][128][8] each: two separate buffers (y_stride = 96*1024) or one interleaved buffer
+// [steps*seq_tiles][dir][96][128][8] (y_b = y_f + 96*1024, y_stride = 2*96*1024 = the Linear GEMM's K = 1536 operand).
+extern "C" int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b,
+                                       long y_stride, int R, int steps, int seq_tiles, int max_groups, int slots, void* sync_ws,
+                                       void* stream) {
   BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y_f && y_b && sync_ws, "blstm_fused768_tc: null pointer");
   BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused768_tc: bad dims");
-  return run_fused<Geo768>("blstm_fused768_tc", xhat, w_fused, zero_tile, y_f, y_b, (long)Geo768::HKC * 128 * 8, R, steps,
-                           seq_tiles, max_groups, slots, sync_ws, stream);
+  BSRNN_CHECK_ARG(y_stride >= (long)Geo768::HKC * 128 * 8 && y_stride % 8 == 0, "blstm_fused768_tc: bad y_stride");
+  return run_fused<Geo768>("blstm_fused768_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles, max_groups,
+                           slots, sync_ws, stream);
 }
 extern "C" int bsrnn_blstm_fused768_max_groups(void) { return fused_max_groups<Geo768>(); }

@@ -156,6 +156,8 @@ def pack_dual_path_steps(mod):
             p.update(gamma=norm.weight.float().contiguous(), beta=norm.bias.float().contiguous(), eps=float(norm.eps),
                      fcw=[to_kb8(w[:, :H], bn, H // 8), to_kb8(w[:, H:], bn, H // 8)], fcb=bias,
                      fcb0=torch.zeros_like(bias), fc_bn=bn, fc_nt=nt)
+            if "wfused" in p:                # fused layer kernel: y is one [dir][96] operand, Linear(2H -> N) is ONE GEMM
+                p["fc1"] = pack_linear_tc(fc)
             e[axis] = p
         layers.append(e)
     return layers
@@ -178,6 +180,8 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
     """In-place 2*num_layer residual blocks on skip (B,T,K,N) f32 with fp16 tensor-core GEMMs and the step-wise BLSTM.
     Same call pattern as runtime.dual_path_f32 (t_emb: list of (B,N) per layer, added after the time-axis GroupNorm)."""
     from .runtime import _layer_norm_tables, region
+    if FLOWSE_FUSED and all("wfused" in lay[ax] for lay in layers for ax in ("time", "freq")):
+        return dual_path_tc_fused768(skip, layers, t_emb)
     B, T, K, N = skip.shape
     dev = skip.device
     st = L.stream_ptr()
@@ -187,7 +191,7 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
     ws = _WS.get(key)
     if ws is None:
         _WS.clear()
-        kc_in = max(layers[0]["time"]["kc_in"], layers[0]["time"].get("kc_fused", 0))
+        kc_in = layers[0]["time"]["kc_in"]
         ntile = max(T * tiles_t, K * tiles_f)
         ws = _WS[key] = dict(xhat=torch.empty(ntile * kc_in * 1024, dtype=torch.float16, device=dev),
                              time=StepsWorkspace(T, tiles_t, H, dev), freq=StepsWorkspace(K, tiles_f, H, dev))
@@ -199,29 +203,78 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
                 R_, steps, tiles, addr = B * K, T, tiles_t, (K, T * K, 1, K)
             else:
                 R_, steps, tiles, addr = B * T, K, tiles_f, (1, K, 0, 1)
-            fused = FLOWSE_FUSED and "wfused" in w
             with region("norm"):
                 scale, shift = _layer_norm_tables(skip, w["gamma"], w["beta"], extra, w["eps"])
-                if fused:                    # 50 k-cores: column 384 = 1 carries the bias through the fused contraction
-                    L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                           ws["xhat"].data_ptr(), N, 0, N, w["kc_fused"], steps * tiles, tiles, R_, *addr, T * K, 1,
-                           w["one_col"], st)
-                else:
-                    L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws["xhat"].data_ptr(),
-                           N, 0, N, w["kc_in"], steps * tiles, tiles, R_, *addr, T * K, 1, st)
+                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), ws["xhat"].data_ptr(),
+                       N, 0, N, w["kc_in"], steps * tiles, tiles, R_, *addr, T * K, 1, st)
             with region(f"lstm_{axis}"):
-                if fused:
-                    # one persistent kernel per BLSTM layer: input projection + all time steps, both directions
-                    sw = ws[axis]
-                    L.call("bsrnn_blstm_fused768_tc", ws["xhat"].data_ptr(), w["wfused"].data_ptr(), sw.zero.data_ptr(),
-                           sw.y[0].data_ptr(), sw.y[1].data_ptr(), R_, steps, tiles, 0, _FUSED_SLOTS[axis],
-                           sw.sync.data_ptr(), st)
-                    y = sw.y
-                else:
-                    y = blstm_steps_tc(ws["xhat"], w, steps, tiles, ws[axis])
+                y = blstm_steps_tc(ws["xhat"], w, steps, tiles, ws[axis])
             with region("fc"):
                 for half, bias in ((0, w["fcb"]), (1, w["fcb0"])):       # skip += y_fwd W_f^T + b, then += y_bwd W_b^T
                     L.call("bsrnn_gemm_tc", y[half].data_ptr(), w["fcw"][half].data_ptr(), bias.data_ptr(), skip.data_ptr(),
                            None, steps * tiles, w["fc_nt"], H // 8, w["fc_bn"], L.TC_RESID_F32, N, N, 0, T * K,
                            tiles, R_, *addr, st)
+    return skip
+
+
+class Fused768Workspace:
+    """Buffers of the fused FlowSE dual path for one (B, T, K) shape."""
+
+    def __init__(self, B, T, K, N, H, kc, dev):
+        from .runtime import _f64
+        tiles_t, tiles_f = (B * K + 127) // 128, (B * T + 127) // 128
+        ntile = max(T * tiles_t, K * tiles_f)
+        self.xhat = torch.empty(ntile * kc * 1024, dtype=torch.float16, device=dev)
+        self.y = torch.empty(ntile * 2 * (H // 8) * 1024, dtype=torch.float16, device=dev)     # [step][tile][dir][96][128][8]
+        self.zero = torch.zeros((H // 8) * 1024, dtype=torch.float16, device=dev)
+        self.sync = torch.zeros(L.lib().bsrnn_blstm_fused_sync_bytes() // 4, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        self.scale = torch.empty(B, N, dtype=torch.float32, device=dev)
+        self.shift = torch.empty(B, N, dtype=torch.float32, device=dev)
+        self.counts = _f64([float(T) * K * N], dev)
+
+
+def dual_path_tc_fused768(skip, layers, t_emb=None):
+    """The 2*num_layer (GN, BLSTM, Linear) residual blocks of BSRNN_flowse (N = 384, H = 768) with ONE persistent kernel per
+    BLSTM layer (bsrnn_blstm_fused768_tc: input projection + every time step of both directions), ONE Linear GEMM whose
+    epilogue adds the residual and accumulates the next GroupNorm's statistics, and one normalise-and-cast pass: 3 launches
+    per block instead of steps + 4."""
+    from .runtime import region, keepalive
+    B, T, K, N = skip.shape
+    dev = skip.device
+    st = L.stream_ptr()
+    H = layers[0]["time"]["H"]
+    tiles_t, tiles_f = (B * K + 127) // 128, (B * T + 127) // 128
+    key = ("fused", B, T, K, N, H, str(dev))
+    ws = _WS.get(key)
+    if ws is None:
+        _WS.clear()
+        ws = _WS[key] = Fused768Workspace(B, T, K, N, H, layers[0]["time"]["kc_fused"], dev)
+    keepalive(ws)
+    y_tile = (H // 8) * 1024
+    L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
+    for i, lay in enumerate(layers):
+        for axis in ("time", "freq"):
+            w = lay[axis]
+            extra = t_emb[i] if (t_emb is not None and axis == "time") else None      # bsrnn_flowse.py:293-294
+            if axis == "time":
+                R_, steps, tiles, addr = B * K, T, tiles_t, (K, T * K, 1, K)
+            else:
+                R_, steps, tiles, addr = B * T, K, tiles_f, (1, K, 0, 1)
+            with region("norm"):
+                L.call("bsrnn_gn_finalize", ws.stats.data_ptr(), w["gamma"].data_ptr(), w["beta"].data_ptr(), L.ptr(extra),
+                       ws.scale.data_ptr(), ws.shift.data_ptr(), B, N, ws.counts.data_ptr(), w["eps"], 1, st)
+                # 50 k-cores: column 384 = 1 carries the bias through the fused contraction
+                L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), ws.scale.data_ptr(), ws.shift.data_ptr(),
+                       ws.xhat.data_ptr(), N, 0, N, w["kc_fused"], steps * tiles, tiles, R_, *addr, T * K, 1, w["one_col"], st)
+            with region(f"lstm_{axis}"):
+                L.call("bsrnn_blstm_fused768_tc", ws.xhat.data_ptr(), w["wfused"].data_ptr(), ws.zero.data_ptr(),
+                       ws.y.data_ptr(), ws.y.data_ptr() + 2 * y_tile, 2 * y_tile, R_, steps, tiles, 0, _FUSED_SLOTS[axis],
+                       ws.sync.data_ptr(), st)
+            with region("fc"):
+                ws.stats.zero_()
+                fc = w["fc1"]
+                L.call("bsrnn_gemm_tc", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
+                       ws.stats.data_ptr(), steps * tiles, fc["nt"], 2 * (H // 8), fc["bn"], L.TC_RESID_F32, N, N, 0, T * K,
+                       tiles, R_, *addr, st)
     return skip
