@@ -139,6 +139,8 @@ int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y
  *     3: GLU on (value,gate)-interleaved columns -> f32 out[token*ldo + col/2], col/2 < n_valid
  *     4: fp16 KB8 tiles out[m_tile][out_kcores][128][8], core = global column / 8 (LSTM input projection in the
  *        layout the recurrence kernel reads with coalesced 16-byte loads)
+ *     7: tanh -> f32 rows out[token*ldo + col], col < n_valid             (GradDecoder Conv1d(N->16 s)+Tanh,
+ *        bsrnn_flowse.py:118-134: the channel-last image of the 5x5 conv)
  * bsrnn_blstm_recurrence_tc: persistent cluster kernel, H = 392 only (csrc/lstm_tc.cu).  Sequences are grouped in
  *     tiles of 128 (seq = j*128 + r, valid iff seq < R); all operands are (step, seq_tile)-major:
  *       gates_x [step][seq_tile][dir][q][26][128][8] fp16 — epilogue 4 of bsrnn_gemm_tc over A tiles built with the

@@ -75,6 +75,7 @@ class BSRNN(nn.Module):
         self._bsx = R.PackedCache(self.band_split_x, R.pack_band_split)
         self._bsy = R.PackedCache(self.band_split_y, R.pack_band_split)
         self._gd = R.PackedCache(self.grad_decoder, R.pack_grad_decoder)
+        self._gd_tc = R.PackedCache(self.grad_decoder, TS.pack_grad_decoder_tc)
 
     # ------------------------------------------------------------------------------------------------ (B,T,F,2) core
     def embed_y(self, y_btf):
@@ -146,6 +147,8 @@ class BSRNN(nn.Module):
             TS.dual_path_tc_steps(skip, self._dual_steps.get(), t_emb=t_emb)
         else:
             R.dual_path_f32(skip, self._dual.get(), t_emb=t_emb)
+        if self.precision in ("fp16", "bf16") and N % 16 == 0:
+            return TS.grad_decoder_tc(skip, plan, self._gd_tc.get(), self.grad_decoder.sub_channel)
         return R.grad_decoder_f32(skip, plan, self._gd.get(), self.grad_decoder.sub_channel)
 
     # ------------------------------------------------------------------------------------------------ reference API

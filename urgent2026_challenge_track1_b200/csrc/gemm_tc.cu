@@ -94,7 +94,7 @@ struct GemmTcArgs {
 };
 
 enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4, EPI_LSTM_STEP = 5,
-       EPI_LSTM_BWD = 6 };
+       EPI_LSTM_BWD = 6, EPI_TANH_F32 = 7 };
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -365,6 +365,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
       uint4 pk = make_uint4(pack_h2(t[0], t[1]), pack_h2(t[2], t[3]), pack_h2(t[4], t[5]), pack_h2(t[6], t[7]));
       *reinterpret_cast<uint4*>(o + (((long)m * a.out_kcores + kc) * 128 + r) * 8) = pk;
     }
+  } else if (EPI == EPI_TANH_F32) {
+    // out[token, gc0 + c] = tanh(v[c]) as f32 rows (GradDecoder Conv1d + Tanh [reference bsrnn_flowse.py:118-134]: the
+    // channel-last image the 5x5 conv kernel reads); n_valid % 4 == 0 is checked by the launcher
+    if (!row_ok) return;
+    float* o = reinterpret_cast<float*>(a.out) + token * a.ldo + gc0;
+#pragma unroll
+    for (int i = 0; i < NC; i += 4)
+      if (gc0 + i + 3 < a.n_valid)
+        *reinterpret_cast<float4*>(o + i) = make_float4(fast_tanh(v[i]), fast_tanh(v[i + 1]), fast_tanh(v[i + 2]), fast_tanh(v[i + 3]));
   } else if (EPI == EPI_GLU_F32) {
     if (!row_ok) return;
     // packed weight rows alternate (value, gate): output column = global column / 2
@@ -876,8 +885,8 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && kcores > 0 && kcores % 2 == 0, "gemm_tc: bad tile counts (kcores=%d)", kcores);
   BSRNN_CHECK_ARG(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc: BN=%d must be a multiple of 16 in [16,256]", BN);
   BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && tokens_per_sample > 0, "gemm_tc: bad row map");
-  BSRNN_CHECK_ARG(epilogue != EPI_RESID_F32 || (n_valid % 4 == 0 && ldo % 4 == 0),
-                  "gemm_tc: the residual epilogue needs n_valid and ldo to be multiples of 4 (got %d, %ld)", n_valid, ldo);
+  BSRNN_CHECK_ARG((epilogue != EPI_RESID_F32 && epilogue != EPI_TANH_F32) || (n_valid % 4 == 0 && ldo % 4 == 0),
+                  "gemm_tc: the f32-row epilogues need n_valid and ldo to be multiples of 4 (got %d, %ld)", n_valid, ldo);
   GemmTcArgs a{};
   a.A = reinterpret_cast<const __half*>(A);
   a.W = reinterpret_cast<const __half*>(W);
@@ -891,6 +900,7 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
     case EPI_TANH_KB8: return launch_tc<EPI_TANH_KB8>(a, st);
     case EPI_GLU_F32: return launch_tc<EPI_GLU_F32>(a, st);
     case EPI_F16_KB8: return launch_tc<EPI_F16_KB8>(a, st);
+    case EPI_TANH_F32: return launch_tc<EPI_TANH_F32>(a, st);
   }
   set_error("gemm_tc: unknown epilogue %d", epilogue);
   return 1;

@@ -119,17 +119,20 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
 // converts from the f32 shared-memory tile: thread = (k-core, row) reads 8 floats, applies the affine and stores one
 // 16-byte KB8 core entry (a warp = 512 contiguous bytes).  The register-staged kernel above held at most 8 loads per
 // thread and measured 0.885 ms = 2.9 TB/s at BASELINE config 2 whatever that count (profiles/r01/call26, call42).
-// Row stride = C floats: for C % 8 == 4 (N = 196) consecutive rows start 4 banks apart, so the 8 rows of one
-// 16-byte-access phase cover all 32 banks.
-__global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs a) {
+// Row stride LD floats with LD % 8 == 4 (C itself for N = 196, C + 4 for N = 384 / 768): consecutive rows start 4 banks
+// apart, so the 8 rows of one 16-byte-access phase cover all 32 banks.  ROWS = 128 (one block per tile) or 64 (two blocks
+// per tile, each owning half of the rows of every k-core) so that the f32 staging tile fits twice per SM at any width.
+template <int ROWS>
+__global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs a, int ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);                    // [128][C]
-  PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)128 * a.C * 4);
-  const int m = blockIdx.x;
+  float* tile = reinterpret_cast<float*>(smem_raw);                    // [ROWS][ld]
+  PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)ROWS * ld * 4);
+  constexpr int PARTS = 128 / ROWS;
+  const int m = blockIdx.x / PARTS, r0 = (blockIdx.x % PARTS) * ROWS;
   const int step = m / a.tiles_per_step, j = m - step * a.tiles_per_step;
-  if (threadIdx.x < 128) {
+  if (threadIdx.x < ROWS) {
     const int r = threadIdx.x;
-    const long seq = (long)j * 128 + r;
+    const long seq = (long)j * 128 + r0 + r;
     PackRow pr{-1, 0};
     if (seq < a.R) {
       pr.tok = (seq / a.seq_inner) * a.seq_outer + (seq % a.seq_inner) * a.seq_inner_stride + (long)step * a.step_stride;
@@ -139,22 +142,22 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs
   }
   __syncthreads();
   const int q4 = a.C >> 2;                                             // 16-byte pieces per row
-  const int items = 128 * q4;
+  const int items = ROWS * q4;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
   for (int idx = threadIdx.x; idx < items; idx += 256) {
     const int r = idx / q4, c4 = idx - r * q4;
     const long tok = rows[r].tok;
     if (tok >= 0) {
       const float* src = a.x + tok * a.ldx + a.col0 + 4 * c4;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (uint32_t)(r * a.C + 4 * c4) * 4), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (uint32_t)(r * ld + 4 * c4) * 4), "l"(src) : "memory");
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   __half* dst = a.out + (size_t)m * a.kcores * 128 * 8;
-  for (int i = threadIdx.x; i < a.kcores * 128; i += 256) {
-    const int kc = i >> 7, r = i & 127;
+  for (int i = threadIdx.x; i < a.kcores * ROWS; i += 256) {
+    const int kc = i / ROWS, r = i % ROWS;
     const PackRow pr = rows[r];
     const int c0 = kc * 8;
     float v[8];
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs
       const int c = c0 + 4 * h;
       float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pr.tok >= 0 && c < a.C) {                                    // C % 4 == 0: a 4-group is all valid or all padding
-        x4 = *reinterpret_cast<const float4*>(tile + r * a.C + c);
+        x4 = *reinterpret_cast<const float4*>(tile + r * ld + c);
         if (a.scale) {
           const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + pr.grp * a.C + c));
           const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + pr.grp * a.C + c));
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs
     }
     const __half2 p0 = __floats2half2_rn(v[0], v[1]), p1 = __floats2half2_rn(v[2], v[3]);
     const __half2 p2 = __floats2half2_rn(v[4], v[5]), p3 = __floats2half2_rn(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) =
+    *reinterpret_cast<uint4*>(dst + ((size_t)kc * 128 + r0 + r) * 8) =
         make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
                    *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
   }
@@ -203,10 +206,20 @@ extern "C" int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, cons
   // asynchronous kernel: vectorisable shapes whose f32 tile fits twice per SM and whose row stride is bank-friendly
   static int force_old = -1;              // BSRNN_PACK_SYNC=1: the register-staged kernel (A/B timing)
   if (force_old < 0) { const char* e = getenv("BSRNN_PACK_SYNC"); force_old = (e && e[0] == '1') ? 1 : 0; }
-  const size_t smem_async = (size_t)128 * C * 4 + 128 * sizeof(PackRow);
-  if (vec_ok && !force_old && C % 8 == 4 && smem_async <= 110 * 1024 && (one_col < 0 || one_col % 4 == 0)) {
-    BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_async));
-    norm_cast_kb8_async_kernel<<<m_tiles, 256, smem_async, (cudaStream_t)stream>>>(a);
+  const int ld = (C % 8 == 4) ? C : C + 4;              // bank-friendly row stride of the staging tile
+  const size_t smem128 = (size_t)128 * ld * 4 + 128 * sizeof(PackRow), smem64 = (size_t)64 * ld * 4 + 64 * sizeof(PackRow);
+  const size_t smem32 = (size_t)32 * ld * 4 + 32 * sizeof(PackRow);
+  if (vec_ok && !force_old && C % 4 == 0 && smem32 <= 110 * 1024 && (one_col < 0 || one_col % 4 == 0)) {
+    if (smem128 <= 110 * 1024) {
+      BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
+      norm_cast_kb8_async_kernel<128><<<m_tiles, 256, smem128, (cudaStream_t)stream>>>(a, ld);
+    } else if (smem64 <= 110 * 1024) {     // wide rows (N = 384: 196 KB per tile): half tiles, still two blocks per SM
+      BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
+      norm_cast_kb8_async_kernel<64><<<2 * m_tiles, 256, smem64, (cudaStream_t)stream>>>(a, ld);
+    } else {                               // 2N = 768 (condition_fc operand): quarter tiles
+      BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+      norm_cast_kb8_async_kernel<32><<<4 * m_tiles, 256, smem32, (cudaStream_t)stream>>>(a, ld);
+    }
     BSRNN_LAUNCH_OK();
     return 0;
   }

@@ -278,3 +278,59 @@ def dual_path_tc_fused768(skip, layers, t_emb=None):
                        ws.stats.data_ptr(), steps * tiles, fc["nt"], 2 * (H // 8), fc["bn"], L.TC_RESID_F32, N, N, 0, T * K,
                        tiles, R_, *addr, st)
     return skip
+
+
+# ------------------------------------------------------------------------------------------------ GradDecoder (FlowSE)
+def pack_grad_decoder_tc(gd):
+    """GradDecoder [reference bsrnn_flowse.py:103-168] for the tensor-core path: per band the Conv1d(N -> 16 s) as KB8
+    weight tiles with rows permuted from c = sc*s + f to c' = f*16 + sc (the GEMM then writes the channel-last
+    (B,T,F',16) image the 5x5 conv kernel reads), plus what runtime.pack_grad_decoder keeps (norm affine, conv weights)."""
+    from .runtime import pack_grad_decoder
+    base = pack_grad_decoder(gd)
+    for name in ("mlp_mask", "mlp_residual"):
+        p = base[name]
+        N = p["w1"][0].shape[1]
+        kc = (N + 15) // 16 * 2
+        w, b, bn, nt = [], [], [], []
+        for k, wk in enumerate(p["w1"]):                    # (16 s, N), rows already in c' order
+            n16 = (wk.shape[0] + 15) // 16 * 16
+            bk = next(x for x in (256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16) if n16 % x == 0)
+            w.append(to_kb8(wk, bk, kc))
+            bb = torch.zeros(n16, device=wk.device); bb[: wk.shape[0]] = p["b1"][k]
+            b.append(bb); bn.append(bk); nt.append(n16 // bk)
+        p.update(w1_tc=w, b1_tc=b, bn=bn, nt=nt, kc=kc)
+    return base
+
+
+def grad_decoder_tc(skip, plan, gd_pack, sub_channel=16):
+    """skip (B,T,K',N) -> mask, resid (B,T,F,2): the per-band Conv1d + Tanh as tcgen05 GEMMs (fp16 operands, f32 image),
+    then the f32 5x5 conv + GLU kernel.  Mirrors runtime.grad_decoder_f32 (35.5 ms of CUDA-core GEMM per evaluation at
+    BASELINE config 4, profiles/r02 call31)."""
+    from .runtime import _decoder_norm_tables, region
+    B, T, K, N = skip.shape
+    F = plan.F
+    Fp = sum(plan.subbands[:K])
+    dev = skip.device
+    st = L.stream_ptr()
+    tabs = _decoder_norm_tables(skip, gd_pack)
+    tiles = (B * T + 127) // 128
+    img = torch.empty(2, B, T, Fp, sub_channel, dtype=torch.float32, device=dev)
+    outs = []
+    with region("graddec"):
+        for gi, name in enumerate(("mlp_mask", "mlp_residual")):
+            p = gd_pack[name]
+            scale, shift = tabs[name][0], tabs[name][1]
+            xhat = torch.empty(K * tiles * p["kc"] * 1024, dtype=torch.float16, device=dev)
+            # rows of tile (k, j) are the (b,t) tokens of band k; GroupNorm(1,N) per (sample, band) folded into the cast
+            L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
+                   p["kc"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, st)
+            base = img.data_ptr() + 4 * gi * B * T * Fp * sub_channel
+            for k in range(K):
+                L.call("bsrnn_gemm_tc", xhat.data_ptr() + 2 * k * tiles * p["kc"] * 1024, p["w1_tc"][k].data_ptr(),
+                       p["b1_tc"][k].data_ptr(), base + 4 * plan.bin0[k] * sub_channel, None, tiles, p["nt"][k], p["kc"],
+                       p["bn"][k], L.TC_TANH_F32, Fp * sub_channel, sub_channel * plan.subbands[k], 0, B * T, tiles, B * T,
+                       1 << 60, 0, 1, 0, st)
+            o = torch.empty(B, T, F, 2, dtype=torch.float32, device=dev)
+            L.call("bsrnn_conv5x5_glu", img[gi].data_ptr(), p["cw"].data_ptr(), p["cb"].data_ptr(), o.data_ptr(), B, T, Fp, F, st)
+            outs.append(o)
+    return outs[0], outs[1]
