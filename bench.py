@@ -386,7 +386,8 @@ def run_config2(ctx, args):
     for rnd in ("r02", "r01"):
         tp = os.path.join(ROOT, "profiles", rnd, "traffic.json")
         if os.path.exists(tp) and B == 64 and args.seconds == 10.0:
-            traffic = json.load(open(tp)).get("blstm_recurrence", {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("blstm_fused" if fused_axes else "blstm_recurrence", tj.get("blstm_recurrence", {})).get("dram_bytes_per_launch")
             break
     # memory-bound kernel families: algorithmic bytes per call at this workload / measured time
     tok = B * T * K

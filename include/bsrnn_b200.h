@@ -206,6 +206,13 @@ int bsrnn_blstm_fused_tc(const void* xhat, const void* w_fused, const void* zero
                          int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
 int bsrnn_blstm_fused_max_groups(void);
 int bsrnn_blstm_fused_sync_bytes(void);
+/* bsrnn_blstm_fused7_tc: bsrnn_blstm_fused_tc on groups of 7 CTA pairs x 56 hidden units (224 gate columns, no padding):
+ *     10 co-resident groups (140 SMs) instead of 9, i.e. 5 per direction - the schedule for sequence-tile counts that 9
+ *     groups split badly (BASELINE config 2 time axis: 9 tile pairs per direction).  w_fused7: fp16
+ *     [2][7][2][76][112][8]; every other argument as bsrnn_blstm_fused_tc. */
+int bsrnn_blstm_fused7_tc(const void* xhat, const void* w_fused7, const void* zero_tile, void* y, int R, int steps,
+                          int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+int bsrnn_blstm_fused7_max_groups(void);
 /* bsrnn_blstm_fused768_tc: the same fused layer kernel for nn.LSTM(N=384, H=768, bidirectional) of BSRNN_flowse
  *     [reference bsrnn_flowse.py:226-238 at the conf/models/BSRNN_flowse.yaml width]: groups of 24 CTA pairs (32 hidden
  *     units = 128 gate columns per pair), replacing the input-projection GEMM + one bsrnn_blstm_step_tc launch per time

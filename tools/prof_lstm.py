@@ -15,6 +15,7 @@ ap.add_argument("--trace-cid", type=int, default=0); ap.add_argument("--flags", 
 ap.add_argument("--ver", type=int, default=0, help="recurrence schedule 4..9 (0 = BSRNN_LSTM_VER / default)")
 ap.add_argument("--flag", action="store_true", help="flag-group schedule (bsrnn_blstm_recurrence_tc_flag)")
 ap.add_argument("--fused", action="store_true", help="fused layer (bsrnn_blstm_fused_tc): x * W_ih inside the recurrence")
+ap.add_argument("--geo", type=int, default=8, help="fused kernel geometry: 8 pairs x 49 units or 7 pairs x 56 units")
 ap.add_argument("--v2", action="store_true"); ap.add_argument("--check", action="store_true"); ap.add_argument("--trace", action="store_true")
 a = ap.parse_args()
 B, T, K, axis = a.B, a.T, a.K, a.axis
@@ -63,7 +64,8 @@ sync = torch.zeros(max(L.lib().bsrnn_blstm_tc_sync_bytes(), L.lib().bsrnn_blstm_
 
 def run():
     if a.fused:
-        L.call("bsrnn_blstm_fused_tc", xhat.data_ptr(), p["wfused"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
+        L.call("bsrnn_blstm_fused7_tc" if a.geo == 7 else "bsrnn_blstm_fused_tc", xhat.data_ptr(),
+               p["wfused7" if a.geo == 7 else "wfused"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
                tiles, a.maxcl, a.slots, sync.data_ptr(), st)
         return
     if a.flag:
@@ -76,11 +78,11 @@ def run():
 
 if a.ver:
     L.lib().bsrnn_debug_set_lstm_schedule(a.ver)
-tag = f"{'FUSED' if a.fused else 'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
+tag = f"{('FUSED7' if a.geo == 7 else 'FUSED') if a.fused else 'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
 if (a.ver or int(os.environ.get('BSRNN_LSTM_VER', '8'))) == 7:
     print(f"[{tag}] co-resident 16-CTA clusters: {L.lib().bsrnn_blstm_tc_max_pair_clusters()}  (8-CTA: {L.lib().bsrnn_blstm_tc_max_clusters()})", flush=True)
 if a.fused:
-    print(f"[{tag}] co-resident fused groups (8 CTA pairs each): {L.lib().bsrnn_blstm_fused_max_groups()}", flush=True)
+    print(f"[{tag}] co-resident fused groups (8 CTA pairs each): {L.lib().bsrnn_blstm_fused7_max_groups() if a.geo == 7 else L.lib().bsrnn_blstm_fused_max_groups()}", flush=True)
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record()

@@ -55,6 +55,13 @@ struct Geo392 {
   static constexpr int EPI_WARPS = 12, ACC = 256, NBUF = 2, EPI_REGS = 152, NC = 17;
   static constexpr int CLS = 2;             // cluster = one CTA pair
 };
+// H = 392 on groups of 7 pairs x 56 units (N = 224, no padding columns): 10 groups = 140 SMs, so the 9 tile pairs per
+// direction of BASELINE config 2's time axis run 2-interleaved on 5 groups per direction instead of 3-interleaved on 3.
+struct Geo392x7 {
+  static constexpr int UPP = 56, BN = 224, PPG = 7, XKC = 26, HKC = 50, KS = 10, STAGES = 4;
+  static constexpr int EPI_WARPS = 16, ACC = 256, NBUF = 2, EPI_REGS = 104, NC = 14;
+  static constexpr int CLS = 2;
+};
 struct Geo768 {
   static constexpr int UPP = 32, BN = 128, PPG = 24, XKC = 50, HKC = 96, KS = 12, STAGES = 3;
   static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 8;
@@ -179,6 +186,46 @@ __device__ __forceinline__ void epif_item392(uint32_t t_col, bool last_third, ui
     if (st) ycore[2 * CORE + Q] = __float2half_rn(h48);
   }
 }
+// H = 392, 7 pairs: thread = (row r, quarter T of the pair's 56 units): 14 units at h columns 56q + 14T + j, i.e. position
+// p = 14T + j of the pair's 7 k-cores (core p/8, slot p%8): the store pattern depends on T only.
+template <int T>
+__device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, float (&c)[14], bool st) {
+  constexpr size_t CORE = 128 * 8;
+  float h[16];
+  uint32_t accA[16], accB[16];
+  tmem_ld_x16(t_col, accA);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 16, accB);
+  tmem_ld_pin16(accA);
+  epif_chunk<0>(accA, c, h);
+  tmem_ld_wait();
+  tmem_ld_x16(t_col + 32, accA);
+  tmem_ld_pin16(accB);
+  epif_chunk<1>(accB, c, h);
+  if (st) {
+    if (T == 0) store_full<0>(ycore, h);                                   // p 0..7   -> core 0
+    if (T == 1) store_partial<6, 8, 0>(ycore + CORE, h);                   // p 14,15  -> core 1 slots 6,7
+    if (T == 2) store_partial<4, 8, 0>(ycore + 3 * CORE, h);               // p 28..31 -> core 3 slots 4..7
+    if (T == 3) store_partial<2, 8, 0>(ycore + 5 * CORE, h);               // p 42..47 -> core 5 slots 2..7
+  }
+  uint32_t a8[8];
+  tmem_ld_wait();
+  tmem_ld_x8(t_col + 48, a8);
+  tmem_ld_pin16(accA);
+  epif_chunk<2>(accA, c, h);
+  tmem_ld_wait();
+  asm volatile("" : "+r"(a8[0]), "+r"(a8[1]), "+r"(a8[2]), "+r"(a8[3]), "+r"(a8[4]), "+r"(a8[5]), "+r"(a8[6]), "+r"(a8[7]));
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    gate_update(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
+                __uint_as_float(a8[4 * u + 3]), c[12 + u], h[12 + u]);
+  if (st) {
+    if (T == 0) store_partial<0, 6, 8>(ycore + CORE, h);                   // p 8..13  -> core 1 slots 0..5
+    if (T == 1) { store_full<2>(ycore + 2 * CORE, h); store_partial<0, 4, 10>(ycore + 3 * CORE, h); }   // p 16..23, 24..27
+    if (T == 2) { store_full<4>(ycore + 4 * CORE, h); store_partial<0, 2, 12>(ycore + 5 * CORE, h); }   // p 32..39, 40,41
+    if (T == 3) store_full<6>(ycore + 6 * CORE, h);                        // p 48..55 -> core 6
+  }
+}
 // H = 768: thread = (row r, quarter T of the pair's 32 units): 8 units = 32 accumulator columns = one 16-byte row of
 // k-core 4q + T of the y tile.
 __device__ __forceinline__ void epif_item768(uint32_t t_col, __half* ycore, float (&c)[8], bool st) {
@@ -200,16 +247,16 @@ template <class G, int Q>
 __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
                                                int ncl, int e, int q, uint32_t leader, uint64_t* acc_full, uint64_t* acc_empty,
                                                uint64_t* w_free, uint32_t ticket) {
-  constexpr bool G392 = G::UPP == 49;
+  constexpr bool G392 = G::UPP == 49, G7 = G::UPP == 56;        // G7: the template parameter Q carries the quarter T
   const int r = quad * 32 + lane;
   long long w_acc = 0, w_busy = 0, w_arr = 0;
   FP_DECL(T == 0 && quad == 0 && lane == 0);
   const bool last_third = T == 2;
-  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (G392 ? 64 : 32) * T;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (G392 ? 64 : G7 ? 56 : 32) * T;
   const uint32_t t_lane48 = tmem_base + ((uint32_t)(quad * 32) << 16) + 192;
   const int ngroups = 2 * a.gpd;
   // this thread's first k-core row inside a y tile
-  const size_t y_off = (size_t)(G392 ? 6 * Q + 2 * T : 4 * q + T) * (128 * 8) + (size_t)r * 8;
+  const size_t y_off = (size_t)(G392 ? 6 * Q + 2 * T : G7 ? 7 * q : 4 * q + T) * (128 * 8) + (size_t)r * 8;
   uint32_t it0 = 0, nfull = 0;
   float c0[G::NC], c1[G::NC], c2[G::NC];
   for (int g = cid; g < ngroups; g += ncl) {
@@ -236,6 +283,10 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
             if (k == 0) epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c0, valid);
             else if (k == 1) epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c1, valid);
             else epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c2, valid);
+          } else if constexpr (G7) {
+            if (k == 0) epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c0, valid);
+            else if (k == 1) epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c1, valid);
+            else epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c2, valid);
           } else {
             if (k == 0) epif_item768(t_lane + buf * G::ACC, ycore, c0, valid);
             else if (k == 1) epif_item768(t_lane + buf * G::ACC, ycore, c1, valid);
@@ -546,6 +597,11 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
         BSRNN_EPIF_CASE(4) BSRNN_EPIF_CASE(5) BSRNN_EPIF_CASE(6) BSRNN_EPIF_CASE(7)
       }
 #undef BSRNN_EPIF_CASE
+    } else if constexpr (G::UPP == 56) {
+#define BSRNN_EPIF_CASE(TT) \
+  case TT: epiloguef_role<G, TT>(a, tmem_base, TT, quad, lane, cid, ncl, e, (int)q, leader, acc_full, acc_empty, w_free, ticket); break;
+      switch (T) { BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3) }
+#undef BSRNN_EPIF_CASE
     } else {
       epiloguef_role<G, 0>(a, tmem_base, T, quad, lane, cid, ncl, e, (int)q, leader, acc_full, acc_empty, w_free, ticket);
     }
@@ -651,6 +707,16 @@ extern "C" int bsrnn_blstm_fused_tc(const void* xhat, const void* w_fused, const
                            steps, seq_tiles, max_groups, slots, sync_ws, stream);
 }
 extern "C" int bsrnn_blstm_fused_max_groups(void) { return fused_max_groups<Geo392>(); }
+// Same layer on groups of 7 pairs x 56 units (Geo392x7): w_fused7 [2][7][2][76][112][8]; x, zero_tile, y, sync_ws as above.
+extern "C" int bsrnn_blstm_fused7_tc(const void* xhat, const void* w_fused7, const void* zero_tile, void* y, int R, int steps,
+                                     int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  BSRNN_CHECK_ARG(xhat && w_fused7 && zero_tile && y && sync_ws, "blstm_fused7_tc: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused7_tc: bad dims");
+  const long y_tile = (long)Geo392x7::HKC * 128 * 8;
+  return run_fused<Geo392x7>("blstm_fused7_tc", xhat, w_fused7, zero_tile, y, reinterpret_cast<__half*>(y) + y_tile, 2 * y_tile,
+                             R, steps, seq_tiles, max_groups, slots, sync_ws, stream);
+}
+extern "C" int bsrnn_blstm_fused7_max_groups(void) { return fused_max_groups<Geo392x7>(); }
 extern "C" int bsrnn_blstm_fused_sync_bytes(void) { return (int)(U_SYNC_WORDS * sizeof(unsigned)); }
 
 // Fused BLSTM layer, H = 768 / N = 384 (BSRNN_flowse): xhat [steps*seq_tiles][50][128][8] (column 384 = 1), w_fused

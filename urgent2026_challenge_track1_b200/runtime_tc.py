@@ -29,6 +29,30 @@ for _kv in os.environ.get("BSRNN_LSTM_FLAG_SLOTS", "").split(","):
 # axes whose BLSTM runs as ONE fused kernel (input projection inside the recurrence, csrc/lstm_fused.cu):
 # BSRNN_LSTM_FUSED="time,freq" (default) | "freq" | "none" (separate input-projection GEMM + bsrnn_blstm_recurrence_tc*)
 FUSED_AXES = tuple(a for a in os.environ.get("BSRNN_LSTM_FUSED", "time,freq").split(",") if a in ("time", "freq"))
+# group geometry of the fused kernel: 8 pairs x 49 units (9 groups) or 7 pairs x 56 units (10 groups = 5 per direction).
+# BSRNN_LSTM_FUSED_GEO = 8 | 7 | auto (default)
+FUSED_GEO = os.environ.get("BSRNN_LSTM_FUSED_GEO", "auto")
+
+
+def _passes(ptiles, groups, slots):
+    """(passes, interleaved pairs) of the cheapest schedule: a step costs max(dependency chain ~ 2.3 items, slots items)."""
+    best = None
+    for s in range(1, min(slots, ptiles) + 1):
+        gpd = (ptiles + s - 1) // s
+        t = ((2 * gpd + groups - 1) // groups) * max(2.3, float(s))
+        if best is None or t < best - 1e-9:
+            best = t
+    return best
+
+
+def fused_geometry(tiles):
+    """7 when the 10-group geometry needs fewer item times for this tile count (an item costs 8 % more there: N = 224)."""
+    if FUSED_GEO in ("7", "8"):
+        return int(FUSED_GEO)
+    ptiles = (tiles + 1) // 2
+    return 7 if 1.08 * _passes(ptiles, 10, 3) < _passes(ptiles, 9, 3) - 1e-9 else 8
+
+
 _FUSED_SLOTS = {"time": 0, "freq": 0}
 for _kv in os.environ.get("BSRNN_LSTM_FUSED_SLOTS", "").split(","):
     if "=" in _kv:
@@ -102,7 +126,32 @@ def pack_lstm_tc(rnn):
         # bsrnn_blstm_fused_tc: [dir][pair q][half e][kc_in k-cores of W_ih (+ bias column) | 50 of W_hh][104 rows][8]
         wf = torch.cat([wih.view(2, CL, kc_in, LBN, 8), whh], 2)
         out["wfused"] = wf.view(2, CL, kc_in + LKC, 2, LBN // 2, 8).permute(0, 1, 3, 2, 4, 5).contiguous()
+        out["wfused7"] = pack_lstm_fused7(rnn, kc_in, one_col)
     return out
+
+
+def pack_lstm_fused7(rnn, kc_in, one_col):
+    """bsrnn_blstm_fused7_tc: groups of 7 pairs x 56 units -> [dir][pair q][half e][kc_in + 50 k-cores][112 rows][8];
+    packed gate row c = 4*u_local + gate of pair q is LSTM row gate*H + 56*q + u_local (i, f, o rows pre-halved)."""
+    H, N = rnn.weight_hh_l0.shape[1], rnn.weight_ih_l0.shape[1]
+    dev = rnn.weight_hh_l0.device
+    P, U = 7, 56
+    ul = torch.arange(U, device=dev)
+    gsc = torch.tensor(GATE_SCALE, device=dev).repeat(U)[:, None]
+    packs = []
+    for sfx in ("", "_reverse"):
+        wi = getattr(rnn, "weight_ih_l0" + sfx).float()
+        wh = getattr(rnn, "weight_hh_l0" + sfx).float()
+        b = (getattr(rnn, "bias_ih_l0" + sfx) + getattr(rnn, "bias_hh_l0" + sfx)).float()
+        for q in range(P):
+            rows = (torch.arange(4, device=dev)[None, :] * H + (U * q + ul)[:, None]).reshape(-1)        # 224 rows
+            w = torch.zeros(rows.numel(), (kc_in + LKC) * 8, device=dev)
+            w[:, :N] = wi[rows]
+            w[:, one_col] = b[rows]
+            w[:, kc_in * 8: kc_in * 8 + H] = wh[rows]
+            w = w * gsc
+            packs.append(w.view(2, rows.numel() // 2, kc_in + LKC, 8).permute(0, 2, 1, 3))              # [e][k-core][112][8]
+    return torch.stack(packs).view(2, P, 2, kc_in + LKC, 2 * U, 8).contiguous().to(torch.float16)
 
 
 def pack_fc_tc(fc, H):
@@ -202,8 +251,12 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
             if axis in FUSED_AXES and "wfused" in w:
                 # input projection inside the recurrence: gates_t = [x_t | h_{t-1}] [W_ih | W_hh]^T, no gates_x tensor
                 with region(f"lstm_{axis}"):
-                    L.call("bsrnn_blstm_fused_tc", ws.xhat.data_ptr(), w["wfused"].data_ptr(), ws.zero_tile.data_ptr(),
-                           ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis], ws.sync.data_ptr(), st)
+                    if fused_geometry(tiles) == 7:
+                        L.call("bsrnn_blstm_fused7_tc", ws.xhat.data_ptr(), w["wfused7"].data_ptr(), ws.zero_tile.data_ptr(),
+                               ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis], ws.sync.data_ptr(), st)
+                    else:
+                        L.call("bsrnn_blstm_fused_tc", ws.xhat.data_ptr(), w["wfused"].data_ptr(), ws.zero_tile.data_ptr(),
+                               ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis], ws.sync.data_ptr(), st)
             else:
                 with region("inproj"):
                     L.call("bsrnn_gemm_tc", ws.xhat.data_ptr(), w["wih"].data_ptr(),
