@@ -213,6 +213,13 @@ int bsrnn_blstm_fused_sync_bytes(void);
 int bsrnn_blstm_fused7_tc(const void* xhat, const void* w_fused7, const void* zero_tile, void* y, int R, int steps,
                           int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
 int bsrnn_blstm_fused7_max_groups(void);
+/* bsrnn_blstm_fused14_tc: the small-batch geometry: groups of 14 CTA pairs x 28 hidden units (112 gate columns), 5
+ *     co-resident groups.  With few sequence tiles the layer is bound by the per-step dependency chain; sharing a tile
+ *     among twice as many CTAs halves the epilogue and MMA time of an item (at twice the L2 traffic per item).
+ *     w_fused14: fp16 [2][14][2][76][56][8]; every other argument as bsrnn_blstm_fused_tc. */
+int bsrnn_blstm_fused14_tc(const void* xhat, const void* w_fused14, const void* zero_tile, void* y, int R, int steps,
+                           int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+int bsrnn_blstm_fused14_max_groups(void);
 /* bsrnn_blstm_fused768_tc: the same fused layer kernel for nn.LSTM(N=384, H=768, bidirectional) of BSRNN_flowse
  *     [reference bsrnn_flowse.py:226-238 at the conf/models/BSRNN_flowse.yaml width]: groups of 24 CTA pairs (32 hidden
  *     units = 128 gate columns per pair), replacing the input-projection GEMM + one bsrnn_blstm_step_tc launch per time

@@ -224,7 +224,7 @@ def test_flowse_tensorcore_steps_vs_golden(fs, graph):
         assert len(m.dnn._graphs) == 1
 
 
-@pytest.mark.parametrize("geo", [8, 7])
+@pytest.mark.parametrize("geo", [8, 7, 14])
 @pytest.mark.parametrize("axis,B,T,slots", [("time", 12, 40, 1), ("time", 10, 24, 2), ("freq", 3, 300, 3), ("freq", 5, 77, 0),
                                              ("time", 40, 30, 0), ("time", 2, 50, 0)])
 def test_blstm_fused_vs_torch(axis, B, T, slots, geo):
@@ -255,8 +255,8 @@ def test_blstm_fused_vs_torch(axis, B, T, slots, geo):
     zero_tile = torch.zeros(50 * 1024, dtype=torch.float16, device="cuda")
     sync = torch.zeros(L.lib().bsrnn_blstm_fused_sync_bytes() // 4, dtype=torch.int32, device="cuda")
     for _ in range(2):                                  # the second launch reuses y and the counters
-        L.call("bsrnn_blstm_fused7_tc" if geo == 7 else "bsrnn_blstm_fused_tc", xhat.data_ptr(),
-               p["wfused7" if geo == 7 else "wfused"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R_, steps,
+        L.call(f"bsrnn_blstm_fused{geo}_tc" if geo in (7, 14) else "bsrnn_blstm_fused_tc", xhat.data_ptr(),
+               tc.fused_weights(p, geo).data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R_, steps,
                tiles, 0, slots, sync.data_ptr(), st)
     yv = y.view(steps, tiles, 2, 50, 128, 8).permute(0, 1, 4, 2, 3, 5).reshape(steps, tiles * 128, 2, 400)[:, :R_, :, :H]
     yv = yv.reshape(steps, R_, 2 * H).float().cpu()

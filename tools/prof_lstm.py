@@ -64,8 +64,8 @@ sync = torch.zeros(max(L.lib().bsrnn_blstm_tc_sync_bytes(), L.lib().bsrnn_blstm_
 
 def run():
     if a.fused:
-        L.call("bsrnn_blstm_fused7_tc" if a.geo == 7 else "bsrnn_blstm_fused_tc", xhat.data_ptr(),
-               p["wfused7" if a.geo == 7 else "wfused"].data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
+        L.call(f"bsrnn_blstm_fused{a.geo}_tc" if a.geo in (7, 14) else "bsrnn_blstm_fused_tc", xhat.data_ptr(),
+               tc.fused_weights(p, a.geo).data_ptr(), zero_tile.data_ptr(), y.data_ptr(), R, steps,
                tiles, a.maxcl, a.slots, sync.data_ptr(), st)
         return
     if a.flag:
@@ -78,11 +78,11 @@ def run():
 
 if a.ver:
     L.lib().bsrnn_debug_set_lstm_schedule(a.ver)
-tag = f"{('FUSED7' if a.geo == 7 else 'FUSED') if a.fused else 'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
+tag = f"{(f'FUSED{a.geo}' if a.geo in (7, 14) else 'FUSED') if a.fused else 'FLAG' if a.flag else 'v' + str(a.ver or os.environ.get('BSRNN_LSTM_VER', '8'))} slots={a.slots} maxcl={a.maxcl}"
 if (a.ver or int(os.environ.get('BSRNN_LSTM_VER', '8'))) == 7:
     print(f"[{tag}] co-resident 16-CTA clusters: {L.lib().bsrnn_blstm_tc_max_pair_clusters()}  (8-CTA: {L.lib().bsrnn_blstm_tc_max_clusters()})", flush=True)
 if a.fused:
-    print(f"[{tag}] co-resident fused groups (8 CTA pairs each): {L.lib().bsrnn_blstm_fused7_max_groups() if a.geo == 7 else L.lib().bsrnn_blstm_fused_max_groups()}", flush=True)
+    print(f"[{tag}] co-resident fused groups (8 CTA pairs each): {getattr(L.lib(), f'bsrnn_blstm_fused{a.geo}_max_groups')() if a.geo in (7, 14) else L.lib().bsrnn_blstm_fused_max_groups()}", flush=True)
 for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record()

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "bsrnn_blstm_fused768_max_groups": [],
     "bsrnn_blstm_fused7_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "bsrnn_blstm_fused7_max_groups": [],
+    "bsrnn_blstm_fused14_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "bsrnn_blstm_fused14_max_groups": [],
     "bsrnn_blstm_fused_max_groups": [],
     "bsrnn_blstm_fused_sync_bytes": [],
     "bsrnn_blstm_tc_flag_max_groups": [],

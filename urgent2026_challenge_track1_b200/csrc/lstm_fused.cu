@@ -62,6 +62,15 @@ struct Geo392x7 {
   static constexpr int EPI_WARPS = 16, ACC = 256, NBUF = 2, EPI_REGS = 104, NC = 14;
   static constexpr int CLS = 2;
 };
+// H = 392 on groups of 14 pairs x 28 units (N = 112): the small-batch geometry.  With few sequence tiles the layer is bound
+// by the per-step dependency chain (epilogue -> publish -> h tile -> MMAs), and both the MUFU work and the MMA time of an
+// item halve when twice as many CTAs share a tile; every CTA still pulls the whole x / h tile, so L2 traffic per item
+// doubles - worthwhile only while few items are in flight (runtime_tc.fused_geometry).
+struct Geo392x14 {
+  static constexpr int UPP = 28, BN = 112, PPG = 14, XKC = 26, HKC = 50, KS = 10, STAGES = 7;
+  static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 7;
+  static constexpr int CLS = 2;
+};
 struct Geo768 {
   static constexpr int UPP = 32, BN = 128, PPG = 24, XKC = 50, HKC = 96, KS = 12, STAGES = 3;
   static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 8;
@@ -83,7 +92,7 @@ struct Der {
   static constexpr int THREADS = (4 + G::EPI_WARPS) * 32;
   static constexpr int NP = G::CLS / 2;                                 // pairs per cluster
   static constexpr int NBARS = 3 * G::STAGES + LNS + G::NBUF + 3;
-  static constexpr size_t SMEM = W_BYTES + G::STAGES * STAGE + NBARS * 8 + 16;
+  static constexpr size_t SMEM = W_BYTES + G::STAGES * STAGE + NBARS * 8 + 32;   // + TMEM address slot + ticket slot (16 B each)
   static_assert(G::HKC % G::KS == 0 && XLAST % 2 == 0 && G::KS % 2 == 0, "stages hold whole K = 16 MMAs");
   static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static_assert(W_BYTES % 64 == 0, "W half is fetched as 4 bulk copies");
@@ -226,6 +235,37 @@ __device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, fl
     if (T == 3) store_full<6>(ycore + 6 * CORE, h);                        // p 48..55 -> core 6
   }
 }
+// H = 392, 14 pairs: thread = (row r, quarter T of the pair's 28 units): 7 units at h columns 28q + 7T + j.  With
+// QP = q & 1 the pair's columns start 4*QP slots into k-core (28q - 4*QP)/8; position p = 4*QP + 7T + j -> core p/8, slot p%8.
+template <int QP, int T>
+__device__ __forceinline__ void epif_item392x14(uint32_t t_col, __half* ycore, float (&c)[7], bool st) {
+  constexpr size_t CORE = 128 * 8;
+  constexpr int P0 = 4 * QP + 7 * T;                 // first position of this thread's units
+  constexpr int C0 = P0 / 8, S0 = P0 % 8;            // first core / slot
+  constexpr int N0 = (8 - S0) < 7 ? (8 - S0) : 7;    // units that fall into the first core
+  float h[16];
+  uint32_t acc[16], a8[8], a4[4];
+  tmem_ld_x16(t_col, acc);
+  tmem_ld_x8(t_col + 16, a8);
+  tmem_ld_x4(t_col + 24, a4);
+  tmem_ld_wait();
+  tmem_ld_pin16(acc);
+  asm volatile("" : "+r"(a8[0]), "+r"(a8[1]), "+r"(a8[2]), "+r"(a8[3]), "+r"(a8[4]), "+r"(a8[5]), "+r"(a8[6]), "+r"(a8[7]));
+  asm volatile("" : "+r"(a4[0]), "+r"(a4[1]), "+r"(a4[2]), "+r"(a4[3]));
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    gate_update(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
+                __uint_as_float(acc[4 * u + 3]), c[u], h[u]);
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+    gate_update(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
+                __uint_as_float(a8[4 * u + 3]), c[4 + u], h[4 + u]);
+  gate_update(__uint_as_float(a4[0]), __uint_as_float(a4[1]), __uint_as_float(a4[2]), __uint_as_float(a4[3]), c[6], h[6]);
+  if (st) {
+    store_partial<S0, S0 + N0, 0>(ycore + C0 * CORE, h);
+    if constexpr (N0 < 7) store_partial<0, 7 - N0, N0>(ycore + (C0 + 1) * CORE, h);
+  }
+}
 // H = 768: thread = (row r, quarter T of the pair's 32 units): 8 units = 32 accumulator columns = one 16-byte row of
 // k-core 4q + T of the y tile.
 __device__ __forceinline__ void epif_item768(uint32_t t_col, __half* ycore, float (&c)[8], bool st) {
@@ -247,16 +287,17 @@ template <class G, int Q>
 __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem_base, int T, int quad, int lane, int cid,
                                                int ncl, int e, int q, uint32_t leader, uint64_t* acc_full, uint64_t* acc_empty,
                                                uint64_t* w_free, uint32_t ticket) {
-  constexpr bool G392 = G::UPP == 49, G7 = G::UPP == 56;        // G7: the template parameter Q carries the quarter T
+  // G7: the template parameter Q carries the quarter T; G14: Q = 4 * (q & 1) + T
+  constexpr bool G392 = G::UPP == 49, G7 = G::UPP == 56, G14 = G::UPP == 28;
   const int r = quad * 32 + lane;
   long long w_acc = 0, w_busy = 0, w_arr = 0;
   FP_DECL(T == 0 && quad == 0 && lane == 0);
   const bool last_third = T == 2;
-  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (G392 ? 64 : G7 ? 56 : 32) * T;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (G392 ? 64 : G7 ? 56 : G14 ? 28 : 32) * T;
   const uint32_t t_lane48 = tmem_base + ((uint32_t)(quad * 32) << 16) + 192;
   const int ngroups = 2 * a.gpd;
   // this thread's first k-core row inside a y tile
-  const size_t y_off = (size_t)(G392 ? 6 * Q + 2 * T : G7 ? 7 * q : 4 * q + T) * (128 * 8) + (size_t)r * 8;
+  const size_t y_off = (size_t)(G392 ? 6 * Q + 2 * T : G7 ? 7 * q : G14 ? (28 * q - 4 * (q & 1)) / 8 : 4 * q + T) * (128 * 8) + (size_t)r * 8;
   uint32_t it0 = 0, nfull = 0;
   float c0[G::NC], c1[G::NC], c2[G::NC];
   for (int g = cid; g < ngroups; g += ncl) {
@@ -287,6 +328,10 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
             if (k == 0) epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c0, valid);
             else if (k == 1) epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c1, valid);
             else epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c2, valid);
+          } else if constexpr (G14) {
+            if (k == 0) epif_item392x14<Q / 4, Q % 4>(t_lane + buf * G::ACC, ycore, c0, valid);
+            else if (k == 1) epif_item392x14<Q / 4, Q % 4>(t_lane + buf * G::ACC, ycore, c1, valid);
+            else epif_item392x14<Q / 4, Q % 4>(t_lane + buf * G::ACC, ycore, c2, valid);
           } else {
             if (k == 0) epif_item768(t_lane + buf * G::ACC, ycore, c0, valid);
             else if (k == 1) epif_item768(t_lane + buf * G::ACC, ycore, c1, valid);
@@ -349,7 +394,9 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
     mbar_init(w_free, G::EPI_WARPS);
     mbar_init(pw_full, 1);
     fence_barrier_init();
-    if (crank == 0) tmem_slot[1] = atomicAdd(a.sync, 1u);   // the cluster's rank within the launch by arrival order
+    // the cluster's rank within the launch by arrival order (its own 16-byte slot: racecheck treats the TMEM allocator's
+    // result write as touching the words next to tmem_slot[0])
+    if (crank == 0) tmem_slot[4] = atomicAdd(a.sync, 1u);
   }
   if (warp == 2) tmem_alloc2(tmem_slot, 512);
   tc_fence_before();
@@ -357,14 +404,14 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
   cluster_sync();                       // both CTAs run and their barriers are initialised
   if (crank != 0 && threadIdx.x == 0) { // the other CTAs read the cluster's ticket from CTA 0's shared memory
     uint32_t remote, v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(tmem_slot + 1)), "r"(0));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(tmem_slot + 4)), "r"(0));
     asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
-    tmem_slot[1] = v;
+    tmem_slot[4] = v;
   }
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot[0];
-  const uint32_t ticket = tmem_slot[1] * D::NP + pc;     // this pair's rank within the launch
+  const uint32_t ticket = tmem_slot[4] * D::NP + pc;     // this pair's rank within the launch
   const uint32_t q = ticket % G::PPG;
   const int cid = (int)(ticket / G::PPG);
   const int ncl = (int)(gridDim.x / (2 * G::PPG));
@@ -602,6 +649,14 @@ __global__ void __launch_bounds__(Der<G>::THREADS, 1) lstm_fused_kernel(const Fu
   case TT: epiloguef_role<G, TT>(a, tmem_base, TT, quad, lane, cid, ncl, e, (int)q, leader, acc_full, acc_empty, w_free, ticket); break;
       switch (T) { BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3) }
 #undef BSRNN_EPIF_CASE
+    } else if constexpr (G::UPP == 28) {
+#define BSRNN_EPIF_CASE(QT) \
+  case QT: epiloguef_role<G, QT>(a, tmem_base, QT % 4, quad, lane, cid, ncl, e, (int)q, leader, acc_full, acc_empty, w_free, ticket); break;
+      switch (4 * (int)(q & 1u) + T) {
+        BSRNN_EPIF_CASE(0) BSRNN_EPIF_CASE(1) BSRNN_EPIF_CASE(2) BSRNN_EPIF_CASE(3)
+        BSRNN_EPIF_CASE(4) BSRNN_EPIF_CASE(5) BSRNN_EPIF_CASE(6) BSRNN_EPIF_CASE(7)
+      }
+#undef BSRNN_EPIF_CASE
     } else {
       epiloguef_role<G, 0>(a, tmem_base, T, quad, lane, cid, ncl, e, (int)q, leader, acc_full, acc_empty, w_free, ticket);
     }
@@ -717,6 +772,16 @@ extern "C" int bsrnn_blstm_fused7_tc(const void* xhat, const void* w_fused7, con
                              R, steps, seq_tiles, max_groups, slots, sync_ws, stream);
 }
 extern "C" int bsrnn_blstm_fused7_max_groups(void) { return fused_max_groups<Geo392x7>(); }
+// Same layer on groups of 14 pairs x 28 units (Geo392x14, the small-batch geometry): w_fused14 [2][14][2][76][56][8].
+extern "C" int bsrnn_blstm_fused14_tc(const void* xhat, const void* w_fused14, const void* zero_tile, void* y, int R, int steps,
+                                      int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  BSRNN_CHECK_ARG(xhat && w_fused14 && zero_tile && y && sync_ws, "blstm_fused14_tc: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused14_tc: bad dims");
+  const long y_tile = (long)Geo392x14::HKC * 128 * 8;
+  return run_fused<Geo392x14>("blstm_fused14_tc", xhat, w_fused14, zero_tile, y, reinterpret_cast<__half*>(y) + y_tile, 2 * y_tile,
+                              R, steps, seq_tiles, max_groups, slots, sync_ws, stream);
+}
+extern "C" int bsrnn_blstm_fused14_max_groups(void) { return fused_max_groups<Geo392x14>(); }
 extern "C" int bsrnn_blstm_fused_sync_bytes(void) { return (int)(U_SYNC_WORDS * sizeof(unsigned)); }
 
 // Fused BLSTM layer, H = 768 / N = 384 (BSRNN_flowse): xhat [steps*seq_tiles][50][128][8] (column 384 = 1), w_fused

@@ -29,9 +29,12 @@ for _kv in os.environ.get("BSRNN_LSTM_FLAG_SLOTS", "").split(","):
 # axes whose BLSTM runs as ONE fused kernel (input projection inside the recurrence, csrc/lstm_fused.cu):
 # BSRNN_LSTM_FUSED="time,freq" (default) | "freq" | "none" (separate input-projection GEMM + bsrnn_blstm_recurrence_tc*)
 FUSED_AXES = tuple(a for a in os.environ.get("BSRNN_LSTM_FUSED", "time,freq").split(",") if a in ("time", "freq"))
-# group geometry of the fused kernel: 8 pairs x 49 units (9 groups) or 7 pairs x 56 units (10 groups = 5 per direction).
-# BSRNN_LSTM_FUSED_GEO = 8 | 7 | auto (default)
+# group geometry of the fused kernel: 8 pairs x 49 units (9 groups), 7 pairs x 56 units (10 groups = 5 per direction) or
+# 14 pairs x 28 units (5 groups; small batches: half the per-step chain).  BSRNN_LSTM_FUSED_GEO = 8 | 7 | 14 | auto (default)
 FUSED_GEO = os.environ.get("BSRNN_LSTM_FUSED_GEO", "auto")
+
+
+GEO14_MAX_PTILES = int(os.environ.get("BSRNN_LSTM_GEO14_MAX_PTILES", "3"))
 
 
 def _passes(ptiles, groups, slots):
@@ -47,9 +50,11 @@ def _passes(ptiles, groups, slots):
 
 def fused_geometry(tiles):
     """7 when the 10-group geometry needs fewer item times for this tile count (an item costs 8 % more there: N = 224)."""
-    if FUSED_GEO in ("7", "8"):
+    if FUSED_GEO in ("7", "8", "14"):
         return int(FUSED_GEO)
     ptiles = (tiles + 1) // 2
+    if ptiles <= GEO14_MAX_PTILES:          # chain-bound regime: few tile pairs, every unit (nearly) alone on a group
+        return 14
     return 7 if 1.08 * _passes(ptiles, 10, 3) < _passes(ptiles, 9, 3) - 1e-9 else 8
 
 
@@ -126,16 +131,27 @@ def pack_lstm_tc(rnn):
         # bsrnn_blstm_fused_tc: [dir][pair q][half e][kc_in k-cores of W_ih (+ bias column) | 50 of W_hh][104 rows][8]
         wf = torch.cat([wih.view(2, CL, kc_in, LBN, 8), whh], 2)
         out["wfused"] = wf.view(2, CL, kc_in + LKC, 2, LBN // 2, 8).permute(0, 1, 3, 2, 4, 5).contiguous()
-        out["wfused7"] = pack_lstm_fused7(rnn, kc_in, one_col)
+        out["_rnn"] = rnn                   # the other group geometries are packed on first use (fused_weights)
     return out
 
 
-def pack_lstm_fused7(rnn, kc_in, one_col):
-    """bsrnn_blstm_fused7_tc: groups of 7 pairs x 56 units -> [dir][pair q][half e][kc_in + 50 k-cores][112 rows][8];
-    packed gate row c = 4*u_local + gate of pair q is LSTM row gate*H + 56*q + u_local (i, f, o rows pre-halved)."""
+def fused_weights(w, geo):
+    """Packed weights of the fused layer kernel for group geometry `geo` (8, 7 or 14), built on first use and kept in the
+    layer's pack dict (which PackedCache rebuilds whenever a parameter changes)."""
+    if geo == 8:
+        return w["wfused"]
+    key = f"wfused{geo}"
+    if key not in w:
+        P, U = (7, 56) if geo == 7 else (14, 28)
+        w[key] = pack_lstm_fused7(w["_rnn"], w["kc_in"], w["one_col"], P=P, U=U)
+    return w[key]
+
+
+def pack_lstm_fused7(rnn, kc_in, one_col, P=7, U=56):
+    """bsrnn_blstm_fused7_tc / _fused14_tc: groups of P pairs x U units -> [dir][pair q][half e][kc_in + 50 k-cores][2U rows][8];
+    packed gate row c = 4*u_local + gate of pair q is LSTM row gate*H + U*q + u_local (i, f, o rows pre-halved)."""
     H, N = rnn.weight_hh_l0.shape[1], rnn.weight_ih_l0.shape[1]
     dev = rnn.weight_hh_l0.device
-    P, U = 7, 56
     ul = torch.arange(U, device=dev)
     gsc = torch.tensor(GATE_SCALE, device=dev).repeat(U)[:, None]
     packs = []
@@ -251,9 +267,11 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
             if axis in FUSED_AXES and "wfused" in w:
                 # input projection inside the recurrence: gates_t = [x_t | h_{t-1}] [W_ih | W_hh]^T, no gates_x tensor
                 with region(f"lstm_{axis}"):
-                    if fused_geometry(tiles) == 7:
-                        L.call("bsrnn_blstm_fused7_tc", ws.xhat.data_ptr(), w["wfused7"].data_ptr(), ws.zero_tile.data_ptr(),
-                               ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis], ws.sync.data_ptr(), st)
+                    geo = fused_geometry(tiles)
+                    if geo in (7, 14):
+                        L.call(f"bsrnn_blstm_fused{geo}_tc", ws.xhat.data_ptr(), fused_weights(w, geo).data_ptr(),
+                               ws.zero_tile.data_ptr(), ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis],
+                               ws.sync.data_ptr(), st)
                     else:
                         L.call("bsrnn_blstm_fused_tc", ws.xhat.data_ptr(), w["wfused"].data_ptr(), ws.zero_tile.data_ptr(),
                                ws.y.data_ptr(), R, steps, tiles, max_clusters, _FUSED_SLOTS[axis], ws.sync.data_ptr(), st)
