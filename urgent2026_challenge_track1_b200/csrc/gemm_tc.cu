@@ -25,7 +25,7 @@ namespace bsrnn {
 using namespace umma;
 
 constexpr int TC_STAGES = 8;       // barrier slots; a launch uses a.stages (4 or 8) of them
-constexpr int TC_KS = 8;            // k-cores (8 halves each) per pipeline stage -> K = 64 per stage
+constexpr int TC_KS = 8;            // default k-cores (8 halves each) per pipeline stage -> K = 64 per stage (a.ks: 8 or 4)
 constexpr int TC_THREADS = 320;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_SCR_LD = 36;                                   // floats per scratch row (32 + 4: conflict-free 16 B rows)
@@ -59,6 +59,7 @@ struct GemmTcArgs {
   int out_kcores;                   // EPI_TANH_KB8: k-cores of the destination operand
   int b_resident;                   // 1: each CTA keeps ONE weight tile in shared memory and streams A tiles only
   int pf_dist;                      // A tile this many tiles ahead is bulk-prefetched into L2 (0 = off)
+  int ks;                           // k-cores per pipeline stage (TC_KS, or 4: twice the stages in the same shared memory)
   const __half* gx;                 // EPI_LSTM_STEP: input projection rows [m*128 + r][ld_gx] fp16 (this step, this direction)
   float* cstate;                    // EPI_LSTM_STEP: cell state [m*128 + r][H] f32 (this direction), updated in place
   long ld_gx;
@@ -462,8 +463,9 @@ template <int EPI, int BNC = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int BN = a.BN;
-  const uint32_t a_stage_bytes = TC_KS * 128 * 16;
-  const uint32_t b_stage_bytes = TC_KS * BN * 16;
+  const int KS = a.ks;
+  const uint32_t a_stage_bytes = KS * 128 * 16;
+  const uint32_t b_stage_bytes = KS * BN * 16;
   uint8_t* sA = smem;
   const uint32_t NST = (uint32_t)a.stages;
   uint8_t* sB = smem + NST * a_stage_bytes;
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         const int mrow = dir2 ? ti.m - a.dir_tiles : (a.ksplit > 1 ? ti.m - split * a.m_log : ti.m);
         const int kbase = split * a.kps;
         const int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - kbase) : a.kcores;
-        const int nstage_t = (kcnt + TC_KS - 1) / TC_KS;
+        const int nstage_t = (kcnt + KS - 1) / KS;
         const uint8_t* gA = reinterpret_cast<const uint8_t*>(dir2 ? a.A2 : a.A) + ((size_t)mrow * a.kcores + kbase) * 2048;
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(dir2 ? a.W2 : a.W) + ((size_t)ti.n * a.kcores + kbase) * BN * 16;
         if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
@@ -532,8 +534,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           if (pf_mod >= a.n_tiles) pf_mod -= a.n_tiles;
         }
         for (int ks = 0; ks < nstage_t; ++ks) {
-          const int kc0 = ks * TC_KS;
-          const int nk = min(TC_KS, kcnt - kc0);
+          const int kc0 = ks * KS;
+          const int nk = min(KS, kcnt - kc0);
           mbar_wait(empty + stage, phase ^ 1);
           mbar_expect_tx(full + stage, (uint32_t)nk * (2048 + (a.b_resident ? 0 : BN * 16)));
           if (a.mc > 1) {                  // my 1/mc of the stage, into the same ring slot of every CTA of the cluster
@@ -566,13 +568,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
           const int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - (ti.m / a.m_log) * a.kps) : a.kcores;
-          const int nstage_t = (kcnt + TC_KS - 1) / TC_KS;
+          const int nstage_t = (kcnt + KS - 1) / KS;
           for (int ks = 0; ks < nstage_t; ++ks) {
-            const int nk = min(TC_KS, kcnt - ks * TC_KS);
+            const int nk = min(KS, kcnt - ks * KS);
             mbar_wait(full + stage, phase);
             tc_fence_after();
             const uint64_t da = da0 + (uint64_t)(stage * (a_stage_bytes >> 4));
-            const uint64_t db = db0 + (uint64_t)(a.b_resident ? (uint32_t)ks * (TC_KS / 2) * b_step : stage * (b_stage_bytes >> 4));
+            const uint64_t db = db0 + (uint64_t)(a.b_resident ? (uint32_t)ks * (KS / 2) * b_step : stage * (b_stage_bytes >> 4));
             for (int j = 0; j < nk / 2; ++j) mma_f16_ss(d_tmem, da + (uint64_t)(j * a_step), db + (uint64_t)(j * b_step), idesc, (ks | j) != 0);
             if (a.mc > 1) mma_commit_multicast(empty + stage, cmask);     // the slot is free once ALL mc CTAs have read it
             else mma_commit(empty + stage);
@@ -737,9 +739,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   }
 }
 
-static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch, int stages) {
-  const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)stages * TC_KS * BN * 16;
-  return (size_t)stages * TC_KS * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0);
+static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch, int stages, int ksz = TC_KS) {
+  const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)stages * ksz * BN * 16;
+  return (size_t)stages * ksz * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0);
 }
 
 template <int EPI>
@@ -777,6 +779,19 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
   if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
   if (force4) a.stages = 4;
+  a.ks = TC_KS;
+  // Streaming mode with a ring that only fits 4 stages of 8 k-cores (Linear 4N->N: the 333 KB weight tile rides beside every
+  // 205 KB activation tile): 8 stages of 4 k-cores hold the same bytes, but 7/8 instead of 3/4 of them are in flight while
+  // one stage is being consumed -- the loads, not the tensor pipe, pace this GEMM (ncu profiles/r02 call24: DRAM 53 %).
+  // MEASURED (profiles/r02 call41): no gain -- Linear+skip 25.6 vs 25.5 ms per step at config 2, FlowSE 38.0 vs 38.0 ms per
+  // evaluation: the ring is not what paces this GEMM.  Default stays 8 k-cores per stage.
+  static int ks_env = -1;                 // BSRNN_GEMM_KS=4 selects the 8 x 4 ring (A/B timing)
+  if (ks_env < 0) { const char* e = getenv("BSRNN_GEMM_KS"); ks_env = (e && e[0] == '4') ? 4 : 8; }
+  if (ks_env == 4 && a.stages == 4 && !a.b_resident && a.mc <= 1 && a.ksplit <= 1 && a.kcores >= 32 && a.kcores % 4 == 0 &&
+      tc_smem_bytes(a.BN, a.kcores, false, EPI == EPI_RESID_F32, 8, 4) <= 227 * 1024) {
+    a.ks = 4;
+    a.stages = 8;
+  }
   // L2 prefetch distance of the A tiles.  Streaming mode has one prefetcher per CTA: at K = 800 (Linear 4N->N, A tile
   // 205 KB) three tiles ahead on 148 CTAs is 91 MB of prefetched lines in a 126 MB L2 that also carries the residual
   // stream -- they were evicted before use and fetched twice (ncu: 9.3 GB read for 5.2 GB algorithmic,
@@ -791,7 +806,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   static int pfd = -2;                    // BSRNN_GEMM_PFDIST=0..3 overrides (A/B timing)
   if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
   if (pfd >= 0) a.pf_dist = pfd;
-  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages);
+  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages, a.ks);
   static size_t smem_set = 0;             // per instantiation: the attribute only ever needs to grow (step-wise launches
   if (smem > smem_set) {                  // call this thousands of times per training step)
     BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
