@@ -117,6 +117,42 @@ def test_kb8_roundtrip_and_lstm_pack():
         tc.pack_lstm_tc(torch.nn.LSTM(16, 32, batch_first=True, bidirectional=True))
 
 
+def test_fused_layer_weight_packs_and_geometry_choice():
+    """Weight packs of the fused BLSTM layer kernel (csrc/lstm_fused.cu) for the three group geometries and the FlowSE
+    width: every packed row is the LSTM row of (gate, unit) it claims to be, the bias rides in operand column N, the i/f/o
+    rows are pre-halved; the geometry heuristic picks the small-batch groups for few tiles and the 10-group split where 9
+    groups divide the tile pairs badly."""
+    from urgent2026_challenge_track1_b200 import runtime_tc as tc, runtime_tc_steps as ts
+    torch.manual_seed(0)
+    rnn = torch.nn.LSTM(196, 392, batch_first=True, bidirectional=True)
+    p = tc.pack_lstm_tc(rnn)
+    H, N, kc_in = 392, 196, 26
+    bsum = (rnn.bias_ih_l0_reverse + rnn.bias_hh_l0_reverse).detach()
+    for geo, (P, U) in {8: (8, 49), 7: (7, 56), 14: (14, 28)}.items():
+        wf = tc.fused_weights(p, geo).float()                        # [dir][pair][half][76][rows/2][8]
+        BH = wf.shape[4]
+        assert wf.shape[:4] == (2, P, 2, kc_in + 50) and BH == (208 if geo == 8 else 4 * U) // 2
+        q, u, gate, d = P - 2, U - 3, 1, 1                           # a forget-gate row of the reverse direction
+        c = 4 * u + gate
+        e, r = divmod(c, BH)
+        row = wf[d, q, e, :, r, :].reshape(-1)                       # K = 208 + 400
+        src = gate * H + U * q + u
+        assert torch.equal(row[:N], (0.5 * rnn.weight_ih_l0_reverse[src]).half().float())
+        assert torch.equal(row[N], (0.5 * bsum[src]).half().float()) and float(row[N + 1: kc_in * 8].abs().max()) == 0
+        assert torch.equal(row[kc_in * 8: kc_in * 8 + H], (0.5 * rnn.weight_hh_l0_reverse[src]).half().float())
+        g_row = wf[0, 0, 0, :, 2, :].reshape(-1)                     # c = 2: cell gate of unit 0, not halved
+        assert torch.equal(g_row[:N], rnn.weight_ih_l0[2 * H].half().float())
+    rnn768 = torch.nn.LSTM(384, 768, batch_first=True, bidirectional=True)
+    w768 = ts.pack_lstm_fused768(rnn768)
+    assert w768["wfused"].shape == (2, 24, 2, 146, 64, 8) and w768["kc_fused"] == 50 and w768["one_col"] == 384
+    row = w768["wfused"][0, 5, 1, :, 3, :].float().reshape(-1)       # pair 5, second half: c = 67 -> unit 16, gate 3
+    src = 3 * 768 + 32 * 5 + 16
+    assert torch.equal(row[400: 400 + 768], (0.5 * rnn768.weight_hh_l0[src]).half().float())
+    # geometry choice (48 kHz: tiles = ceil(34 B / 128) on the time axis, ceil(1001 B / 128) on the band axis)
+    assert [tc.fused_geometry(t) for t in (1, 3, 5, 6)] == [14, 14, 14, 14]
+    assert tc.fused_geometry(17) == 7 and tc.fused_geometry(501) == 7 and tc.fused_geometry(9) == 8
+
+
 def _shard_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
