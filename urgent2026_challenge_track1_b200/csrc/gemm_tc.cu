@@ -26,10 +26,17 @@ using namespace umma;
 
 constexpr int TC_STAGES = 8;       // barrier slots; a launch uses a.stages (4 or 8) of them
 constexpr int TC_KS = 8;            // default k-cores (8 halves each) per pipeline stage -> K = 64 per stage (a.ks: 8 or 4)
-constexpr int TC_THREADS = 320;
 constexpr int TC_EPI_WARPS = 8;
+// Epilogue warps per CTA.  The residual epilogue (Linear + skip) runs 12 (16 would cap the kernel at 96 registers and spill 4 KB): it is a scattered-row read-modify-write of the f32
+// residual stream whose cost is set by the bytes its warps keep in flight (profiles/r02 call43: 0.81 ms without the
+// residual traffic, 1.45 ms store-only, 1.80 ms full, all with 8 warps).  -DBSRNN_RESID_EPI_WARPS=8 restores 8.
+#ifndef BSRNN_RESID_EPI_WARPS
+#define BSRNN_RESID_EPI_WARPS 12
+#endif
+__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi == 1 /* EPI_RESID_F32 */ ? BSRNN_RESID_EPI_WARPS : TC_EPI_WARPS; }
+__host__ __device__ constexpr int tc_threads(int epi) { return (2 + tc_epi_warps(epi)) * 32; }
 constexpr int TC_SCR_LD = 36;                                   // floats per scratch row (32 + 4: conflict-free 16 B rows)
-constexpr int TC_SCR_BYTES = TC_EPI_WARPS * 32 * TC_SCR_LD * 4;  // residual epilogue only
+constexpr int TC_SCR_BYTES = tc_epi_warps(1) * 32 * TC_SCR_LD * 4;  // residual epilogue only
 constexpr int TC_ACC_COLS = 256;
 
 struct RowMap {                     // global row (m_tile, r) -> token
@@ -194,6 +201,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
     // out[token, gc0 + c] += v[c].  Thread r owns row r; the rows of a warp are 32 scattered tokens of ldo floats, so
     // the chunk goes through the warp's scratch (row stride 36 floats): afterwards 8 lanes cover one row's 128
     // bytes and a warp instruction touches 4 whole lines instead of 32 partial ones.
+    if (a.debug & 4) return;             // A/B (BSRNN_GEMM_DEBUG=4): no residual traffic at all -- loads + MMAs only
     float* my = scr + (r & 31) * TC_SCR_LD;
 #pragma unroll
     for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(my + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -211,7 +219,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
       const long tok = __shfl_sync(0xffffffffu, token, rr);
       optr[i] = (((okmask >> rr) & 1u) && col_ok) ? reinterpret_cast<float*>(a.out) + tok * a.ldo + gc0 + c4 : nullptr;
       old[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (optr[i] && a.ksplit <= 1) old[i] = *reinterpret_cast<const float4*>(optr[i]);
+      if (optr[i] && a.ksplit <= 1 && !(a.debug & 8)) old[i] = *reinterpret_cast<const float4*>(optr[i]);   // debug 8: store only
     }
     if (a.ksplit > 1) {                  // split-K: several CTAs add into the same rows
 #pragma unroll
@@ -235,7 +243,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmTcArgs& a, int m, int n
       }
     }
     __syncwarp();
-    if (row_ok && a.stats) {
+    if (row_ok && a.stats && !(a.debug & 16)) {        // debug 16: no statistics
 #pragma unroll
       for (int i = 0; i < NC; i += 4) {
         if (gc0 + i + 3 < a.n_valid) {
@@ -460,7 +468,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // projection (EPI_F16_KB8): its epilogue is then straight-line code (profiles/r01/call26: the generic epilogue spent
 // ~440 instructions per tile and warp on 70 useful ones and paced the kernel at 2.8x the MMA time).
 template <int EPI, int BNC = 0>
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs a) {
+__global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int BN = a.BN;
   const int KS = a.ks;
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, a.mc > 1 ? a.mc : 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, BNC ? TC_EPI_WARPS / 2 : TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, BNC ? TC_EPI_WARPS / 2 : tc_epi_warps(EPI)); }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -648,7 +656,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
       if (leader) bulk_store_wait_all();
     } else {
     const int nch = (BN + 31) >> 5;            // 32-column chunks (the last one may be 16 wide)
-    const int ch0 = half == 0 ? 0 : (nch + 1) >> 1, ch1 = half == 0 ? (nch + 1) >> 1 : nch;
+    constexpr int NPART = tc_epi_warps(EPI) / 4;                 // warps per TMEM lane quadrant: each takes a share of the chunks
+    const int ch0 = (half * nch + NPART - 1) / NPART, ch1 = ((half + 1) * nch + NPART - 1) / NPART;
     float* scr = reinterpret_cast<float*>(smem_scr) + (warp - 2) * 32 * TC_SCR_LD;
     TileIter ti(a);
     for (int it = 0; ti.valid(); ti.next(), ++it) {
@@ -665,7 +674,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         if (t2.valid() && a.rows.map(m2, r, &tok2)) {
           const char* p = reinterpret_cast<const char*>(reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + n2 * a.BN);
           const int nbytes = (a.n_valid - n2 * a.BN < a.BN ? a.n_valid - n2 * a.BN : a.BN) * 4;
-          for (int off = half * 128; off < nbytes; off += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+          for (int off = half * 128; off < nbytes; off += NPART * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
         }
       }
       float bl[4] = {0.f, 0.f, 0.f, 0.f};          // this lane's bias column of each of the warp's (<= 4) chunks
@@ -693,6 +702,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
         if (c0 + 32 <= BN) epilogue_chunk<EPI, 32>(a, m, n, r, c0, src, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
         else epilogue_chunk<EPI, 16>(a, m, n, r, c0, src, row_ok, token, s_sum, s_sq, scr, lane, bl[i]);
       };
+      if constexpr (EPI == EPI_RESID_F32 && tc_epi_warps(EPI) > 8) {
+        // many warps per SM hide the TMEM latency by themselves: one register buffer (32 registers fewer under the
+        // lower per-thread cap of a 14-warp CTA)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = ch0 + i;
+          if (ch >= ch1) break;
+          issue(ch, acc0);
+          tmem_ld_wait();
+          consume(ch, i, acc0);
+        }
+      } else {
       if (ch0 < ch1) issue(ch0, acc0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -706,6 +727,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const GemmTcArgs
           if (ch + 1 < ch1) issue(ch + 1, acc0);
           consume(ch, i, acc1);
         }
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -776,6 +798,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
     }
   }
   a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8) <= 227 * 1024 ? 8 : 4;
+  if (a.stages == 4 && tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 4) > 227 * 1024) a.stages = 3;
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
   if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
   if (force4) a.stages = 4;
@@ -801,7 +824,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   // competes with the residual stream.  Streaming mode: off.  Weight-resident mode (short K): 3 tiles ahead.
   a.pf_dist = a.b_resident ? 3 : 0;
   static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("BSRNN_GEMM_DEBUG"); dbg = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 0; }
+  if (dbg < 0) { const char* e = getenv("BSRNN_GEMM_DEBUG"); dbg = (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : 0; }
   a.debug = dbg;
   static int pfd = -2;                    // BSRNN_GEMM_PFDIST=0..3 overrides (A/B timing)
   if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
@@ -831,7 +854,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
     if (mc > 1 && (a.n_tiles % mc != 0 || a.m_tiles < 2 * (sms / a.n_tiles))) mc = 1;
     if (mc > 1) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_ip; cfg.stream = st;
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads(EPI)); cfg.dynamicSmemBytes = smem_ip; cfg.stream = st;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -855,11 +878,11 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
       }
     }
     a.mc = 1;
-    gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, TC_THREADS, smem_ip, st>>>(a);
+    gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, tc_threads(EPI_F16_KB8), smem_ip, st>>>(a);
   } else if (step_mc > 1) {
     // cluster launch: mc consecutive CTAs = mc consecutive N tiles of the same (direction, M walk)
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads(EPI)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = step_mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -880,10 +903,10 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
       BSRNN_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<EPI>, a));
     } else {
       a.mc = 1;
-      gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
+      gemm_tc_kernel<EPI><<<grid, tc_threads(EPI), smem, st>>>(a);
     }
   } else {
-    gemm_tc_kernel<EPI><<<grid, TC_THREADS, smem, st>>>(a);
+    gemm_tc_kernel<EPI><<<grid, tc_threads(EPI), smem, st>>>(a);
   }
   BSRNN_LAUNCH_OK();
   return 0;

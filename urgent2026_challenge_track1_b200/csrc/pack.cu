@@ -3,6 +3,7 @@
 // fused with the layout change the tensor-core GEMMs need, so the normalised activation is written exactly once, in
 // the form the next GEMM's bulk copies fetch.
 #include "common.cuh"
+#include "umma.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -20,6 +21,7 @@ struct PackArgs {
   long tokens_per_sample;  // scale row = (token / tokens_per_sample) * g_inner + (g_inner > 1 ? token % g_inner : 0)
   int g_inner;
   int one_col;           // >= C: this operand column is the constant 1 (bias row of the weights); -1 = none
+  int bulk;              // async kernel: rows arrive by cp.async.bulk (1) or by 16-byte cp.async (0, BSRNN_PACK_BULK=0)
 };
 
 // grid (m_tiles), block 256, dynamic smem 128 * (kcores*8 + 8) halves + 128 row descriptors.
@@ -141,6 +143,24 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs
     rows[r] = pr;
   }
   __syncthreads();
+  if (a.bulk) {
+    // one bulk (1-D TMA) copy per row: C*4 contiguous bytes, completion counted on one mbarrier.  The DMA engine issues
+    // whole-row bursts instead of 6 272 separate 16-byte cp.async requests per tile.
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) { umma::mbar_init(&bar, ROWS); umma::fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x < ROWS) {
+      const int r = threadIdx.x;
+      const long tok = rows[r].tok;
+      if (tok >= 0) {
+        umma::mbar_expect_tx(&bar, (uint32_t)a.C * 4);
+        umma::bulk_g2s(tile + (size_t)r * ld, a.x + tok * a.ldx + a.col0, (uint32_t)a.C * 4, &bar);
+      } else {
+        umma::mbar_arrive(&bar);
+      }
+    }
+    umma::mbar_wait(&bar, 0);
+  } else {
   const int q4 = a.C >> 2;                                             // 16-byte pieces per row
   const int items = ROWS * q4;
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
@@ -154,6 +174,7 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
   __syncthreads();
   __half* dst = a.out + (size_t)m * a.kcores * 128 * 8;
   for (int i = threadIdx.x; i < a.kcores * ROWS; i += 256) {
@@ -207,6 +228,9 @@ extern "C" int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, cons
   static int force_old = -1;              // BSRNN_PACK_SYNC=1: the register-staged kernel (A/B timing)
   if (force_old < 0) { const char* e = getenv("BSRNN_PACK_SYNC"); force_old = (e && e[0] == '1') ? 1 : 0; }
   const int ld = (C % 8 == 4) ? C : C + 4;              // bank-friendly row stride of the staging tile
+  static int bulk_env = -1;
+  if (bulk_env < 0) { const char* e = getenv("BSRNN_PACK_BULK"); bulk_env = (e && e[0] == '0') ? 0 : 1; }
+  a.bulk = bulk_env;
   const size_t smem128 = (size_t)128 * ld * 4 + 128 * sizeof(PackRow), smem64 = (size_t)64 * ld * 4 + 64 * sizeof(PackRow);
   const size_t smem32 = (size_t)32 * ld * 4 + 32 * sizeof(PackRow);
   if (vec_ok && !force_old && C % 4 == 0 && smem32 <= 110 * 1024 && (one_col < 0 || one_col % 4 == 0)) {
