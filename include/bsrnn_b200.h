@@ -141,6 +141,9 @@ int bsrnn_blstm_recurrence_f32(const float* gates_x, const float* w_hh, float* y
  *        layout the recurrence kernel reads with coalesced 16-byte loads)
  *     7: tanh -> f32 rows out[token*ldo + col], col < n_valid             (GradDecoder Conv1d(N->16 s)+Tanh,
  *        bsrnn_flowse.py:118-134: the channel-last image of the 5x5 conv)
+ *     8: epilogue 1 (f32 residual + statistics) with the tile's residual row segments moved by one bulk (TMA) copy
+ *        per row into a shared-memory row buffer, updated there and stored back by one bulk store per row; rows must be
+ *        16-byte aligned (ldo % 4 == 0, BN % 4 == 0, out 16-byte aligned)
  * bsrnn_blstm_recurrence_tc: persistent cluster kernel, H = 392 only (csrc/lstm_tc.cu).  Sequences are grouped in
  *     tiles of 128 (seq = j*128 + r, valid iff seq < R); all operands are (step, seq_tile)-major:
  *       gates_x [step][seq_tile][dir][q][26][128][8] fp16 — epilogue 4 of bsrnn_gemm_tc over A tiles built with the

@@ -10,6 +10,7 @@ from urgent2026_challenge_track1_b200 import runtime_tc as tc, _lib as L
 ap = argparse.ArgumentParser()
 ap.add_argument("--which", default="inproj", choices=["inproj", "fc"])
 ap.add_argument("--axis", default="time"); ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--tma", action="store_true", help="fc: residual rows through the TMA unit (epilogue 8)")
 ap.add_argument("--nobias", action="store_true", help="inproj: bias folded into the weights (bias pointer NULL)")
 ap.add_argument("--B", type=int, default=64); ap.add_argument("--T", type=int, default=1001); ap.add_argument("--K", type=int, default=34)
 a = ap.parse_args()
@@ -45,7 +46,7 @@ else:
     out = torch.randn(B, T, K, N, device=dev)
     stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
     run = lambda: L.call("bsrnn_gemm_tc", A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), stats.data_ptr(), ntile, 1, kc,
-                         208, L.TC_RESID_F32, N, N, 0, T * K, tiles, R, *addr, st)
+                         208, L.TC_RESID_TMA if a.tma else L.TC_RESID_F32, N, N, 0, T * K, tiles, R, *addr, st)
     bytes_alg = A.numel() * 2 + 2 * out.numel() * 4
     flops = 2.0 * ntile * 128 * 800 * 208
 run(); torch.cuda.synchronize()
@@ -53,4 +54,4 @@ for _ in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"[gemm {a.which} {a.axis}{' nobias' if a.nobias else ''} stages={os.environ.get('BSRNN_GEMM_STAGES', '8')}] {ms:.3f} ms  {bytes_alg / ms / 1e6:.0f} GB/s algorithmic  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)
+    print(f"[gemm {a.which} {a.axis}{' nobias' if a.nobias else ''}{' tma' if a.tma else ''} stages={os.environ.get('BSRNN_GEMM_STAGES', '8')}] {ms:.3f} ms  {bytes_alg / ms / 1e6:.0f} GB/s algorithmic  {flops / ms / 1e9:.0f} TFLOP/s", flush=True)

@@ -105,6 +105,7 @@ assert GEMM_DESC.itemsize == 144
 EPI_STORE, EPI_TANH, EPI_RESIDUAL, EPI_GLU = 0, 1, 2, 3
 TC_F16_ROWS, TC_RESID_F32, TC_TANH_KB8, TC_GLU_F32, TC_F16_KB8 = 0, 1, 2, 3, 4      # bsrnn_gemm_tc epilogues
 TC_TANH_F32 = 7
+TC_RESID_TMA = 8        # epilogue 1 with the residual rows moved by bulk (TMA) copies through a shared-memory row buffer
 
 _lib = None
 

@@ -33,7 +33,7 @@ constexpr int TC_EPI_WARPS = 8;
 #ifndef BSRNN_RESID_EPI_WARPS
 #define BSRNN_RESID_EPI_WARPS 12
 #endif
-__host__ __device__ constexpr int tc_epi_warps(int epi) { return epi == 1 /* EPI_RESID_F32 */ ? BSRNN_RESID_EPI_WARPS : TC_EPI_WARPS; }
+__host__ __device__ constexpr int tc_epi_warps(int epi) { return (epi == 1 /* EPI_RESID_F32 */ || epi == 8 /* EPI_RESID_TMA */) ? BSRNN_RESID_EPI_WARPS : TC_EPI_WARPS; }
 __host__ __device__ constexpr int tc_threads(int epi) { return (2 + tc_epi_warps(epi)) * 32; }
 constexpr int TC_SCR_LD = 36;                                   // floats per scratch row (32 + 4: conflict-free 16 B rows)
 constexpr int TC_SCR_BYTES = tc_epi_warps(1) * 32 * TC_SCR_LD * 4;  // residual epilogue only
@@ -102,7 +102,7 @@ struct GemmTcArgs {
 };
 
 enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4, EPI_LSTM_STEP = 5,
-       EPI_LSTM_BWD = 6, EPI_TANH_F32 = 7 };
+       EPI_LSTM_BWD = 6, EPI_TANH_F32 = 7, EPI_RESID_TMA = 8 };
 
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
@@ -484,14 +484,16 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
   uint64_t* acc_full = bars + 2 * TC_STAGES;     // [2]
   uint64_t* acc_empty = bars + 2 * TC_STAGES + 2;  // [2]
   uint64_t* b_full = bars + 2 * TC_STAGES + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 5);
-  uint8_t* smem_scr = reinterpret_cast<uint8_t*>(bars + 2 * TC_STAGES + 8);     // 16-byte aligned (EPI_RESID_F32 only)
+  uint64_t* res_full = bars + 2 * TC_STAGES + 5;   // EPI_RESID_TMA: the tile's residual rows have landed in the row buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 6);
+  uint8_t* smem_scr = reinterpret_cast<uint8_t*>(bars + 2 * TC_STAGES + 8);     // 16-byte aligned (residual epilogues only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, a.mc > 1 ? a.mc : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, BNC ? TC_EPI_WARPS / 2 : tc_epi_warps(EPI)); }
     mbar_init(b_full, 1);
+    mbar_init(res_full, 128);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 2 * TC_ACC_COLS);
@@ -654,6 +656,120 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         if (leader && do_store) bulk_s2g(gdst + 14 * 2048, stg, 11 * 2048);
       }
       if (leader) bulk_store_wait_all();
+    } else if constexpr (EPI == EPI_RESID_TMA) {
+      // Linear + skip with the residual rows moved by the TMA unit: out[token, n*BN + c] += acc (+ bias), c < ncols.
+      // The tile's 128 residual row segments (ncols*4 bytes each, contiguous in HBM) arrive in a shared-memory row buffer
+      // by one bulk copy per row, are updated there, and leave by one bulk store per row -- instead of 16-byte
+      // loads / stores from 12 warps whose bytes in flight bound the register-staged epilogue (profiles/r02 call43/44).
+      // Thread r of epilogue warps 2..5 owns row r's copies; a single buffer suffices: load(i+1) is issued as soon as the
+      // stores of tile i have been read out of it, and lands while the MMAs of tile i+1 run.
+      constexpr int NPART = tc_epi_warps(EPI) / 4;
+      const int nch = (BN + 31) >> 5;
+      const int ch0 = (half * nch + NPART - 1) / NPART, ch1 = ((half + 1) * nch + NPART - 1) / NPART;
+      float* resbuf = reinterpret_cast<float*>(smem_scr);
+      const int ncmax = a.n_valid < BN ? a.n_valid : BN;
+      const int ldr = (ncmax % 8 == 4) ? ncmax : ncmax + 4;          // bank-friendly row stride (floats)
+      const bool loader = half == 0;                                   // warps 2..5: one thread per tile row
+      float* myrow = resbuf + (size_t)r * ldr;
+      auto issue_loads = [&](const TileIter& t) {                      // this thread's row of tile t -> row buffer
+        const int m2 = t.m, n2 = t.n;
+        long tok2 = 0;
+        const int nc2 = (a.n_valid - n2 * BN < BN ? a.n_valid - n2 * BN : BN);
+        if (a.rows.map(m2, r, &tok2) && nc2 > 0) {
+          mbar_expect_tx(res_full, (uint32_t)nc2 * 4);
+          bulk_g2s(myrow, reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + (long)n2 * BN, (uint32_t)nc2 * 4, res_full);
+        } else {
+          mbar_arrive(res_full);
+        }
+      };
+      TileIter ti(a);
+      if (loader && ti.valid()) issue_loads(ti);
+      for (int it = 0; ti.valid(); ti.next(), ++it) {
+        const int m = ti.m, n = ti.n;
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        long token = 0;
+        const bool row_ok = a.rows.map(m, r, &token);
+        const int ncols = (a.n_valid - n * BN < BN ? a.n_valid - n * BN : BN);
+        float s_sum = 0.f, s_sq = 0.f;
+        const TileIter tn = ti.ahead(1);
+        {                                              // next tile's residual rows -> L2 while this tile is processed
+          long tok2 = 0;
+          if (tn.valid() && a.rows.map(tn.m, r, &tok2)) {
+            const char* p = reinterpret_cast<const char*>(reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + (long)tn.n * BN);
+            const int nbytes = (a.n_valid - tn.n * BN < BN ? a.n_valid - tn.n * BN : BN) * 4;
+            for (int off = half * 128; off < nbytes; off += NPART * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+          }
+        }
+        float bl[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.bias) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = (ch0 + i) * 32 + lane;
+            if (ch0 + i < ch1 && c < BN) bl[i] = __ldg(a.bias + n * BN + c);
+          }
+        }
+        const float osc = a.out_scale_ptr ? __ldg(a.out_scale_ptr) : (a.out_scale != 0.f ? a.out_scale : 1.f);
+        mbar_wait(acc_full + buf, acc_phase);
+        tc_fence_after();
+        mbar_wait(res_full, (uint32_t)(it & 1));
+        const uint32_t t_addr = tmem_base + buf * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = ch0 + i;
+          if (ch >= ch1) break;
+          const int c0 = ch * 32;
+          uint32_t acc[32];
+          const bool wide = c0 + 32 <= BN;
+          if (wide) tmem_ld_x32(t_addr + c0, acc);
+          else tmem_ld_x16(t_addr + c0, reinterpret_cast<uint32_t(&)[16]>(acc));
+          tmem_ld_wait();
+          tmem_ld_pin(acc);
+          const int nc = wide ? 32 : 16;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j >= nc || c0 + j + 3 >= ncols) continue;      // warp-uniform; n_valid % 4 == 0: a 4-group is all valid or all padding
+            const float b0 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j) : 0.f, b1 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j + 1) : 0.f;
+            const float b2 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j + 2) : 0.f, b3 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j + 3) : 0.f;
+            if (row_ok) {
+              float4 o = *reinterpret_cast<float4*>(myrow + c0 + j);
+              o.x += (__uint_as_float(acc[j]) + b0) * osc; o.y += (__uint_as_float(acc[j + 1]) + b1) * osc;
+              o.z += (__uint_as_float(acc[j + 2]) + b2) * osc; o.w += (__uint_as_float(acc[j + 3]) + b3) * osc;
+              *reinterpret_cast<float4*>(myrow + c0 + j) = o;
+              s_sum += o.x + o.y + o.z + o.w;
+              s_sq += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + buf);
+        fence_proxy_async_shared();                    // this thread's generic-proxy writes -> the bulk stores' reads
+        named_bar_sync(3, tc_epi_warps(EPI) * 32);     // every warp has updated its share of the row buffer
+        if (loader) {
+          if (row_ok && ncols > 0) bulk_s2g(reinterpret_cast<float*>(a.out) + token * a.ldo + (long)n * BN, myrow, (uint32_t)ncols * 4);
+          bulk_store_wait_read();                      // the store has finished READING the row: the buffer may be refilled
+          named_bar_sync(4, 128);                      // ... for all 128 rows
+          if (tn.valid()) issue_loads(tn);
+        }
+        if (a.stats) {
+          const long samp = row_ok ? token / a.tokens_per_sample : -1;
+          unsigned todo = __ballot_sync(0xffffffffu, row_ok);
+          while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const long ls = __shfl_sync(0xffffffffu, samp, leader);
+            const bool mine = row_ok && samp == ls;
+            const float ps = warp_sum(mine ? s_sum : 0.f);
+            const float pq = warp_sum(mine ? s_sq : 0.f);
+            if (lane == leader) {
+              atomicAdd(a.stats + 2 * ls, (double)ps);
+              atomicAdd(a.stats + 2 * ls + 1, (double)pq);
+            }
+            todo &= ~__ballot_sync(0xffffffffu, mine);
+          }
+        }
+      }
+      if (loader) bulk_store_wait_all();
     } else {
     const int nch = (BN + 31) >> 5;            // 32-column chunks (the last one may be 16 wide)
     constexpr int NPART = tc_epi_warps(EPI) / 4;                 // warps per TMEM lane quadrant: each takes a share of the chunks
@@ -761,9 +877,15 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
   }
 }
 
-static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch, int stages, int ksz = TC_KS) {
+static size_t tc_smem_bytes(int BN, int kcores, bool resident, bool scratch, int stages, int ksz = TC_KS, size_t extra = 0) {
   const size_t b = resident ? (size_t)kcores * BN * 16 : (size_t)stages * ksz * BN * 16;
-  return (size_t)stages * ksz * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0);
+  return (size_t)stages * ksz * 128 * 16 + b + (2 * TC_STAGES + 8) * 8 + (scratch ? TC_SCR_BYTES : 0) + extra;
+}
+// EPI_RESID_TMA: 128 residual rows of min(BN, n_valid) floats, row stride padded to 4 (mod 8) floats
+static size_t tc_resbuf_bytes(int BN, int n_valid) {
+  const int nc = n_valid < BN ? n_valid : BN;
+  const int ldr = (nc % 8 == 4) ? nc : nc + 4;
+  return (size_t)128 * ldr * 4;
 }
 
 template <int EPI>
@@ -797,8 +919,9 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
       if (mc_env > 1 && a.n_tiles % mc_env == 0) step_mc = mc_env;
     }
   }
-  a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8) <= 227 * 1024 ? 8 : 4;
-  if (a.stages == 4 && tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 4) > 227 * 1024) a.stages = 3;
+  const size_t extra_smem = EPI == EPI_RESID_TMA ? tc_resbuf_bytes(a.BN, a.n_valid) : 0;
+  a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8, TC_KS, extra_smem) <= 227 * 1024 ? 8 : 4;
+  while (a.stages > 2 && tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages, TC_KS, extra_smem) > 227 * 1024) --a.stages;
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
   if (force4 < 0) { const char* e = getenv("BSRNN_GEMM_STAGES"); force4 = (e && e[0] == '4') ? 1 : 0; }
   if (force4) a.stages = 4;
@@ -811,7 +934,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   static int ks_env = -1;                 // BSRNN_GEMM_KS=4 selects the 8 x 4 ring (A/B timing)
   if (ks_env < 0) { const char* e = getenv("BSRNN_GEMM_KS"); ks_env = (e && e[0] == '4') ? 4 : 8; }
   if (ks_env == 4 && a.stages == 4 && !a.b_resident && a.mc <= 1 && a.ksplit <= 1 && a.kcores >= 32 && a.kcores % 4 == 0 &&
-      tc_smem_bytes(a.BN, a.kcores, false, EPI == EPI_RESID_F32, 8, 4) <= 227 * 1024) {
+      tc_smem_bytes(a.BN, a.kcores, false, EPI == EPI_RESID_F32, 8, 4, extra_smem) <= 227 * 1024) {
     a.ks = 4;
     a.stages = 8;
   }
@@ -829,7 +952,7 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   static int pfd = -2;                    // BSRNN_GEMM_PFDIST=0..3 overrides (A/B timing)
   if (pfd == -2) { const char* e = getenv("BSRNN_GEMM_PFDIST"); pfd = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : -1; }
   if (pfd >= 0) a.pf_dist = pfd;
-  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages, a.ks);
+  const size_t smem = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages, a.ks, extra_smem);
   static size_t smem_set = 0;             // per instantiation: the attribute only ever needs to grow (step-wise launches
   if (smem > smem_set) {                  // call this thousands of times per training step)
     BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -923,7 +1046,7 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && kcores > 0 && kcores % 2 == 0, "gemm_tc: bad tile counts (kcores=%d)", kcores);
   BSRNN_CHECK_ARG(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc: BN=%d must be a multiple of 16 in [16,256]", BN);
   BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && tokens_per_sample > 0, "gemm_tc: bad row map");
-  BSRNN_CHECK_ARG((epilogue != EPI_RESID_F32 && epilogue != EPI_TANH_F32) || (n_valid % 4 == 0 && ldo % 4 == 0),
+  BSRNN_CHECK_ARG((epilogue != EPI_RESID_F32 && epilogue != EPI_TANH_F32 && epilogue != EPI_RESID_TMA) || (n_valid % 4 == 0 && ldo % 4 == 0),
                   "gemm_tc: the f32-row epilogues need n_valid and ldo to be multiples of 4 (got %d, %ld)", n_valid, ldo);
   GemmTcArgs a{};
   a.A = reinterpret_cast<const __half*>(A);
@@ -939,6 +1062,9 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
     case EPI_GLU_F32: return launch_tc<EPI_GLU_F32>(a, st);
     case EPI_F16_KB8: return launch_tc<EPI_F16_KB8>(a, st);
     case EPI_TANH_F32: return launch_tc<EPI_TANH_F32>(a, st);
+    case EPI_RESID_TMA:
+      BSRNN_CHECK_ARG(BN % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm_tc: the TMA residual epilogue needs 16-byte aligned rows");
+      return launch_tc<EPI_RESID_TMA>(a, st);
   }
   set_error("gemm_tc: unknown epilogue %d", epilogue);
   return 1;

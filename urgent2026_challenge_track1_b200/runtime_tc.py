@@ -63,6 +63,9 @@ for _kv in os.environ.get("BSRNN_LSTM_FUSED_SLOTS", "").split(","):
     if "=" in _kv:
         _ax, _sv = _kv.split("=")
         _FUSED_SLOTS[_ax] = int(_sv)
+# epilogue of the Linear(4N->N) + skip GEMM: residual rows through the TMA unit (bsrnn_gemm_tc epilogue 8, default) or
+# register-staged 16-byte loads / stores (epilogue 1, BSRNN_FC_EPI=ldst)
+FC_EPI = L.TC_RESID_F32 if os.environ.get("BSRNN_FC_EPI", "tma") == "ldst" else L.TC_RESID_TMA
 CL, LU, LBN, LKC = 8, 49, 208, 50       # cluster size, units per CTA, gate columns per CTA, k-cores of h (K = 400)
 LGC = LBN // 8                           # gates_x cores per CTA
 GATE_SCALE = (0.5, 0.5, 1.0, 0.5)       # i, f, o rows pre-halved: sigmoid(x) = 0.5*tanh(x/2) + 0.5 in the kernel
@@ -293,7 +296,7 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
                 ws.stats.zero_()
                 fc = w["fc"]
                 L.call("bsrnn_gemm_tc", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
-                       ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], L.TC_RESID_F32, N, N, 0, T * K,
+                       ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], FC_EPI, N, N, 0, T * K,
                        tiles, R, *addr, st)
                 if _EXACT_STATS:                       # diagnosis: statistics from a separate pass over skip
                     ws.stats.zero_()

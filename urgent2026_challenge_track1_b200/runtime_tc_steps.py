@@ -17,7 +17,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
-from .runtime_tc import GATE_SCALE, to_kb8
+from .runtime_tc import GATE_SCALE, to_kb8, FC_EPI
 
 
 def _bn_for(cols, kcores=None):
@@ -275,7 +275,7 @@ def dual_path_tc_fused768(skip, layers, t_emb=None):
                 ws.stats.zero_()
                 fc = w["fc1"]
                 L.call("bsrnn_gemm_tc", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
-                       ws.stats.data_ptr(), steps * tiles, fc["nt"], 2 * (H // 8), fc["bn"], L.TC_RESID_F32, N, N, 0, T * K,
+                       ws.stats.data_ptr(), steps * tiles, fc["nt"], 2 * (H // 8), fc["bn"], FC_EPI, N, N, 0, T * K,
                        tiles, R_, *addr, st)
     return skip
 
