@@ -133,7 +133,7 @@ class BSRNN(nn.Module):
                    m_tiles, M, 1 << 40, 0, 1, 0, M, 1, st)
             skip.zero_()
             L.call("bsrnn_gemm_tc", xz.data_ptr(), cp["w"].data_ptr(), cp["b"].data_ptr(), skip.data_ptr(), None, m_tiles,
-                   cp["nt"], 2 * N // 8, cp["bn"], L.TC_RESID_F32, N, N, 0, M, m_tiles, M, 1 << 40, 0, 1, 0, st)
+                   cp["nt"], 2 * N // 8, cp["bn"], TS.FC_EPI, N, N, 0, M, m_tiles, M, 1 << 40, 0, 1, 0, st)
         else:
             dl = R.DescList()
             w, b = self.condition_fc.weight, self.condition_fc.bias               # bsrnn_flowse.py:284-285

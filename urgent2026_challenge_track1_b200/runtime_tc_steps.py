@@ -212,7 +212,7 @@ def dual_path_tc_steps(skip, layers, t_emb=None):
             with region("fc"):
                 for half, bias in ((0, w["fcb"]), (1, w["fcb0"])):       # skip += y_fwd W_f^T + b, then += y_bwd W_b^T
                     L.call("bsrnn_gemm_tc", y[half].data_ptr(), w["fcw"][half].data_ptr(), bias.data_ptr(), skip.data_ptr(),
-                           None, steps * tiles, w["fc_nt"], H // 8, w["fc_bn"], L.TC_RESID_F32, N, N, 0, T * K,
+                           None, steps * tiles, w["fc_nt"], H // 8, w["fc_bn"], FC_EPI, N, N, 0, T * K,
                            tiles, R_, *addr, st)
     return skip
 

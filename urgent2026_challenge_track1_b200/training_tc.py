@@ -22,7 +22,7 @@ import math
 import torch
 
 from . import _lib as L
-from .runtime_tc import GATE_SCALE, to_kb8
+from .runtime_tc import GATE_SCALE, to_kb8, FC_EPI
 
 BIG = 1 << 40
 
@@ -159,7 +159,7 @@ class BLSTMBlockTC(torch.autograd.Function):
         zbias = torch.zeros_like(bias)
         for half, bb in ((0, bias), (1, zbias)):                   # out = y_fwd W_f^T + b, then += y_bwd W_b^T
             L.call("bsrnn_gemm_tc", y[half].data_ptr(), p["fcw"][half].data_ptr(), bb.data_ptr(), out.data_ptr(), None,
-                   m_all, p["fc_nt"], p["kc_h"], p["fc_bn"], L.TC_RESID_F32, N, N, 0, T * K, tiles, R, *addr, st)
+                   m_all, p["fc_nt"], p["kc_h"], p["fc_bn"], FC_EPI, N, N, 0, T * K, tiles, R, *addr, st)
         ctx.p, ctx.dims = p, (B, T, K, N, axis)
         ctx.save_for_backward(xhat, gates, y[0], y[1], c_all[0], c_all[1])
         return out
