@@ -165,6 +165,34 @@ int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, do
                   int kcores, int BN, int epilogue, long ldo, int n_valid, int out_kcores, long tokens_per_sample,
                   int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
                   void* stream);
+/* bsrnn_gemm_tc_ex: bsrnn_gemm_tc with two extras of the f32-row epilogues 1 / 8.
+ *     stats_inner > 1: the statistics row is (token / tokens_per_sample) * stats_inner + token % stats_inner, i.e. per
+ *       (sample, band) on the (B,T,K,N) residual stream with stats_inner = K: the reduction half of the mask decoder's
+ *       per-band GroupNorm(1, N) over (N, T) [espnet2 MaskDecoder; bsrnn_flowse.py:146-152] taken in the epilogue of the
+ *       last Linear + skip instead of a separate pass over the stream;
+ *     flags bit 0 (epilogue 8 only): store only, out[token*ldo + col] = A W^T + bias (no residual read) -- the
+ *       tensor-core BandSplit Conv1d(2 s_k -> N, 1) [bsrnn_flowse.py:65-86], whose statistics are those of the first
+ *       dual-path GroupNorm.
+ * bsrnn_band_norm_cast_kb8: the operand of that GEMM for ALL bands in one launch: band k's slice of the spectrum (rows,
+ *     F2 = 2F floats), zero-padded to 2 s_k = c_off[k+1] - c_off[k] channels BEFORE the per-(sample, band) affine scale /
+ *     shift (B*K, cmax), as fp16 tiles [tile][kc_k][128][8] at out + a_off[k] halves, kc_k = 2 * ceil(2 s_k / 16). */
+int bsrnn_gemm_tc_ex(const void* A, const void* W, const float* bias, void* out, double* stats, int m_tiles, int n_tiles,
+                     int kcores, int BN, int epilogue, long ldo, int n_valid, int out_kcores, long tokens_per_sample,
+                     int tiles_per_step, int R, long seq_inner, long seq_outer, long seq_inner_stride, long step_stride,
+                     int stats_inner, int flags, void* stream);
+/* bsrnn_gemm_tc_grouped: the store-only GEMM of bsrnn_gemm_tc_ex (epilogue 8, flags 1) for n_groups bands in ONE launch:
+ *     out[token*ldo + out_off_g + c] = A_g W_g^T + bias_g, c < n_valid, tile order (row tile, band) with the band innermost so
+ *     that co-running CTAs write adjacent segments of the same output rows.  groups: device int64 [n_groups][5] =
+ *     {a_off (halves into A: the group's tile 0), w_off (halves into W), out_off (floats), bias_off (floats), kcores};
+ *     A_g tiles [row tile][kcores_g][128][8], W_g [kcores_g][BN][8]; kc_max = max kcores_g; m_tiles = row tiles per group;
+ *     the row map (tiles_per_step ...) applies to the row tile.  BandSplit Conv1d(2 s_k -> N, 1) [bsrnn_flowse.py:65-86]. */
+int bsrnn_gemm_tc_grouped(const void* A, const void* W, const float* bias, void* out, double* stats,
+                          const long long* groups, int n_groups, int m_tiles, int kc_max, int BN, long ldo, int n_valid,
+                          long tokens_per_sample, int tiles_per_step, int R, long seq_inner, long seq_outer,
+                          long seq_inner_stride, long step_stride, void* stream);
+int bsrnn_band_norm_cast_kb8(const float* spec, const float* scale, const float* shift, void* out, const int32_t* c_off,
+                             const int32_t* bin0, const int32_t* width2, const long long* a_off, int K, long rows, int T,
+                             int F2, int cmax, void* stream);
 /* bsrnn_lstm_step_tc: ONE time step of one LSTM direction on tensor cores for any hidden size H % 16 == 0 (FlowSE: H = 768,
  *     which does not fit the persistent kernel above) [nn.LSTM, bsrnn_flowse.py:226-238]: h_{t-1} * W_hh^T as a tcgen05 GEMM
  *     whose epilogue adds the input projection, applies the gates, updates c in place and writes h_t as the KB8 tile that is

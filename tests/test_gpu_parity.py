@@ -287,6 +287,67 @@ def test_bsrnn_se_fused_and_unfused_schedules_agree(monkeypatch):
     assert 0 < e_ab < 2e-3 and 0 < e_ac < 2e-3
 
 
+@pytest.mark.parametrize("fs,B,n", [(48000, 3, 24000), (16000, 2, 9000), (44100, 2, 15000)])
+def test_band_split_tc_matches_f32_kernel(rt, fs, B, n):
+    """Tensor-core BandSplit (operand builder + store-only tcgen05 GEMM per band) against the f32 CUDA-core kernel on the
+    same spectrum, incl. the truncated last band (16 k / 44.1 k); its epilogue statistics against bsrnn_gn_stats."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE, runtime_tc as tc, _lib as L
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=196, num_layer=1, precision="fp16").cuda()
+    core = m.bsrnn.bsrnn
+    n_fft, hop = rt.stft_dims(fs, m.N_FFT, m.HOP, m.DEFAULT_FS)
+    plan = rt.BandPlan.make(core.band_split.subbands, n_fft // 2 + 1)
+    x = R.synth_noisy(B, n, fs, seed=2).cuda()
+    lens = torch.tensor([n - 311 * i for i in range(B)], dtype=torch.int32).cuda()
+    spec, bstats = rt.stft(x, lens, n_fft, hop, plan=plan)
+    ref = rt.band_split_f32(spec, plan, m._bs.get(), 196, stats=bstats.clone())
+    got = tc.band_split_tc(spec, plan, m._bs.get(), m._bs_tc.get(), 196, bstats)
+    torch.cuda.synchronize()
+    e = rel_l2(got.cpu(), ref.cpu())
+    print(f"fs={fs} band split tc vs f32: {e:.3e}")
+    assert got.shape == ref.shape and 0 < e < 1e-3
+    Bq, T, K, N = got.shape
+    want = torch.zeros(Bq, 2, dtype=torch.float64, device="cuda")
+    L.call("bsrnn_gn_stats", got.data_ptr(), want.data_ptr(), Bq, T * K, N, N, L.stream_ptr())
+    have = tc.workspace(Bq, T, K, N, got.device).stats
+    torch.cuda.synchronize()
+    assert torch.allclose(have[:Bq].cpu(), want.cpu(), rtol=1e-5, atol=1e-3)
+
+
+def test_decoder_statistics_from_last_linear_epilogue(monkeypatch):
+    """Per-(sample, band) sums taken by the last Linear + skip epilogue (stats_inner = K) equal a separate pass of
+    bsrnn_band_stats over the final stream, and the enhanced output agrees with the separate-pass schedule."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE, runtime as rtm, runtime_tc as tc, _lib as L
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=196, num_layer=2, precision="fp16").cuda()
+    fs, n = 24000, 12000
+    x = R.synth_noisy(3, n, fs, seed=5)
+    lens = torch.tensor([n, n - 700, n - 1301])
+    seen = {}
+    orig = rtm._decoder_norm_tables
+
+    def spy(skip, packs, stats=None):
+        if stats is not None:
+            Bq, T, K, N = skip.shape
+            ref = torch.empty(Bq, K, 2, dtype=torch.float64, device=skip.device)
+            off = rtm._i32([k * N for k in range(K)], skip.device)
+            wid = rtm._i32([N] * K, skip.device)
+            L.call("bsrnn_band_stats", skip.data_ptr(), ref.data_ptr(), Bq, T, K * N, off.data_ptr(), wid.data_ptr(), K, L.stream_ptr())
+            torch.cuda.synchronize()
+            seen["ref"], seen["got"] = ref.cpu(), stats.cpu().clone()
+        return orig(skip, packs, stats=stats)
+
+    monkeypatch.setattr(rtm, "_decoder_norm_tables", spy)
+    a = m(x, lens, fs)[0].clone()
+    assert "got" in seen and torch.allclose(seen["got"], seen["ref"], rtol=1e-5, atol=1e-3)
+    monkeypatch.setattr(tc, "FC_EPI", L.TC_RESID_F32)               # register-staged epilogue: separate statistics pass
+    monkeypatch.setattr(tc, "BAND_SPLIT_TC", False)
+    b = m(x, lens, fs)[0].clone()
+    e = rel_l2(a.cpu(), b.cpu())
+    print(f"fused statistics + tc band split vs separate passes: {e:.3e}")
+    assert 0 < e < 2e-3
+
+
 def test_lstm_step_tc_vs_torch_h768():
     """bsrnn_lstm_step_tc at the FlowSE width (N = 384, H = 768), ragged last tile: against torch.nn.LSTM on the CPU."""
     from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L

@@ -39,6 +39,12 @@ PROTOTYPES = {
                                  c_int, c_long, c_long, c_long, c_long, c_long, c_int, c_int, c_void_p],
     "bsrnn_gemm_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long,
                       c_int, c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
+    "bsrnn_gemm_tc_ex": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_long,
+                         c_int, c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_int, c_int, c_void_p],
+    "bsrnn_gemm_tc_grouped": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long,
+                              c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
+    "bsrnn_band_norm_cast_kb8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_long, c_int, c_int, c_int, c_void_p],
     "bsrnn_lstm_step_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long, c_void_p],
     "bsrnn_blstm_step_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                             c_int, c_int, c_int, c_int, c_long, c_void_p],

@@ -60,6 +60,7 @@ class BSRNN_SE(nn.Module):
         self._md = R.PackedCache(core.mask_decoder, R.pack_mask_decoder)
         self._dual_tc = R.PackedCache(core, TC.pack_dual_path_tc)
         self._md_tc = R.PackedCache(core.mask_decoder, TC.pack_mask_decoder_tc)
+        self._bs_tc = R.PackedCache(core.band_split, TC.pack_band_split_tc)
 
     # ------------------------------------------------------------------------------------------------
     def _device(self):
@@ -117,9 +118,15 @@ class BSRNN_SE(nn.Module):
                 raise NotImplementedError(
                     f"the tensor-core BLSTM kernel is specialised for num_channel=196 (H=392); got {self.num_channel}. "
                     "Use precision='fp32' for other widths.")
-            skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel, stats=bstats)
-            TC.dual_path_tc(skip, self._dual_tc.get())
-            mask, resid = TC.mask_decoder_tc(skip, plan, self._md_tc.get())
+            B, T = spec.shape[0], spec.shape[1]
+            tc_bs = TC.BAND_SPLIT_TC and self.num_channel % 4 == 0
+            if tc_bs:                                  # Conv1d(2 s_k -> N) on tcgen05, first GroupNorm's sums in its epilogue
+                skip = TC.band_split_tc(spec, plan, self._bs.get(), self._bs_tc.get(), self.num_channel, bstats)
+            else:
+                skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel, stats=bstats)
+            dec_stats = torch.zeros(B, plan.K, 2, dtype=torch.float64, device=spec.device)
+            have = TC.dual_path_tc(skip, self._dual_tc.get(), stats_ready=tc_bs, band_stats=dec_stats)
+            mask, resid = TC.mask_decoder_tc(skip, plan, self._md_tc.get(), band_stats=dec_stats if have else None)
         else:
             raise NotImplementedError(f"precision {self.precision!r}")
         wav_out, est = R.istft(spec, mask, resid, L_out, n_fft, hop, want_spec=True)

@@ -6,6 +6,7 @@
 // and each warp writes whole 784-byte output rows.  It replaces the generic 64x64x16 SIMT grouped GEMM (gemm_f32.cu), which
 // spent 2.83 ms on it (10 % of the copy bandwidth, profiles/r01 call47 / r02 call08).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace bsrnn {
 
@@ -89,6 +90,60 @@ __global__ void __launch_bounds__(kBsThreads, 2) band_split_kernel(const BandSpl
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- tensor-core operand
+// Tensor-core BandSplit (fp16 mode): the per-band GroupNorm(1, 2 s_k) is applied while the band's slice of the spectrum
+// is re-tiled into the fp16 KB8 operand of a tcgen05 GEMM (bsrnn_gemm_tc_ex, store-only TMA epilogue: out rows of band k
+// = A_k W_k^T + b_k, with the statistics of the first dual-path GroupNorm in the epilogue).  One launch covers all bands:
+// grid (row tiles, K); band k's tiles start at a_off[k] halves, [tile][kc_k][128][8] with kc_k = 2 * ceil(2 s_k / 16).
+struct BandCastArgs {
+  const float* spec;        // (rows, F2)
+  const float* scale;       // (B * K, cmax)
+  const float* shift;
+  __half* out;
+  const int* c_off;         // [K + 1]
+  const int* bin0;          // [K]
+  const int* width2;        // [K]
+  const long long* a_off;   // [K] halves
+  long rows;
+  int T, F2, K, cmax;
+};
+
+__global__ void __launch_bounds__(256) band_norm_cast_kb8_kernel(const BandCastArgs a) {
+  extern __shared__ __align__(16) unsigned char bc_smem[];
+  __half* tile = reinterpret_cast<__half*>(bc_smem);
+  const int k = blockIdx.y;
+  const int C = a.c_off[k + 1] - a.c_off[k];
+  const int kc = ((C + 15) >> 4) << 1;
+  const int kw = kc * 8;
+  const int ld = kw + 8;                               // +8 halves: rows land in different banks
+  const int cvalid = a.width2[k];
+  const int col0 = 2 * a.bin0[k];
+  const long r0 = (long)blockIdx.x * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < 128; r += 8) {
+    const long row = r0 + r;
+    const bool ok = row < a.rows;
+    const long b = ok ? row / a.T : 0;
+    const float* src = a.spec + (ok ? row : 0) * a.F2 + col0;
+    const size_t g = ((size_t)b * a.K + k) * a.cmax;
+    for (int c = lane; c < kw; c += 32) {
+      float v = 0.f;
+      if (ok && c < C) {
+        const float x = c < cvalid ? __ldg(src + c) : 0.f;      // truncated band: zero-padded BEFORE the norm
+        v = fmaf(x, __ldg(a.scale + g + c), __ldg(a.shift + g + c));
+      }
+      tile[r * ld + c] = __float2half_rn(v);
+    }
+  }
+  __syncthreads();
+  __half* dst = a.out + a.a_off[k] + (size_t)blockIdx.x * kc * 1024;
+  for (int i = threadIdx.x; i < kc * 128; i += 256) {
+    const int c8 = i >> 7, r = i & 127;
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = *reinterpret_cast<const uint4*>(tile + r * ld + c8 * 8);
+  }
+}
+
 }  // namespace bsrnn
 using namespace bsrnn;
 
@@ -121,5 +176,22 @@ extern "C" int bsrnn_band_split_fwd(const float* spec, const float* scale, const
     BSRNN_LAUNCH_OK();
     k = e;
   }
+  return 0;
+}
+
+// Operand builder of the tensor-core BandSplit (see band_norm_cast_kb8_kernel).  a_off: device [K] offsets in halves.
+extern "C" int bsrnn_band_norm_cast_kb8(const float* spec, const float* scale, const float* shift, void* out,
+                                        const int32_t* c_off, const int32_t* bin0, const int32_t* width2,
+                                        const long long* a_off, int K, long rows, int T, int F2, int cmax, void* stream) {
+  BSRNN_CHECK_ARG(spec && scale && shift && out && c_off && bin0 && width2 && a_off, "band_norm_cast_kb8: null pointer");
+  BSRNN_CHECK_ARG(K > 0 && rows > 0 && T > 0 && F2 > 0 && cmax > 0, "band_norm_cast_kb8: bad dims");
+  const int kc_max = ((cmax + 15) >> 4) << 1;
+  const size_t smem = (size_t)128 * (kc_max * 8 + 8) * 2;
+  BSRNN_CHECK_ARG(smem <= 227 * 1024, "band_norm_cast_kb8: band of %d channels does not fit in shared memory", cmax);
+  BSRNN_CUDA_OK(cudaFuncSetAttribute(band_norm_cast_kb8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BandCastArgs a{spec, scale, shift, reinterpret_cast<__half*>(out), c_off, bin0, width2, a_off, rows, T, F2, K, cmax};
+  dim3 grid((unsigned)((rows + 127) / 128), K);
+  band_norm_cast_kb8_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  BSRNN_LAUNCH_OK();
   return 0;
 }

@@ -303,9 +303,13 @@ extern "C" int bsrnn_istft_fwd(const float* spec, const float* mask, const float
   BSRNN_CHECK_ARG(B > 0 && T > 0 && L_out > 0 && n_fft >= 4 && hop > 0, "istft_fwd: bad dims");
   FftPlan plan;
   BSRNN_CHECK_ARG(make_plan(n_fft, &plan), "istft_fwd: cannot factorise n_fft=%d", n_fft);
-  const int G = 8;
+  int G = 8;
   int fpb = 8;                                        // frames per batch = 2 x frame pairs
   while (fpb > 2 && (size_t)n_fft * 8 * (1 + 2 * ((fpb + 1) / 2)) + (size_t)G * hop * 4 > 100 * 1024) fpb >>= 1;
+  // A block of G hops is touched by G + ceil(N / hop) - 1 frames.  When that fits ONE batch, take G = fpb - overlap: with
+  // G = fpb = 8 at N = 2 hop every block ran a second batch for its 9th frame (one frame pair at the latency of four).
+  const int overlap = (n_fft + hop - 1) / hop - 1;
+  if (fpb - overlap >= 4) G = fpb - overlap;
   const size_t smem = (size_t)n_fft * 8 * (1 + 2 * ((fpb + 1) / 2)) + (size_t)G * hop * 4;
   BSRNN_CUDA_OK(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long span = (long)G * hop;

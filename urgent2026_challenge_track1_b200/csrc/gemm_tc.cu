@@ -99,6 +99,17 @@ struct GemmTcArgs {
   const float* c_cur; const float* c_cur2;    // c_t rows [m*128 + r][H]
   const float* c_prev; const float* c_prev2;  // c_{t-1} rows (null at the first step of the sequence = zeros)
   int valid_rows;                   // rows >= valid_rows (padding of the last sequence tile) get zero gradients
+  // EPI_RESID_TMA extras (bsrnn_gemm_tc_ex)
+  // Grouped launch (EPI_RESID_TMA, one N tile, streaming weights): tile index t = row_tile * n_groups + g; group g (a band of
+  // BandSplit) has its own operand / weight / bias / output offsets and K extent: groups[g] = {a_off (halves, tile 0 of the
+  // group), w_off (halves), out_off (floats), bias_off (floats), kcores}.  Bands innermost: CTAs that run together write
+  // adjacent 784-byte segments of the same output rows.
+  const long long* groups;
+  int n_groups;
+  int run_merge;                    // 1: rows of consecutive tokens move as one bulk copy (set by the launcher, see run_rows)
+  int no_resid;                     // 1: out = acc + bias (store only: the residual rows are neither loaded nor added)
+  int stats_inner;                  // > 1: statistics row = (token / tokens_per_sample) * stats_inner + token % stats_inner
+                                    // (per (sample, band) sums for the mask decoder's GroupNorm(1, N) over (N, T))
 };
 
 enum { EPI_F16_ROWS = 0, EPI_RESID_F32 = 1, EPI_TANH_KB8 = 2, EPI_GLU_F32 = 3, EPI_F16_KB8 = 4, EPI_LSTM_STEP = 5,
@@ -532,10 +543,16 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         const int split = a.ksplit > 1 ? ti.m / a.m_log : 0;
         const int mrow = dir2 ? ti.m - a.dir_tiles : (a.ksplit > 1 ? ti.m - split * a.m_log : ti.m);
         const int kbase = split * a.kps;
-        const int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - kbase) : a.kcores;
-        const int nstage_t = (kcnt + KS - 1) / KS;
+        int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - kbase) : a.kcores;
         const uint8_t* gA = reinterpret_cast<const uint8_t*>(dir2 ? a.A2 : a.A) + ((size_t)mrow * a.kcores + kbase) * 2048;
         const uint8_t* gB = reinterpret_cast<const uint8_t*>(dir2 ? a.W2 : a.W) + ((size_t)ti.n * a.kcores + kbase) * BN * 16;
+        if (a.groups) {
+          const long long* G = a.groups + 5 * (ti.m % a.n_groups);
+          kcnt = (int)__ldg(G + 4);
+          gA = reinterpret_cast<const uint8_t*>(a.A + __ldg(G)) + (size_t)(ti.m / a.n_groups) * kcnt * 2048;
+          gB = reinterpret_cast<const uint8_t*>(a.W + __ldg(G + 1));
+        }
+        const int nstage_t = (kcnt + KS - 1) / KS;
         if (a.pf_dist > 0) {                       // the A tile pf_dist tiles ahead -> L2 (one bulk prefetch)
           const TileIter t3 = ti.ahead(a.pf_dist);
           if (t3.valid() && (a.b_resident ? ti.n == pf_mod : t3.n == 0))
@@ -577,7 +594,8 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
           mbar_wait(acc_empty + buf, acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * TC_ACC_COLS;
-          const int kcnt = a.ksplit > 1 ? min(a.kps, a.kcores - (ti.m / a.m_log) * a.kps) : a.kcores;
+          const int kcnt = a.groups ? (int)__ldg(a.groups + 5 * (ti.m % a.n_groups) + 4)
+                                    : (a.ksplit > 1 ? min(a.kps, a.kcores - (ti.m / a.m_log) * a.kps) : a.kcores);
           const int nstage_t = (kcnt + KS - 1) / KS;
           for (int ks = 0; ks < nstage_t; ++ks) {
             const int nk = min(KS, kcnt - ks * KS);
@@ -598,7 +616,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
     const int q = warp & 3;                    // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;          // which half of the tile's column chunks
     const int r = q * 32 + lane;               // row of the tile
-    if constexpr (EPI == EPI_F16_KB8 && BNC == 208) {
+    if constexpr ((EPI == EPI_F16_KB8 || EPI == EPI_TANH_KB8) && BNC == 208) {
       // The two 4-warp groups take ALTERNATE tiles (group g <-> TMEM buffer g), each warp the whole 208-column row
       // of its lane quadrant in two passes (cores [0,14) and [14,26) of the tile's 26 KB8 cores).  A pass is
       // converted into the group's shared-memory staging block -- already in the global layout, a pass is ONE
@@ -617,6 +635,18 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
       const bool leader = (warp == 2 + 4 * half) && lane == 0;          // issues and tracks the group's bulk stores
       const uint32_t t_row = tmem_base + half * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
       const int bar_id = 1 + half;                                      // named barrier of the group (128 threads)
+      // EPI_TANH_KB8 (MaskDecoder Conv1d(N->4N)+Tanh, bias folded into the weights through the operand's ones column): the
+      // last N tile may reach past the destination's out_kcores k-cores -- its two stores are clipped to the cores that exist
+      const int cores_left = a.out_kcores - n * (BNC / 8);
+      const uint32_t nA = (uint32_t)(cores_left < 14 ? (cores_left < 0 ? 0 : cores_left) : 14);
+      const uint32_t nB = (uint32_t)(cores_left - 14 < 0 ? 0 : (cores_left - 14 > 11 ? 11 : cores_left - 14));
+      auto act = [](uint32_t (&v)[32], int cnt) {
+        if constexpr (EPI == EPI_TANH_KB8) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < cnt) v[i] = __float_as_uint(fast_tanh(__uint_as_float(v[i])));
+        }
+      };
       uint32_t acc_phase = 0;
       for (int m = blockIdx.x / a.n_tiles + half * mstep; m < a.m_tiles; m += 2 * mstep, acc_phase ^= 1) {
         uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -629,6 +659,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         tmem_ld_x16(t_row + 96, reinterpret_cast<uint32_t(&)[16]>(v3));
         tmem_ld_wait();
         tmem_ld_pin(v0); tmem_ld_pin(v1); tmem_ld_pin(v2); tmem_ld_pin(v3);
+        act(v0, 32); act(v1, 32); act(v2, 32); act(v3, 16);
         if (leader) bulk_store_wait_read();                             // previous store has finished reading the staging block
         named_bar_sync(bar_id, 128);
         store_kb8_cores_smem<4>(my_stg, v0);
@@ -637,7 +668,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         store_kb8_cores_smem<2>(my_stg + 12 * 2048, v3);
         fence_proxy_async_shared();                                     // generic-proxy smem writes -> the bulk copy's reads
         named_bar_sync(bar_id, 128);
-        if (leader && do_store) bulk_s2g(gdst, stg, 14 * 2048);
+        if (leader && do_store && nA) bulk_s2g(gdst, stg, nA * 2048);
         tmem_ld_x32(t_row + 112, v0);
         tmem_ld_x32(t_row + 144, v1);
         tmem_ld_x32(t_row + 176, v2);
@@ -646,6 +677,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + half);                   // the accumulator sits in registers: back to the MMA warp
+        act(v0, 32); act(v1, 32); act(v2, 24);
         if (leader) bulk_store_wait_read();
         named_bar_sync(bar_id, 128);
         store_kb8_cores_smem<4>(my_stg, v0);
@@ -653,7 +685,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         store_kb8_cores_smem<3>(my_stg + 8 * 2048, v2);                 // core 25 (columns 200..207) is padding nobody reads
         fence_proxy_async_shared();
         named_bar_sync(bar_id, 128);
-        if (leader && do_store) bulk_s2g(gdst + 14 * 2048, stg, 11 * 2048);
+        if (leader && do_store && nB) bulk_s2g(gdst + 14 * 2048, stg, nB * 2048);
       }
       if (leader) bulk_store_wait_all();
     } else if constexpr (EPI == EPI_RESID_TMA) {
@@ -671,13 +703,29 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
       const int ldr = (ncmax % 8 == 4) ? ncmax : ncmax + 4;          // bank-friendly row stride (floats)
       const bool loader = half == 0;                                   // warps 2..5: one thread per tile row
       float* myrow = resbuf + (size_t)r * ldr;
+      // a.run_merge (dense rows: ldo == n_valid == ldr, one N tile): consecutive rows of a warp whose tokens are consecutive
+      // form ONE contiguous run in HBM and in the row buffer (time axis: the 34 bands of a frame) and move as one bulk copy --
+      // the TMA unit then sees ~8 copies per tile and direction instead of 128 of 784 bytes.  Returns the rows of the run
+      // headed by this thread (0 for the other rows).
+      auto run_rows = [&](bool ok, long tok) -> uint32_t {
+        if (!a.run_merge) return ok ? 1u : 0u;
+        const long ptok = __shfl_up_sync(0xffffffffu, tok, 1);
+        const bool pok = __shfl_up_sync(0xffffffffu, ok ? 1 : 0, 1) != 0;
+        const bool head = ok && (lane == 0 || !pok || tok != ptok + 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, head), oks = __ballot_sync(0xffffffffu, ok);
+        if (!head) return 0u;
+        const unsigned above = lane == 31 ? 0u : ((heads | ~oks) & ~((2u << lane) - 1u));
+        return (uint32_t)((above ? __ffs(above) - 1 : 32) - lane);
+      };
       auto issue_loads = [&](const TileIter& t) {                      // this thread's row of tile t -> row buffer
         const int m2 = t.m, n2 = t.n;
         long tok2 = 0;
         const int nc2 = (a.n_valid - n2 * BN < BN ? a.n_valid - n2 * BN : BN);
-        if (a.rows.map(m2, r, &tok2) && nc2 > 0) {
-          mbar_expect_tx(res_full, (uint32_t)nc2 * 4);
-          bulk_g2s(myrow, reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + (long)n2 * BN, (uint32_t)nc2 * 4, res_full);
+        const bool ok2 = !a.no_resid && a.rows.map(m2, r, &tok2) && nc2 > 0;
+        const uint32_t nr = run_rows(ok2, tok2);
+        if (nr) {
+          mbar_expect_tx(res_full, nr * (uint32_t)nc2 * 4);
+          bulk_g2s(myrow, reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + (long)n2 * BN, nr * (uint32_t)nc2 * 4, res_full);
         } else {
           mbar_arrive(res_full);
         }
@@ -685,7 +733,14 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
       TileIter ti(a);
       if (loader && ti.valid()) issue_loads(ti);
       for (int it = 0; ti.valid(); ti.next(), ++it) {
-        const int m = ti.m, n = ti.n;
+        const int m = a.groups ? ti.m / a.n_groups : ti.m, n = ti.n;
+        const float* g_bias = a.bias;
+        float* g_out = reinterpret_cast<float*>(a.out);
+        if (a.groups) {                                // grouped launch (store only): this tile's band
+          const long long* G = a.groups + 5 * (ti.m % a.n_groups);
+          g_out += __ldg(G + 2);
+          if (g_bias) g_bias += __ldg(G + 3);
+        }
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         long token = 0;
@@ -695,7 +750,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         const TileIter tn = ti.ahead(1);
         {                                              // next tile's residual rows -> L2 while this tile is processed
           long tok2 = 0;
-          if (tn.valid() && a.rows.map(tn.m, r, &tok2)) {
+          if (!a.no_resid && tn.valid() && a.rows.map(tn.m, r, &tok2)) {
             const char* p = reinterpret_cast<const char*>(reinterpret_cast<const float*>(a.out) + tok2 * a.ldo + (long)tn.n * BN);
             const int nbytes = (a.n_valid - tn.n * BN < BN ? a.n_valid - tn.n * BN : BN) * 4;
             for (int off = half * 128; off < nbytes; off += NPART * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
@@ -706,7 +761,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = (ch0 + i) * 32 + lane;
-            if (ch0 + i < ch1 && c < BN) bl[i] = __ldg(a.bias + n * BN + c);
+            if (ch0 + i < ch1 && c < BN) bl[i] = __ldg(g_bias + n * BN + c);
           }
         }
         const float osc = a.out_scale_ptr ? __ldg(a.out_scale_ptr) : (a.out_scale != 0.f ? a.out_scale : 1.f);
@@ -732,7 +787,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
             const float b0 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j) : 0.f, b1 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j + 1) : 0.f;
             const float b2 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j + 2) : 0.f, b3 = a.bias ? __shfl_sync(0xffffffffu, bl[i], j + 3) : 0.f;
             if (row_ok) {
-              float4 o = *reinterpret_cast<float4*>(myrow + c0 + j);
+              float4 o = a.no_resid ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<float4*>(myrow + c0 + j);
               o.x += (__uint_as_float(acc[j]) + b0) * osc; o.y += (__uint_as_float(acc[j + 1]) + b1) * osc;
               o.z += (__uint_as_float(acc[j + 2]) + b2) * osc; o.w += (__uint_as_float(acc[j + 3]) + b3) * osc;
               *reinterpret_cast<float4*>(myrow + c0 + j) = o;
@@ -747,13 +802,14 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         fence_proxy_async_shared();                    // this thread's generic-proxy writes -> the bulk stores' reads
         named_bar_sync(3, tc_epi_warps(EPI) * 32);     // every warp has updated its share of the row buffer
         if (loader) {
-          if (row_ok && ncols > 0) bulk_s2g(reinterpret_cast<float*>(a.out) + token * a.ldo + (long)n * BN, myrow, (uint32_t)ncols * 4);
+          const uint32_t nr = run_rows(row_ok && ncols > 0, token);
+          if (nr) bulk_s2g(g_out + token * a.ldo + (long)n * BN, myrow, nr * (uint32_t)ncols * 4);
           bulk_store_wait_read();                      // the store has finished READING the row: the buffer may be refilled
           named_bar_sync(4, 128);                      // ... for all 128 rows
           if (tn.valid()) issue_loads(tn);
         }
         if (a.stats) {
-          const long samp = row_ok ? token / a.tokens_per_sample : -1;
+          const long samp = row_ok ? (a.stats_inner > 1 ? (token / a.tokens_per_sample) * a.stats_inner + token % a.stats_inner : token / a.tokens_per_sample) : -1;
           unsigned todo = __ballot_sync(0xffffffffu, row_ok);
           while (todo) {
             const int leader = __ffs(todo) - 1;
@@ -850,7 +906,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
       if (lane == 0) mbar_arrive(acc_empty + buf);
       if (EPI == EPI_RESID_F32 && a.stats) {
         // rows of a warp are consecutive sequences: usually one sample, sometimes two or three
-        const long samp = row_ok ? token / a.tokens_per_sample : -1;
+        const long samp = row_ok ? (a.stats_inner > 1 ? (token / a.tokens_per_sample) * a.stats_inner + token % a.stats_inner : token / a.tokens_per_sample) : -1;
         unsigned todo = __ballot_sync(0xffffffffu, row_ok);
         while (todo) {
           const int leader = __ffs(todo) - 1;
@@ -888,6 +944,12 @@ static size_t tc_resbuf_bytes(int BN, int n_valid) {
   return (size_t)128 * ldr * 4;
 }
 
+static bool tanh_bulk_enabled() {         // BSRNN_TANH_BULK=0: the generic epilogue for EPI_TANH_KB8 (A/B timing)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BSRNN_TANH_BULK"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 template <int EPI>
 static int launch_tc(GemmTcArgs a, cudaStream_t st) {
   static int sms = 0;                     // one process per GPU: the SM count is queried once
@@ -920,6 +982,11 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
     }
   }
   const size_t extra_smem = EPI == EPI_RESID_TMA ? tc_resbuf_bytes(a.BN, a.n_valid) : 0;
+  if (EPI == EPI_RESID_TMA) {
+    static int runs_env = -1;             // BSRNN_FC_RUNS=0: one bulk copy per row (A/B timing)
+    if (runs_env < 0) { const char* e = getenv("BSRNN_FC_RUNS"); runs_env = (e && e[0] == '0') ? 0 : 1; }
+    a.run_merge = (runs_env && a.n_tiles == 1 && a.n_valid <= a.BN && a.ldo == a.n_valid && a.n_valid % 8 == 4) ? 1 : 0;
+  }
   a.stages = tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, 8, TC_KS, extra_smem) <= 227 * 1024 ? 8 : 4;
   while (a.stages > 2 && tc_smem_bytes(a.BN, a.kcores, a.b_resident, EPI == EPI_RESID_F32, a.stages, TC_KS, extra_smem) > 227 * 1024) --a.stages;
   static int force4 = -1;                 // BSRNN_GEMM_STAGES=4: previous pipeline depth (A/B timing)
@@ -1002,6 +1069,15 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
     }
     a.mc = 1;
     gemm_tc_kernel<EPI_F16_KB8, 208><<<grid, tc_threads(EPI_F16_KB8), smem_ip, st>>>(a);
+  } else if (EPI == EPI_TANH_KB8 && a.BN == 208 && a.kcores == 26 && a.bias == nullptr && a.b_resident &&
+             a.out_kcores > (a.n_tiles - 1) * 26 && tanh_bulk_enabled()) {
+    // MaskDecoder Conv1d(N->4N)+Tanh on the specialised kernel of the input projection (straight-line epilogue, tile staged in
+    // shared memory in the destination layout, bulk stores): the st.global path of the generic epilogue paced it
+    a.stages = 5;
+    a.mc = 1;
+    const size_t smem_ip = tc_smem_bytes(a.BN, a.kcores, true, false, a.stages) + 2 * 14 * 2048;
+    BSRNN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<EPI_TANH_KB8, 208>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ip));
+    gemm_tc_kernel<EPI_TANH_KB8, 208><<<grid, tc_threads(EPI_TANH_KB8), smem_ip, st>>>(a);
   } else if (step_mc > 1) {
     // cluster launch: mc consecutive CTAs = mc consecutive N tiles of the same (direction, M walk)
     cudaLaunchConfig_t cfg = {};
@@ -1038,10 +1114,13 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
 }  // namespace bsrnn
 using namespace bsrnn;
 
-extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, double* stats,
-                               int m_tiles, int n_tiles, int kcores, int BN, int epilogue, long ldo, int n_valid,
-                               int out_kcores, long tokens_per_sample, int tiles_per_step, int R, long seq_inner,
-                               long seq_outer, long seq_inner_stride, long step_stride, void* stream) {
+// bsrnn_gemm_tc with two extras of the f32-row epilogues 1 / 8: stats_inner (> 1: statistics per (sample, token %
+// stats_inner) instead of per sample) and flags (bit 0, epilogue 8 only: store only -- out = A W^T + bias, no residual read).
+extern "C" int bsrnn_gemm_tc_ex(const void* A, const void* W, const float* bias, void* out, double* stats,
+                                  int m_tiles, int n_tiles, int kcores, int BN, int epilogue, long ldo, int n_valid,
+                                  int out_kcores, long tokens_per_sample, int tiles_per_step, int R, long seq_inner,
+                                  long seq_outer, long seq_inner_stride, long step_stride, int stats_inner, int flags,
+                                  void* stream) {
   BSRNN_CHECK_ARG(A && W && out, "gemm_tc: null pointer");
   BSRNN_CHECK_ARG(m_tiles > 0 && n_tiles > 0 && kcores > 0 && kcores % 2 == 0, "gemm_tc: bad tile counts (kcores=%d)", kcores);
   BSRNN_CHECK_ARG(BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc: BN=%d must be a multiple of 16 in [16,256]", BN);
@@ -1054,6 +1133,10 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   a.bias = bias; a.out = out; a.stats = stats; a.ldo = ldo; a.tokens_per_sample = tokens_per_sample;
   a.m_tiles = m_tiles; a.n_tiles = n_tiles; a.kcores = kcores; a.BN = BN; a.n_valid = n_valid; a.out_kcores = out_kcores;
   a.rows = RowMap{tiles_per_step, R, seq_inner, seq_outer, seq_inner_stride, step_stride};
+  BSRNN_CHECK_ARG(stats_inner >= 1 && (flags & ~1) == 0 && (!(flags & 1) || epilogue == EPI_RESID_TMA),
+                  "gemm_tc: bad stats_inner / flags (store-only needs epilogue 8)");
+  a.stats_inner = stats_inner;
+  a.no_resid = flags & 1;
   cudaStream_t st = (cudaStream_t)stream;
   switch (epilogue) {
     case EPI_F16_ROWS: return launch_tc<EPI_F16_ROWS>(a, st);
@@ -1068,6 +1151,35 @@ extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, vo
   }
   set_error("gemm_tc: unknown epilogue %d", epilogue);
   return 1;
+}
+// Grouped store-only GEMM (tensor-core BandSplit): out[token*ldo + out_off_g + c] = A_g W_g^T + bias_g for n_groups bands in
+// ONE launch, bands innermost in the tile order.  groups: device [n_groups][5] int64 {a_off, w_off, out_off, bias_off,
+// kcores} relative to A / W / out / bias; kc_max = largest kcores (sizes the pipeline); m_tiles = row tiles per group.
+extern "C" int bsrnn_gemm_tc_grouped(const void* A, const void* W, const float* bias, void* out, double* stats,
+                                       const long long* groups, int n_groups, int m_tiles, int kc_max, int BN, long ldo,
+                                       int n_valid, long tokens_per_sample, int tiles_per_step, int R, long seq_inner,
+                                       long seq_outer, long seq_inner_stride, long step_stride, void* stream) {
+  BSRNN_CHECK_ARG(A && W && out && groups && n_groups > 0, "gemm_tc_grouped: null pointer");
+  BSRNN_CHECK_ARG(m_tiles > 0 && kc_max > 0 && kc_max % 2 == 0 && BN >= 16 && BN <= 256 && BN % 16 == 0, "gemm_tc_grouped: bad tile dims");
+  BSRNN_CHECK_ARG(n_valid > 0 && n_valid <= BN && n_valid % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  "gemm_tc_grouped: rows must be 16-byte aligned, n_valid <= BN");
+  BSRNN_CHECK_ARG(tiles_per_step > 0 && seq_inner > 0 && tokens_per_sample > 0, "gemm_tc_grouped: bad row map");
+  GemmTcArgs a{};
+  a.A = reinterpret_cast<const __half*>(A);
+  a.W = reinterpret_cast<const __half*>(W);
+  a.bias = bias; a.out = out; a.stats = stats; a.ldo = ldo; a.tokens_per_sample = tokens_per_sample;
+  a.m_tiles = m_tiles * n_groups; a.n_tiles = 1; a.kcores = kc_max; a.BN = BN; a.n_valid = n_valid;
+  a.rows = RowMap{tiles_per_step, R, seq_inner, seq_outer, seq_inner_stride, step_stride};
+  a.stats_inner = 1; a.no_resid = 1; a.groups = groups; a.n_groups = n_groups;
+  return launch_tc<EPI_RESID_TMA>(a, (cudaStream_t)stream);
+}
+
+extern "C" int bsrnn_gemm_tc(const void* A, const void* W, const float* bias, void* out, double* stats,
+                               int m_tiles, int n_tiles, int kcores, int BN, int epilogue, long ldo, int n_valid,
+                               int out_kcores, long tokens_per_sample, int tiles_per_step, int R, long seq_inner,
+                               long seq_outer, long seq_inner_stride, long step_stride, void* stream) {
+  return bsrnn_gemm_tc_ex(A, W, bias, out, stats, m_tiles, n_tiles, kcores, BN, epilogue, ldo, n_valid, out_kcores,
+                          tokens_per_sample, tiles_per_step, R, seq_inner, seq_outer, seq_inner_stride, step_stride, 1, 0, stream);
 }
 
 // One time step of an LSTM direction on tensor cores, any H % 8 == 0 (csrc/gemm_tc.cu, EPI_LSTM_STEP):

@@ -515,15 +515,17 @@ def dual_path_f32(skip, layers, t_emb=None):
     return skip
 
 
-def _decoder_norm_tables(skip, packs):
-    """Per-(sample, band) GroupNorm(1,N) over (N,T) for each MLP family -> {name: (scale, shift)} (B*K, N)."""
+def _decoder_norm_tables(skip, packs, stats=None):
+    """Per-(sample, band) GroupNorm(1,N) over (N,T) for each MLP family -> {name: (scale, shift)} (B*K, N).
+    stats: (B,K,2) f64 sums already taken by the last Linear + skip epilogue (tensor-core mode), else one pass here."""
     B, T, K, N = skip.shape
     dev = skip.device
     st = L.stream_ptr()
-    stats = torch.empty(B, K, 2, dtype=torch.float64, device=dev)
-    off = _i32([k * N for k in range(K)], dev)
-    wid = _i32([N] * K, dev)
-    L.call("bsrnn_band_stats", skip.data_ptr(), stats.data_ptr(), B, T, K * N, off.data_ptr(), wid.data_ptr(), K, st)
+    if stats is None:
+        stats = torch.empty(B, K, 2, dtype=torch.float64, device=dev)
+        off = _i32([k * N for k in range(K)], dev)
+        wid = _i32([N] * K, dev)
+        L.call("bsrnn_band_stats", skip.data_ptr(), stats.data_ptr(), B, T, K * N, off.data_ptr(), wid.data_ptr(), K, st)
     counts = _f64([float(N) * T] * K, dev)
     out = {}
     for name, p in packs.items():

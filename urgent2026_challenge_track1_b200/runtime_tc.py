@@ -243,17 +243,22 @@ def workspace(B, T, K, N, dev):
 _EXACT_STATS = os.environ.get("BSRNN_TC_EXACT_STATS", "0") == "1"
 
 
-def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
-    """In-place 2*num_layer residual blocks on skip (B,T,K,N) f32, tensor-core mode."""
+def dual_path_tc(skip, layers, t_emb=None, max_clusters=0, stats_ready=False, band_stats=None):
+    """In-place 2*num_layer residual blocks on skip (B,T,K,N) f32, tensor-core mode.
+    stats_ready: the per-sample sums of `skip` already sit in workspace(...).stats (written by band_split_tc's GEMM
+    epilogues).  band_stats: (B,K,2) f64 zeros -- the last Linear + skip then accumulates per-(sample, band) sums of the
+    final stream there (the statistics of the mask decoder's GroupNorms) instead of the per-sample ones nobody reads."""
     B, T, K, N = skip.shape
     dev = skip.device
     st = L.stream_ptr()
     ws = workspace(B, T, K, N, dev)
     keepalive(ws)
     M = B * T * K
-    L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
+    if not stats_ready:
+        L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
     for i, lay in enumerate(layers):
         for axis in ("time", "freq"):
+            last = band_stats is not None and FC_EPI == L.TC_RESID_TMA and i == len(layers) - 1 and axis == "freq"
             w = lay[axis]
             extra = t_emb[i] if (t_emb is not None and axis == "time") else None
             if axis == "time":
@@ -295,16 +300,91 @@ def dual_path_tc(skip, layers, t_emb=None, max_clusters=0):
             with region("fc"):
                 ws.stats.zero_()
                 fc = w["fc"]
-                L.call("bsrnn_gemm_tc", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
-                       ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], FC_EPI, N, N, 0, T * K,
-                       tiles, R, *addr, st)
+                L.call("bsrnn_gemm_tc_ex", ws.y.data_ptr(), fc["w"].data_ptr(), fc["b"].data_ptr(), skip.data_ptr(),
+                       band_stats.data_ptr() if last else ws.stats.data_ptr(), steps * tiles, 1, 2 * LKC, fc["BN"], FC_EPI,
+                       N, N, 0, T * K, tiles, R, *addr, K if last else 1, 0, st)
                 if _EXACT_STATS:                       # diagnosis: statistics from a separate pass over skip
                     ws.stats.zero_()
                     L.call("bsrnn_gn_stats", skip.data_ptr(), ws.stats.data_ptr(), B, T * K, N, N, st)
-    return skip
+    return band_stats is not None and FC_EPI == L.TC_RESID_TMA          # True: band_stats holds the decoder statistics
+
+
+# ------------------------------------------------------------------------------------------------ band split
+BAND_SPLIT_TC = os.environ.get("BSRNN_BAND_SPLIT_TC", "1") == "1"      # 0: the f32 CUDA-core kernel (A/B, bandsplit.cu)
+BAND_SPLIT_GROUPED = os.environ.get("BSRNN_BAND_SPLIT_GROUPED", "1") == "1"   # 0: one GEMM launch per band (A/B)
+
+
+def pack_band_split_tc(bs):
+    """BandSplit Conv1d(2 s_k -> N, 1) weights as fp16 KB8 tiles (one 208-row N tile per band, K padded to 16) + bias table;
+    a_unit[k] = k-cores of band k's operand tile."""
+    K = len(bs.subbands)
+    N = bs.fc[0].weight.shape[0]
+    dev = bs.fc[0].weight.device
+    BN = (N + 15) // 16 * 16
+    kcs = [((2 * s + 15) // 16) * 2 for s in bs.subbands]
+    w = [to_kb8(bs.fc[k].weight[:, :, 0].float(), BN, kcs[k]).reshape(-1) for k in range(K)]
+    w_off, tot = [], 0
+    for k in range(K):
+        w_off.append(tot)
+        tot += w[k].numel()
+    bias = torch.zeros(K, BN, device=dev)
+    for k in range(K):
+        bias[k, :N] = bs.fc[k].bias
+    return dict(w=torch.cat(w).contiguous(), w_off=w_off, bias=bias, kcs=kcs, BN=BN, N=N)
+
+
+def band_split_tc(spec, plan, bs_pack, bs_tc, N, stats):
+    """spec (B,T,F,2) -> skip (B,T,K',N) f32 on tensor cores [reference bsrnn_flowse.py:65-86]: one operand-builder launch
+    (per-band GroupNorm applied on the fly) + one store-only tcgen05 GEMM per band.  The GEMM epilogues also accumulate the
+    per-sample sums of the result into workspace(...).stats: the first dual-path GroupNorm needs no pass of its own."""
+    from .runtime import _i32, _const_table
+    B, T, F, _ = spec.shape
+    dev = spec.device
+    K = plan.K
+    cmax = bs_pack["cmax"]
+    st = L.stream_ptr()
+    ws = workspace(B, T, K, N, dev)
+    keepalive(ws)
+    counts = _f64([2.0 * plan.subbands[k] * T for k in range(K)], dev)      # padded bins count (bsrnn_flowse.py:68-73)
+    scale = torch.empty(B * K, cmax, dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    L.call("bsrnn_gn_finalize", stats.data_ptr(), bs_pack["gamma"].data_ptr(), bs_pack["beta"].data_ptr(), None,
+           scale.data_ptr(), shift.data_ptr(), B * K, cmax, counts.data_ptr(), bs_pack["eps"], K, st)
+    tiles = (B * T + 127) // 128
+    offs, tot = [], 0
+    for k in range(K):
+        offs.append(tot)
+        tot += tiles * bs_tc["kcs"][k] * 1024
+    a_off_d = _const_table(offs, torch.int64, dev)
+    xhat = torch.empty(tot, dtype=torch.float16, device=dev)
+    wid = _i32([2 * w for w in plan.width], dev)
+    bin0 = _i32(list(plan.bin0), dev)
+    L.call("bsrnn_band_norm_cast_kb8", spec.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(),
+           bs_pack["c_off"].data_ptr(), bin0.data_ptr(), wid.data_ptr(), a_off_d.data_ptr(), K, B * T, T, 2 * F, cmax, st)
+    out = torch.empty(B, T, K, N, dtype=torch.float32, device=dev)
+    ws.stats.zero_()
+    if BAND_SPLIT_GROUPED and bs_tc["BN"] >= N:
+        # one launch for all bands, band innermost in the tile order: co-running CTAs write adjacent 4N-byte segments of the
+        # same rows of the (B,T,K,N) stream
+        desc = []
+        for k in range(K):
+            desc += [offs[k], bs_tc["w_off"][k], k * N, k * bs_tc["BN"], bs_tc["kcs"][k]]
+        groups = _const_table(desc, torch.int64, dev)
+        L.call("bsrnn_gemm_tc_grouped", xhat.data_ptr(), bs_tc["w"].data_ptr(), bs_tc["bias"].data_ptr(), out.data_ptr(),
+               ws.stats.data_ptr(), groups.data_ptr(), K, tiles, max(bs_tc["kcs"][:K]), bs_tc["BN"], K * N, N, T, tiles,
+               B * T, BIG, 0, 1, 0, st)
+        return out
+    for k in range(K):
+        L.call("bsrnn_gemm_tc_ex", xhat.data_ptr() + 2 * offs[k], bs_tc["w"].data_ptr() + 2 * bs_tc["w_off"][k],
+               bs_tc["bias"][k].data_ptr(), out.data_ptr() + 4 * k * N, ws.stats.data_ptr(), tiles, 1, bs_tc["kcs"][k],
+               bs_tc["BN"], L.TC_RESID_TMA, K * N, N, 0, T, tiles, B * T, BIG, 0, 1, 0, 1, 1, st)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ mask decoder
+MASKDEC_ONES = os.environ.get("BSRNN_MASKDEC_ONES", "1") == "1"      # 0: separate bias vector, generic tanh epilogue (A/B)
+
+
 def pack_mask_decoder_tc(md):
     """espnet2-style MaskDecoder for the tensor-core path: Conv1d(N,4N) as 208-column tiles, Conv1d(4N,4s) with rows
     interleaved (value, gate) so the GLU pairs sit in adjacent accumulator columns."""
@@ -317,8 +397,14 @@ def pack_mask_decoder_tc(md):
         kc2 = (H4 + 15) // 16 * 2
         nt1 = (H4 + LBN - 1) // LBN
         w1, b1, w2, b2, bn2 = [], [], [], [], []
+        # bias of Conv1d(N,4N) as weight column N against the operand's constant-one column (bsrnn_norm_cast_kb8_ones): the
+        # GEMM then runs bias-free on the bulk-store tanh kernel (gemm_tc.cu, EPI_TANH_KB8 / BNC = 208)
+        one_col = N if (MASKDEC_ONES and N % 4 == 0 and kc1 * 8 > N) else -1
         for k, m in enumerate(mlps):
-            w1.append(to_kb8(m[1].weight[:, :, 0].float(), LBN, kc1))
+            wk = m[1].weight[:, :, 0].float()
+            if one_col >= 0:
+                wk = torch.cat([wk, m[1].bias.float()[:, None]], 1)
+            w1.append(to_kb8(wk, LBN, kc1))
             bb = torch.zeros(nt1 * LBN, device=m[1].bias.device); bb[:H4] = m[1].bias
             b1.append(bb)
             w = m[3].weight[:, :, 0].float()                     # (4s, 4N): first 2s rows = value, last 2s = gate
@@ -331,19 +417,20 @@ def pack_mask_decoder_tc(md):
             bn2.append(BN)
         out[name] = dict(gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
                          beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
-                         w1=w1, b1=b1, w2=w2, b2=b2, bn2=bn2, kc1=kc1, kc2=kc2, nt1=nt1, N=N,
+                         w1=w1, b1=b1, w2=w2, b2=b2, bn2=bn2, kc1=kc1, kc2=kc2, nt1=nt1, N=N, one_col=one_col,
                          eps=float(mlps[0][0].eps))
     return out
 
 
-def mask_decoder_tc(skip, plan, md_pack):
-    """skip (B,T,K',N) -> mask, resid (B,T,F,2) f32, tensor-core mode."""
+def mask_decoder_tc(skip, plan, md_pack, band_stats=None):
+    """skip (B,T,K',N) -> mask, resid (B,T,F,2) f32, tensor-core mode.  band_stats: (B,K,2) per-(sample, band) sums of
+    skip when the last Linear + skip already took them (dual_path_tc)."""
     from .runtime import _decoder_norm_tables
     B, T, K, N = skip.shape
     F = plan.F
     dev = skip.device
     st = L.stream_ptr()
-    tabs = _decoder_norm_tables(skip, md_pack)
+    tabs = _decoder_norm_tables(skip, md_pack, stats=band_stats)
     tiles = (B * T + 127) // 128
     outs = {}
     # The mask and the residual MLP families are independent chains of 2 x K small GEMMs: they run on two streams (two
@@ -368,11 +455,12 @@ def mask_decoder_tc(skip, plan, md_pack):
             with torch.cuda.stream(stream):
                 st = L.stream_ptr()
                 # rows of tile (k, j) are the (b,t) tokens of band k: same row map as the band-axis BLSTM
-                L.call("bsrnn_norm_cast_kb8", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
-                       p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, st)
+                L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
+                       p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, p["one_col"], st)
                 for k in range(K):
                     L.call("bsrnn_gemm_tc", xhat.data_ptr() + 2 * k * tiles * p["kc1"] * 1024, p["w1"][k].data_ptr(),
-                           p["b1"][k].data_ptr(), hidden.data_ptr(), None, tiles, p["nt1"], p["kc1"], LBN, L.TC_TANH_KB8,
+                           None if p["one_col"] >= 0 else p["b1"][k].data_ptr(), hidden.data_ptr(), None, tiles, p["nt1"],
+                           p["kc1"], LBN, L.TC_TANH_KB8,
                            0, 4 * N, p["kc2"], B * T, tiles, B * T, BIG, 0, 1, 0, st)
                     L.call("bsrnn_gemm_tc", hidden.data_ptr(), p["w2"][k].data_ptr(), p["b2"][k].data_ptr(),
                            o.data_ptr() + 8 * plan.bin0[k], None, tiles, 1, p["kc2"], p["bn2"][k], L.TC_GLU_F32, 2 * F,
