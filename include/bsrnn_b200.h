@@ -190,6 +190,10 @@ int bsrnn_gemm_tc_grouped(const void* A, const void* W, const float* bias, void*
                           const long long* groups, int n_groups, int m_tiles, int kc_max, int BN, long ldo, int n_valid,
                           long tokens_per_sample, int tiles_per_step, int R, long seq_inner, long seq_outer,
                           long seq_inner_stride, long step_stride, void* stream);
+/* bsrnn_gemm_tc_limit_ctas: upper bound on the persistent CTAs of the following bsrnn_gemm_tc* launches of this process (0 =
+ *     every SM); returns the previous bound.  The mask decoder's two MLP families [espnet2 MaskDecoder: mlp_mask /
+ *     mlp_residual] run on two streams with half of the SMs each. */
+int bsrnn_gemm_tc_limit_ctas(int n);
 int bsrnn_band_norm_cast_kb8(const float* spec, const float* scale, const float* shift, void* out, const int32_t* c_off,
                              const int32_t* bin0, const int32_t* width2, const long long* a_off, int K, long rows, int T,
                              int F2, int cmax, void* stream);

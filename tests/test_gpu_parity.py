@@ -348,6 +348,31 @@ def test_decoder_statistics_from_last_linear_epilogue(monkeypatch):
     assert 0 < e < 2e-3
 
 
+def test_weight_resident_gemm_paths_match_a_small_batch():
+    """The weight-resident / specialised GEMM schedules only start at >= 74 row tiles (9 472 tokens per band), which none of
+    the oracle-sized tests reach: rows of a 12 x 8 s batch must equal the same utterances in a batch of 2 (generic schedules),
+    and the batch of 2 must match the oracle."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=196, num_layer=1, precision="fp16")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.cuda()
+    fs, n, B = 48000, 8 * 48000, 12
+    base = R.synth_noisy(3, n, fs, seed=7)
+    x = base[torch.tensor([i % 3 for i in range(B)])].contiguous()
+    lens = torch.full((B,), n, dtype=torch.int32)
+    big = m(x, lens, fs)[0].cpu()
+    small = m(base[:2].contiguous(), lens[:2], fs)[0].cpu()
+    e0, e1 = rel_l2(big[0], small[0]), rel_l2(big[1], small[1])
+    print(f"12 x 8 s batch vs batch of 2: rel_l2 {e0:.2e} {e1:.2e}")
+    assert e0 < 2e-3 and e1 < 2e-3
+    with torch.no_grad():
+        ref, _ = R.bsrnn_se_forward(sd, base[:1], lens[:1].long(), fs, num_layer=1)
+    e = rel_l2(big[:1], ref)
+    print(f"12 x 8 s batch row 0 vs oracle: {e:.3e}")
+    assert e < 1e-2
+
+
 def test_lstm_step_tc_vs_torch_h768():
     """bsrnn_lstm_step_tc at the FlowSE width (N = 384, H = 768), ragged last tile: against torch.nn.LSTM on the CPU."""
     from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L

@@ -18,6 +18,7 @@
 // MaskDecoder].
 #include "common.cuh"
 #include "umma.cuh"
+#include "tmap.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -46,9 +47,16 @@ struct RowMap {                     // global row (m_tile, r) -> token
   __device__ __forceinline__ bool map(int m_tile, int r, long* token) const {
     const int step = m_tile / tiles_per_step;
     const int j = m_tile - step * tiles_per_step;
-    const long seq = (long)j * 128 + r;
+    const int seq = j * 128 + r;                   // < R (int)
     if (seq >= R) return false;
-    *token = (seq / seq_inner) * seq_outer + (seq % seq_inner) * seq_inner_stride + (long)step * step_stride;
+    // the general form costs two 64-bit divisions per row and tile (9 % of the Linear+skip epilogue's samples, profiles/r02
+    // call52): band axis / plain rows need none, the time axis one 32-bit division
+    if (seq_inner == 1) *token = (long)seq * seq_outer + (long)step * step_stride;
+    else if (seq_inner >= (long)R) *token = (long)seq * seq_inner_stride + (long)step * step_stride;
+    else {
+      const int si = (int)seq_inner, q = seq / si;
+      *token = (long)q * seq_outer + (long)(seq - q * si) * seq_inner_stride + (long)step * step_stride;
+    }
     return true;
   }
 };
@@ -99,6 +107,7 @@ struct GemmTcArgs {
   const float* c_cur; const float* c_cur2;    // c_t rows [m*128 + r][H]
   const float* c_prev; const float* c_prev2;  // c_{t-1} rows (null at the first step of the sequence = zeros)
   int valid_rows;                   // rows >= valid_rows (padding of the last sequence tile) get zero gradients
+  alignas(64) CUtensorMap tmap;     // use_tmap: the matrix view of `out` (read through the kernel's __grid_constant__ parameter)
   // EPI_RESID_TMA extras (bsrnn_gemm_tc_ex)
   // Grouped launch (EPI_RESID_TMA, one N tile, streaming weights): tile index t = row_tile * n_groups + g; group g (a band of
   // BandSplit) has its own operand / weight / bias / output offsets and K extent: groups[g] = {a_off (halves, tile 0 of the
@@ -106,6 +115,14 @@ struct GemmTcArgs {
   // adjacent 784-byte segments of the same output rows.
   const long long* groups;
   int n_groups;
+  // L2 residency of the MaskDecoder's hidden activation (the same 100 MB buffer is written by every band's Conv1d+Tanh and
+  // read back by its Conv1d+GLU): bit 0 = bulk stores of the output (EPI_TANH_KB8 / BNC = 208), bit 1 = bulk loads of the A
+  // operand carry the evict_last policy, so the buffer stays in the 126 MB L2 instead of making a DRAM round trip per band
+  int l2_keep;
+  // EPI_RESID_TMA with a 2-D tensor map (tmap.cuh): the tile's rows are `rows [j*128, +128) x cols [step*tm_col_step (+ group
+  // offset), +n_valid)` of a row-major matrix over `out` (band axis, BandSplit): ONE tensor copy per tile and direction
+  int use_tmap;
+  int tm_col_step;
   int run_merge;                    // 1: rows of consecutive tokens move as one bulk copy (set by the launcher, see run_rows)
   int no_resid;                     // 1: out = acc + bias (store only: the residual rows are neither loaded nor added)
   int stats_inner;                  // > 1: statistics row = (token / tokens_per_sample) * stats_inner + token % stats_inner
@@ -479,7 +496,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // projection (EPI_F16_KB8): its epilogue is then straight-line code (profiles/r01/call26: the generic epilogue spent
 // ~440 instructions per tile and warp on 70 useful ones and paced the kernel at 2.8x the MMA time).
 template <int EPI, int BNC = 0>
-__global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmTcArgs a) {
+__global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __grid_constant__ GemmTcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int BN = a.BN;
   const int KS = a.ks;
@@ -569,7 +586,9 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
             const uint32_t slice = (uint32_t)nk * 2048 / (uint32_t)a.mc;
             bulk_g2s_multicast(sA + stage * a_stage_bytes + crank * slice, gA + (size_t)kc0 * 2048 + crank * slice, slice,
                                full + stage, cmask);
-          } else
+          } else if (a.l2_keep & 2)
+            bulk_g2s_hint(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage, l2_policy_evict_last());
+          else
           bulk_g2s(sA + stage * a_stage_bytes, gA + (size_t)kc0 * 2048, nk * 2048, full + stage);
           if (!a.b_resident)
             bulk_g2s(sB + stage * b_stage_bytes, gB + (size_t)kc0 * BN * 16, nk * BN * 16, full + stage);
@@ -639,7 +658,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
       // last N tile may reach past the destination's out_kcores k-cores -- its two stores are clipped to the cores that exist
       const int cores_left = a.out_kcores - n * (BNC / 8);
       const uint32_t nA = (uint32_t)(cores_left < 14 ? (cores_left < 0 ? 0 : cores_left) : 14);
-      const uint32_t nB = (uint32_t)(cores_left - 14 < 0 ? 0 : (cores_left - 14 > 11 ? 11 : cores_left - 14));
+      // pass B: the input projection's 26th core (columns 200..207 = the 12 pad gate columns of a 49-unit slice) is never read
+      // and not stored; the MaskDecoder's hidden tile uses all 208 columns
+      constexpr int NB_MAX = EPI == EPI_TANH_KB8 ? 12 : 11;
+      const uint32_t nB = (uint32_t)(cores_left - 14 < 0 ? 0 : (cores_left - 14 > NB_MAX ? NB_MAX : cores_left - 14));
       auto act = [](uint32_t (&v)[32], int cnt) {
         if constexpr (EPI == EPI_TANH_KB8) {
 #pragma unroll
@@ -668,7 +690,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         store_kb8_cores_smem<2>(my_stg + 12 * 2048, v3);
         fence_proxy_async_shared();                                     // generic-proxy smem writes -> the bulk copy's reads
         named_bar_sync(bar_id, 128);
-        if (leader && do_store && nA) bulk_s2g(gdst, stg, nA * 2048);
+        if (leader && do_store && nA) {
+          if (EPI == EPI_TANH_KB8 && (a.l2_keep & 1)) bulk_s2g_hint(gdst, stg, nA * 2048, l2_policy_evict_last());
+          else bulk_s2g(gdst, stg, nA * 2048);
+        }
         tmem_ld_x32(t_row + 112, v0);
         tmem_ld_x32(t_row + 144, v1);
         tmem_ld_x32(t_row + 176, v2);
@@ -677,15 +702,19 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + half);                   // the accumulator sits in registers: back to the MMA warp
-        act(v0, 32); act(v1, 32); act(v2, 24);
+        act(v0, 32); act(v1, 32); act(v2, 32);
         if (leader) bulk_store_wait_read();
         named_bar_sync(bar_id, 128);
         store_kb8_cores_smem<4>(my_stg, v0);
         store_kb8_cores_smem<4>(my_stg + 4 * 2048, v1);
-        store_kb8_cores_smem<3>(my_stg + 8 * 2048, v2);                 // core 25 (columns 200..207) is padding nobody reads
+        if constexpr (EPI == EPI_TANH_KB8) store_kb8_cores_smem<4>(my_stg + 8 * 2048, v2);
+        else store_kb8_cores_smem<3>(my_stg + 8 * 2048, v2);            // core 25 (columns 200..207) is padding nobody reads
         fence_proxy_async_shared();
         named_bar_sync(bar_id, 128);
-        if (leader && do_store && nB) bulk_s2g(gdst + 14 * 2048, stg, nB * 2048);
+        if (leader && do_store && nB) {
+          if (EPI == EPI_TANH_KB8 && (a.l2_keep & 1)) bulk_s2g_hint(gdst + 14 * 2048, stg, nB * 2048, l2_policy_evict_last());
+          else bulk_s2g(gdst + 14 * 2048, stg, nB * 2048);
+        }
       }
       if (leader) bulk_store_wait_all();
     } else if constexpr (EPI == EPI_RESID_TMA) {
@@ -698,7 +727,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
       constexpr int NPART = tc_epi_warps(EPI) / 4;
       const int nch = (BN + 31) >> 5;
       const int ch0 = (half * nch + NPART - 1) / NPART, ch1 = ((half + 1) * nch + NPART - 1) / NPART;
-      float* resbuf = reinterpret_cast<float*>(smem_scr);
+      float* resbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_scr) + 127) & ~(uintptr_t)127);   // TMA box: 128 B
       const int ncmax = a.n_valid < BN ? a.n_valid : BN;
       const int ldr = (ncmax % 8 == 4) ? ncmax : ncmax + 4;          // bank-friendly row stride (floats)
       const bool loader = half == 0;                                   // warps 2..5: one thread per tile row
@@ -721,6 +750,16 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         const int m2 = t.m, n2 = t.n;
         long tok2 = 0;
         const int nc2 = (a.n_valid - n2 * BN < BN ? a.n_valid - n2 * BN : BN);
+        if (a.use_tmap) {                                              // one tensor copy for the whole tile (thread of row 0)
+          if (r == 0 && !a.no_resid) {
+            const int step2 = m2 / a.rows.tiles_per_step;
+            mbar_expect_tx(res_full, 128u * (uint32_t)nc2 * 4);
+            tma_load_2d(resbuf, &a.tmap, step2 * a.tm_col_step + n2 * BN, (m2 - step2 * a.rows.tiles_per_step) * 128, res_full);
+          } else {
+            mbar_arrive(res_full);
+          }
+          return;
+        }
         const bool ok2 = !a.no_resid && a.rows.map(m2, r, &tok2) && nc2 > 0;
         const uint32_t nr = run_rows(ok2, tok2);
         if (nr) {
@@ -736,9 +775,11 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         const int m = a.groups ? ti.m / a.n_groups : ti.m, n = ti.n;
         const float* g_bias = a.bias;
         float* g_out = reinterpret_cast<float*>(a.out);
+        int tm_col = 0;
         if (a.groups) {                                // grouped launch (store only): this tile's band
           const long long* G = a.groups + 5 * (ti.m % a.n_groups);
-          g_out += __ldg(G + 2);
+          tm_col = (int)__ldg(G + 2);
+          g_out += tm_col;
           if (g_bias) g_bias += __ldg(G + 3);
         }
         const int buf = it & 1;
@@ -802,8 +843,15 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const GemmT
         fence_proxy_async_shared();                    // this thread's generic-proxy writes -> the bulk stores' reads
         named_bar_sync(3, tc_epi_warps(EPI) * 32);     // every warp has updated its share of the row buffer
         if (loader) {
+          if (a.use_tmap) {
+            if (r == 0) {
+              const int step = m / a.rows.tiles_per_step;
+              tma_store_2d(&a.tmap, tm_col + step * a.tm_col_step + n * BN, (m - step * a.rows.tiles_per_step) * 128, resbuf);
+            }
+          } else {
           const uint32_t nr = run_rows(row_ok && ncols > 0, token);
           if (nr) bulk_s2g(g_out + token * a.ldo + (long)n * BN, myrow, nr * (uint32_t)ncols * 4);
+          }
           bulk_store_wait_read();                      // the store has finished READING the row: the buffer may be refilled
           named_bar_sync(4, 128);                      // ... for all 128 rows
           if (tn.valid()) issue_loads(tn);
@@ -944,6 +992,11 @@ static size_t tc_resbuf_bytes(int BN, int n_valid) {
   return (size_t)128 * ldr * 4;
 }
 
+// Upper bound on the persistent CTAs of the following bsrnn_gemm_tc* launches (0 = every SM).  The mask decoder runs its two
+// MLP families on two streams: with each launch on half of the SMs the Conv1d+Tanh GEMM of one family (MUFU / store path)
+// and the Conv1d+GLU GEMM of the other (HBM reads) share the chip instead of taking turns on all of it.
+static int g_cta_limit = 0;
+
 static bool tanh_bulk_enabled() {         // BSRNN_TANH_BULK=0: the generic epilogue for EPI_TANH_KB8 (A/B timing)
   static int v = -1;
   if (v < 0) { const char* e = getenv("BSRNN_TANH_BULK"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -981,8 +1034,32 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
       if (mc_env > 1 && a.n_tiles % mc_env == 0) step_mc = mc_env;
     }
   }
-  const size_t extra_smem = EPI == EPI_RESID_TMA ? tc_resbuf_bytes(a.BN, a.n_valid) : 0;
+  if (EPI == EPI_TANH_KB8 || EPI == EPI_GLU_F32) {
+    // MEASURED (profiles/r02 call51, launch lists with / without): no effect -- Conv1d+GLU 32.1 us per band either way; the
+    // policy does not keep the 100 MB buffer resident against the streaming traffic around it.  Default off.
+    static int keep_env = -1;             // BSRNN_HIDDEN_L2=1: evict_last policy on the hidden activation (A/B timing)
+    if (keep_env < 0) { const char* e = getenv("BSRNN_HIDDEN_L2"); keep_env = (e && e[0] == '1') ? 1 : 0; }
+    a.l2_keep = keep_env ? (EPI == EPI_TANH_KB8 ? 1 : 2) : 0;
+  }
+  const size_t extra_smem = EPI == EPI_RESID_TMA ? tc_resbuf_bytes(a.BN, a.n_valid) + 128 : 0;
   if (EPI == EPI_RESID_TMA) {
+    // matrix view of the output for the tensor-map path: address = seq * row_stride + step * col_step (+ group offset)
+    static int tmap_env = -1;             // BSRNN_FC_TMAP=0: 1-D bulk copies per row / run (A/B timing)
+    if (tmap_env < 0) { const char* e = getenv("BSRNN_FC_TMAP"); tmap_env = (e && e[0] == '0') ? 0 : 1; }
+    long row_stride = 0, col_step = 0;
+    if (a.rows.seq_inner == 1) { row_stride = a.rows.seq_outer * a.ldo; col_step = a.rows.step_stride * a.ldo; }
+    else if (a.rows.seq_inner >= (long)a.rows.R) { row_stride = a.rows.seq_inner_stride * a.ldo; col_step = a.rows.step_stride * a.ldo; }
+    const long steps = (a.groups ? a.m_tiles / a.n_groups : a.m_tiles) / a.rows.tiles_per_step;
+    a.use_tmap = 0;
+    if (tmap_env && a.n_tiles == 1 && a.n_valid <= a.BN && a.n_valid % 8 == 4 && row_stride > 0 && a.ksplit <= 1 &&
+        a.out_scale == 0.f && a.out_scale_ptr == nullptr && (steps - 1) * col_step + a.n_valid <= row_stride &&
+        (!a.groups || col_step == 0) && col_step < (1L << 30) &&
+        make_tmap_2d_f32(&a.tmap, a.out, (uint64_t)row_stride, (uint64_t)a.rows.R, (uint64_t)row_stride * 4, (uint32_t)a.n_valid, 128)) {
+      a.use_tmap = 1;
+      a.tm_col_step = (int)col_step;
+    }
+  }
+  if (EPI == EPI_RESID_TMA && !a.use_tmap) {
     static int runs_env = -1;             // BSRNN_FC_RUNS=0: one bulk copy per row (A/B timing)
     if (runs_env < 0) { const char* e = getenv("BSRNN_FC_RUNS"); runs_env = (e && e[0] == '0') ? 0 : 1; }
     a.run_merge = (runs_env && a.n_tiles == 1 && a.n_valid <= a.BN && a.ldo == a.n_valid && a.n_valid % 8 == 4) ? 1 : 0;
@@ -1026,10 +1103,12 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
     smem_set = smem;
   }
   const int total = a.m_tiles * a.n_tiles;
-  int grid = total < sms ? total : sms;
+  const int sms_use = (g_cta_limit > 0 && g_cta_limit < sms) ? g_cta_limit : sms;
+  int grid = total < sms_use ? total : sms_use;
   if (a.b_resident) {
     const int nt_all = a.n_tiles * (a.dir_tiles > 0 ? 2 : 1);
-    grid = (sms / nt_all) * nt_all;
+    grid = (sms_use / nt_all) * nt_all;
+    if (grid < nt_all) grid = nt_all;
     if (a.dir_tiles > 0) a.pf_dist = 0;             // the A-tile L2 prefetcher is not direction-aware
   }
   if (EPI == EPI_F16_KB8 && a.BN == 208 && a.kcores == 26 && a.bias == nullptr && a.b_resident &&
@@ -1152,6 +1231,12 @@ extern "C" int bsrnn_gemm_tc_ex(const void* A, const void* W, const float* bias,
   set_error("gemm_tc: unknown epilogue %d", epilogue);
   return 1;
 }
+extern "C" int bsrnn_gemm_tc_limit_ctas(int n) {
+  const int prev = g_cta_limit;
+  g_cta_limit = n > 0 ? n : 0;
+  return prev;
+}
+
 // Grouped store-only GEMM (tensor-core BandSplit): out[token*ldo + out_off_g + c] = A_g W_g^T + bias_g for n_groups bands in
 // ONE launch, bands innermost in the tile order.  groups: device [n_groups][5] int64 {a_off, w_off, out_off, bias_off,
 // kcores} relative to A / W / out / bias; kc_max = largest kcores (sizes the pipeline); m_tiles = row tiles per group.

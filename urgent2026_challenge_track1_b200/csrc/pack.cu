@@ -4,6 +4,7 @@
 // the form the next GEMM's bulk copies fetch.
 #include "common.cuh"
 #include "umma.cuh"
+#include "tmap.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -21,7 +22,10 @@ struct PackArgs {
   long tokens_per_sample;  // scale row = (token / tokens_per_sample) * g_inner + (g_inner > 1 ? token % g_inner : 0)
   int g_inner;
   int one_col;           // >= C: this operand column is the constant 1 (bias row of the weights); -1 = none
-  int bulk;              // async kernel: rows arrive by cp.async.bulk (1) or by 16-byte cp.async (0, BSRNN_PACK_BULK=0)
+  int bulk;              // async kernel: rows arrive by cp.async.bulk (1; 2 = contiguous runs of rows merged), by ONE 2-D tensor
+                         // copy per tile (3, band axis, tmap.cuh) or by 16-byte cp.async (0, BSRNN_PACK_BULK=0)
+  int tm_col_step;       // bulk == 3: the tile is rows [j*128, +128) x cols [step*tm_col_step, +C) of the matrix view `tmap`
+  alignas(64) CUtensorMap tmap;
 };
 
 // grid (m_tiles), block 256, dynamic smem 128 * (kcores*8 + 8) halves + 128 row descriptors.
@@ -36,7 +40,7 @@ struct PackRow {
 };
 
 __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, int vec_ok) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int ld = a.kcores * 8 + 8;                 // +8 halves: rows land in different banks
   __half* tile = reinterpret_cast<__half*>(smem_raw);
   PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)128 * ld * 2);
@@ -125,8 +129,8 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_kernel(const PackArgs a, in
 // apart, so the 8 rows of one 16-byte-access phase cover all 32 banks.  ROWS = 128 (one block per tile) or 64 (two blocks
 // per tile, each owning half of the rows of every k-core) so that the f32 staging tile fits twice per SM at any width.
 template <int ROWS>
-__global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs a, int ld) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const __grid_constant__ PackArgs a, int ld) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);                    // [ROWS][ld]
   PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)ROWS * ld * 4);
   constexpr int PARTS = 128 / ROWS;
@@ -149,12 +153,33 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const PackArgs
     __shared__ uint64_t bar;
     if (threadIdx.x == 0) { umma::mbar_init(&bar, ROWS); umma::fence_barrier_init(); }
     __syncthreads();
+    if (a.bulk == 3) {
+      if (threadIdx.x < ROWS) {
+        if (threadIdx.x == 0) {
+          umma::mbar_expect_tx(&bar, (uint32_t)ROWS * (uint32_t)a.C * 4);
+          tma_load_2d(tile, &a.tmap, step * a.tm_col_step, j * 128 + r0, &bar);
+        } else {
+          umma::mbar_arrive(&bar);
+        }
+      }
+    } else
     if (threadIdx.x < ROWS) {
       const int r = threadIdx.x;
       const long tok = rows[r].tok;
-      if (tok >= 0) {
-        umma::mbar_expect_tx(&bar, (uint32_t)a.C * 4);
-        umma::bulk_g2s(tile + (size_t)r * ld, a.x + tok * a.ldx + a.col0, (uint32_t)a.C * 4, &bar);
+      // dense rows (ldx == C == ld, time axis: the K bands of a frame are consecutive tokens): the rows of a warp whose
+      // tokens are consecutive are one contiguous run in HBM and in the tile and arrive by ONE bulk copy
+      uint32_t nr = tok >= 0 ? 1u : 0u;
+      if (a.bulk == 2) {
+        const int lane = threadIdx.x & 31;
+        const long ptok = __shfl_up_sync(0xffffffffu, tok, 1);
+        const bool head = tok >= 0 && (lane == 0 || ptok < 0 || tok != ptok + 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, head), oks = __ballot_sync(0xffffffffu, tok >= 0);
+        const unsigned above = lane == 31 ? 0u : ((heads | ~oks) & ~((2u << lane) - 1u));
+        nr = head ? (uint32_t)((above ? __ffs(above) - 1 : 32) - lane) : 0u;
+      }
+      if (nr) {
+        umma::mbar_expect_tx(&bar, nr * (uint32_t)a.C * 4);
+        umma::bulk_g2s(tile + (size_t)r * ld, a.x + tok * a.ldx + a.col0, nr * (uint32_t)a.C * 4, &bar);
       } else {
         umma::mbar_arrive(&bar);
       }
@@ -231,13 +256,37 @@ extern "C" int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, cons
   static int bulk_env = -1;
   if (bulk_env < 0) { const char* e = getenv("BSRNN_PACK_BULK"); bulk_env = (e && e[0] == '0') ? 0 : 1; }
   a.bulk = bulk_env;
+  static int runs_env = -1;               // BSRNN_PACK_RUNS=0: one bulk copy per row even where rows are contiguous (A/B timing)
+  if (runs_env < 0) { const char* e = getenv("BSRNN_PACK_RUNS"); runs_env = (e && e[0] == '0') ? 0 : 1; }
+  if (a.bulk && runs_env && ld == C && ldx == C && col0 == 0) a.bulk = 2;
   const size_t smem128 = (size_t)128 * ld * 4 + 128 * sizeof(PackRow), smem64 = (size_t)64 * ld * 4 + 64 * sizeof(PackRow);
   const size_t smem32 = (size_t)32 * ld * 4 + 32 * sizeof(PackRow);
+  // band axis (seq_inner == 1: token = seq * seq_outer + step * step_stride): the tile is a box of the row-major matrix
+  // [R rows][seq_outer * ldx floats] -> one tensor copy (the box is ROWS x C; full tiles only: ROWS = 128)
+  static int tmap_env = -1;               // BSRNN_PACK_TMAP=0: per-row bulk copies on the band axis (A/B timing)
+  if (tmap_env < 0) { const char* e = getenv("BSRNN_PACK_TMAP"); tmap_env = (e && e[0] == '0') ? 0 : 1; }
+  // rows per block: 128 when the f32 tile fits twice per SM, else 64 / 32.  BSRNN_PACK_ROWS=64|32 forces smaller blocks
+  // (more blocks per SM: a block loads, waits, then converts -- only co-resident blocks overlap those phases)
+  // MEASURED (profiles/r02 call53, N = 196, config 2): 128-row blocks (2 per SM) 595 / 614 us per call (time / band axis),
+  // 64-row blocks (4 per SM) 463 / 541 us -- the kernel was bound by the load-wait-convert sequence of too few resident blocks,
+  // not by HBM or by the number of bulk copies.  Default: 32-row blocks.
+  static int rows_env = -1;
+  if (rows_env < 0) { const char* e = getenv("BSRNN_PACK_ROWS"); rows_env = e ? atoi(e) : 0; }
+  const int rows_fit = smem128 <= 110 * 1024 ? 128 : (smem64 <= 110 * 1024 ? 64 : 32);
+  int rows_sel = 32;                      // call54: 32-row blocks (8 per SM at N = 196) 402 / 447 us; FlowSE config 4 5.78 s (32) vs 5.84 s (64)
+  if ((rows_env == 128 || rows_env == 64 || rows_env == 32) && rows_env <= rows_fit) rows_sel = rows_env;
+  if (a.bulk && tmap_env && ld == C && col0 == 0 && seq_inner == 1 && seq_inner_stride == 0 &&
+      (long)(m_tiles / tiles_per_step - 1) * step_stride * ldx + C <= seq_outer * ldx && step_stride * ldx < (1L << 30) &&
+      make_tmap_2d_f32(&a.tmap, x, (uint64_t)(seq_outer * ldx), (uint64_t)R, (uint64_t)(seq_outer * ldx) * 4, (uint32_t)C,
+                       (uint32_t)rows_sel)) {
+    a.bulk = 3;
+    a.tm_col_step = (int)(step_stride * ldx);
+  }
   if (vec_ok && !force_old && C % 4 == 0 && smem32 <= 110 * 1024 && (one_col < 0 || one_col % 4 == 0)) {
-    if (smem128 <= 110 * 1024) {
+    if (rows_sel == 128) {
       BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
       norm_cast_kb8_async_kernel<128><<<m_tiles, 256, smem128, (cudaStream_t)stream>>>(a, ld);
-    } else if (smem64 <= 110 * 1024) {     // wide rows (N = 384: 196 KB per tile): half tiles, still two blocks per SM
+    } else if (rows_sel == 64) {           // wide rows (N = 384: 196 KB per tile): half tiles, still two blocks per SM
       BSRNN_CUDA_OK(cudaFuncSetAttribute(norm_cast_kb8_async_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64));
       norm_cast_kb8_async_kernel<64><<<2 * m_tiles, 256, smem64, (cudaStream_t)stream>>>(a, ld);
     } else {                               // 2N = 768 (condition_fc operand): quarter tiles
@@ -270,7 +319,7 @@ extern "C" int bsrnn_norm_cast_kb8(const float* x, const float* scale, const flo
 namespace bsrnn {
 __global__ void __launch_bounds__(256) kb8_transpose_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int kc_src,
                                                             int BN, long dst_kcores, long dst_kc0, int src_m0) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __half* tile = reinterpret_cast<__half*>(smem_raw);            // [128][BN + 8]
   const int ld = BN + 8;
   const int m = blockIdx.x, n = blockIdx.y;

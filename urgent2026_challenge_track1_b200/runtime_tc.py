@@ -383,6 +383,8 @@ def band_split_tc(spec, plan, bs_pack, bs_tc, N, stats):
 
 # ------------------------------------------------------------------------------------------------ mask decoder
 MASKDEC_ONES = os.environ.get("BSRNN_MASKDEC_ONES", "1") == "1"      # 0: separate bias vector, generic tanh epilogue (A/B)
+MASKDEC_SMS = int(os.environ.get("BSRNN_MASKDEC_SMS", "0"))          # persistent CTAs per mask-decoder GEMM launch (0 = all SMs)
+MASKDEC_SHARED_NORM = os.environ.get("BSRNN_MASKDEC_SHARED_NORM", "1") == "1"   # 0: one normalised operand per MLP family
 
 
 def pack_mask_decoder_tc(md):
@@ -403,7 +405,13 @@ def pack_mask_decoder_tc(md):
         for k, m in enumerate(mlps):
             wk = m[1].weight[:, :, 0].float()
             if one_col >= 0:
-                wk = torch.cat([wk, m[1].bias.float()[:, None]], 1)
+                bk = m[1].bias.float()
+                if MASKDEC_SHARED_NORM:
+                    # W (z * gamma + beta) + b = (W diag(gamma)) z + (W beta + b): with the per-channel affine of this family's
+                    # GroupNorm folded in, BOTH families read one operand z = (x - mean) * rstd (one norm_cast, not two)
+                    bk = bk + wk @ m[0].bias.float()
+                    wk = wk * m[0].weight.float()[None, :]
+                wk = torch.cat([wk, bk[:, None]], 1)
             w1.append(to_kb8(wk, LBN, kc1))
             bb = torch.zeros(nt1 * LBN, device=m[1].bias.device); bb[:H4] = m[1].bias
             b1.append(bb)
@@ -418,6 +426,7 @@ def pack_mask_decoder_tc(md):
         out[name] = dict(gamma=torch.stack([m[0].weight for m in mlps]).float().contiguous(),
                          beta=torch.stack([m[0].bias for m in mlps]).float().contiguous(),
                          w1=w1, b1=b1, w2=w2, b2=b2, bn2=bn2, kc1=kc1, kc2=kc2, nt1=nt1, N=N, one_col=one_col,
+                         shared_norm=bool(MASKDEC_SHARED_NORM and one_col >= 0),
                          eps=float(mlps[0][0].eps))
     return out
 
@@ -430,7 +439,15 @@ def mask_decoder_tc(skip, plan, md_pack, band_stats=None):
     F = plan.F
     dev = skip.device
     st = L.stream_ptr()
-    tabs = _decoder_norm_tables(skip, md_pack, stats=band_stats)
+    names = ("mlp_residual", "mlp_mask")
+    shared = (all(md_pack[n]["shared_norm"] for n in names) and len({md_pack[n]["eps"] for n in names}) == 1
+              and len({(md_pack[n]["kc1"], md_pack[n]["one_col"]) for n in names}) == 1)
+    if shared:        # the affine halves live in the weights: one table of (rstd, -mean * rstd) per (sample, band)
+        ones = _ones_pack(K, N, dev, md_pack[names[0]]["eps"])
+        tabs = _decoder_norm_tables(skip, {"shared": ones}, stats=band_stats)
+        tabs = {n: tabs["shared"] for n in names}
+    else:
+        tabs = _decoder_norm_tables(skip, md_pack, stats=band_stats)
     tiles = (B * T + 127) // 128
     outs = {}
     # The mask and the residual MLP families are independent chains of 2 x K small GEMMs: they run on two streams (two
@@ -440,14 +457,25 @@ def mask_decoder_tc(skip, plan, md_pack, band_stats=None):
     fork = torch.cuda.Event()
     capturing = torch.cuda.is_current_stream_capturing()
     bufs = {}
-    for name in ("mlp_residual", "mlp_mask"):            # every buffer belongs to the main stream's allocator pool
+    xshared = None
+    for name in names:                                   # every buffer belongs to the main stream's allocator pool
         p = md_pack[name]
-        bufs[name] = (torch.empty(K * tiles * p["kc1"] * 1024, dtype=torch.float16, device=dev),
+        if xshared is None or not shared:
+            xshared = torch.empty(K * tiles * p["kc1"] * 1024, dtype=torch.float16, device=dev)
+        bufs[name] = (xshared,
                       torch.empty(tiles * p["kc2"] * 1024, dtype=torch.float16, device=dev),
                       torch.empty(B, T, F, 2, dtype=torch.float32, device=dev))
     with region("maskdec"):
+        if shared:
+            p = md_pack[names[0]]
+            scale, shift = tabs[names[0]][0], tabs[names[0]][1]
+            L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xshared.data_ptr(), N, 0, N,
+                   p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, p["one_col"], st)
         fork.record(main)
         side.wait_event(fork)
+        # each family's GEMMs on MASKDEC_SMS persistent CTAs (0 = all): with half of the SMs per launch the two streams' kernels
+        # really run side by side (a 148-CTA launch holds every SM: 200 KB of shared memory and all of TMEM per CTA)
+        prev_limit = L.lib().bsrnn_gemm_tc_limit_ctas(MASKDEC_SMS)
         for name, stream in (("mlp_residual", side), ("mlp_mask", main)):
             p = md_pack[name]
             scale, shift = tabs[name][0], tabs[name][1]
@@ -455,8 +483,9 @@ def mask_decoder_tc(skip, plan, md_pack, band_stats=None):
             with torch.cuda.stream(stream):
                 st = L.stream_ptr()
                 # rows of tile (k, j) are the (b,t) tokens of band k: same row map as the band-axis BLSTM
-                L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0, N,
-                       p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, p["one_col"], st)
+                if not shared:
+                    L.call("bsrnn_norm_cast_kb8_ones", skip.data_ptr(), scale.data_ptr(), shift.data_ptr(), xhat.data_ptr(), N, 0,
+                           N, p["kc1"], K * tiles, tiles, B * T, 1, K, 0, 1, T * K, K, p["one_col"], st)
                 for k in range(K):
                     L.call("bsrnn_gemm_tc", xhat.data_ptr() + 2 * k * tiles * p["kc1"] * 1024, p["w1"][k].data_ptr(),
                            None if p["one_col"] >= 0 else p["b1"][k].data_ptr(), hidden.data_ptr(), None, tiles, p["nt1"],
@@ -469,11 +498,21 @@ def mask_decoder_tc(skip, plan, md_pack, band_stats=None):
                 for t in (xhat, hidden, o, skip, scale, shift):
                     t.record_stream(side)
             outs[name] = o
+        L.lib().bsrnn_gemm_tc_limit_ctas(prev_limit)
         main.wait_stream(side)
     return outs["mlp_mask"], outs["mlp_residual"]
 
 
 _SIDE = {}
+_ONES = {}
+
+
+def _ones_pack(K, N, dev, eps):
+    key = (K, N, str(dev), eps)
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = dict(gamma=torch.ones(K, N, device=dev), beta=torch.zeros(K, N, device=dev), eps=eps)
+    return t
 
 
 def _side_stream(dev):
