@@ -254,6 +254,15 @@ int bsrnn_blstm_fused7_max_groups(void);
  *     w_fused14: fp16 [2][14][2][76][56][8]; every other argument as bsrnn_blstm_fused_tc. */
 int bsrnn_blstm_fused14_tc(const void* xhat, const void* w_fused14, const void* zero_tile, void* y, int R, int steps,
                            int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+/* bsrnn_blstm_fused_train_tc: TRAINING forward of the BLSTM layer (H = 392) on the fused kernel: geo = 7 | 14 as
+ *     bsrnn_blstm_fused7_tc / _fused14_tc, separate output buffers per direction (block (step, tile) of direction d at
+ *     y_d + (step*seq_tiles + tile) * y_stride halves, [50][128][8], k-core 49 stays zero), and the activations BPTT needs
+ *     written by the epilogue: gates rows [(step*seq_tiles + tile)*128 + r][8H] fp16 = ACTIVATED i, f, g, o at column
+ *     dir*4H + 4u + gate; c_f / c_b [step][seq_tiles*128][H] f32 -- the buffers bsrnn_blstm_train_bwd_tc reads
+ *     [autograd's saved tensors of nn.LSTM in SEModel.training_step, d_model.py:61-95]. */
+int bsrnn_blstm_fused_train_tc(int geo, const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b,
+                               long y_stride, void* gates, float* c_f, float* c_b, int R, int steps, int seq_tiles,
+                               int max_groups, int slots, void* sync_ws, void* stream);
 int bsrnn_blstm_fused14_max_groups(void);
 /* bsrnn_blstm_fused768_tc: the same fused layer kernel for nn.LSTM(N=384, H=768, bidirectional) of BSRNN_flowse
  *     [reference bsrnn_flowse.py:226-238 at the conf/models/BSRNN_flowse.yaml width]: groups of 24 CTA pairs (32 hidden

@@ -85,3 +85,47 @@ def test_flat_gradient_allreduce_two_gloo_ranks(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("OK" in o for o in outs), outs
+
+
+@pytest.mark.parametrize("fs", [48000, 16000, 44100])
+def test_batched_band_ops_equal_the_per_band_loops(fs):
+    """training.band_split_batched / mask_decoder_batched (one gather + batched GEMMs over zero-padded bands) against the
+    per-band loops that mirror the reference modules: outputs and every parameter gradient, in f64, incl. truncated bands."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE, runtime as RT, training as TR
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=16, num_layer=1, precision="fp32").double()
+    core = m.bsrnn.bsrnn
+    n_fft, hop = RT.stft_dims(fs, m.N_FFT, m.HOP, m.DEFAULT_FS)
+    Fb = n_fft // 2 + 1
+    plan = RT.BandPlan.make(core.band_split.subbands, Fb)
+    spec = torch.randn(2, 7, Fb, 2, dtype=torch.float64)
+    for p in m.parameters():
+        p.data = p.data + 0.1 * torch.randn_like(p)
+
+    def run(bsf, mdf):
+        for p in m.parameters():
+            p.grad = None
+        skip = bsf(core.band_split, spec, plan)
+        mc, rc = mdf(core.mask_decoder, skip, plan, Fb)
+        ((mc.abs() ** 2).sum() + (rc.real * 1.3 + rc.imag * 0.7).sum() + 0.01 * (skip ** 2).sum()).backward()
+        return skip.detach(), mc.detach(), rc.detach(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    a = run(TR.band_split_diff, TR.mask_decoder_diff)
+    b = run(TR.band_split_batched, TR.mask_decoder_batched)
+    rel = lambda x, y: float((x - y).abs().max() / (y.abs().max() + 1e-30))
+    assert rel(b[0], a[0]) < 1e-12 and rel(b[1], a[1]) < 1e-12 and rel(b[2], a[2]) < 1e-12
+    assert set(a[3]) == set(b[3])                       # bands the spectrum does not reach get no gradient in either
+    assert max(rel(b[3][n], a[3][n]) for n in a[3]) < 1e-11
+
+
+@pytest.mark.parametrize("geo,P,U", [(7, 7, 56), (14, 14, 28)])
+def test_fused_training_weight_pack_equals_the_inference_pack(geo, P, U):
+    """training_tc.pack_fused_train (batched, runs inside every training step) builds bit-identical operands to
+    runtime_tc.pack_lstm_fused7 (the inference packer of the fused layer kernel)."""
+    from urgent2026_challenge_track1_b200 import runtime_tc as TC, training_tc as TT
+    torch.manual_seed(1)
+    rnn = torch.nn.LSTM(196, 392, bidirectional=True, batch_first=True)
+    ws = tuple(getattr(rnn, n + sfx) for sfx in ("", "_reverse") for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"))
+    a = TC.pack_lstm_fused7(rnn, 26, 196, P=P, U=U)
+    b = TT.pack_fused_train(ws, geo, 26, 196)
+    assert a.shape == b.shape == (2, P, 2, 76, 2 * U, 8) and bool((a == b).all())

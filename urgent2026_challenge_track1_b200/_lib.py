@@ -44,6 +44,8 @@ PROTOTYPES = {
     "bsrnn_gemm_tc_grouped": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long,
                               c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
     "bsrnn_gemm_tc_limit_ctas": [c_int],
+    "bsrnn_blstm_fused_train_tc": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p,
+                                   c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "bsrnn_band_norm_cast_kb8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_long, c_int, c_int, c_int, c_void_p],
     "bsrnn_lstm_step_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long, c_void_p],

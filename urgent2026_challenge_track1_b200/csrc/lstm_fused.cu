@@ -51,6 +51,7 @@
 namespace bsrnn {
 
 struct Geo392 {
+  static constexpr bool SAVE = false;     // training forward: also write activated gates + c_t (the *S geometries)
   static constexpr int UPP = 49, BN = 208, PPG = 8, XKC = 26, HKC = 50, KS = 10, STAGES = 5;
   static constexpr int EPI_WARPS = 12, ACC = 256, NBUF = 2, EPI_REGS = 152, NC = 17;
   static constexpr int CLS = 2;             // cluster = one CTA pair
@@ -58,6 +59,7 @@ struct Geo392 {
 // H = 392 on groups of 7 pairs x 56 units (N = 224, no padding columns): 10 groups = 140 SMs, so the 9 tile pairs per
 // direction of BASELINE config 2's time axis run 2-interleaved on 5 groups per direction instead of 3-interleaved on 3.
 struct Geo392x7 {
+  static constexpr bool SAVE = false;     // training forward: also write activated gates + c_t (the *S geometries)
   static constexpr int UPP = 56, BN = 224, PPG = 7, XKC = 26, HKC = 50, KS = 10, STAGES = 4;
   static constexpr int EPI_WARPS = 16, ACC = 256, NBUF = 2, EPI_REGS = 104, NC = 14;
   static constexpr int CLS = 2;
@@ -67,11 +69,13 @@ struct Geo392x7 {
 // item halve when twice as many CTAs share a tile; every CTA still pulls the whole x / h tile, so L2 traffic per item
 // doubles - worthwhile only while few items are in flight (runtime_tc.fused_geometry).
 struct Geo392x14 {
+  static constexpr bool SAVE = false;     // training forward: also write activated gates + c_t (the *S geometries)
   static constexpr int UPP = 28, BN = 112, PPG = 14, XKC = 26, HKC = 50, KS = 10, STAGES = 7;
   static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 7;
   static constexpr int CLS = 2;
 };
 struct Geo768 {
+  static constexpr bool SAVE = false;     // training forward: also write activated gates + c_t (the *S geometries)
   static constexpr int UPP = 32, BN = 128, PPG = 24, XKC = 50, HKC = 96, KS = 12, STAGES = 3;
   static constexpr int EPI_WARPS = 16, ACC = 128, NBUF = 4, EPI_REGS = 104, NC = 8;
   // -DBSRNN_FUSED768_CLS=4: clusters of 2 CTA pairs, the two CTAs of a parity fetch half of each ring stage and
@@ -80,6 +84,8 @@ struct Geo768 {
   // of 3, so the default stays one pair per cluster.
   static constexpr int CLS = BSRNN_FUSED768_CLS;
 };
+struct Geo392x7S : Geo392x7 { static constexpr bool SAVE = true; };
+struct Geo392x14S : Geo392x14 { static constexpr bool SAVE = true; };
 template <class G>
 struct Der {
   static constexpr int BH = G::BN / 2;                                  // B rows (gate columns) per CTA
@@ -112,7 +118,13 @@ struct FusedArgs {
   int gpd;                   // work groups per direction (each = up to `slots` consecutive tile PAIRS)
   unsigned* sync;            // [0] ticket counter, [32 + 32*((3*group + slot)*2 + parity)] h_ready counters
   long long* probe;          // debug (-DBSRNN_FUSED_PROBE): per-role wait / busy cycle totals of pair 0, [16*e + i]
+  // training forward (SAVE instantiations): activated gates, rows [(step*seq_tiles + tile)*128 + r][8H] fp16 with column
+  // dir*4H + 4u + gate, and c_t per direction [step][seq_tiles*128][H] f32 -- the layout bsrnn_blstm_train_bwd_tc reads
+  __half* sv_gates;
+  float* sv_c0;
+  float* sv_c1;
 };
+constexpr int FH = 392;      // hidden size of the H = 392 geometries (row strides of the saved activations)
 
 #ifdef BSRNN_FUSED_PROBE
 #define FP_DECL(cond) const bool prb_ = a.probe && ticket == 0 && (cond); long long pt_ = prb_ ? clock64() : 0
@@ -197,8 +209,27 @@ __device__ __forceinline__ void epif_item392(uint32_t t_col, bool last_third, ui
 }
 // H = 392, 7 pairs: thread = (row r, quarter T of the pair's 56 units): 14 units at h columns 56q + 14T + j, i.e. position
 // p = 14T + j of the pair's 7 k-cores (core p/8, slot p%8): the store pattern depends on T only.
-template <int T>
-__device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, float (&c)[14], bool st) {
+// one accumulator chunk of 4 units; SAVE: activated gates / c_t of unit U0 + u go to sg + 4*(U0+u) / sc + U0 + u
+template <int CH, int NC, int NH, bool SAVE>
+__device__ __forceinline__ void epif_chunk_sv(const uint32_t (&acc)[16], float (&c)[NC], float (&h)[NH], __half* sg, float* sc, bool st) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (SAVE && st)
+      gate_update_save(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
+                       __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u], sg + 4 * (4 * CH + u), sc + 4 * CH + u);
+    else
+      gate_update(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
+                  __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u]);
+  }
+}
+template <bool SAVE>
+__device__ __forceinline__ void gate_update_sv(float pi, float pf, float pg, float po, float& c, float& h, __half* sg, float* sc, bool st) {
+  if (SAVE && st) gate_update_save(pi, pf, pg, po, c, h, sg, sc);
+  else gate_update(pi, pf, pg, po, c, h);
+}
+template <int T, bool SAVE = false>
+__device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, float (&c)[14], bool st, __half* sg = nullptr,
+                                               float* sc = nullptr) {
   constexpr size_t CORE = 128 * 8;
   float h[16];
   uint32_t accA[16], accB[16];
@@ -206,11 +237,11 @@ __device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, fl
   tmem_ld_wait();
   tmem_ld_x16(t_col + 16, accB);
   tmem_ld_pin16(accA);
-  epif_chunk<0>(accA, c, h);
+  epif_chunk_sv<0, 14, 16, SAVE>(accA, c, h, sg, sc, st);
   tmem_ld_wait();
   tmem_ld_x16(t_col + 32, accA);
   tmem_ld_pin16(accB);
-  epif_chunk<1>(accB, c, h);
+  epif_chunk_sv<1, 14, 16, SAVE>(accB, c, h, sg, sc, st);
   if (st) {
     if (T == 0) store_full<0>(ycore, h);                                   // p 0..7   -> core 0
     if (T == 1) store_partial<6, 8, 0>(ycore + CORE, h);                   // p 14,15  -> core 1 slots 6,7
@@ -221,13 +252,13 @@ __device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, fl
   tmem_ld_wait();
   tmem_ld_x8(t_col + 48, a8);
   tmem_ld_pin16(accA);
-  epif_chunk<2>(accA, c, h);
+  epif_chunk_sv<2, 14, 16, SAVE>(accA, c, h, sg, sc, st);
   tmem_ld_wait();
   asm volatile("" : "+r"(a8[0]), "+r"(a8[1]), "+r"(a8[2]), "+r"(a8[3]), "+r"(a8[4]), "+r"(a8[5]), "+r"(a8[6]), "+r"(a8[7]));
 #pragma unroll
   for (int u = 0; u < 2; ++u)
-    gate_update(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
-                __uint_as_float(a8[4 * u + 3]), c[12 + u], h[12 + u]);
+    gate_update_sv<SAVE>(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
+                         __uint_as_float(a8[4 * u + 3]), c[12 + u], h[12 + u], sg + 4 * (12 + u), sc + 12 + u, st);
   if (st) {
     if (T == 0) store_partial<0, 6, 8>(ycore + CORE, h);                   // p 8..13  -> core 1 slots 0..5
     if (T == 1) { store_full<2>(ycore + 2 * CORE, h); store_partial<0, 4, 10>(ycore + 3 * CORE, h); }   // p 16..23, 24..27
@@ -237,8 +268,9 @@ __device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, fl
 }
 // H = 392, 14 pairs: thread = (row r, quarter T of the pair's 28 units): 7 units at h columns 28q + 7T + j.  With
 // QP = q & 1 the pair's columns start 4*QP slots into k-core (28q - 4*QP)/8; position p = 4*QP + 7T + j -> core p/8, slot p%8.
-template <int QP, int T>
-__device__ __forceinline__ void epif_item392x14(uint32_t t_col, __half* ycore, float (&c)[7], bool st) {
+template <int QP, int T, bool SAVE = false>
+__device__ __forceinline__ void epif_item392x14(uint32_t t_col, __half* ycore, float (&c)[7], bool st, __half* sg = nullptr,
+                                                float* sc = nullptr) {
   constexpr size_t CORE = 128 * 8;
   constexpr int P0 = 4 * QP + 7 * T;                 // first position of this thread's units
   constexpr int C0 = P0 / 8, S0 = P0 % 8;            // first core / slot
@@ -254,13 +286,14 @@ __device__ __forceinline__ void epif_item392x14(uint32_t t_col, __half* ycore, f
   asm volatile("" : "+r"(a4[0]), "+r"(a4[1]), "+r"(a4[2]), "+r"(a4[3]));
 #pragma unroll
   for (int u = 0; u < 4; ++u)
-    gate_update(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
-                __uint_as_float(acc[4 * u + 3]), c[u], h[u]);
+    gate_update_sv<SAVE>(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
+                         __uint_as_float(acc[4 * u + 3]), c[u], h[u], sg + 4 * u, sc + u, st);
 #pragma unroll
   for (int u = 0; u < 2; ++u)
-    gate_update(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
-                __uint_as_float(a8[4 * u + 3]), c[4 + u], h[4 + u]);
-  gate_update(__uint_as_float(a4[0]), __uint_as_float(a4[1]), __uint_as_float(a4[2]), __uint_as_float(a4[3]), c[6], h[6]);
+    gate_update_sv<SAVE>(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
+                         __uint_as_float(a8[4 * u + 3]), c[4 + u], h[4 + u], sg + 4 * (4 + u), sc + 4 + u, st);
+  gate_update_sv<SAVE>(__uint_as_float(a4[0]), __uint_as_float(a4[1]), __uint_as_float(a4[2]), __uint_as_float(a4[3]), c[6], h[6],
+                       sg + 4 * 6, sc + 6, st);
   if (st) {
     store_partial<S0, S0 + N0, 0>(ycore + C0 * CORE, h);
     if constexpr (N0 < 7) store_partial<0, 7 - N0, N0>(ycore + (C0 + 1) * CORE, h);
@@ -325,13 +358,27 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
             else if (k == 1) epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c1, valid);
             else epif_item392<Q>(t_lane + buf * G::ACC, last_third, t_lane48 + buf * G::ACC, ycore, c2, valid);
           } else if constexpr (G7) {
-            if (k == 0) epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c0, valid);
-            else if (k == 1) epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c1, valid);
-            else epif_item392x7<Q>(t_lane + buf * G::ACC, ycore, c2, valid);
+            __half* sg = nullptr; float* sc = nullptr;
+            if constexpr (G::SAVE) {
+              const size_t row = tile * 128 + (size_t)r;
+              const int u0 = 56 * q + 14 * T;
+              sg = a.sv_gates + row * (8 * FH) + GR.d * 4 * FH + 4 * u0;
+              sc = (GR.d == 0 ? a.sv_c0 : a.sv_c1) + row * FH + u0;
+            }
+            if (k == 0) epif_item392x7<Q, G::SAVE>(t_lane + buf * G::ACC, ycore, c0, valid, sg, sc);
+            else if (k == 1) epif_item392x7<Q, G::SAVE>(t_lane + buf * G::ACC, ycore, c1, valid, sg, sc);
+            else epif_item392x7<Q, G::SAVE>(t_lane + buf * G::ACC, ycore, c2, valid, sg, sc);
           } else if constexpr (G14) {
-            if (k == 0) epif_item392x14<Q / 4, Q % 4>(t_lane + buf * G::ACC, ycore, c0, valid);
-            else if (k == 1) epif_item392x14<Q / 4, Q % 4>(t_lane + buf * G::ACC, ycore, c1, valid);
-            else epif_item392x14<Q / 4, Q % 4>(t_lane + buf * G::ACC, ycore, c2, valid);
+            __half* sg = nullptr; float* sc = nullptr;
+            if constexpr (G::SAVE) {
+              const size_t row = tile * 128 + (size_t)r;
+              const int u0 = 28 * q + 7 * T;
+              sg = a.sv_gates + row * (8 * FH) + GR.d * 4 * FH + 4 * u0;
+              sc = (GR.d == 0 ? a.sv_c0 : a.sv_c1) + row * FH + u0;
+            }
+            if (k == 0) epif_item392x14<Q / 4, Q % 4, G::SAVE>(t_lane + buf * G::ACC, ycore, c0, valid, sg, sc);
+            else if (k == 1) epif_item392x14<Q / 4, Q % 4, G::SAVE>(t_lane + buf * G::ACC, ycore, c1, valid, sg, sc);
+            else epif_item392x14<Q / 4, Q % 4, G::SAVE>(t_lane + buf * G::ACC, ycore, c2, valid, sg, sc);
           } else {
             if (k == 0) epif_item768(t_lane + buf * G::ACC, ycore, c0, valid);
             else if (k == 1) epif_item768(t_lane + buf * G::ACC, ycore, c1, valid);
@@ -721,7 +768,8 @@ static int auto_slots(int ptiles, int cap) {
 
 template <class G>
 static int run_fused(const char* what, const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b,
-                     long y_stride, int R, int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+                     long y_stride, int R, int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream,
+                     void* sv_gates = nullptr, float* sv_c0 = nullptr, float* sv_c1 = nullptr) {
   int cap = fused_max_groups<G>();
   if (cap <= 0) {
     cudaGetLastError();
@@ -735,7 +783,8 @@ static int run_fused(const char* what, const void* xhat, const void* w_fused, co
   if (slots > ptiles) slots = ptiles;
   FusedArgs a{reinterpret_cast<const __half*>(xhat), reinterpret_cast<const __half*>(w_fused),
               reinterpret_cast<const __half*>(zero_tile), reinterpret_cast<__half*>(y_f), reinterpret_cast<__half*>(y_b),
-              y_stride, R, steps, seq_tiles, (ptiles + slots - 1) / slots, reinterpret_cast<unsigned*>(sync_ws), g_fused_probe};
+              y_stride, R, steps, seq_tiles, (ptiles + slots - 1) / slots, reinterpret_cast<unsigned*>(sync_ws), g_fused_probe,
+              reinterpret_cast<__half*>(sv_gates), sv_c0, sv_c1};
   int ncl = 2 * a.gpd;
   if (ncl > cap) ncl = cap;
   cudaStream_t st = (cudaStream_t)stream;
@@ -798,3 +847,22 @@ extern "C" int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, co
                            slots, sync_ws, stream);
 }
 extern "C" int bsrnn_blstm_fused768_max_groups(void) { return fused_max_groups<Geo768>(); }
+
+// Training forward of the BLSTM layer (H = 392) on the fused kernel: as bsrnn_blstm_fused7_tc / _fused14_tc (geo = 7 | 14) with
+// separate output buffers per direction (block (step, tile) of direction d at y_d + (step*seq_tiles + tile) * y_stride halves,
+// [50][128][8] each) and the activations BPTT needs written by the epilogue: gates rows [(step*seq_tiles + tile)*128 + r][8H]
+// fp16 = ACTIVATED i, f, g, o at column dir*4H + 4u + gate, c_f / c_b [step][seq_tiles*128][H] f32 -- the buffers
+// bsrnn_blstm_train_bwd_tc reads [replaces autograd's saved tensors of nn.LSTM, d_model.py:61-95 / train_se.py:74-84].
+extern "C" int bsrnn_blstm_fused_train_tc(int geo, const void* xhat, const void* w_fused, const void* zero_tile, void* y_f,
+                                          void* y_b, long y_stride, void* gates, float* c_f, float* c_b, int R, int steps,
+                                          int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y_f && y_b && gates && c_f && c_b && sync_ws, "blstm_fused_train_tc: null pointer");
+  BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused_train_tc: bad dims");
+  BSRNN_CHECK_ARG(geo == 7 || geo == 14, "blstm_fused_train_tc: geo must be 7 or 14");
+  BSRNN_CHECK_ARG(y_stride >= (long)Geo392x7::HKC * 128 * 8 && y_stride % 8 == 0, "blstm_fused_train_tc: bad y_stride");
+  if (geo == 7)
+    return run_fused<Geo392x7S>("blstm_fused_train_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles, max_groups,
+                                slots, sync_ws, stream, gates, c_f, c_b);
+  return run_fused<Geo392x14S>("blstm_fused_train_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles, max_groups,
+                               slots, sync_ws, stream, gates, c_f, c_b);
+}

@@ -43,6 +43,18 @@ __device__ __forceinline__ void gate_update(float pi, float pf, float pg, float 
   h = og * tanh_fast(c);
 }
 
+// training forward: the same update, and the ACTIVATED gates (i, f, g, o as 4 halves) + c_t written out for BPTT
+// [what bsrnn_blstm_step_train_tc saves: gemm_tc.cu EPI_LSTM_STEP with save_gates]
+__device__ __forceinline__ void gate_update_save(float pi, float pf, float pg, float po, float& c, float& h, __half* g4, float* cs) {
+  const float ig = fmaf(tanh_fast(pi), 0.5f, 0.5f), fg = fmaf(tanh_fast(pf), 0.5f, 0.5f);
+  const float gg = tanh_fast(pg), og = fmaf(tanh_fast(po), 0.5f, 0.5f);
+  c = fmaf(fg, c, ig * gg);
+  h = og * tanh_fast(c);
+  const __half2 a = __floats2half2_rn(ig, fg), b = __floats2half2_rn(gg, og);
+  *reinterpret_cast<uint2*>(g4) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  *cs = c;
+}
+
 // (f32 accumulator pair) + (fp16 pair packed in one register): sm_100a mixed-precision FHADD takes the fp16 operand
 // (either half of the register) directly -- one instruction per gate instead of a convert and an add.
 __device__ __forceinline__ float2 add_h2_f32(uint32_t g, uint32_t a0, uint32_t a1) {

@@ -17,6 +17,7 @@ What runs where (round-1 state):
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -114,6 +115,93 @@ def band_split_diff(bs, spec, plan):
         xk = _gn(xk, (1, 2), bs.norm[k].weight, bs.norm[k].bias, bs.norm[k].eps)
         zs.append(F.linear(xk, bs.fc[k].weight[:, :, 0], bs.fc[k].bias))
     return torch.stack(zs, dim=2)
+
+
+_BAND_TABLES = {}
+
+
+def _band_tables(plan, dev):
+    """Index tables of the batched per-band ops, cached per (plan, device): gather index into the flattened (F*2) axis,
+    validity mask and per-band channel count of BandSplit; the (band, bin) -> output bin selection of the decoders."""
+    key = (plan.subbands, plan.F, plan.K, str(dev))
+    t = _BAND_TABLES.get(key)
+    if t is None:
+        K = plan.K
+        smax = max(plan.subbands[:K])
+        idx = torch.zeros(K, 2 * smax, dtype=torch.long)
+        mask = torch.zeros(K, 2 * smax)
+        sel = []
+        for k in range(K):
+            s, b0, w = plan.subbands[k], plan.bin0[k], plan.width[k]
+            idx[k, : 2 * w] = 2 * b0 + torch.arange(2 * w)
+            mask[k, : 2 * w] = 1.0
+            sel += [k * smax + f for f in range(s)]
+        chans = torch.tensor([2.0 * plan.subbands[k] for k in range(K)])
+        t = _BAND_TABLES[key] = dict(smax=smax, idx=idx.to(dev), mask=mask.to(dev), chans=chans.to(dev),
+                                     sel=torch.tensor(sel[: plan.F], dtype=torch.long, device=dev))
+    return t
+
+
+def _pad_rows(w, rows):
+    return w if w.shape[0] == rows else F.pad(w, (0, 0, 0, rows - w.shape[0]))
+
+
+def band_split_batched(bs, spec, plan):
+    """band_split_diff with the K' per-band GroupNorm + Conv1d pairs as ONE gather, one set of reductions and one batched
+    GEMM over zero-padded bands (the loop launches ~40 tiny kernels per band in forward + backward; at the training batch the
+    step was bound by their count, not their work).  Same arithmetic per band: statistics over the 2 s_k channels x T frames
+    (zeros of a truncated band included), padded channels carry zero weights."""
+    B, T = spec.shape[0], spec.shape[1]
+    K = plan.K
+    tb = _band_tables(plan, spec.device)
+    cmax = 2 * tb["smax"]
+    x = spec.reshape(B, T, -1)[:, :, tb["idx"]] * tb["mask"]                     # (B,T,K,cmax)
+    cnt = (tb["chans"] * T)[None, :]                                            # (1,K)
+    mean = x.sum(dim=(1, 3)) / cnt                                              # (B,K)
+    d = (x - mean[:, None, :, None]) * (torch.arange(cmax, device=x.device)[None, :] < tb["chans"][:, None])
+    var = (d * d).sum(dim=(1, 3)) / cnt
+    eps = bs.norm[0].eps
+    gamma = torch.stack([F.pad(bs.norm[k].weight, (0, cmax - 2 * plan.subbands[k])) for k in range(K)])    # (K,cmax)
+    beta = torch.stack([F.pad(bs.norm[k].bias, (0, cmax - 2 * plan.subbands[k])) for k in range(K)])
+    xn = d * torch.rsqrt(var + eps)[:, None, :, None] * gamma + beta
+    W = torch.stack([F.pad(bs.fc[k].weight[:, :, 0], (0, cmax - 2 * plan.subbands[k])) for k in range(K)])  # (K,N,cmax)
+    bias = torch.stack([bs.fc[k].bias for k in range(K)])                       # (K,N)
+    z = torch.bmm(xn.permute(2, 0, 1, 3).reshape(K, B * T, cmax), W.transpose(1, 2)) + bias[:, None, :]
+    return z.reshape(K, B, T, -1).permute(1, 2, 0, 3).contiguous()
+
+
+def mask_decoder_batched(md, skip, plan, F_bins):
+    """mask_decoder_diff with the per-band MLPs as three batched GEMMs per family (bands zero-padded to the widest one in
+    the last Conv1d, value and gate halves padded separately so that GLU pairs stay aligned)."""
+    B, T, K, N = skip.shape
+    tb = _band_tables(plan, skip.device)
+    smax = tb["smax"]
+    mean = skip.mean(dim=(1, 3), keepdim=True)
+    d = skip - mean
+    var = (d * d).mean(dim=(1, 3), keepdim=True)
+    outs = []
+    for mlps in (md.mlp_mask, md.mlp_residual):
+        m0 = mlps[0]
+        gamma = torch.stack([mlps[k][0].weight for k in range(K)])              # (K,N)
+        beta = torch.stack([mlps[k][0].bias for k in range(K)])
+        xn = d * torch.rsqrt(var + m0[0].eps) * gamma + beta                    # (B,T,K,N)
+        W1 = torch.stack([mlps[k][1].weight[:, :, 0] for k in range(K)])        # (K,4N,N)
+        b1 = torch.stack([mlps[k][1].bias for k in range(K)])
+        h = torch.tanh(torch.bmm(xn.permute(2, 0, 1, 3).reshape(K, B * T, N), W1.transpose(1, 2)) + b1[:, None, :])
+        W2, b2 = [], []
+        for k in range(K):
+            w, b = mlps[k][3].weight[:, :, 0], mlps[k][3].bias                   # (4s, 4N): rows [0,2s) value, [2s,4s) gate
+            hs = w.shape[0] // 2
+            W2.append(torch.cat([_pad_rows(w[:hs], 2 * smax), _pad_rows(w[hs:], 2 * smax)], 0))
+            b2.append(torch.cat([F.pad(b[:hs], (0, 2 * smax - hs)), F.pad(b[hs:], (0, 2 * smax - hs))], 0))
+        W2, b2 = torch.stack(W2), torch.stack(b2)                               # (K,4 smax,4N), (K,4 smax)
+        o = F.glu(torch.bmm(h, W2.transpose(1, 2)) + b2[:, None, :], dim=-1)    # (K,B*T,2 smax)
+        o = o.reshape(K, B, T, smax, 2).permute(1, 2, 0, 3, 4).reshape(B, T, K * smax, 2)
+        outs.append(torch.view_as_complex(o[:, :, tb["sel"], :].contiguous()))
+    return outs[0], outs[1]
+
+
+BATCHED_BANDS = os.environ.get("BSRNN_TRAIN_BATCHED_BANDS", "1") == "1"   # 0: the per-band loops (band_split_diff, mask_decoder_diff)
 
 
 def block_f32(x, rnn, fc, axis):
@@ -218,9 +306,9 @@ def bsrnn_se_train_forward(model, wav, lens, fs, blstm_fn=None):
     lens_dev = R.device_lengths(lens, wav.device)
     with torch.no_grad():
         spec = R.stft(wav.contiguous().float(), lens_dev, n_fft, hop)           # (B,T,F,2), frames >= olens are zeros
-    skip = band_split_diff(core.band_split, spec, plan)                          # (B,T,K',N)
+    skip = (band_split_batched if BATCHED_BANDS else band_split_diff)(core.band_split, spec, plan)      # (B,T,K',N)
     skip = dual_path_diff(core, skip, blstm_fn=blstm_fn)
-    m_c, r_c = mask_decoder_diff(core.mask_decoder, skip, plan, F_bins)
+    m_c, r_c = (mask_decoder_batched if BATCHED_BANDS else mask_decoder_diff)(core.mask_decoder, skip, plan, F_bins)
     est = m_c * torch.view_as_complex(spec) + r_c                               # (B,T,F)
     L_out = int(torch.as_tensor(lens).max()) if not (torch.is_tensor(lens) and lens.is_cuda) else int(lens.max())
     wav_out = ISTFTFunction.apply(torch.view_as_real(est), L_out, n_fft, hop)
@@ -233,8 +321,9 @@ def flow_bsrnn_train_forward(dnn, x_btf, y_btf, t, blstm_fn=None):
     import math
     F_bins = x_btf.shape[2]
     plan = R.BandPlan.make(dnn.band_split_x.subbands, F_bins)
-    xx = band_split_diff(dnn.band_split_x, x_btf, plan)
-    yy = band_split_diff(dnn.band_split_y, y_btf, plan)
+    bsf = band_split_batched if BATCHED_BANDS else band_split_diff
+    xx = bsf(dnn.band_split_x, x_btf, plan)
+    yy = bsf(dnn.band_split_y, y_btf, plan)
     skip = F.linear(torch.cat([xx, yy], dim=-1), dnn.condition_fc.weight, dnn.condition_fc.bias)    # :284-285
     t = t.to(device=x_btf.device, dtype=torch.float32)
     t_emb = []

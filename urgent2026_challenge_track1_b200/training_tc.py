@@ -18,6 +18,7 @@ Gradients are loss-scaled by a power of two chosen per call from max|d_out| so t
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -93,6 +94,42 @@ def pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, nar
     return p
 
 
+# BLSTM forward of the training step on the fused layer kernel (bsrnn_blstm_fused_train_tc, H = 392): one persistent launch per
+# block instead of one input-projection GEMM + one launch per time step.  BSRNN_TRAIN_FUSED=0: the step-wise forward.
+FUSED_TRAIN = os.environ.get("BSRNN_TRAIN_FUSED", "1") == "1"
+_FUSED_IDX = {}
+
+
+def pack_fused_train(ws, geo, kc_in, one_col):
+    """pack_lstm_fused7's layout ([dir][pair q][half e][kc_in + 50 k-cores][2U rows][8] fp16) from the 8 raw LSTM tensors
+    (w_ih, w_hh, b_ih, b_hh, and the reverse four) in a handful of batched ops: it runs inside every training step."""
+    w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r = ws
+    H, N = w_hh.shape[1], w_ih.shape[1]
+    P, U = (7, 56) if geo == 7 else (14, 28)
+    dev = w_hh.device
+    key = (H, P, U, str(dev))
+    t = _FUSED_IDX.get(key)
+    if t is None:
+        q = torch.arange(P, device=dev)[:, None, None]
+        u = torch.arange(U, device=dev)[None, :, None]
+        g = torch.arange(4, device=dev)[None, None, :]
+        rows = (g * H + U * q + u).reshape(P, 4 * U)                      # packed row 4*u_local + gate of pair q
+        gsc = torch.tensor(GATE_SCALE, device=dev).repeat(U)[None, None, :, None]
+        t = _FUSED_IDX[key] = (rows, gsc)
+    rows, gsc = t
+    ktot = (kc_in + LKC_H) * 8
+    full = torch.zeros(2, 4 * H, ktot, dtype=torch.float32, device=dev)
+    for d, (wi, wh, bi, bh) in enumerate(((w_ih, w_hh, b_ih, b_hh), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))):
+        full[d, :, :N] = wi.detach().float()
+        full[d, :, one_col] = (bi.detach() + bh.detach()).float()
+        full[d, :, kc_in * 8: kc_in * 8 + H] = wh.detach().float()
+    w = full[:, rows] * gsc                                               # (2, P, 4U, ktot)
+    return w.view(2, P, 2, 2 * U, kc_in + LKC_H, 8).permute(0, 1, 2, 4, 3, 5).contiguous().to(torch.float16)
+
+
+LKC_H = 50                    # k-cores of the H = 392 recurrent operand (K = 400)
+
+
 def _geom(B, T, K, axis):
     if axis == "time":
         R, steps, addr = B * K, T, (K, T * K, 1, K)
@@ -141,17 +178,32 @@ class BLSTMBlockTC(torch.autograd.Function):
         H, BN, nt = p["H"], p["BN"], p["n_tiles"]
         m_all = steps * tiles
         x = x.contiguous().float()
-        xhat = _cast_kb8(x, p["kc_in"], steps, tiles, R, addr, T * K)
         gates = torch.empty(m_all * 128, 8 * H, dtype=torch.float16, device=dev)
-        L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bias"].data_ptr(), gates.data_ptr(), None, m_all,
-               2 * nt, p["kc_in"], BN, L.TC_F16_ROWS, 8 * H, 8 * H, 0, 1, m_all, m_all * 128, BIG, 0, 1, 0, st)
         tile_halves = p["kc_h"] * 1024
         y = [torch.zeros(m_all * tile_halves, dtype=torch.float16, device=dev) for _ in range(2)]     # pad k-core stays 0
         c_all = [torch.empty(steps, tiles * 128, H, dtype=torch.float32, device=dev) for _ in range(2)]
         zero = torch.zeros(tiles * tile_halves, dtype=torch.float16, device=dev)
-        with torch.profiler.record_function("tc_fwd_steps"):
-          L.call("bsrnn_blstm_train_fwd_tc", zero.data_ptr(), y[0].data_ptr(), y[1].data_ptr(), p["whh"][0].data_ptr(),
-               p["whh"][1].data_ptr(), gates.data_ptr(), c_all[0].data_ptr(), c_all[1].data_ptr(), steps, tiles, nt, BN, H, st)
+        fused = FUSED_TRAIN and H == 392 and p["kc_h"] == LKC_H and N % 4 == 0 and N < p["kc_in"] * 8
+        if fused:
+            # x -> operand tiles with the constant-one column (the bias rides in the weights), then ONE persistent launch:
+            # input projection + recurrence, activated gates and c_t saved by the epilogue for BPTT
+            geo = 14 if (tiles + 1) // 2 <= 3 else 7
+            xhat = torch.empty(m_all * p["kc_in"] * 1024, dtype=torch.float16, device=dev)
+            L.call("bsrnn_norm_cast_kb8_ones", x.data_ptr(), None, None, xhat.data_ptr(), N, 0, N, p["kc_in"], m_all, tiles, R,
+                   *addr, T * K, 1, N, st)
+            wf = pack_fused_train((w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r), geo, p["kc_in"], N)
+            sync = torch.empty(L.lib().bsrnn_blstm_fused_sync_bytes(), dtype=torch.uint8, device=dev)
+            with torch.profiler.record_function("tc_fwd_fused"):
+                L.call("bsrnn_blstm_fused_train_tc", geo, xhat.data_ptr(), wf.data_ptr(), zero.data_ptr(), y[0].data_ptr(),
+                       y[1].data_ptr(), tile_halves, gates.data_ptr(), c_all[0].data_ptr(), c_all[1].data_ptr(), R, steps, tiles,
+                       0, 0, sync.data_ptr(), st)
+        else:
+            xhat = _cast_kb8(x, p["kc_in"], steps, tiles, R, addr, T * K)
+            L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bias"].data_ptr(), gates.data_ptr(), None, m_all,
+                   2 * nt, p["kc_in"], BN, L.TC_F16_ROWS, 8 * H, 8 * H, 0, 1, m_all, m_all * 128, BIG, 0, 1, 0, st)
+            with torch.profiler.record_function("tc_fwd_steps"):
+                L.call("bsrnn_blstm_train_fwd_tc", zero.data_ptr(), y[0].data_ptr(), y[1].data_ptr(), p["whh"][0].data_ptr(),
+                       p["whh"][1].data_ptr(), gates.data_ptr(), c_all[0].data_ptr(), c_all[1].data_ptr(), steps, tiles, nt, BN, H, st)
         out = torch.zeros(B, T, K, N, dtype=torch.float32, device=dev)
         n16 = p["fc_nt"] * p["fc_bn"]
         bias = torch.zeros(n16, dtype=torch.float32, device=dev)
