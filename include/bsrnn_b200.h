@@ -261,8 +261,11 @@ int bsrnn_blstm_fused14_tc(const void* xhat, const void* w_fused14, const void* 
  *     dir*4H + 4u + gate; c_f / c_b [step][seq_tiles*128][H] f32 -- the buffers bsrnn_blstm_train_bwd_tc reads
  *     [autograd's saved tensors of nn.LSTM in SEModel.training_step, d_model.py:61-95]. */
 int bsrnn_blstm_fused_train_tc(int geo, const void* xhat, const void* w_fused, const void* zero_tile, void* y_f, void* y_b,
-                               long y_stride, void* gates, float* c_f, float* c_b, int R, int steps, int seq_tiles,
-                               int max_groups, int slots, void* sync_ws, void* stream);
+                               long y_stride, void* gates, float* c_f, float* c_b, void* scratch, int R, int steps,
+                               int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream);
+/* scratch of the call above in bytes: the epilogue stores the activations unit-major ([unit][128 rows], coalesced over a
+ * warp's rows) and a transpose kernel inside the call writes the row-major buffers. */
+long bsrnn_blstm_fused_train_scratch_bytes(int steps, int seq_tiles);
 int bsrnn_blstm_fused14_max_groups(void);
 /* bsrnn_blstm_fused768_tc: the same fused layer kernel for nn.LSTM(N=384, H=768, bidirectional) of BSRNN_flowse
  *     [reference bsrnn_flowse.py:226-238 at the conf/models/BSRNN_flowse.yaml width]: groups of 24 CTA pairs (32 hidden

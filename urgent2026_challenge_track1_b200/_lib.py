@@ -45,7 +45,8 @@ PROTOTYPES = {
                               c_int, c_long, c_int, c_int, c_long, c_long, c_long, c_long, c_void_p],
     "bsrnn_gemm_tc_limit_ctas": [c_int],
     "bsrnn_blstm_fused_train_tc": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p, c_void_p,
-                                   c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "bsrnn_blstm_fused_train_scratch_bytes": [c_int, c_int],
     "bsrnn_band_norm_cast_kb8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                  c_long, c_int, c_int, c_int, c_void_p],
     "bsrnn_lstm_step_tc": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_long, c_void_p],
@@ -137,6 +138,7 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = c_int
         handle.bsrnn_launch_count.restype = C.c_long
+        handle.bsrnn_blstm_fused_train_scratch_bytes.restype = C.c_long
         handle.bsrnn_last_error.restype = C.c_char_p
         handle.bsrnn_last_error.argtypes = []
         _lib = handle

@@ -118,13 +118,15 @@ struct FusedArgs {
   int gpd;                   // work groups per direction (each = up to `slots` consecutive tile PAIRS)
   unsigned* sync;            // [0] ticket counter, [32 + 32*((3*group + slot)*2 + parity)] h_ready counters
   long long* probe;          // debug (-DBSRNN_FUSED_PROBE): per-role wait / busy cycle totals of pair 0, [16*e + i]
-  // training forward (SAVE instantiations): activated gates, rows [(step*seq_tiles + tile)*128 + r][8H] fp16 with column
-  // dir*4H + 4u + gate, and c_t per direction [step][seq_tiles*128][H] f32 -- the layout bsrnn_blstm_train_bwd_tc reads
+  // training forward (SAVE instantiations): activated gates [tile = step*seq_tiles + j][dir][unit][128 rows][4] fp16 and c_t
+  // per direction [tile][unit][128 rows] f32 (unit-major scratch; saved_transpose_kernel makes them row-major for BPTT)
   __half* sv_gates;
   float* sv_c0;
   float* sv_c1;
 };
-constexpr int FH = 392;      // hidden size of the H = 392 geometries (row strides of the saved activations)
+constexpr int FH = 392;      // hidden size of the H = 392 geometries
+// saved activations, UNIT-major per (tile, direction): gates [tile][dir][unit][128 rows][4] fp16, c [tile][unit][128 rows] f32
+constexpr int SVG = 128 * 4, SVC = 128;
 
 #ifdef BSRNN_FUSED_PROBE
 #define FP_DECL(cond) const bool prb_ = a.probe && ticket == 0 && (cond); long long pt_ = prb_ ? clock64() : 0
@@ -216,7 +218,7 @@ __device__ __forceinline__ void epif_chunk_sv(const uint32_t (&acc)[16], float (
   for (int u = 0; u < 4; ++u) {
     if (SAVE && st)
       gate_update_save(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
-                       __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u], sg + 4 * (4 * CH + u), sc + 4 * CH + u);
+                       __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u], sg + SVG * (4 * CH + u), sc + SVC * (4 * CH + u));
     else
       gate_update(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
                   __uint_as_float(acc[4 * u + 3]), c[4 * CH + u], h[4 * CH + u]);
@@ -258,7 +260,7 @@ __device__ __forceinline__ void epif_item392x7(uint32_t t_col, __half* ycore, fl
 #pragma unroll
   for (int u = 0; u < 2; ++u)
     gate_update_sv<SAVE>(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
-                         __uint_as_float(a8[4 * u + 3]), c[12 + u], h[12 + u], sg + 4 * (12 + u), sc + 12 + u, st);
+                         __uint_as_float(a8[4 * u + 3]), c[12 + u], h[12 + u], sg + SVG * (12 + u), sc + SVC * (12 + u), st);
   if (st) {
     if (T == 0) store_partial<0, 6, 8>(ycore + CORE, h);                   // p 8..13  -> core 1 slots 0..5
     if (T == 1) { store_full<2>(ycore + 2 * CORE, h); store_partial<0, 4, 10>(ycore + 3 * CORE, h); }   // p 16..23, 24..27
@@ -287,13 +289,13 @@ __device__ __forceinline__ void epif_item392x14(uint32_t t_col, __half* ycore, f
 #pragma unroll
   for (int u = 0; u < 4; ++u)
     gate_update_sv<SAVE>(__uint_as_float(acc[4 * u]), __uint_as_float(acc[4 * u + 1]), __uint_as_float(acc[4 * u + 2]),
-                         __uint_as_float(acc[4 * u + 3]), c[u], h[u], sg + 4 * u, sc + u, st);
+                         __uint_as_float(acc[4 * u + 3]), c[u], h[u], sg + SVG * u, sc + SVC * u, st);
 #pragma unroll
   for (int u = 0; u < 2; ++u)
     gate_update_sv<SAVE>(__uint_as_float(a8[4 * u]), __uint_as_float(a8[4 * u + 1]), __uint_as_float(a8[4 * u + 2]),
-                         __uint_as_float(a8[4 * u + 3]), c[4 + u], h[4 + u], sg + 4 * (4 + u), sc + 4 + u, st);
+                         __uint_as_float(a8[4 * u + 3]), c[4 + u], h[4 + u], sg + SVG * (4 + u), sc + SVC * (4 + u), st);
   gate_update_sv<SAVE>(__uint_as_float(a4[0]), __uint_as_float(a4[1]), __uint_as_float(a4[2]), __uint_as_float(a4[3]), c[6], h[6],
-                       sg + 4 * 6, sc + 6, st);
+                       sg + SVG * 6, sc + SVC * 6, st);
   if (st) {
     store_partial<S0, S0 + N0, 0>(ycore + C0 * CORE, h);
     if constexpr (N0 < 7) store_partial<0, 7 - N0, N0>(ycore + (C0 + 1) * CORE, h);
@@ -360,10 +362,9 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
           } else if constexpr (G7) {
             __half* sg = nullptr; float* sc = nullptr;
             if constexpr (G::SAVE) {
-              const size_t row = tile * 128 + (size_t)r;
               const int u0 = 56 * q + 14 * T;
-              sg = a.sv_gates + row * (8 * FH) + GR.d * 4 * FH + 4 * u0;
-              sc = (GR.d == 0 ? a.sv_c0 : a.sv_c1) + row * FH + u0;
+              sg = a.sv_gates + (((tile * 2 + GR.d) * FH + u0) * 128 + (size_t)r) * 4;
+              sc = (GR.d == 0 ? a.sv_c0 : a.sv_c1) + (tile * FH + u0) * 128 + (size_t)r;
             }
             if (k == 0) epif_item392x7<Q, G::SAVE>(t_lane + buf * G::ACC, ycore, c0, valid, sg, sc);
             else if (k == 1) epif_item392x7<Q, G::SAVE>(t_lane + buf * G::ACC, ycore, c1, valid, sg, sc);
@@ -371,10 +372,9 @@ __device__ __forceinline__ void epiloguef_role(const FusedArgs& a, uint32_t tmem
           } else if constexpr (G14) {
             __half* sg = nullptr; float* sc = nullptr;
             if constexpr (G::SAVE) {
-              const size_t row = tile * 128 + (size_t)r;
               const int u0 = 28 * q + 7 * T;
-              sg = a.sv_gates + row * (8 * FH) + GR.d * 4 * FH + 4 * u0;
-              sc = (GR.d == 0 ? a.sv_c0 : a.sv_c1) + row * FH + u0;
+              sg = a.sv_gates + (((tile * 2 + GR.d) * FH + u0) * 128 + (size_t)r) * 4;
+              sc = (GR.d == 0 ? a.sv_c0 : a.sv_c1) + (tile * FH + u0) * 128 + (size_t)r;
             }
             if (k == 0) epif_item392x14<Q / 4, Q % 4, G::SAVE>(t_lane + buf * G::ACC, ycore, c0, valid, sg, sc);
             else if (k == 1) epif_item392x14<Q / 4, Q % 4, G::SAVE>(t_lane + buf * G::ACC, ycore, c1, valid, sg, sc);
@@ -848,21 +848,71 @@ extern "C" int bsrnn_blstm_fused768_tc(const void* xhat, const void* w_fused, co
 }
 extern "C" int bsrnn_blstm_fused768_max_groups(void) { return fused_max_groups<Geo768>(); }
 
+namespace bsrnn {
+// unit-major scratch of the SAVE kernels -> the row-major buffers of bsrnn_blstm_train_bwd_tc.  grid (tiles, 2 directions).
+__global__ void __launch_bounds__(256) saved_transpose_kernel(const uint2* __restrict__ gT, const float* __restrict__ cT0,
+                                                             const float* __restrict__ cT1, uint2* __restrict__ gates,
+                                                             float* __restrict__ c0, float* __restrict__ c1) {
+  __shared__ uint2 tg[32][33];
+  __shared__ float tc[32][33];
+  const int tile = blockIdx.x, d = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                 // 32 x 8
+  const uint2* sg = gT + ((size_t)(tile * 2 + d) * FH) * 128;             // [unit][row]
+  const float* sc = (d == 0 ? cT0 : cT1) + (size_t)tile * FH * 128;
+  uint2* dg = gates + (size_t)tile * 128 * (2 * FH) + (size_t)d * FH;     // row stride 2*FH uint2 (= 8H halves)
+  float* dc = (d == 0 ? c0 : c1) + (size_t)tile * 128 * FH;
+  for (int u0 = 0; u0 < FH; u0 += 32) {
+    for (int r0 = 0; r0 < 128; r0 += 32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int u = u0 + ty + 8 * k;
+        if (u < FH) {
+          tg[ty + 8 * k][tx] = sg[(size_t)u * 128 + r0 + tx];
+          tc[ty + 8 * k][tx] = sc[(size_t)u * 128 + r0 + tx];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int r = r0 + ty + 8 * k, u = u0 + tx;
+        if (u < FH) {
+          dg[(size_t)r * (2 * FH) + u] = tg[tx][ty + 8 * k];
+          dc[(size_t)r * FH + u] = tc[tx][ty + 8 * k];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+}  // namespace bsrnn
+
 // Training forward of the BLSTM layer (H = 392) on the fused kernel: as bsrnn_blstm_fused7_tc / _fused14_tc (geo = 7 | 14) with
 // separate output buffers per direction (block (step, tile) of direction d at y_d + (step*seq_tiles + tile) * y_stride halves,
 // [50][128][8] each) and the activations BPTT needs written by the epilogue: gates rows [(step*seq_tiles + tile)*128 + r][8H]
 // fp16 = ACTIVATED i, f, g, o at column dir*4H + 4u + gate, c_f / c_b [step][seq_tiles*128][H] f32 -- the buffers
 // bsrnn_blstm_train_bwd_tc reads [replaces autograd's saved tensors of nn.LSTM, d_model.py:61-95 / train_se.py:74-84].
+// scratch: (2 * steps*seq_tiles*128*4H halves) + (2 * steps*seq_tiles*128*H floats) = bsrnn_blstm_fused_train_scratch_bytes().
+extern "C" long bsrnn_blstm_fused_train_scratch_bytes(int steps, int seq_tiles) {
+  return (long)steps * seq_tiles * 128 * FH * (2 * 4 * 2 + 2 * 4);
+}
 extern "C" int bsrnn_blstm_fused_train_tc(int geo, const void* xhat, const void* w_fused, const void* zero_tile, void* y_f,
-                                          void* y_b, long y_stride, void* gates, float* c_f, float* c_b, int R, int steps,
-                                          int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
-  BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y_f && y_b && gates && c_f && c_b && sync_ws, "blstm_fused_train_tc: null pointer");
+                                          void* y_b, long y_stride, void* gates, float* c_f, float* c_b, void* scratch, int R,
+                                          int steps, int seq_tiles, int max_groups, int slots, void* sync_ws, void* stream) {
+  BSRNN_CHECK_ARG(xhat && w_fused && zero_tile && y_f && y_b && gates && c_f && c_b && sync_ws && scratch, "blstm_fused_train_tc: null pointer");
   BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused_train_tc: bad dims");
   BSRNN_CHECK_ARG(geo == 7 || geo == 14, "blstm_fused_train_tc: geo must be 7 or 14");
   BSRNN_CHECK_ARG(y_stride >= (long)Geo392x7::HKC * 128 * 8 && y_stride % 8 == 0, "blstm_fused_train_tc: bad y_stride");
-  if (geo == 7)
-    return run_fused<Geo392x7S>("blstm_fused_train_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles, max_groups,
-                                slots, sync_ws, stream, gates, c_f, c_b);
-  return run_fused<Geo392x14S>("blstm_fused_train_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles, max_groups,
-                               slots, sync_ws, stream, gates, c_f, c_b);
+  const size_t m_all = (size_t)steps * seq_tiles;
+  __half* gT = reinterpret_cast<__half*>(scratch);
+  float* cT0 = reinterpret_cast<float*>(gT + m_all * 128 * 8 * FH);
+  float* cT1 = cT0 + m_all * 128 * FH;
+  const int rc = geo == 7 ? run_fused<Geo392x7S>("blstm_fused_train_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles,
+                                                 max_groups, slots, sync_ws, stream, gT, cT0, cT1)
+                          : run_fused<Geo392x14S>("blstm_fused_train_tc", xhat, w_fused, zero_tile, y_f, y_b, y_stride, R, steps, seq_tiles,
+                                                  max_groups, slots, sync_ws, stream, gT, cT0, cT1);
+  if (rc) return rc;
+  saved_transpose_kernel<<<dim3((unsigned)m_all, 2), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint2*>(gT), cT0, cT1, reinterpret_cast<uint2*>(gates), c_f, c_b);
+  BSRNN_LAUNCH_OK();
+  return 0;
 }

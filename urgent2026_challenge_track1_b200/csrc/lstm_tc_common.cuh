@@ -45,6 +45,9 @@ __device__ __forceinline__ void gate_update(float pi, float pf, float pg, float 
 
 // training forward: the same update, and the ACTIVATED gates (i, f, g, o as 4 halves) + c_t written out for BPTT
 // [what bsrnn_blstm_step_train_tc saves: gemm_tc.cu EPI_LSTM_STEP with save_gates]
+// (the fused kernel stores them UNIT-major -- [unit][128 rows]: a warp's 32 rows are contiguous -- and a small transpose kernel
+// turns them into the row-major buffers BPTT reads: per-row stores from the epilogue cost 32 sectors per instruction and
+// tripled the step time, profiles/r02 call59)
 __device__ __forceinline__ void gate_update_save(float pi, float pf, float pg, float po, float& c, float& h, __half* g4, float* cs) {
   const float ig = fmaf(tanh_fast(pi), 0.5f, 0.5f), fg = fmaf(tanh_fast(pf), 0.5f, 0.5f);
   const float gg = tanh_fast(pg), og = fmaf(tanh_fast(po), 0.5f, 0.5f);

@@ -59,7 +59,7 @@ def _gate_tables(H, dev):
     return t
 
 
-def pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, narrow_bwd=False):
+def pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, narrow_bwd=False, fwd_steps=True):
     """All tensor-core operands of one block, from the f32 master weights (nn.LSTM / nn.Linear layouts).
     narrow_bwd: BPTT output tiles of 64 hidden units instead of up to 256 (few row tiles = small batch: more CTAs share a
     step and each epilogue warp owns a single 32-unit chunk)."""
@@ -79,12 +79,15 @@ def pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, nar
     wih, bias, whh, whhT, wihT = [], [], [], [], []
     for wi, wh, bi, bh in ((w_ih, w_hh, b_ih, b_hh), (w_ih_r, w_hh_r, b_ih_r, b_hh_r)):
         wi_p, wh_p = wi.detach().float()[perm], wh.detach().float()[perm]               # interleaved rows, TRUE weights
-        wih.append(wi_p * gsc)
-        bias.append((bi.detach() + bh.detach()).float()[perm] * gsc[:, 0])
-        whh.append(to_kb8(wh_p * gsc, BN, kc_h))
+        if fwd_steps:                                  # operands of the step-wise forward (the fused forward packs its own)
+            wih.append(wi_p * gsc)
+            bias.append((bi.detach() + bh.detach()).float()[perm] * gsc[:, 0])
+            whh.append(to_kb8(wh_p * gsc, BN, kc_h))
         whhT.append(to_kb8(wh_p.t().contiguous(), bn_h, 4 * H // 8))                    # rows = unit u, K = gate column
         wihT.append(to_kb8(wi_p.t().contiguous(), bn_n, 4 * H // 8))                    # rows = input n, K = gate column
-    p.update(wih=to_kb8(torch.cat(wih, 0), BN, kc_in), bias=torch.cat(bias).contiguous(), whh=whh, whhT=whhT, wihT=wihT)
+    p.update(whhT=whhT, wihT=wihT)
+    if fwd_steps:
+        p.update(wih=to_kb8(torch.cat(wih, 0), BN, kc_in), bias=torch.cat(bias).contiguous(), whh=whh)
     fw = fc_w.detach().float()                                                           # (N, 2H)
     n16 = (N + 15) // 16 * 16
     fc_bn = _bn_div(n16, 16)
@@ -173,8 +176,10 @@ class BLSTMBlockTC(torch.autograd.Function):
         dev = x.device
         st = L.stream_ptr()
         R, steps, tiles, addr = _geom(B, T, K, axis)
+        Hh, Nn = w_hh.shape[1], w_ih.shape[1]
+        fused = FUSED_TRAIN and Hh == 392 and Nn % 4 == 0 and Nn % 16 != 0
         with torch.profiler.record_function("tc_pack_block"):
-            p = pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, narrow_bwd=tiles <= 16)
+            p = pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, narrow_bwd=tiles <= 16, fwd_steps=not fused)
         H, BN, nt = p["H"], p["BN"], p["n_tiles"]
         m_all = steps * tiles
         x = x.contiguous().float()
@@ -183,7 +188,7 @@ class BLSTMBlockTC(torch.autograd.Function):
         y = [torch.zeros(m_all * tile_halves, dtype=torch.float16, device=dev) for _ in range(2)]     # pad k-core stays 0
         c_all = [torch.empty(steps, tiles * 128, H, dtype=torch.float32, device=dev) for _ in range(2)]
         zero = torch.zeros(tiles * tile_halves, dtype=torch.float16, device=dev)
-        fused = FUSED_TRAIN and H == 392 and p["kc_h"] == LKC_H and N % 4 == 0 and N < p["kc_in"] * 8
+        assert not fused or (p["kc_h"] == LKC_H and N < p["kc_in"] * 8)
         if fused:
             # x -> operand tiles with the constant-one column (the bias rides in the weights), then ONE persistent launch:
             # input projection + recurrence, activated gates and c_t saved by the epilogue for BPTT
@@ -193,10 +198,11 @@ class BLSTMBlockTC(torch.autograd.Function):
                    *addr, T * K, 1, N, st)
             wf = pack_fused_train((w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r), geo, p["kc_in"], N)
             sync = torch.empty(L.lib().bsrnn_blstm_fused_sync_bytes(), dtype=torch.uint8, device=dev)
+            scratch = torch.empty(m_all * 128 * H * 24, dtype=torch.uint8, device=dev)      # bsrnn_blstm_fused_train_scratch_bytes
             with torch.profiler.record_function("tc_fwd_fused"):
                 L.call("bsrnn_blstm_fused_train_tc", geo, xhat.data_ptr(), wf.data_ptr(), zero.data_ptr(), y[0].data_ptr(),
-                       y[1].data_ptr(), tile_halves, gates.data_ptr(), c_all[0].data_ptr(), c_all[1].data_ptr(), R, steps, tiles,
-                       0, 0, sync.data_ptr(), st)
+                       y[1].data_ptr(), tile_halves, gates.data_ptr(), c_all[0].data_ptr(), c_all[1].data_ptr(),
+                       scratch.data_ptr(), R, steps, tiles, 0, 0, sync.data_ptr(), st)
         else:
             xhat = _cast_kb8(x, p["kc_in"], steps, tiles, R, addr, T * K)
             L.call("bsrnn_gemm_tc", xhat.data_ptr(), p["wih"].data_ptr(), p["bias"].data_ptr(), gates.data_ptr(), None, m_all,
@@ -272,7 +278,8 @@ class BLSTMBlockTC(torch.autograd.Function):
             dwhh = torch.zeros(4 * H, H, dtype=torch.float32, device=dev)
             L.call("bsrnn_gemm_tc_scaled", dGT.data_ptr(), hT.data_ptr(), None, dwhh.data_ptr(), nt_g, p["nt_h"], kc_tok, p["bn_h"],
                    H, H, 0.0, inv_s.data_ptr(), ksplit, 1 << 30, 4 * H, 4, 1, H, 0, st)
-            db = dG[d].view(m_all, kc_g, 128, 8).float().sum(dim=(0, 2)).reshape(H, 4).t().reshape(4 * H) * inv_s
+            # (f32 accumulation straight from the fp16 tiles: .float() first materialised a 2x copy of dG per direction)
+            db = dG[d].view(m_all, kc_g, 128, 8).sum(dim=(0, 2), dtype=torch.float32).reshape(H, 4).t().reshape(4 * H) * inv_s
             grads_w.append((dwih, dwhh, db))
         nt_d = (N + 127) // 128
         dDT = _transpose(dD, 0, m_all, kc_in, 128, nt_d, kc_tok, 0, zero=False)
