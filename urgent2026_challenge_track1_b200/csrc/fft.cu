@@ -81,6 +81,28 @@ stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, flo
     if (i >= L) i = 2 * (L - 1) - i;
     return row[i] * w;
   };
+  if constexpr (!ADJ) {
+    // sample n of every live frame at once: up to 8 independent global loads in flight per thread and no division (the
+    // one-element-at-a-time loop spent 45 % of the kernel's samples waiting on its single load, profiles/r02 call49)
+    const long base0 = (long)t0 * hop - N / 2;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float w = 0.5f - 0.5f * tw[n].x;            // periodic Hann: cos(2*pi*n/N) = Re tw[n]
+      float v[8];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        v[f] = 0.f;
+        if (f < nlive) {
+          long i = base0 + (long)f * hop + n;
+          if (i < 0) i = -i;
+          if (i >= L) i = 2 * ((long)L - 1) - i;
+          v[f] = __ldg(row + i);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < npair) buf0[(size_t)p * N + n] = make_float2(v[2 * p] * w, v[2 * p + 1] * w);
+    }
+  } else {
   for (int idx = threadIdx.x; idx < npair * N; idx += blockDim.x) {
     const int p = idx / N;
     const int n = idx - p * N;
@@ -88,13 +110,13 @@ stft_kernel(const float* __restrict__ wav, const int32_t* __restrict__ lens, flo
     const float xb = (2 * p + 1 < nlive) ? sample(2 * p + 1, n) : 0.f;
     buf0[idx] = make_float2(xa, xb);
   }
+  }
   __syncthreads();
   float2* res = buf0;
   if (npair > 0) res = fft_frames<false>(buf0, buf1, tw, plan, npair);
   float2* outb = (res == buf0) ? buf1 : buf0;        // the finished spectra of the block's frames (for the statistics)
-  for (int idx = threadIdx.x; idx < nfr * F; idx += blockDim.x) {
-    const int f = idx / F;
-    const int k = idx - f * F;
+  for (int f = 0; f < nfr; ++f)
+  for (int k = threadIdx.x; k < F; k += blockDim.x) {
     float2 v = make_float2(0.f, 0.f);
     if (f < nlive) {
       const float2 zk = res[(size_t)(f >> 1) * N + k];
@@ -193,14 +215,20 @@ istft_kernel(const float2* __restrict__ spec, const float2* __restrict__ mask, c
       if (k == 0 || (nyq && k == N / 2)) v.y = 0.f;   // irfft ignores Im of DC / Nyquist
       return v;
     };
-    for (int idx = threadIdx.x; idx < npair * F; idx += blockDim.x) {
-      const int p = idx / F;
-      const int k = idx - p * F;
-      const float2 va = masked(2 * p, k);
-      const float2 vb = (2 * p + 1 < nfr) ? masked(2 * p + 1, k) : make_float2(0.f, 0.f);
-      float2* fr = buf0 + (size_t)p * N;
-      fr[k] = make_float2(va.x - vb.y, va.y + vb.x);
-      if (k != 0 && !(nyq && k == N / 2)) fr[N - k] = make_float2(va.x + vb.y, vb.x - va.y);
+    // bin k of every frame of the batch at once (fpb <= 8): the loads of all frames are independent and in flight together
+    for (int k = threadIdx.x; k < F; k += blockDim.x) {
+      float2 v[8];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) v[f] = (f < nfr) ? masked(f, k) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (p < npair) {
+          const float2 va = v[2 * p], vb = v[2 * p + 1];
+          float2* fr = buf0 + (size_t)p * N;
+          fr[k] = make_float2(va.x - vb.y, va.y + vb.x);
+          if (k != 0 && !(nyq && k == N / 2)) fr[N - k] = make_float2(va.x + vb.y, vb.x - va.y);
+        }
+      }
     }
     __syncthreads();
     float2* res = fft_frames<true>(buf0, buf1, tw, plan, npair);

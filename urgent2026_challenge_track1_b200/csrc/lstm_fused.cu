@@ -84,6 +84,9 @@ struct Geo768 {
   // of 3, so the default stays one pair per cluster.
   static constexpr int CLS = BSRNN_FUSED768_CLS;
 };
+// small-batch geometry in clusters of 2 pairs: the two CTAs of a parity fetch half of every ring stage and multicast it to
+// both (the 100 KB h tile of a step is on the dependency chain of a chain-bound launch).  BSRNN_FUSED14_CLS=4 selects it.
+struct Geo392x14M : Geo392x14 { static constexpr int CLS = 4; };
 struct Geo392x7S : Geo392x7 { static constexpr bool SAVE = true; };
 struct Geo392x14S : Geo392x14 { static constexpr bool SAVE = true; };
 template <class G>
@@ -827,6 +830,11 @@ extern "C" int bsrnn_blstm_fused14_tc(const void* xhat, const void* w_fused14, c
   BSRNN_CHECK_ARG(xhat && w_fused14 && zero_tile && y && sync_ws, "blstm_fused14_tc: null pointer");
   BSRNN_CHECK_ARG(R > 0 && steps > 0 && (long)seq_tiles * 128 >= R, "blstm_fused14_tc: bad dims");
   const long y_tile = (long)Geo392x14::HKC * 128 * 8;
+  static int cls_env = -1;
+  if (cls_env < 0) { const char* e = getenv("BSRNN_FUSED14_CLS"); cls_env = (e && e[0] == '4') ? 4 : 2; }
+  if (cls_env == 4)
+    return run_fused<Geo392x14M>("blstm_fused14_tc", xhat, w_fused14, zero_tile, y, reinterpret_cast<__half*>(y) + y_tile, 2 * y_tile,
+                                 R, steps, seq_tiles, max_groups, slots, sync_ws, stream);
   return run_fused<Geo392x14>("blstm_fused14_tc", xhat, w_fused14, zero_tile, y, reinterpret_cast<__half*>(y) + y_tile, 2 * y_tile,
                               R, steps, seq_tiles, max_groups, slots, sync_ws, stream);
 }
