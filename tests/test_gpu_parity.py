@@ -373,6 +373,28 @@ def test_weight_resident_gemm_paths_match_a_small_batch():
     assert e < 1e-2
 
 
+@pytest.mark.parametrize("width,fs", [(192, 16000), (32, 48000), (64, 22050)])
+def test_bsrnn_se_tensorcore_other_widths_vs_oracle(width, fs):
+    """Tensor-core mode at widths other than the published 196 (the reference constructor's default is num_channel=192): the
+    step-wise tensor-core BLSTM kernels serve any num_channel % 8 == 0.  Bar 1e-2 (16-bit mode)."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=width, num_layer=2, precision="fp16")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.cuda()
+    n = fs // 2
+    x = R.synth_noisy(2, n, fs, seed=1)
+    lens = torch.tensor([n, n - 801])
+    with torch.no_grad():
+        ref_wav, ref_spec = R.bsrnn_se_forward(sd, x, lens, fs, num_layer=2)
+    out, spec = m(x, lens, fs)
+    e_w, e_s = rel_l2(out.cpu(), ref_wav), rel_l2(spec.cpu(), ref_spec)
+    print(f"width={width} fs={fs} tensor-core rel_l2 wav={e_w:.3e} spec={e_s:.3e}")
+    assert e_w < 1e-2 and e_s < 1e-2
+    with pytest.raises(NotImplementedError):
+        BSRNN_SE(num_channel=20, num_layer=1, precision="fp16").cuda()(x, lens, fs)
+
+
 def test_lstm_step_tc_vs_torch_h768():
     """bsrnn_lstm_step_tc at the FlowSE width (N = 384, H = 768), ragged last tile: against torch.nn.LSTM on the CPU."""
     from urgent2026_challenge_track1_b200 import runtime_tc_steps as S, _lib as L

@@ -61,6 +61,7 @@ class BSRNN_SE(nn.Module):
         self._dual_tc = R.PackedCache(core, TC.pack_dual_path_tc)
         self._md_tc = R.PackedCache(core.mask_decoder, TC.pack_mask_decoder_tc)
         self._bs_tc = R.PackedCache(core.band_split, TC.pack_band_split_tc)
+        self._dual_steps = None                          # step-wise tensor-core packs, built on first use (widths != 196)
 
     # ------------------------------------------------------------------------------------------------
     def _device(self):
@@ -115,9 +116,20 @@ class BSRNN_SE(nn.Module):
             mask, resid = R.mask_decoder_f32(skip, plan, self._md.get())
         elif self.precision == "fp16":
             if 2 * self.num_channel != TC.CL * TC.LU:
-                raise NotImplementedError(
-                    f"the tensor-core BLSTM kernel is specialised for num_channel=196 (H=392); got {self.num_channel}. "
-                    "Use precision='fp32' for other widths.")
+                # other widths (e.g. the constructor default num_channel=192): the step-wise tensor-core BLSTM kernels of the
+                # FlowSE / training paths serve any H = 2N with H % 16 == 0; the persistent fused layer kernel is H = 392 / 768 only
+                if self.num_channel % 8:
+                    raise NotImplementedError(
+                        f"tensor-core mode needs num_channel % 8 == 0 (or 196, the published width); got {self.num_channel}. "
+                        "Use precision='fp32' for other widths.")
+                from . import runtime_tc_steps as TS
+                if self._dual_steps is None:
+                    self._dual_steps = R.PackedCache(core, TS.pack_dual_path_steps)
+                skip = R.band_split_f32(spec, plan, self._bs.get(), self.num_channel, stats=bstats)
+                TS.dual_path_tc_steps(skip, self._dual_steps.get())
+                mask, resid = TC.mask_decoder_tc(skip, plan, self._md_tc.get())
+                wav_out, est = R.istft(spec, mask, resid, L_out, n_fft, hop, want_spec=True)
+                return wav_out, torch.view_as_complex(est)
             B, T = spec.shape[0], spec.shape[1]
             tc_bs = TC.BAND_SPLIT_TC and self.num_channel % 4 == 0
             if tc_bs:                                  # Conv1d(2 s_k -> N) on tcgen05, first GroupNorm's sums in its epilogue
