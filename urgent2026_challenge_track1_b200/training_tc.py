@@ -218,7 +218,7 @@ class BLSTMBlockTC(torch.autograd.Function):
         for half, bb in ((0, bias), (1, zbias)):                   # out = y_fwd W_f^T + b, then += y_bwd W_b^T
             L.call("bsrnn_gemm_tc", y[half].data_ptr(), p["fcw"][half].data_ptr(), bb.data_ptr(), out.data_ptr(), None,
                    m_all, p["fc_nt"], p["kc_h"], p["fc_bn"], FC_EPI, N, N, 0, T * K, tiles, R, *addr, st)
-        ctx.p, ctx.dims = p, (B, T, K, N, axis)
+        ctx.p, ctx.dims, ctx.fused = p, (B, T, K, N, axis), fused
         ctx.save_for_backward(xhat, gates, y[0], y[1], c_all[0], c_all[1])
         return out
 
@@ -266,9 +266,13 @@ class BLSTMBlockTC(torch.autograd.Function):
         grads_w = []
         for d in (0, 1):
             dGT = _transpose(dG[d], 0, m_all, kc_g, 128, nt_g, kc_tok, 0, zero=False)
-            dwih = torch.zeros(4 * H, N, dtype=torch.float32, device=dev)
-            L.call("bsrnn_gemm_tc_scaled", dGT.data_ptr(), xT.data_ptr(), None, dwih.data_ptr(), nt_g, p["nt_n"], kc_tok, p["bn_n"],
-                   N, N, 0.0, inv_s.data_ptr(), ksplit, 1 << 30, 4 * H, 4, 1, H, 0, st)   # GEMM row 4u+g -> gradient row g*H + u
+            # fused forward: xhat carries the constant-one column N, so column N of dG^T xhat IS the bias gradient (sum of dG over
+            # tokens) -- 4 more output columns instead of a reduction pass over dG per direction
+            nv = N + 4 if ctx.fused else N
+            dwih_full = torch.zeros(4 * H, nv, dtype=torch.float32, device=dev)
+            L.call("bsrnn_gemm_tc_scaled", dGT.data_ptr(), xT.data_ptr(), None, dwih_full.data_ptr(), nt_g, p["nt_n"], kc_tok,
+                   p["bn_n"], nv, nv, 0.0, inv_s.data_ptr(), ksplit, 1 << 30, 4 * H, 4, 1, H, 0, st)   # GEMM row 4u+g -> gradient row g*H + u
+            dwih = dwih_full[:, :N]
             # h_{t-1}: the y tiles shifted by one step along the direction of the recurrence (zeros at its first step)
             if steps > 1:
                 hT = _transpose(y[d], 0 if d == 0 else tiles, m_all - tiles, p["kc_h"], p["bn_h"], p["nt_h"], kc_tok,
@@ -279,7 +283,10 @@ class BLSTMBlockTC(torch.autograd.Function):
             L.call("bsrnn_gemm_tc_scaled", dGT.data_ptr(), hT.data_ptr(), None, dwhh.data_ptr(), nt_g, p["nt_h"], kc_tok, p["bn_h"],
                    H, H, 0.0, inv_s.data_ptr(), ksplit, 1 << 30, 4 * H, 4, 1, H, 0, st)
             # (f32 accumulation straight from the fp16 tiles: .float() first materialised a 2x copy of dG per direction)
-            db = dG[d].view(m_all, kc_g, 128, 8).sum(dim=(0, 2), dtype=torch.float32).reshape(H, 4).t().reshape(4 * H) * inv_s
+            if ctx.fused:
+                db = dwih_full[:, N]
+            else:
+                db = dG[d].view(m_all, kc_g, 128, 8).sum(dim=(0, 2), dtype=torch.float32).reshape(H, 4).t().reshape(4 * H) * inv_s
             grads_w.append((dwih, dwhh, db))
         nt_d = (N + 127) // 128
         dDT = _transpose(dD, 0, m_all, kc_in, 128, nt_d, kc_tok, 0, zero=False)
