@@ -119,6 +119,10 @@ struct GemmTcArgs {
   // read back by its Conv1d+GLU): bit 0 = bulk stores of the output (EPI_TANH_KB8 / BNC = 208), bit 1 = bulk loads of the A
   // operand carry the evict_last policy, so the buffer stays in the 126 MB L2 instead of making a DRAM round trip per band
   int l2_keep;
+  // streaming launches with one N tile walk the M tiles from the LAST one down: the MaskDecoder's Conv1d+GLU GEMM reads the 100 MB
+  // hidden tile its predecessor has just written in ascending order, so the most recently written (still L2-resident) tiles come
+  // first instead of the evicted ones
+  int reverse_m;
   // EPI_RESID_TMA with a 2-D tensor map (tmap.cuh): the tile's rows are `rows [j*128, +128) x cols [step*tm_col_step (+ group
   // offset), +n_valid)` of a row-major matrix over `out` (band axis, BandSplit): ONE tensor copy per tile and direction
   int use_tmap;
@@ -451,8 +455,14 @@ struct TileIter {
     m = (int)blockIdx.x / n_tiles;
     dm = (int)gridDim.x / n_tiles;
     dn = resident ? 0 : (int)gridDim.x - dm * n_tiles;
+    if (a.reverse_m && n_tiles == 1 && !resident) {      // last M tile first (see GemmTcArgs::reverse_m)
+      rev = true;
+      m = m_tiles - 1 - (int)blockIdx.x;
+      dm = -(int)gridDim.x;
+    }
   }
-  __device__ __forceinline__ bool valid() const { return m < m_tiles; }
+  bool rev = false;
+  __device__ __forceinline__ bool valid() const { return rev ? m >= 0 : m < m_tiles; }
   __device__ __forceinline__ void next() {
     m += dm; n += dn;
     if (n >= n_tiles) { n -= n_tiles; ++m; }
@@ -1033,6 +1043,11 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
       a.b_resident = 1;
       if (mc_env > 1 && a.n_tiles % mc_env == 0) step_mc = mc_env;
     }
+  }
+  if (EPI == EPI_GLU_F32) {
+    static int rev_env = -1;              // BSRNN_GLU_REVERSE=0: ascending tile order (A/B timing)
+    if (rev_env < 0) { const char* e = getenv("BSRNN_GLU_REVERSE"); rev_env = (e && e[0] == '0') ? 0 : 1; }
+    a.reverse_m = rev_env;
   }
   if (EPI == EPI_TANH_KB8 || EPI == EPI_GLU_F32) {
     // MEASURED (profiles/r02 call51, launch lists with / without): no effect -- Conv1d+GLU 32.1 us per band either way; the
