@@ -123,6 +123,10 @@ struct GemmTcArgs {
   // hidden tile its predecessor has just written in ascending order, so the most recently written (still L2-resident) tiles come
   // first instead of the evicted ones
   int reverse_m;
+  // band-axis Linear+skip (tensor-map path): tiles are walked with the STEP (= band) innermost, tile = (lin % m_inner) *
+  // tiles_per_step + lin / m_inner, so that the CTAs running together read / write adjacent 784-byte segments of the same rows
+  // of the residual stream (whole 26.6 KB rows per DRAM page visit) instead of one segment of 148 x 128 different rows
+  int m_inner;
   // EPI_RESID_TMA with a 2-D tensor map (tmap.cuh): the tile's rows are `rows [j*128, +128) x cols [step*tm_col_step (+ group
   // offset), +n_valid)` of a row-major matrix over `out` (band axis, BandSplit): ONE tensor copy per tile and direction
   int use_tmap;
@@ -459,11 +463,21 @@ struct TileIter {
       rev = true;
       m = m_tiles - 1 - (int)blockIdx.x;
       dm = -(int)gridDim.x;
+    } else if (a.m_inner > 1 && n_tiles == 1 && !resident) {   // steps innermost (see GemmTcArgs::m_inner)
+      inner = a.m_inner; tps = a.rows.tiles_per_step;
+      lin = (int)blockIdx.x;
+      m = (lin % inner) * tps + lin / inner;
     }
   }
   bool rev = false;
-  __device__ __forceinline__ bool valid() const { return rev ? m >= 0 : m < m_tiles; }
+  int inner = 0, tps = 0, lin = 0;
+  __device__ __forceinline__ bool valid() const { return rev ? m >= 0 : (inner ? lin < m_tiles : m < m_tiles); }
   __device__ __forceinline__ void next() {
+    if (inner) {
+      lin += dm;
+      m = (lin % inner) * tps + lin / inner;
+      return;
+    }
     m += dm; n += dn;
     if (n >= n_tiles) { n -= n_tiles; ++m; }
   }
@@ -736,7 +750,10 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1) gemm_tc_kernel(const __gri
       // stores of tile i have been read out of it, and lands while the MMAs of tile i+1 run.
       constexpr int NPART = tc_epi_warps(EPI) / 4;
       const int nch = (BN + 31) >> 5;
-      const int ch0 = (half * nch + NPART - 1) / NPART, ch1 = ((half + 1) * nch + NPART - 1) / NPART;
+      // floor partition of the column chunks: BN = 208 / N = 196 gives the three warps of a quadrant 64 / 64 / 68 valid columns
+      // (chunks [0,2) [2,4) [4,7); the 7th chunk holds 4 valid columns).  The ceil partition gave 96 / 64 / 36, and the tile
+      // waits for its slowest warp at the named barrier below (23 % of the samples, profiles/r02 call52)
+      const int ch0 = (half * nch) / NPART, ch1 = ((half + 1) * nch) / NPART;
       float* resbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_scr) + 127) & ~(uintptr_t)127);   // TMA box: 128 B
       const int ncmax = a.n_valid < BN ? a.n_valid : BN;
       const int ldr = (ncmax % 8 == 4) ? ncmax : ncmax + 4;          // bank-friendly row stride (floats)
@@ -1072,6 +1089,9 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
         make_tmap_2d_f32(&a.tmap, a.out, (uint64_t)row_stride, (uint64_t)a.rows.R, (uint64_t)row_stride * 4, (uint32_t)a.n_valid, 128)) {
       a.use_tmap = 1;
       a.tm_col_step = (int)col_step;
+      static int inner_env = -1;          // BSRNN_FC_BAND_INNER=0: step-major tile order on the band axis (A/B timing)
+      if (inner_env < 0) { const char* e = getenv("BSRNN_FC_BAND_INNER"); inner_env = (e && e[0] == '0') ? 0 : 1; }
+      if (inner_env && !a.groups && steps > 1 && col_step > 0 && a.m_tiles == steps * a.rows.tiles_per_step) a.m_inner = (int)steps;
     }
   }
   if (EPI == EPI_RESID_TMA && !a.use_tmap) {

@@ -24,6 +24,8 @@ struct PackArgs {
   int one_col;           // >= C: this operand column is the constant 1 (bias row of the weights); -1 = none
   int bulk;              // async kernel: rows arrive by cp.async.bulk (1; 2 = contiguous runs of rows merged), by ONE 2-D tensor
                          // copy per tile (3, band axis, tmap.cuh) or by 16-byte cp.async (0, BSRNN_PACK_BULK=0)
+  int m_inner;           // bulk == 3: blocks walk the tiles with the step (= band) innermost: co-running blocks read adjacent
+                         // segments of the same rows of the residual stream
   int tm_col_step;       // bulk == 3: the tile is rows [j*128, +128) x cols [step*tm_col_step, +C) of the matrix view `tmap`
   alignas(64) CUtensorMap tmap;
 };
@@ -134,7 +136,9 @@ __global__ void __launch_bounds__(256) norm_cast_kb8_async_kernel(const __grid_c
   float* tile = reinterpret_cast<float*>(smem_raw);                    // [ROWS][ld]
   PackRow* rows = reinterpret_cast<PackRow*>(smem_raw + (size_t)ROWS * ld * 4);
   constexpr int PARTS = 128 / ROWS;
-  const int m = blockIdx.x / PARTS, r0 = (blockIdx.x % PARTS) * ROWS;
+  int m = blockIdx.x / PARTS;
+  const int r0 = (blockIdx.x % PARTS) * ROWS;
+  if (a.m_inner > 1) m = (m % a.m_inner) * a.tiles_per_step + m / a.m_inner;     // band innermost (see PackArgs::m_inner)
   const int step = m / a.tiles_per_step, j = m - step * a.tiles_per_step;
   if (threadIdx.x < ROWS) {
     const int r = threadIdx.x;
@@ -281,6 +285,9 @@ extern "C" int bsrnn_norm_cast_kb8_ones(const float* x, const float* scale, cons
                        (uint32_t)rows_sel)) {
     a.bulk = 3;
     a.tm_col_step = (int)(step_stride * ldx);
+    static int inner_env = -1;            // BSRNN_PACK_BAND_INNER=0: step-major block order (A/B timing)
+    if (inner_env < 0) { const char* e = getenv("BSRNN_PACK_BAND_INNER"); inner_env = (e && e[0] == '0') ? 0 : 1; }
+    if (inner_env && m_tiles % tiles_per_step == 0 && m_tiles / tiles_per_step > 1) a.m_inner = m_tiles / tiles_per_step;
   }
   if (vec_ok && !force_old && C % 4 == 0 && smem32 <= 110 * 1024 && (one_col < 0 || one_col % 4 == 0)) {
     if (rows_sel == 128) {
