@@ -31,13 +31,13 @@ struct BandSplitArgs {
 
 __global__ void __launch_bounds__(kBsThreads, 2) band_split_kernel(const BandSplitArgs a) {
   extern __shared__ __align__(16) float bs_smem[];
-  const int k = a.k_lo + blockIdx.y;
+  const int k = a.k_lo + blockIdx.x;                  // band fastest: co-running CTAs write adjacent segments of the same rows
   const int C = a.c_off[k + 1] - a.c_off[k];          // 2 s_k
   const int Cp = (C + 3) & ~3;                        // padded to float4
   const int N = a.N;
   float* Ws = bs_smem;                                // [Cp][N]
   float* xs = bs_smem + (size_t)Cp * N;               // [128][Cp]
-  const long r0 = (long)blockIdx.x * kBsRows;
+  const long r0 = (long)blockIdx.y * kBsRows;
   const float* wsrc = a.wT + (size_t)a.c_off[k] * N;
   for (int i = threadIdx.x; i < Cp * N; i += kBsThreads) Ws[i] = i < C * N ? wsrc[i] : 0.f;
   const int cvalid = a.width2[k];
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kBsThreads, 2) band_split_kernel(const BandSpl
 // Tensor-core BandSplit (fp16 mode): the per-band GroupNorm(1, 2 s_k) is applied while the band's slice of the spectrum
 // is re-tiled into the fp16 KB8 operand of a tcgen05 GEMM (bsrnn_gemm_tc_ex, store-only TMA epilogue: out rows of band k
 // = A_k W_k^T + b_k, with the statistics of the first dual-path GroupNorm in the epilogue).  One launch covers all bands:
-// grid (row tiles, K); band k's tiles start at a_off[k] halves, [tile][kc_k][128][8] with kc_k = 2 * ceil(2 s_k / 16).
+// grid (K, row tiles); band k's tiles start at a_off[k] halves, [tile][kc_k][128][8] with kc_k = 2 * ceil(2 s_k / 16).
 struct BandCastArgs {
   const float* spec;        // (rows, F2)
   const float* scale;       // (B * K, cmax)
@@ -112,14 +112,14 @@ struct BandCastArgs {
 __global__ void __launch_bounds__(256) band_norm_cast_kb8_kernel(const BandCastArgs a) {
   extern __shared__ __align__(16) unsigned char bc_smem[];
   __half* tile = reinterpret_cast<__half*>(bc_smem);
-  const int k = blockIdx.y;
+  const int k = blockIdx.x;                           // band fastest: co-running blocks read adjacent slices of the same rows
   const int C = a.c_off[k + 1] - a.c_off[k];
   const int kc = ((C + 15) >> 4) << 1;
   const int kw = kc * 8;
   const int ld = kw + 8;                               // +8 halves: rows land in different banks
   const int cvalid = a.width2[k];
   const int col0 = 2 * a.bin0[k];
-  const long r0 = (long)blockIdx.x * 128;
+  const long r0 = (long)blockIdx.y * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < 128; r += 8) {
     const long row = r0 + r;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) band_norm_cast_kb8_kernel(const BandCastA
     }
   }
   __syncthreads();
-  __half* dst = a.out + a.a_off[k] + (size_t)blockIdx.x * kc * 1024;
+  __half* dst = a.out + a.a_off[k] + (size_t)blockIdx.y * kc * 1024;
   for (int i = threadIdx.x; i < kc * 128; i += 256) {
     const int c8 = i >> 7, r = i & 127;
     *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = *reinterpret_cast<const uint4*>(tile + r * ld + c8 * 8);
@@ -171,7 +171,7 @@ extern "C" int bsrnn_band_split_fwd(const float* spec, const float* scale, const
     BSRNN_CHECK_ARG(need <= 227 * 1024, "band_split_fwd: band of %d channels does not fit in shared memory", c_off_host[k + 1] - c_off_host[k]);
     BSRNN_CUDA_OK(cudaFuncSetAttribute(band_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     a.k_lo = k;
-    dim3 grid((unsigned)((rows + kBsRows - 1) / kBsRows), e - k);
+    dim3 grid(e - k, (unsigned)((rows + kBsRows - 1) / kBsRows));
     band_split_kernel<<<grid, kBsThreads, need, (cudaStream_t)stream>>>(a);
     BSRNN_LAUNCH_OK();
     k = e;
@@ -190,7 +190,7 @@ extern "C" int bsrnn_band_norm_cast_kb8(const float* spec, const float* scale, c
   BSRNN_CHECK_ARG(smem <= 227 * 1024, "band_norm_cast_kb8: band of %d channels does not fit in shared memory", cmax);
   BSRNN_CUDA_OK(cudaFuncSetAttribute(band_norm_cast_kb8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BandCastArgs a{spec, scale, shift, reinterpret_cast<__half*>(out), c_off, bin0, width2, a_off, rows, T, F2, K, cmax};
-  dim3 grid((unsigned)((rows + 127) / 128), K);
+  dim3 grid(K, (unsigned)((rows + 127) / 128));
   band_norm_cast_kb8_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   BSRNN_LAUNCH_OK();
   return 0;
