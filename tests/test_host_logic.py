@@ -153,6 +153,42 @@ def test_fused_layer_weight_packs_and_geometry_choice():
     assert tc.fused_geometry(17) == 7 and tc.fused_geometry(501) == 7 and tc.fused_geometry(9) == 8
 
 
+def test_band_split_and_mask_decoder_tensorcore_packs():
+    """Host side of the round-2 small-kernel work: the tensor-core BandSplit pack (one 208-row weight tile per band, K
+    padded to 16, offsets of the grouped launch) and the mask-decoder pack with each family's GroupNorm affine folded into
+    its first Conv1d: W (z*gamma + beta) + b == (W diag(gamma)) z + (W beta + b), bias in operand column N."""
+    from urgent2026_challenge_track1_b200 import BSRNN_SE, runtime_tc as tc
+    torch.manual_seed(0)
+    m = BSRNN_SE(num_channel=196, num_layer=1, precision="fp16")
+    for p in m.parameters():
+        p.data.add_(0.05 * torch.randn_like(p))
+    core = m.bsrnn.bsrnn
+    bs = tc.pack_band_split_tc(core.band_split)
+    K = len(core.band_split.subbands)
+    assert bs["BN"] == 208 and bs["bias"].shape == (K, 208) and len(bs["kcs"]) == K
+    assert all(kc == ((2 * s + 15) // 16) * 2 for kc, s in zip(bs["kcs"], core.band_split.subbands))
+    k = 26                                                               # a 40-bin band: 80 channels -> 10 k-cores
+    kc = bs["kcs"][k]
+    w = tc.from_kb8(bs["w"][bs["w_off"][k]: bs["w_off"][k] + kc * 208 * 8].view(1, kc, 208, 8), 196, 2 * core.band_split.subbands[k])
+    assert torch.equal(w, core.band_split.fc[k].weight[:, :, 0].half().float())
+    assert bs["w_off"][k + 1] - bs["w_off"][k] == kc * 208 * 8 and float(bs["bias"][k, 196:].abs().max()) == 0
+    md = tc.pack_mask_decoder_tc(core.mask_decoder)
+    for name in ("mlp_mask", "mlp_residual"):
+        p = md[name]
+        assert p["one_col"] == 196 and p["shared_norm"] and p["kc1"] == 26 and p["kc2"] == 98 and p["nt1"] == 4
+        mlp = getattr(core.mask_decoder, name)[k]
+        W, b = mlp[1].weight[:, :, 0].double(), mlp[1].bias.double()
+        gamma, beta = mlp[0].weight.double(), mlp[0].bias.double()
+        packed = tc.from_kb8(p["w1"][k], 4 * 196, 208).double()          # (784, 208): columns [0,196) weights, 196 bias
+        assert float((packed[:, :196] - W * gamma[None, :]).abs().max()) < 2e-3 * float((W * gamma[None, :]).abs().max())
+        assert float((packed[:, 196] - (b + W @ beta)).abs().max()) < 2e-3 * float((b + W @ beta).abs().max())
+        assert float(packed[:, 197:].abs().max()) == 0
+        z = torch.randn(5, 196, dtype=torch.float64)                     # the identity the fold relies on, on the packed operands
+        ref = (z * gamma + beta) @ W.t() + b
+        got = torch.cat([z, torch.ones(5, 1, dtype=torch.float64), torch.zeros(5, 11, dtype=torch.float64)], 1) @ packed.t()
+        assert float((got - ref).abs().max()) < 5e-3 * float(ref.abs().max())
+
+
 def _shard_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
