@@ -463,9 +463,9 @@ struct TileIter {
       rev = true;
       m = m_tiles - 1 - (int)blockIdx.x;
       dm = -(int)gridDim.x;
-    } else if (a.m_inner > 1 && n_tiles == 1 && !resident) {   // steps innermost (see GemmTcArgs::m_inner)
+    } else if (a.m_inner > 1 && !resident && dn == 0) {        // steps innermost (see GemmTcArgs::m_inner); n stays fixed per CTA
       inner = a.m_inner; tps = a.rows.tiles_per_step;
-      lin = (int)blockIdx.x;
+      lin = m;
       m = (lin % inner) * tps + lin / inner;
     }
   }
@@ -1094,6 +1094,8 @@ static int launch_tc(GemmTcArgs a, cudaStream_t st) {
       if (inner_env && !a.groups && steps > 1 && col_step > 0 && a.m_tiles == steps * a.rows.tiles_per_step) a.m_inner = (int)steps;
     }
   }
+  // (the same band-innermost walk without a tensor map -- FlowSE, N = 384 = two N tiles of 192, one bulk copy per row -- measures
+  // no difference: 5.75 vs 5.73 s on config 4, profiles/r02 call72; it stays step-major there)
   if (EPI == EPI_RESID_TMA && !a.use_tmap) {
     static int runs_env = -1;             // BSRNN_FC_RUNS=0: one bulk copy per row (A/B timing)
     if (runs_env < 0) { const char* e = getenv("BSRNN_FC_RUNS"); runs_env = (e && e[0] == '0') ? 0 : 1; }
