@@ -44,6 +44,7 @@ def _bn_cover(rows, mult=16):
 
 
 _CONST = {}
+NARROW_BN = int(os.environ.get("BSRNN_BWD_BN", "0"))      # 0 = automatic (see pack_block)
 
 
 def _gate_tables(H, dev):
@@ -73,7 +74,11 @@ def pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, nar
     BN = _bn_div(4 * H, 32)
     bn_h, nt_h = _bn_cover(H, 32)                    # BPTT output tiles over the H hidden units (32-column chunks)
     if narrow_bwd and H > 64:
-        bn_h, nt_h = 64, (H + 63) // 64
+        # one BPTT step is a single wave of tiles x ceil(H / bn) x 2 CTAs that each stream the whole 4H-wide dG tile: the narrowest
+        # tile that still fits one wave of 148 SMs (config 5: 63.3 ms per step with 32, 68.0 with 64, 75.0 with 128; call74)
+        bn_h = NARROW_BN if NARROW_BN > 0 else (32 if isinstance(narrow_bwd, int) and not isinstance(narrow_bwd, bool)
+                                                 and 2 * narrow_bwd * ((H + 31) // 32) <= 148 else 64)
+        nt_h = (H + bn_h - 1) // bn_h
     bn_n, nt_n = _bn_cover(N, 16)
     p = dict(H=H, N=N, kc_in=kc_in, kc_h=kc_h, BN=BN, n_tiles=4 * H // BN, bn_h=bn_h, nt_h=nt_h, bn_n=bn_n, nt_n=nt_n, perm=perm)
     wih, bias, whh, whhT, wihT = [], [], [], [], []
@@ -179,7 +184,7 @@ class BLSTMBlockTC(torch.autograd.Function):
         Hh, Nn = w_hh.shape[1], w_ih.shape[1]
         fused = FUSED_TRAIN and Hh == 392 and Nn % 4 == 0 and Nn % 16 != 0
         with torch.profiler.record_function("tc_pack_block"):
-            p = pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, narrow_bwd=tiles <= 16, fwd_steps=not fused)
+            p = pack_block(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, fc_w, narrow_bwd=(tiles if tiles <= 16 else False), fwd_steps=not fused)
         H, BN, nt = p["H"], p["BN"], p["n_tiles"]
         m_all = steps * tiles
         x = x.contiguous().float()
