@@ -708,6 +708,8 @@ def run_config5(ctx, args):
                          "frac": tf / ctx.peak_tf, "traffic": None, "algorithmic_flops_per_step": flops,
                          "peak_source": ctx.peak_source},
             "impl_notes": {"batch_per_gpu": B, "samples": ns, "precision": tr.precision,
+                           "blstm": "forward: fused layer kernel with the activations for BPTT saved by its epilogue; backward: one "
+                                    "tensor-core step kernel per time step, split-K weight-gradient GEMMs",
                            "launch": "host launches" if args.no_graph else "CUDA graph replay of forward + loss + backward; "
                                      "allreduce and the fused clip+AdamW tail eager"}}
     _emit(line)
